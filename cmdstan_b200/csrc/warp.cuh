@@ -1,0 +1,42 @@
+// Warp-cooperation primitives for the chain kernels: one NUTS chain occupies one warp, lane l owns vector
+// elements l, l+32, l+64, ... of every per-chain vector ("owner lane" rule: an element is only ever read or
+// written by its owner, so no __syncwarp is needed between vector passes).  Scalars are warp-uniform: every
+// lane holds the same value, reductions are xor-butterflies (bitwise identical result in all lanes, fixed
+// summation order => run-to-run reproducible).
+//
+// B200_HOST_EMUL builds the same source for the host with a "warp" of one lane; it exists only so that the
+// CPU test-suite can drive the device state machine without a GPU (tests/host_emul).  It is never part of the
+// shipped library.
+#pragma once
+#include <cstdint>
+
+#ifdef B200_HOST_EMUL
+#include <cmath>
+#define B200_DEV inline
+#define B200_HD inline
+namespace b200 {
+constexpr int kWarp = 1;
+constexpr unsigned kFull = 1u;
+inline int lane_id() { return 0; }
+inline double bcast0(double v) { return v; }
+inline int bcast0i(int v) { return v; }
+inline double warp_sum(double v) { return v; }
+inline void warp_sync() {}
+}  // namespace b200
+#else
+#define B200_DEV __device__ __forceinline__
+#define B200_HD __host__ __device__ inline
+namespace b200 {
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+B200_DEV int lane_id() { return threadIdx.x & 31; }
+B200_DEV double bcast0(double v) { return __shfl_sync(kFull, v, 0); }
+B200_DEV int bcast0i(int v) { return __shfl_sync(kFull, v, 0); }
+B200_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+B200_DEV void warp_sync() { __syncwarp(); }
+}  // namespace b200
+#endif

@@ -45,6 +45,7 @@ typedef struct {
 static const uint64_t kSkip[128][MM_N] = {
 #include "mixmax_skip_n17.inc"
 };
+#define B200_TABLE static const
 #include "ziggurat_tables.inc"
 
 static inline uint64_t mod61(uint64_t k) { return (k & M61) + (k >> 61); }

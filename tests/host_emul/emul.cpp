@@ -1,0 +1,48 @@
+// TEST-ONLY: builds the device state machine (cmdstan_b200/csrc/nuts.cuh) for the host with a one-lane "warp"
+// (B200_HOST_EMUL) so that the CPU suite can check its logic against the oracle without a GPU.
+// This file is never part of libb200nuts.so; the product has no CPU path.
+#include <cmath>
+#include <cstring>
+#include <vector>
+using std::isnan; using std::isfinite;
+#include "../../cmdstan_b200/csrc/nuts.cuh"
+#include "../../cmdstan_b200/csrc/host_seed.h"
+
+using namespace b200;
+
+extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const double* sigma, int sum_y,
+                              unsigned seed, unsigned chain_id, int num_warmup, int num_samples, int num_thin, int save_warmup,
+                              double stepsize, double jitter, int max_depth, double delta, double gamma, double kappa, double t0,
+                              unsigned init_buffer, unsigned term_buffer, unsigned window, double init_radius, int adapt_engaged,
+                              const double* q0, const double* inv_metric0, double* draws, double* adapt_out, long long* n_grad) {
+  ModelData m{};
+  m.kind = kind; m.D = D; m.N = N; m.yr = yr; m.sigma = sigma; m.sum_y = sum_y;
+  SamplerCfg cfg{};
+  cfg.D = D; cfg.ld = D; cfg.max_depth = max_depth;
+  cfg.num_warmup = num_warmup; cfg.num_samples = num_samples; cfg.num_thin = num_thin; cfg.save_warmup = save_warmup;
+  cfg.adapt_engaged = adapt_engaged; cfg.user_inits = q0 != nullptr;
+  cfg.stepsize = stepsize; cfg.stepsize_jitter = (jitter > 0 && jitter < 1) ? jitter : 0.0;
+  cfg.delta = (delta > 0 && delta < 1) ? delta : 0.5; cfg.gamma = gamma > 0 ? gamma : 0.05;
+  cfg.kappa = kappa > 0 ? kappa : 0.75; cfg.t0 = t0 > 0 ? t0 : 10; cfg.init_radius = init_radius;
+  resolve_window(&cfg, adapt_engaged ? num_warmup : 0, init_buffer, term_buffer, window);
+  cfg.ncol = 7 + D;
+  cfg.rows_per_chain = (save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0) + (num_samples + num_thin - 1) / num_thin;
+  std::vector<double> slab((size_t)num_vec_slots(max_depth) * D, 0.0), q(D), g(D);
+  ChainS s;
+  std::memset(&s, 0, sizeof s);
+  chain_init_scalars(&s, cfg);
+  seed_stream(s.rng, seed, chain_id);
+  double zV = 0;
+  ChainView c{&s, q.data(), g.data(), &zV, slab.data(), draws, q0};
+  for (int i = 0; i < D; i++) slab[(size_t)V_IM * D + i] = inv_metric0 ? inv_metric0[i] : 1.0;
+  s.iter_end = num_warmup + num_samples;
+  while (advance(c, cfg, 0) == ADV_NEED_GRAD) {
+    double lp = lp_grad_small(m, q.data(), g.data(), 0);
+    for (int i = 0; i < D; i++) g[i] = -g[i];
+    zV = -lp;
+  }
+  adapt_out[0] = s.eps_nom;
+  for (int i = 0; i < D; i++) adapt_out[1 + i] = slab[(size_t)V_IM * D + i];
+  *n_grad = s.n_grad;
+  return s.err;
+}
