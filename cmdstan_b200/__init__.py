@@ -1,0 +1,265 @@
+"""cmdstan_b200 -- B200-native NUTS (diag_e, adaptive) engine behind CmdStan's sampling surface.
+
+Python host side of the C ABI in include/b200nuts.h (ctypes; no torch types cross the boundary).  The public call mirrors
+the reference service stan::services::sample::hmc_nuts_diag_e_adapt (stan/src/stan/services/sample/
+hmc_nuts_diag_e_adapt.hpp:331-407): same argument names, meaning, defaults and error codes.
+
+There is no CPU path: importing works anywhere (the shared library loads without a driver), but every compute call
+fails loudly with error code 70 when no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS"]
+
+MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
+ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
+SAMPLER_COLUMNS = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
+
+# stan::services::error_codes (stan/src/stan/services/error_codes.hpp)
+OK, USAGE, DATAERR, NOINPUT, SOFTWARE, CONFIG = 0, 64, 65, 66, 70, 78
+
+
+class Config(C.Structure):
+    _fields_ = [("model", C.c_int32), ("num_chains", C.c_int32), ("random_seed", C.c_uint32), ("init_chain_id", C.c_uint32),
+                ("init_radius", C.c_double), ("num_warmup", C.c_int32), ("num_samples", C.c_int32), ("num_thin", C.c_int32),
+                ("save_warmup", C.c_int32), ("stepsize", C.c_double), ("stepsize_jitter", C.c_double), ("max_depth", C.c_int32),
+                ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double), ("t0", C.c_double),
+                ("init_buffer", C.c_uint32), ("term_buffer", C.c_uint32), ("window", C.c_uint32), ("adapt_engaged", C.c_int32),
+                ("engine", C.c_int32), ("device", C.c_int32), ("store_draws", C.c_int32), ("row_shards", C.c_int32),
+                ("row_shard_rank", C.c_int32)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b200nuts_last_error", "b200nuts_set_data_f64",
+           "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
+           "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_rows_saved",
+           "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce"]
+
+_lib = None
+
+
+class B200NutsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200nuts error {code}: {msg}")
+        self.code = code
+
+
+def load_library(build=True):
+    """Loads (building first if sources changed) cmdstan_b200/libb200nuts.so.  Raises if it is missing: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build and _build.needs_build():
+        _build.build()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -m cmdstan_b200._build` (nvcc, sm_100a); there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+    lib.b200nuts_default_config.argtypes = [C.POINTER(Config)]
+    lib.b200nuts_default_config.restype = None
+    lib.b200nuts_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.b200nuts_destroy.argtypes = [vp]
+    lib.b200nuts_destroy.restype = None
+    lib.b200nuts_last_error.argtypes = [vp]
+    lib.b200nuts_last_error.restype = C.c_char_p
+    for f in ("b200nuts_set_data_f64", "b200nuts_set_data_i32", "b200nuts_set_data_i8"):
+        getattr(lib, f).argtypes = [vp, C.c_char_p, vp, i64p, C.c_int]
+    lib.b200nuts_num_params.argtypes = [vp, i64p, i64p]
+    lib.b200nuts_set_inits.argtypes = [vp, vp]
+    lib.b200nuts_set_inv_metric.argtypes = [vp, vp]
+    lib.b200nuts_init_chains.argtypes = [vp]
+    lib.b200nuts_log_prob_grad.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp]
+    lib.b200nuts_run.argtypes = [vp, C.c_int]
+    lib.b200nuts_fetch_draws.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp]
+    lib.b200nuts_rows_saved.argtypes = [vp]
+    lib.b200nuts_rows_saved.restype = C.c_int64
+    lib.b200nuts_get_adaptation.argtypes = [vp, vp, vp]
+    lib.b200nuts_get_chain_status.argtypes = [vp, vp, vp, vp]
+    lib.b200nuts_get_timing.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double)]
+    lib.b200nuts_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    _lib = lib
+    return lib
+
+
+def _np(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Engine:
+    """One engine = one GPU (one rank): owns the model data and the state of `num_chains` chains on `device`."""
+
+    def __init__(self, model, data, num_chains=1, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
+                 num_samples=1000, num_thin=1, save_warmup=False, stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8,
+                 gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50, window=25, adapt_engaged=True, engine="auto",
+                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None):
+        self.lib = load_library()
+        cfg = Config()
+        self.lib.b200nuts_default_config(C.byref(cfg))
+        cfg.model = MODELS[model] if isinstance(model, str) else int(model)
+        cfg.num_chains, cfg.random_seed, cfg.init_chain_id = int(num_chains), int(random_seed), int(init_chain_id)
+        cfg.init_radius, cfg.num_warmup, cfg.num_samples, cfg.num_thin = float(init_radius), int(num_warmup), int(num_samples), int(num_thin)
+        cfg.save_warmup, cfg.stepsize, cfg.stepsize_jitter, cfg.max_depth = int(bool(save_warmup)), float(stepsize), float(stepsize_jitter), int(max_depth)
+        cfg.delta, cfg.gamma, cfg.kappa, cfg.t0 = float(delta), float(gamma), float(kappa), float(t0)
+        cfg.init_buffer, cfg.term_buffer, cfg.window = int(init_buffer), int(term_buffer), int(window)
+        cfg.adapt_engaged, cfg.engine, cfg.device, cfg.store_draws = int(bool(adapt_engaged)), ENGINES[engine], int(device), int(bool(store_draws))
+        cfg.row_shards, cfg.row_shard_rank = int(row_shards), int(row_shard_rank)
+        self.cfg = cfg
+        self.model = model
+        self.h = C.c_void_p()
+        rc = self.lib.b200nuts_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            raise B200NutsError(rc, self.lib.b200nuts_last_error(None).decode())
+        self._cb = None
+        try:
+            self._set_data(data or {})
+            nu, no = C.c_int64(), C.c_int64()
+            self._chk(self.lib.b200nuts_num_params(self.h, C.byref(nu), C.byref(no)))
+            self.D, self.K = nu.value, no.value
+            if allreduce is not None:
+                self._cb = ALLREDUCE_FN(allreduce)
+                self._chk(self.lib.b200nuts_set_allreduce(self.h, self._cb, None))
+        except Exception:
+            self.close()
+            raise
+        self.num_chains = int(num_chains)
+
+    # -- plumbing
+    def _chk(self, rc):
+        if rc:
+            raise B200NutsError(rc, self.lib.b200nuts_last_error(self.h).decode())
+
+    def _set_data(self, data):
+        for name, val in data.items():
+            a = np.asarray(val)
+            if a.dtype == np.int8:
+                fn, a = self.lib.b200nuts_set_data_i8, _np(a, np.int8)
+            elif np.issubdtype(a.dtype, np.integer) or a.dtype == np.bool_:
+                fn, a = self.lib.b200nuts_set_data_i32, _np(a, np.int32)
+            else:
+                fn, a = self.lib.b200nuts_set_data_f64, _np(a, np.float64)
+            if self.model in ("eight_schools_nc", 2) and name in ("y", "sigma"):
+                fn, a = self.lib.b200nuts_set_data_f64, _np(a, np.float64)
+            if self.model in ("irt_2pl", 4) and name == "y":
+                fn, a = self.lib.b200nuts_set_data_i8, _np(a, np.int8)
+            dims = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+            self._chk(fn(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), dims, max(a.ndim, 1)))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.b200nuts_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the path
+    def set_inits(self, q0):
+        a = None if q0 is None else _np(q0, np.float64).reshape(self.num_chains, self.D)
+        self._chk(self.lib.b200nuts_set_inits(self.h, None if a is None else a.ctypes.data_as(C.c_void_p)))
+
+    def set_inv_metric(self, im):
+        a = None if im is None else _np(im, np.float64).reshape(self.num_chains, self.D)
+        self._chk(self.lib.b200nuts_set_inv_metric(self.h, None if a is None else a.ctypes.data_as(C.c_void_p)))
+
+    def init_chains(self):
+        self._chk(self.lib.b200nuts_init_chains(self.h))
+
+    def log_prob_grad(self, q, jacobian=True):
+        q = _np(q, np.float64)
+        q2 = q.reshape(-1, self.D)
+        lp = np.empty(len(q2))
+        g = np.empty_like(q2)
+        self._chk(self.lib.b200nuts_log_prob_grad(self.h, q2.ctypes.data_as(C.c_void_p), len(q2), int(jacobian),
+                                                  lp.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p)))
+        return (lp[0], g[0]) if q.ndim == 1 else (lp, g)
+
+    def run(self, n_iter):
+        self._chk(self.lib.b200nuts_run(self.h, int(n_iter)))
+
+    def rows_saved(self):
+        return int(self.lib.b200nuts_rows_saved(self.h))
+
+    def fetch_draws(self, chain0=0, nchains=None, row0=0, nrows=None, constrained=True, out=None):
+        nchains = self.num_chains - chain0 if nchains is None else nchains
+        nrows = self.rows_saved() - row0 if nrows is None else nrows
+        k = self.K if constrained else self.D
+        if out is None:
+            out = np.empty((nchains, nrows, 7 + k))
+        self._chk(self.lib.b200nuts_fetch_draws(self.h, chain0, nchains, row0, nrows, int(constrained), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def adaptation(self):
+        eps = np.empty(self.num_chains)
+        im = np.empty((self.num_chains, self.D))
+        self._chk(self.lib.b200nuts_get_adaptation(self.h, eps.ctypes.data_as(C.c_void_p), im.ctypes.data_as(C.c_void_p)))
+        return eps, im
+
+    def chain_status(self):
+        err = np.empty(self.num_chains, dtype=np.int32)
+        it = np.empty(self.num_chains, dtype=np.int32)
+        ng = np.empty(self.num_chains, dtype=np.int64)
+        self._chk(self.lib.b200nuts_get_chain_status(self.h, err.ctypes.data_as(C.c_void_p), it.ctypes.data_as(C.c_void_p), ng.ctypes.data_as(C.c_void_p)))
+        return err, it, ng
+
+    def timing(self):
+        s, n, g = C.c_double(), C.c_int64(), C.c_double()
+        self._chk(self.lib.b200nuts_get_timing(self.h, C.byref(s), C.byref(n), C.byref(g)))
+        return s.value, n.value, g.value
+
+
+def hmc_nuts_diag_e_adapt(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1,
+                          init_radius=2.0, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=False, refresh=100,
+                          stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0,
+                          init_buffer=75, term_buffer=50, window=25, logger=None, device=0, engine="auto"):
+    """Mirror of stan::services::sample::hmc_nuts_diag_e_adapt (multi-chain overload,
+    stan/src/stan/services/sample/hmc_nuts_diag_e_adapt.hpp:331-407).
+
+    Returns (return_code, result) with return_code in stan::services::error_codes; result is a dict with
+    `draws` [num_chains, rows, 7 + K], `columns`, `stepsize` [num_chains], `inv_metric` [num_chains, D], `timing`.
+    `init` are unconstrained initial values [num_chains, D] (None: uniform(-init_radius, init_radius) from each chain's
+    own stream, like util::initialize); `init_inv_metric` [num_chains, D] (None: ones).
+    """
+    log = logger or (lambda msg: None)
+    try:
+        e = Engine(model, data, num_chains=num_chains, random_seed=random_seed, init_chain_id=init_chain_id,
+                   init_radius=init_radius, num_warmup=num_warmup, num_samples=num_samples, num_thin=num_thin,
+                   save_warmup=save_warmup, stepsize=stepsize, stepsize_jitter=stepsize_jitter, max_depth=max_depth, delta=delta,
+                   gamma=gamma, kappa=kappa, t0=t0, init_buffer=init_buffer, term_buffer=term_buffer, window=window,
+                   adapt_engaged=True, engine=engine, device=device)
+    except B200NutsError as ex:
+        log(str(ex))
+        return ex.code, None
+    try:
+        if init is not None:
+            e.set_inits(init)
+        if init_inv_metric is not None:
+            e.set_inv_metric(init_inv_metric)
+        e.init_chains()
+        e.run(num_warmup)
+        warm_s = e.timing()[0]
+        e.run(num_samples)
+        samp_s = e.timing()[0]
+        err, it, ng = e.chain_status()
+        if (err != 0).any():
+            code = int(err[err != 0][0])
+            log("chain(s) %s stopped: %s" % (np.nonzero(err)[0].tolist(), {78: "Initialization failed.", 70: "step size / metric adaptation failure"}.get(code, code)))
+            return code, None
+        eps, im = e.adaptation()
+        draws = e.fetch_draws()
+        names = SAMPLER_COLUMNS + [f"v{i + 1}" for i in range(e.K)]
+        return OK, dict(draws=draws, columns=names, stepsize=eps, inv_metric=im, timing=dict(warmup=warm_s, sampling=samp_s), n_grad=ng)
+    except B200NutsError as ex:
+        log(str(ex))
+        return ex.code, None
+    finally:
+        e.close()

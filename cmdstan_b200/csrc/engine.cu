@@ -1,0 +1,822 @@
+// libb200nuts.so -- engine + C ABI (include/b200nuts.h).
+//
+// Two ways of running the per-chain state machine of nuts.cuh:
+//
+//  * fused engine (models 0-2: a gradient is tens of flops): one persistent warp per chain; the model's log density and
+//    gradient are inlined, a chain runs all requested transitions without leaving the kernel.  One launch per
+//    b200nuts_run.  Chain state lives in global memory but is private to its warp, so it stays in that SM's L1/L2.
+//  * lock-step engine (GLMs, IRT: a gradient is 10^7..10^9 flops and shares the data matrix across chains): every chain
+//    is advanced to its next "gradient wanted" point (advance_kernel, warp per chain), then ONE cross-chain kernel
+//    evaluates all chains' gradients (glm.cu / irt.cu), and so on -- "asynchronous chains, synchronous leapfrogs".
+//    Chains never wait for each other at transition boundaries; the only global synchronisation is the end of the run.
+//
+// Chain c of an engine uses the MIXMAX stream create_rng(seed, init_chain_id + c) and its output depends on nothing
+// else (parallel-match invariant, ST/unit/services/sample/hmc_nuts_diag_e_adapt_parallel_match_test.cpp:73-153), which
+// is what makes chain sharding across GPUs communication-free.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nuts.h"
+#include "host_seed.h"
+#include "kernels.h"
+#include "nuts.cuh"
+
+using namespace b200;
+
+namespace {
+
+std::string g_create_error;
+
+#define CUDA_TRY(e, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t err__ = (call);                                                                   \
+    if (err__ != cudaSuccess) {                                                                   \
+      (e)->err = std::string(#call) + ": " + cudaGetErrorString(err__);                           \
+      return B200NUTS_SOFTWARE;                                                                   \
+    }                                                                                             \
+  } while (0)
+
+constexpr int kChainsPerBlock = 4;  // 4 warps per CTA
+
+struct DeviceChains {
+  ChainS* cs;
+  double *q, *g, *zV, *slab, *draws;
+  const double* user_q0;
+  size_t slab_stride, draws_stride;
+};
+
+__device__ __forceinline__ ChainView make_view(const DeviceChains& d, const SamplerCfg& cfg, int c) {
+  ChainView v;
+  v.s = d.cs + c;
+  v.q = d.q + (size_t)c * cfg.ld;
+  v.g = d.g + (size_t)c * cfg.ld;
+  v.zV = d.zV + c;
+  v.v = d.slab + (size_t)c * d.slab_stride;
+  v.draws = d.draws ? d.draws + (size_t)c * d.draws_stride : nullptr;
+  v.user_q0 = d.user_q0 ? d.user_q0 + (size_t)c * cfg.ld : nullptr;
+  return v;
+}
+
+// ---- fused engine: advance + inlined model gradient, looped until the chain is idle
+__global__ void __launch_bounds__(32 * kChainsPerBlock) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C) {
+  const int c = blockIdx.x * kChainsPerBlock + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  ChainView v = make_view(d, cfg, c);
+  while (advance(v, cfg, lane) == ADV_NEED_GRAD) {
+    __syncwarp();
+    const double lp = lp_grad_small(md, v.q, v.g, lane);
+    for (int i = lane; i < cfg.D; i += 32) v.g[i] = -v.g[i];
+    *v.zV = -lp;
+    __syncwarp();
+  }
+}
+
+// ---- lock-step engine: advance every chain to its next gradient request
+__global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCfg cfg, DeviceChains d, int C, int* active,
+                                                                          int* n_active) {
+  const int c = blockIdx.x * kChainsPerBlock + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  ChainView v = make_view(d, cfg, c);
+  const int r = advance(v, cfg, lane);
+  if (lane == 0) {
+    const int a = r == ADV_NEED_GRAD ? 1 : 0;
+    active[c] = a;
+    if (a) atomicAdd(n_active, 1);
+  }
+}
+
+// gradient stage of the lock-step engine for the small models (used for engine-equivalence tests)
+__global__ void __launch_bounds__(128) grad_small_kernel(ModelData md, const double* Q, double* G, double* zV, const int* active,
+                                                           int C, int ld) {
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  if (active && !active[c]) return;
+  const int lane = threadIdx.x & 31;
+  const double* q = Q + (size_t)c * ld;
+  double* g = G + (size_t)c * ld;
+  const double lp = lp_grad_small(md, q, g, lane);
+  __syncwarp();
+  for (int i = lane; i < md.D; i += 32) g[i] = -g[i];
+  if (lane == 0) zV[c] = -lp;
+}
+
+__global__ void set_iter_end_kernel(ChainS* cs, int C, int add, int cap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int e = cs[c].iter_end + add;
+  cs[c].iter_end = e > cap ? cap : e;
+}
+
+__global__ void init_metric_kernel(double* slab, size_t slab_stride, int ld, int D, int C, const double* user_im) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * D) return;
+  const int c = (int)(idx / D), i = (int)(idx - (long long)c * D);
+  slab[(size_t)c * slab_stride + (size_t)V_IM * ld + i] = user_im ? user_im[(size_t)c * D + i] : 1.0;
+}
+
+// rows of the draws buffer -> output rows with write_array applied: one thread per (chain, row)
+__global__ void fetch_kernel(const double* draws, size_t draws_stride, int ncol, int kind, int D, int N, int K, int K_out,
+                             int constrained, long long chain0, long long nchains, long long row0, long long nrows, double* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nchains * nrows) return;
+  const long long c = idx / nrows, r = idx - c * nrows;
+  const double* src = draws + (size_t)(chain0 + c) * draws_stride + (size_t)(row0 + r) * ncol;
+  const int kout = constrained ? K_out : D;
+  double* dst = out + (size_t)idx * (7 + kout);
+  for (int i = 0; i < 7; i++) dst[i] = src[i];
+  if (constrained) model_write_array(kind, D, N, K, src + 7, dst + 7);
+  else for (int i = 0; i < D; i++) dst[7 + i] = src[7 + i];
+}
+
+__global__ void gather_status_kernel(const ChainS* cs, int C, int* err, int* iter, long long* n_grad, double* eps, int* rows) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  err[c] = cs[c].err;
+  iter[c] = cs[c].iter;
+  n_grad[c] = cs[c].n_grad;
+  eps[c] = cs[c].eps_nom;
+  rows[c] = cs[c].draws_row;
+}
+
+__global__ void gather_metric_kernel(const double* slab, size_t slab_stride, int ld, int D, int C, double* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * D) return;
+  const int c = (int)(idx / D), i = (int)(idx - (long long)c * D);
+  out[idx] = slab[(size_t)c * slab_stride + (size_t)V_IM * ld + i];
+}
+
+// log_prob with jacobian = 0: remove the log-Jacobian terms (and their derivatives) of the constraining transforms.
+// in: zV = -lp, G = -grad (jacobian = 1).  One thread per point.
+__global__ void remove_jacobian_kernel(int kind, int D, int N, int K, const double* Q, double* G, double* zV, int n, int ld) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const double* q = Q + (size_t)c * ld;
+  double* g = G + (size_t)c * ld;
+  if (kind == MODEL_BERNOULLI) {
+    const double u = q[0], au = fabs(u);
+    const double th = dev_inv_logit(u);
+    zV[c] += -au - 2.0 * dev_log1p_exp(-au);
+    g[0] += 1 - 2 * th;
+  } else if (kind == MODEL_EIGHT_SCHOOLS) {
+    zV[c] += q[1];
+    g[1] += 1.0;
+  } else if (kind == MODEL_IRT2PL) {
+    const int I = N, J = K;
+    double s = q[0] + q[1 + I] + q[3 + I + J];
+    g[0] += 1.0;
+    g[1 + I] += 1.0;
+    g[3 + I + J] += 1.0;
+    for (int j = 0; j < J; j++) {
+      s += q[2 + I + j];
+      g[2 + I + j] += 1.0;
+    }
+    zV[c] += s;
+  }
+}
+
+}  // namespace
+
+struct b200nuts_engine {
+  b200nuts_config cfg;
+  SamplerCfg scfg;
+  ModelData md;
+  std::string err;
+  bool fused = false, data_ready = false, chains_ready = false;
+  int C = 0, D = 0, ld = 0, K_out = 0;
+  int sm_count = 148;
+  // host staging of model data
+  std::vector<double> h_X, h_yr, h_sigma;
+  std::vector<int> h_yi;
+  std::vector<int8_t> h_y8;
+  int64_t x_rows = 0, x_cols = 0, y8_rows = 0, y8_cols = 0;
+  int std_normal_D = 3;
+  // device
+  double *d_X = nullptr, *d_yr = nullptr, *d_sigma = nullptr;
+  int* d_yi = nullptr;
+  signed char* d_y8 = nullptr;
+  DeviceChains dc{};
+  double *d_user_q0 = nullptr, *d_user_im = nullptr;
+  std::vector<double> h_user_q0, h_user_im;
+  int *d_active = nullptr, *d_nactive = nullptr;
+  int* h_nactive = nullptr;  // pinned
+  void* d_glm_ws = nullptr;
+  GlmWorkspace glm_ws;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> grad_events;
+  allreduce_fn ar = nullptr;
+  void* ar_user = nullptr;
+  double last_run_s = 0, last_grad_s = 0;
+  long long last_launches = 0;
+};
+
+extern "C" {
+
+void b200nuts_default_config(b200nuts_config* c) {
+  std::memset(c, 0, sizeof *c);
+  c->model = B200NUTS_STD_NORMAL;
+  c->num_chains = 1;
+  c->random_seed = 0;
+  c->init_chain_id = 1;
+  c->init_radius = 2.0;
+  c->num_warmup = 1000;
+  c->num_samples = 1000;
+  c->num_thin = 1;
+  c->save_warmup = 0;
+  c->stepsize = 1.0;
+  c->stepsize_jitter = 0.0;
+  c->max_depth = 10;
+  c->delta = 0.8;
+  c->gamma = 0.05;
+  c->kappa = 0.75;
+  c->t0 = 10.0;
+  c->init_buffer = 75;
+  c->term_buffer = 50;
+  c->window = 25;
+  c->adapt_engaged = 1;
+  c->engine = B200NUTS_ENGINE_AUTO;
+  c->device = 0;
+  c->store_draws = 1;
+  c->row_shards = 1;
+  c->row_shard_rank = 0;
+}
+
+const char* b200nuts_last_error(const b200nuts_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
+  *out = nullptr;
+  // argument validation mirrors the reference's argument tree (src/cmdstan/arguments/arg_*.hpp is_valid)
+  if (cfg->num_chains < 1) { g_create_error = "num_chains must be >= 1"; return B200NUTS_USAGE; }
+  if (cfg->model < 0 || cfg->model > 5) { g_create_error = "unknown model"; return B200NUTS_USAGE; }
+  if (cfg->num_warmup < 0 || cfg->num_samples < 0 || cfg->num_thin < 1) { g_create_error = "num_warmup/num_samples must be >= 0 and thin >= 1"; return B200NUTS_USAGE; }
+  if (cfg->max_depth < 1 || cfg->max_depth > kMaxDepthCap) { g_create_error = "max_depth must be in 1..16"; return B200NUTS_USAGE; }
+  if (cfg->adapt_engaged && cfg->num_warmup == 0) {  // command.hpp:569-574
+    g_create_error = "Model is adapting but num_warmup is 0: disable adaptation (adapt engaged=0) or set num_warmup > 0";
+    return B200NUTS_USAGE;
+  }
+  if (!(cfg->delta > 0.1 - 1e-15 && cfg->delta < 1.0)) { g_create_error = "delta must be in [0.1, 1)"; return B200NUTS_USAGE; }
+  if (!(cfg->stepsize > 0) || !(cfg->gamma > 0) || !(cfg->kappa > 0) || !(cfg->t0 > 0)) { g_create_error = "stepsize, gamma, kappa, t0 must be > 0"; return B200NUTS_USAGE; }
+  if (cfg->stepsize_jitter < 0 || cfg->stepsize_jitter > 1) { g_create_error = "stepsize_jitter must be in [0, 1]"; return B200NUTS_USAGE; }
+  if (cfg->init_radius < 0) { g_create_error = "init radius must be >= 0"; return B200NUTS_USAGE; }
+  if (cfg->row_shards < 1 || cfg->row_shard_rank < 0 || cfg->row_shard_rank >= cfg->row_shards) { g_create_error = "bad row shard configuration"; return B200NUTS_USAGE; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available (libb200nuts has no CPU path): ") + cudaGetErrorString(ce);
+    return B200NUTS_SOFTWARE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return B200NUTS_USAGE; }
+  auto* e = new b200nuts_engine();
+  e->cfg = *cfg;
+  e->C = cfg->num_chains;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaSetDevice / cudaStreamCreate failed";
+    delete e;
+    return B200NUTS_SOFTWARE;
+  }
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  std::memset(&e->md, 0, sizeof e->md);
+  e->md.kind = cfg->model;
+  *out = e;
+  return B200NUTS_OK;
+}
+
+static void free_dev(void* p) { if (p) cudaFree(p); }
+
+void b200nuts_destroy(b200nuts_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8);
+  free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws);
+  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
+  if (e->h_nactive) cudaFreeHost(e->h_nactive);
+  for (auto ev : e->grad_events) cudaEventDestroy(ev);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int64_t prod(const int64_t* dims, int nd) {
+  int64_t p = 1;
+  for (int i = 0; i < nd; i++) p *= dims[i];
+  return p;
+}
+
+int b200nuts_set_data_f64(b200nuts_engine* e, const char* name, const double* host, const int64_t* dims, int nd) {
+  const std::string n(name);
+  const int64_t cnt = prod(dims, nd);
+  if (n == "X" && nd == 2) {
+    e->h_X.assign(host, host + cnt);
+    e->x_rows = dims[0];
+    e->x_cols = dims[1];
+  } else if (n == "y" && e->cfg.model == B200NUTS_EIGHT_SCHOOLS_NC) {
+    e->h_yr.assign(host, host + cnt);
+  } else if (n == "sigma") {
+    for (int64_t i = 0; i < cnt; i++)
+      if (!(host[i] > 0)) { e->err = "sigma must be positive"; return B200NUTS_DATAERR; }
+    e->h_sigma.assign(host, host + cnt);
+  } else {
+    e->err = "unknown f64 data variable '" + n + "' for this model";
+    return B200NUTS_DATAERR;
+  }
+  e->data_ready = false;
+  return B200NUTS_OK;
+}
+
+int b200nuts_set_data_i32(b200nuts_engine* e, const char* name, const int32_t* host, const int64_t* dims, int nd) {
+  const std::string n(name);
+  const int64_t cnt = prod(dims, nd);
+  if (n == "y") {
+    if (e->cfg.model == B200NUTS_BERNOULLI || e->cfg.model == B200NUTS_LOGISTIC_GLM) {
+      for (int64_t i = 0; i < cnt; i++)
+        if (host[i] < 0 || host[i] > 1) { e->err = "y must be in [0, 1]"; return B200NUTS_DATAERR; }
+    } else if (e->cfg.model == B200NUTS_POISSON_GLM) {
+      for (int64_t i = 0; i < cnt; i++)
+        if (host[i] < 0) { e->err = "y must be nonnegative"; return B200NUTS_DATAERR; }
+    }
+    e->h_yi.assign(host, host + cnt);
+  } else if (n == "D" && cnt == 1) {
+    e->std_normal_D = host[0];
+  } else {
+    e->err = "unknown i32 data variable '" + n + "' for this model";
+    return B200NUTS_DATAERR;
+  }
+  e->data_ready = false;
+  return B200NUTS_OK;
+}
+
+int b200nuts_set_data_i8(b200nuts_engine* e, const char* name, const int8_t* host, const int64_t* dims, int nd) {
+  const std::string n(name);
+  if (n == "y" && nd == 2 && e->cfg.model == B200NUTS_IRT_2PL) {
+    const int64_t cnt = prod(dims, nd);
+    for (int64_t i = 0; i < cnt; i++)
+      if (host[i] < 0 || host[i] > 1) { e->err = "y must be in [0, 1]"; return B200NUTS_DATAERR; }
+    e->h_y8.assign(host, host + cnt);
+    e->y8_rows = dims[0];
+    e->y8_cols = dims[1];
+    e->data_ready = false;
+    return B200NUTS_OK;
+  }
+  e->err = "unknown i8 data variable '" + n + "' for this model";
+  return B200NUTS_DATAERR;
+}
+
+// validates the data against the model, uploads it, fixes D / ld / engine kind
+static int finalize_data(b200nuts_engine* e) {
+  if (e->data_ready) return B200NUTS_OK;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  ModelData& m = e->md;
+  const int kind = e->cfg.model;
+  m.kind = kind;
+  auto upload = [&](void** dptr, const void* src, size_t bytes) -> cudaError_t {
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    cudaError_t r = cudaMalloc(dptr, bytes ? bytes : 8);
+    if (r != cudaSuccess) return r;
+    return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+  };
+  switch (kind) {
+    case B200NUTS_STD_NORMAL:
+      if (e->std_normal_D < 1) { e->err = "D must be >= 1"; return B200NUTS_DATAERR; }
+      m.D = e->std_normal_D;
+      m.N = 0;
+      break;
+    case B200NUTS_BERNOULLI: {
+      if (e->h_yi.empty()) { e->err = "bernoulli: data variable y missing"; return B200NUTS_NOINPUT; }
+      m.D = 1;
+      m.N = (int)e->h_yi.size();
+      int s = 0;
+      for (int v : e->h_yi) s += v;
+      m.sum_y = s;
+      break;
+    }
+    case B200NUTS_EIGHT_SCHOOLS_NC: {
+      if (e->h_yr.empty() || e->h_yr.size() != e->h_sigma.size()) { e->err = "eight_schools: y and sigma must be given with equal sizes"; return B200NUTS_NOINPUT; }
+      m.N = (int)e->h_yr.size();
+      m.D = m.N + 2;
+      CUDA_TRY(e, upload((void**)&e->d_yr, e->h_yr.data(), e->h_yr.size() * 8));
+      CUDA_TRY(e, upload((void**)&e->d_sigma, e->h_sigma.data(), e->h_sigma.size() * 8));
+      m.yr = e->d_yr;
+      m.sigma = e->d_sigma;
+      break;
+    }
+    case B200NUTS_LOGISTIC_GLM:
+    case B200NUTS_POISSON_GLM: {
+      if (e->h_X.empty() || (int64_t)e->h_yi.size() != e->x_rows) { e->err = "glm: X[N][K] and y[N] must be given"; return B200NUTS_NOINPUT; }
+      m.N = (int)e->x_rows;
+      m.K = (int)e->x_cols;
+      m.D = m.K + 1;
+      if (((m.D + 3) & ~3) > glm_max_dim()) { e->err = "glm: too many covariates for this build (D <= 176)"; return B200NUTS_CONFIG; }
+      m.ldx = (m.D + 3) & ~3;
+      // padded design matrix [1 | X | 0]
+      std::vector<double> xp((size_t)m.N * m.ldx, 0.0);
+      for (int i = 0; i < m.N; i++) {
+        double* row = xp.data() + (size_t)i * m.ldx;
+        row[0] = 1.0;
+        std::memcpy(row + 1, e->h_X.data() + (size_t)i * m.K, (size_t)m.K * 8);
+      }
+      CUDA_TRY(e, upload((void**)&e->d_X, xp.data(), xp.size() * 8));
+      CUDA_TRY(e, upload((void**)&e->d_yi, e->h_yi.data(), e->h_yi.size() * 4));
+      m.X = e->d_X;
+      m.yi = e->d_yi;
+      break;
+    }
+    case B200NUTS_IRT_2PL: {
+      if (e->h_y8.empty()) { e->err = "irt_2pl: y[I][J] missing"; return B200NUTS_NOINPUT; }
+      m.N = (int)e->y8_rows;
+      m.K = (int)e->y8_cols;
+      if (m.K > irt_max_items()) { e->err = "irt_2pl: too many items for this build (J <= 128)"; return B200NUTS_CONFIG; }
+      m.D = 4 + m.N + 2 * m.K;
+      CUDA_TRY(e, upload((void**)&e->d_y8, e->h_y8.data(), e->h_y8.size()));
+      m.y8 = e->d_y8;
+      break;
+    }
+  }
+  e->D = m.D;
+  e->ld = (m.D + 3) & ~3;
+  e->K_out = model_num_outputs(kind, m.D, m.N);
+  const bool small = kind <= B200NUTS_EIGHT_SCHOOLS_NC;
+  if (e->cfg.engine == B200NUTS_ENGINE_FUSED && !small) { e->err = "the fused engine supports models 0-2 only"; return B200NUTS_CONFIG; }
+  e->fused = e->cfg.engine == B200NUTS_ENGINE_FUSED || (e->cfg.engine == B200NUTS_ENGINE_AUTO && small);
+  if (e->cfg.row_shards > 1 && !(kind == B200NUTS_LOGISTIC_GLM || kind == B200NUTS_POISSON_GLM)) { e->err = "row sharding is available for the GLMs only"; return B200NUTS_CONFIG; }
+  e->data_ready = true;
+  return B200NUTS_OK;
+}
+
+int b200nuts_num_params(const b200nuts_engine* ce, int64_t* nu, int64_t* no) {
+  auto* e = const_cast<b200nuts_engine*>(ce);
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  if (nu) *nu = e->D;
+  if (no) *no = e->K_out;
+  return B200NUTS_OK;
+}
+
+int b200nuts_set_inits(b200nuts_engine* e, const double* q0) {
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  if (q0) e->h_user_q0.assign(q0, q0 + (size_t)e->C * e->D);
+  else e->h_user_q0.clear();
+  return B200NUTS_OK;
+}
+
+int b200nuts_set_inv_metric(b200nuts_engine* e, const double* im) {
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  if (im) {
+    for (size_t i = 0; i < (size_t)e->C * e->D; i++)
+      if (!(im[i] > 0) || !std::isfinite(im[i])) { e->err = "Inverse Euclidean metric not positive definite."; return B200NUTS_CONFIG; }  // validate_diag_inv_metric
+    e->h_user_im.assign(im, im + (size_t)e->C * e->D);
+  } else {
+    e->h_user_im.clear();
+  }
+  return B200NUTS_OK;
+}
+
+int b200nuts_set_allreduce(b200nuts_engine* e, b200nuts_allreduce_fn fn, void* user) {
+  e->ar = fn;
+  e->ar_user = user;
+  return B200NUTS_OK;
+}
+
+static int ensure_glm_ws(b200nuts_engine* e, int C) {
+  if (!(e->md.kind == MODEL_LOGISTIC || e->md.kind == MODEL_POISSON)) return B200NUTS_OK;
+  if (e->d_glm_ws && e->glm_ws.C >= C) return B200NUTS_OK;
+  free_dev(e->d_glm_ws);
+  e->d_glm_ws = nullptr;
+  size_t bytes = glm_workspace_bytes(e->md.N, e->md.D, C, &e->glm_ws);
+  CUDA_TRY(e, cudaMalloc(&e->d_glm_ws, bytes));
+  glm_workspace_bind(&e->glm_ws, e->d_glm_ws);
+  const char* v = getenv("B200NUTS_GLM_VARIANT");
+  e->glm_ws.variant = v ? atoi(v) : 1;
+  return B200NUTS_OK;
+}
+
+int b200nuts_init_chains(b200nuts_engine* e) {
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  const b200nuts_config& c = e->cfg;
+  SamplerCfg& s = e->scfg;
+  std::memset(&s, 0, sizeof s);
+  s.D = e->D;
+  s.ld = e->ld;
+  s.max_depth = c.max_depth;
+  s.num_warmup = c.num_warmup;
+  s.num_samples = c.num_samples;
+  s.num_thin = c.num_thin;
+  s.save_warmup = c.save_warmup;
+  s.adapt_engaged = c.adapt_engaged;
+  s.user_inits = !e->h_user_q0.empty();
+  s.stepsize = c.stepsize;
+  s.stepsize_jitter = (c.stepsize_jitter > 0 && c.stepsize_jitter < 1) ? c.stepsize_jitter : 0.0;  // base_hmc::set_stepsize_jitter
+  s.delta = c.delta;
+  s.gamma = c.gamma;
+  s.kappa = c.kappa;
+  s.t0 = c.t0;
+  s.init_radius = c.init_radius;
+  resolve_window(&s, c.adapt_engaged ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
+  s.ncol = 7 + e->D;
+  s.rows_per_chain = c.store_draws ? (c.save_warmup ? (c.num_warmup + c.num_thin - 1) / c.num_thin : 0) + (c.num_samples + c.num_thin - 1) / c.num_thin : 0;
+
+  const int C = e->C;
+  DeviceChains& d = e->dc;
+  free_dev(d.cs); free_dev(d.q); free_dev(d.g); free_dev(d.zV); free_dev(d.slab); free_dev(d.draws);
+  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_nactive);
+  d = DeviceChains{};
+  e->d_user_q0 = e->d_user_im = nullptr;
+  d.slab_stride = (size_t)num_vec_slots(c.max_depth) * e->ld;
+  d.draws_stride = (size_t)s.rows_per_chain * s.ncol;
+  CUDA_TRY(e, cudaMalloc(&d.cs, sizeof(ChainS) * C));
+  CUDA_TRY(e, cudaMalloc(&d.q, sizeof(double) * C * e->ld));
+  CUDA_TRY(e, cudaMalloc(&d.g, sizeof(double) * C * e->ld));
+  CUDA_TRY(e, cudaMalloc(&d.zV, sizeof(double) * C));
+  CUDA_TRY(e, cudaMalloc(&d.slab, sizeof(double) * C * d.slab_stride));
+  CUDA_TRY(e, cudaMemset(d.q, 0, sizeof(double) * C * e->ld));
+  CUDA_TRY(e, cudaMemset(d.g, 0, sizeof(double) * C * e->ld));
+  CUDA_TRY(e, cudaMemset(d.zV, 0, sizeof(double) * C));
+  CUDA_TRY(e, cudaMemset(d.slab, 0, sizeof(double) * C * d.slab_stride));
+  if (d.draws_stride) {
+    cudaError_t r = cudaMalloc(&d.draws, sizeof(double) * C * d.draws_stride);
+    if (r != cudaSuccess) {
+      e->err = "cannot allocate the draws buffer (" + std::to_string(sizeof(double) * C * d.draws_stride >> 20) + " MiB): " + cudaGetErrorString(r) + "; use store_draws=0, thin, or fewer chains per GPU";
+      d.draws = nullptr;
+      return B200NUTS_SOFTWARE;
+    }
+  }
+  CUDA_TRY(e, cudaMalloc(&e->d_active, sizeof(int) * C));
+  CUDA_TRY(e, cudaMalloc(&e->d_nactive, sizeof(int)));
+  if (!e->h_nactive) CUDA_TRY(e, cudaMallocHost(&e->h_nactive, sizeof(int)));
+  // per-chain scalars + seeded streams (host), then upload
+  std::vector<ChainS> hs(C);
+  for (int i = 0; i < C; i++) {
+    std::memset(&hs[i], 0, sizeof(ChainS));
+    chain_init_scalars(&hs[i], s);
+    seed_stream(hs[i].rng, c.random_seed, c.init_chain_id + (uint32_t)i);
+  }
+  CUDA_TRY(e, cudaMemcpy(d.cs, hs.data(), sizeof(ChainS) * C, cudaMemcpyHostToDevice));
+  if (!e->h_user_q0.empty()) {
+    std::vector<double> padded((size_t)C * e->ld, 0.0);
+    for (int i = 0; i < C; i++) std::memcpy(padded.data() + (size_t)i * e->ld, e->h_user_q0.data() + (size_t)i * e->D, sizeof(double) * e->D);
+    CUDA_TRY(e, cudaMalloc(&e->d_user_q0, sizeof(double) * padded.size()));
+    CUDA_TRY(e, cudaMemcpy(e->d_user_q0, padded.data(), sizeof(double) * padded.size(), cudaMemcpyHostToDevice));
+    d.user_q0 = e->d_user_q0;
+  }
+  if (!e->h_user_im.empty()) {
+    CUDA_TRY(e, cudaMalloc(&e->d_user_im, sizeof(double) * e->h_user_im.size()));
+    CUDA_TRY(e, cudaMemcpy(e->d_user_im, e->h_user_im.data(), sizeof(double) * e->h_user_im.size(), cudaMemcpyHostToDevice));
+  }
+  {
+    const long long tot = (long long)C * e->D;
+    init_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(d.slab, d.slab_stride, e->ld, e->D, C, e->d_user_im);
+  }
+  rc = ensure_glm_ws(e, C);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaGetLastError());
+  e->chains_ready = true;
+  return B200NUTS_OK;
+}
+
+// gradient stage of the lock-step engine; returns the number of kernels launched
+static int launch_gradient(b200nuts_engine* e, const GradBatch& b) {
+  switch (e->md.kind) {
+    case MODEL_LOGISTIC:
+    case MODEL_POISSON:
+      return launch_glm_grad(e->md, b, e->glm_ws, e->cfg.row_shards > 1 ? e->ar : nullptr, e->ar_user, true, e->stream);
+    case MODEL_IRT2PL:
+      return launch_irt_grad(e->md, b, e->stream);
+    default:
+      grad_small_kernel<<<(b.C + 3) / 4, 128, 0, e->stream>>>(e->md, b.Q, b.G, b.zV, b.active, b.C, b.ld);
+      return 1;
+  }
+}
+
+int b200nuts_run(b200nuts_engine* e, int n_iter) {
+  if (!e->chains_ready) { e->err = "b200nuts_init_chains must be called first"; return B200NUTS_USAGE; }
+  if (e->cfg.row_shards > 1 && !e->ar) { e->err = "row_shards > 1 needs b200nuts_set_allreduce"; return B200NUTS_USAGE; }
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  const int C = e->C;
+  const int total = e->cfg.num_warmup + e->cfg.num_samples;
+  long long launches = 0;
+  double grad_ms = 0;
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  set_iter_end_kernel<<<(C + 255) / 256, 256, 0, e->stream>>>(e->dc.cs, C, n_iter, total);
+  launches++;
+  const int blocks = (C + kChainsPerBlock - 1) / kChainsPerBlock;
+  if (e->fused) {
+    fused_chain_kernel<<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C);
+    launches++;
+  } else {
+    GradBatch b{e->dc.q, e->dc.g, e->dc.zV, e->d_active, C, e->ld};
+    const int kCheck = 16;
+    // two CUDA events bracket every gradient stage so that the dominant kernel family is timed live (bench.py roofline)
+    size_t ev_used = 0;
+    auto next_event = [&]() -> cudaEvent_t {
+      if (ev_used == e->grad_events.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->grad_events.push_back(ev);
+      }
+      return e->grad_events[ev_used++];
+    };
+    for (long long step = 0;; step++) {
+      const bool check = (step % kCheck) == 0;
+      if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int), e->stream));
+      advance_kernel<<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_nactive);
+      launches++;
+      if (check) {
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_nactive, e->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        // harvest finished event pairs
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, e->grad_events[i], e->grad_events[i + 1]);
+          grad_ms += ms;
+        }
+        ev_used = 0;
+        if (*e->h_nactive == 0) break;
+      }
+      cudaEvent_t a = next_event(), bb = next_event();
+      cudaEventRecord(a, e->stream);
+      launches += launch_gradient(e, b);
+      cudaEventRecord(bb, e->stream);
+    }
+  }
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->last_run_s = ms * 1e-3;
+  e->last_grad_s = grad_ms * 1e-3;
+  e->last_launches = launches;
+  return B200NUTS_OK;
+}
+
+int b200nuts_get_timing(b200nuts_engine* e, double* run_s, int64_t* launches, double* grad_s) {
+  if (run_s) *run_s = e->last_run_s;
+  if (launches) *launches = e->last_launches;
+  if (grad_s) *grad_s = e->last_grad_s;
+  return B200NUTS_OK;
+}
+
+int b200nuts_log_prob_grad(b200nuts_engine* e, const double* q, int64_t n, int jacobian, double* lp, double* grad) {
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  if (e->cfg.row_shards > 1 && !e->ar) { e->err = "row_shards > 1 needs b200nuts_set_allreduce"; return B200NUTS_USAGE; }
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  const int D = e->D, ld = e->ld;
+  // evaluate in batches so that temporary memory stays bounded
+  const int64_t batch = std::min<int64_t>(n, 4096);
+  double *dQ = nullptr, *dG = nullptr, *dV = nullptr;
+  CUDA_TRY(e, cudaMalloc(&dQ, sizeof(double) * batch * ld));
+  CUDA_TRY(e, cudaMalloc(&dG, sizeof(double) * batch * ld));
+  CUDA_TRY(e, cudaMalloc(&dV, sizeof(double) * batch));
+  rc = ensure_glm_ws(e, (int)std::max<int64_t>(batch, e->C));
+  if (rc) { cudaFree(dQ); cudaFree(dG); cudaFree(dV); return rc; }
+  std::vector<double> hq((size_t)batch * ld, 0.0), hg((size_t)batch * ld), hv(batch);
+  for (int64_t off = 0; off < n; off += batch) {
+    const int m = (int)std::min<int64_t>(batch, n - off);
+    for (int i = 0; i < m; i++) std::memcpy(hq.data() + (size_t)i * ld, q + (size_t)(off + i) * D, sizeof(double) * D);
+    cudaMemcpyAsync(dQ, hq.data(), sizeof(double) * m * ld, cudaMemcpyHostToDevice, e->stream);
+    GradBatch b{dQ, dG, dV, nullptr, m, ld};
+    launch_gradient(e, b);
+    if (!jacobian) remove_jacobian_kernel<<<(m + 127) / 128, 128, 0, e->stream>>>(e->md.kind, D, e->md.N, e->md.K, dQ, dG, dV, m, ld);
+    cudaMemcpyAsync(hg.data(), dG, sizeof(double) * m * ld, cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(hv.data(), dV, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t r = cudaStreamSynchronize(e->stream);
+    if (r == cudaSuccess) r = cudaGetLastError();
+    if (r != cudaSuccess) {
+      e->err = std::string("log_prob_grad: ") + cudaGetErrorString(r);
+      cudaFree(dQ); cudaFree(dG); cudaFree(dV);
+      return B200NUTS_SOFTWARE;
+    }
+    for (int i = 0; i < m; i++) {
+      lp[off + i] = -hv[i];
+      for (int k = 0; k < D; k++) grad[(size_t)(off + i) * D + k] = -hg[(size_t)i * ld + k];
+    }
+  }
+  cudaFree(dQ); cudaFree(dG); cudaFree(dV);
+  return B200NUTS_OK;
+}
+
+static int gather_status(b200nuts_engine* e, std::vector<int>& err, std::vector<int>& iter, std::vector<long long>& ng,
+                         std::vector<double>& eps, std::vector<int>& rows) {
+  const int C = e->C;
+  int *d_err, *d_iter, *d_rows;
+  long long* d_ng;
+  double* d_eps;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  CUDA_TRY(e, cudaMalloc(&d_err, 4 * C));
+  CUDA_TRY(e, cudaMalloc(&d_iter, 4 * C));
+  CUDA_TRY(e, cudaMalloc(&d_rows, 4 * C));
+  CUDA_TRY(e, cudaMalloc(&d_ng, 8 * C));
+  CUDA_TRY(e, cudaMalloc(&d_eps, 8 * C));
+  gather_status_kernel<<<(C + 255) / 256, 256, 0, e->stream>>>(e->dc.cs, C, d_err, d_iter, d_ng, d_eps, d_rows);
+  err.resize(C); iter.resize(C); ng.resize(C); eps.resize(C); rows.resize(C);
+  cudaMemcpyAsync(err.data(), d_err, 4 * C, cudaMemcpyDeviceToHost, e->stream);
+  cudaMemcpyAsync(iter.data(), d_iter, 4 * C, cudaMemcpyDeviceToHost, e->stream);
+  cudaMemcpyAsync(rows.data(), d_rows, 4 * C, cudaMemcpyDeviceToHost, e->stream);
+  cudaMemcpyAsync(ng.data(), d_ng, 8 * C, cudaMemcpyDeviceToHost, e->stream);
+  cudaMemcpyAsync(eps.data(), d_eps, 8 * C, cudaMemcpyDeviceToHost, e->stream);
+  cudaError_t r = cudaStreamSynchronize(e->stream);
+  cudaFree(d_err); cudaFree(d_iter); cudaFree(d_rows); cudaFree(d_ng); cudaFree(d_eps);
+  if (r != cudaSuccess) { e->err = cudaGetErrorString(r); return B200NUTS_SOFTWARE; }
+  return B200NUTS_OK;
+}
+
+int b200nuts_get_chain_status(b200nuts_engine* e, int32_t* err, int32_t* iter, int64_t* n_grad) {
+  if (!e->chains_ready) { e->err = "chains not initialised"; return B200NUTS_USAGE; }
+  std::vector<int> ve, vi, vr;
+  std::vector<long long> vg;
+  std::vector<double> veps;
+  int rc = gather_status(e, ve, vi, vg, veps, vr);
+  if (rc) return rc;
+  for (int c = 0; c < e->C; c++) {
+    if (err) err[c] = ve[c];
+    if (iter) iter[c] = vi[c];
+    if (n_grad) n_grad[c] = vg[c];
+  }
+  return B200NUTS_OK;
+}
+
+int64_t b200nuts_rows_saved(const b200nuts_engine* ce) {
+  auto* e = const_cast<b200nuts_engine*>(ce);
+  if (!e->chains_ready) return 0;
+  std::vector<int> ve, vi, vr;
+  std::vector<long long> vg;
+  std::vector<double> veps;
+  if (gather_status(e, ve, vi, vg, veps, vr)) return -1;
+  int mn = vr.empty() ? 0 : vr[0];
+  for (int v : vr) mn = std::min(mn, v);
+  return mn;
+}
+
+int b200nuts_get_adaptation(b200nuts_engine* e, double* stepsize, double* inv_metric) {
+  if (!e->chains_ready) { e->err = "chains not initialised"; return B200NUTS_USAGE; }
+  std::vector<int> ve, vi, vr;
+  std::vector<long long> vg;
+  std::vector<double> veps;
+  int rc = gather_status(e, ve, vi, vg, veps, vr);
+  if (rc) return rc;
+  if (stepsize) std::memcpy(stepsize, veps.data(), sizeof(double) * e->C);
+  if (inv_metric) {
+    double* d_out;
+    const long long tot = (long long)e->C * e->D;
+    CUDA_TRY(e, cudaMalloc(&d_out, sizeof(double) * tot));
+    gather_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->dc.slab, e->dc.slab_stride, e->ld, e->D, e->C, d_out);
+    cudaMemcpyAsync(inv_metric, d_out, sizeof(double) * tot, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t r = cudaStreamSynchronize(e->stream);
+    cudaFree(d_out);
+    if (r != cudaSuccess) { e->err = cudaGetErrorString(r); return B200NUTS_SOFTWARE; }
+  }
+  return B200NUTS_OK;
+}
+
+int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, int64_t row0, int64_t nrows, int constrained,
+                         double* out) {
+  if (!e->chains_ready || !e->dc.draws) { e->err = "no draws are stored (store_draws=0 or chains not initialised)"; return B200NUTS_USAGE; }
+  if (chain0 < 0 || nchains < 0 || chain0 + nchains > e->C || row0 < 0 || nrows < 0 || row0 + nrows > e->scfg.rows_per_chain) {
+    e->err = "fetch_draws: range out of bounds";
+    return B200NUTS_USAGE;
+  }
+  if (nchains == 0 || nrows == 0) return B200NUTS_OK;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  const int kout = constrained ? e->K_out : e->D;
+  const size_t row_bytes = sizeof(double) * (7 + kout);
+  // chunk over chains so that the staging buffer stays <= ~1 GiB
+  int64_t chunk = std::max<int64_t>(1, (int64_t)((1ull << 30) / (row_bytes * (size_t)nrows)));
+  chunk = std::min(chunk, nchains);
+  double* d_out;
+  CUDA_TRY(e, cudaMalloc(&d_out, row_bytes * nrows * chunk));
+  for (int64_t off = 0; off < nchains; off += chunk) {
+    const int64_t m = std::min(chunk, nchains - off);
+    const long long tot = m * nrows;
+    fetch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, e->stream>>>(e->dc.draws, e->dc.draws_stride, e->scfg.ncol, e->md.kind, e->D,
+                                                                       e->md.N, e->md.K, e->K_out, constrained, chain0 + off, m, row0,
+                                                                       nrows, d_out);
+    cudaMemcpyAsync(out + (size_t)off * nrows * (7 + kout), d_out, row_bytes * nrows * m, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t r = cudaStreamSynchronize(e->stream);
+    if (r == cudaSuccess) r = cudaGetLastError();
+    if (r != cudaSuccess) {
+      cudaFree(d_out);
+      e->err = std::string("fetch_draws: ") + cudaGetErrorString(r);
+      return B200NUTS_SOFTWARE;
+    }
+  }
+  cudaFree(d_out);
+  return B200NUTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Hierarchical IRT 2PL log-density + gradient for the lock-step engine (config c4), one CTA per chain.
+//
+//   parameters (declaration order = unconstrained layout, positive ones as logs with Jacobian +u, lb_constrain.hpp:97):
+//     sigma_theta, theta[I], sigma_a, a[J], mu_b, sigma_b, b[J]                              D = 4 + I + 2J
+//   model: sigma_* ~ cauchy(0,2) (cauchy_lpdf.hpp:80-86); theta ~ normal(0, sigma_theta), b ~ normal(mu_b, sigma_b)
+//          (normal_lpdf.hpp:83-89, keeps -N log sigma); a ~ lognormal(0, sigma_a) (lognormal_lpdf.hpp:72-80, keeps
+//          N * NEG_LOG_SQRT_TWO_PI even under propto); mu_b ~ normal(0,5);
+//          y[i,j] ~ bernoulli_logit(a_j (theta_i - b_j)) (bernoulli_logit_lpmf.hpp:73-89, cutoff +-20).
+//
+// Work distribution: lanes own items (j = lane, lane+32, ...: their a/b gradients accumulate in registers), warps
+// stride over persons; the theta_i gradient is one warp reduction per person.  y is shared by all chains (int8,
+// L2-resident); per chain the kernel reads q (D doubles) and writes g (D doubles).  All cross-warp sums are done in a
+// fixed order => deterministic.  Bound: FP64 ALU + transcendental throughput (2 I J exp/log1p per chain-gradient).
+#include "kernels.h"
+
+namespace b200 {
+
+constexpr int IRT_NT = 256;
+constexpr int IRT_NW = IRT_NT / 32;
+constexpr int IRT_IPL = 4;  // items per lane
+
+int irt_max_items() { return 32 * IRT_IPL; }
+
+__global__ void __launch_bounds__(IRT_NT) irt_grad_kernel(const signed char* __restrict__ y, int I, int J, int D,
+                                                          const double* __restrict__ Q, double* __restrict__ G,
+                                                          double* __restrict__ zV, const int* __restrict__ active, int ld) {
+  const int c = blockIdx.x;
+  if (active && !active[c]) return;
+  const double* q = Q + (size_t)c * ld;
+  double* g = G + (size_t)c * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_ga[IRT_NW][32 * IRT_IPL];
+  __shared__ double s_gb[IRT_NW][32 * IRT_IPL];
+  __shared__ double s_lp[IRT_NW];
+  __shared__ double s_s2[IRT_NW];
+
+  const double u_st = q[0];
+  const double* theta = q + 1;
+  const double u_sa = q[1 + I];
+  const double* u_a = q + 2 + I;
+  const double mu_b = q[2 + I + J];
+  const double u_sb = q[3 + I + J];
+  const double* bq = q + 4 + I + J;
+  const double st = exp(u_st), sa = exp(u_sa), sb = exp(u_sb);
+
+  double a[IRT_IPL], b[IRT_IPL], ga[IRT_IPL], gb[IRT_IPL];
+#pragma unroll
+  for (int t = 0; t < IRT_IPL; t++) {
+    const int j = lane + 32 * t;
+    a[t] = j < J ? exp(u_a[j]) : 0.0;
+    b[t] = j < J ? bq[j] : 0.0;
+    ga[t] = 0.0;
+    gb[t] = 0.0;
+  }
+  double lp = 0.0, s2 = 0.0;
+  for (int i = warp; i < I; i += IRT_NW) {
+    const double th = theta[i];
+    const signed char* yrow = y + (size_t)i * J;
+    double gth = 0.0;
+#pragma unroll
+    for (int t = 0; t < IRT_IPL; t++) {
+      const int j = lane + 32 * t;
+      if (j < J) {
+        const double sgn = 2.0 * yrow[j] - 1.0;
+        const double diff = th - b[t];
+        const double tt = sgn * (a[t] * diff);
+        const double e = exp(-tt);
+        double d;
+        if (tt > 20.0) {
+          lp += -e;
+          d = -e;
+        } else if (tt < -20.0) {
+          lp += tt;
+          d = sgn;
+        } else {
+          lp += -log1p(e);
+          d = sgn * e / (e + 1.0);
+        }
+        gth += d * a[t];
+        gb[t] -= d * a[t];
+        ga[t] += d * diff;
+      }
+    }
+    gth = warp_sum(gth);
+    if (lane == 0) {
+      const double z = th / st;  // theta ~ normal(0, sigma_theta)
+      s2 += z * z;
+      g[1 + i] = -(gth - z / st);
+    }
+  }
+  lp = warp_sum(lp);
+  if (lane == 0) {
+    s_lp[warp] = lp;
+    s_s2[warp] = s2;
+  }
+#pragma unroll
+  for (int t = 0; t < IRT_IPL; t++) {
+    s_ga[warp][lane + 32 * t] = ga[t];
+    s_gb[warp][lane + 32 * t] = gb[t];
+  }
+  __syncthreads();
+  // ---- item-level terms: thread j sums the per-warp partials in warp order, adds the priors
+  double s2a = 0.0, sua = 0.0, s2b = 0.0, gmub = 0.0;
+  if (tid < 32 * IRT_IPL) {
+    const int j = tid;
+    if (j < J) {
+      double gaj = 0.0, gbj = 0.0;
+      for (int w = 0; w < IRT_NW; w++) {
+        gaj += s_ga[w][j];
+        gbj += s_gb[w][j];
+      }
+      const double ua = u_a[j];
+      const double aj = exp(ua);
+      const double za = ua / sa;                 // a ~ lognormal(0, sigma_a), a = exp(ua), Jacobian +ua
+      const double zb = (bq[j] - mu_b) / sb;     // b ~ normal(mu_b, sigma_b)
+      s2a = za * za;
+      sua = ua;
+      s2b = zb * zb;
+      gmub = zb / sb;
+      g[2 + I + j] = -(gaj * aj + (-za / sa - 1.0 + 1.0));
+      g[4 + I + J + j] = -(gbj - zb / sb);
+    }
+  }
+  // block-wide fixed-order sums of the four item statistics (threads 0..127 hold them): warp sums, then warp order
+  __shared__ double s_it[4][IRT_NW];
+  s2a = warp_sum(s2a);
+  sua = warp_sum(sua);
+  s2b = warp_sum(s2b);
+  gmub = warp_sum(gmub);
+  if (lane == 0) {
+    s_it[0][warp] = s2a;
+    s_it[1][warp] = sua;
+    s_it[2][warp] = s2b;
+    s_it[3][warp] = gmub;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double NEG_LOG_SQRT_TWO_PI = -0.91893853320467274178;
+    double lpl = 0.0, S2 = 0.0, S2A = 0.0, SUA = 0.0, S2B = 0.0, GMUB = 0.0;
+    for (int w = 0; w < IRT_NW; w++) {
+      lpl += s_lp[w];
+      S2 += s_s2[w];
+      S2A += s_it[0][w];
+      SUA += s_it[1][w];
+      S2B += s_it[2][w];
+      GMUB += s_it[3][w];
+    }
+    double total = u_st + u_sa + u_sb;  // Jacobians of the three scalar lower bounds
+    bool ok = st > 0 && isfinite(st) && sa > 0 && isfinite(sa) && sb > 0 && isfinite(sb);
+    double h = st / 2.0;
+    total += -log1p(h * h);
+    double g_st = -2.0 * h * h / (1.0 + h * h);
+    total += -0.5 * S2 - I * u_st;
+    g_st += S2 - I;
+    h = sa / 2.0;
+    total += -log1p(h * h);
+    double g_sa = -2.0 * h * h / (1.0 + h * h);
+    total += J * NEG_LOG_SQRT_TWO_PI - 0.5 * S2A - J * u_sa - SUA + SUA;
+    g_sa += S2A - J;
+    const double zmb = mu_b / 5.0;
+    total += -0.5 * zmb * zmb;
+    const double g_mub = -zmb / 5.0 + GMUB;
+    h = sb / 2.0;
+    total += -log1p(h * h);
+    double g_sb = -2.0 * h * h / (1.0 + h * h);
+    total += -0.5 * S2B - J * u_sb;
+    g_sb += S2B - J;
+    total += lpl;
+    g[0] = -(g_st + 1.0);
+    g[1 + I] = -(g_sa + 1.0);
+    g[2 + I + J] = -g_mub;
+    g[3 + I + J] = -(g_sb + 1.0);
+    zV[c] = ok ? -total : INFINITY;  // check_positive_finite on a scale => domain_error => V = +inf
+  }
+}
+
+int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream) {
+  irt_grad_kernel<<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.ld);
+  return 1;
+}
+
+}  // namespace b200

@@ -1,0 +1,46 @@
+// Host-callable launchers of the cross-chain gradient kernels (lock-step engine).  Every launcher computes, for each
+// chain c with active[c] != 0 (active == nullptr: all), the potential and its gradient at Q[c][:] :
+//     zV[c] = -lp(Q[c]) ,  G[c][:] = -grad lp(Q[c])          (base_hamiltonian::update_potential_gradient,
+//                                                              S/mcmc/hmc/hamiltonians/base_hamiltonian.hpp:61-70)
+// with lp = log_prob_propto_jacobian.  Results for a chain depend only on that chain's q (fixed reduction order),
+// so a chain's draws do not depend on which other chains share the batch
+// (the invariant of ST/unit/services/sample/hmc_nuts_diag_e_adapt_parallel_match_test.cpp:73-153).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "models.cuh"
+
+namespace b200 {
+
+typedef int (*allreduce_fn)(void* device_buf, int64_t count, void* cuda_stream, void* user);
+
+struct GradBatch {
+  const double* Q;     // [C][ld]
+  double* G;           // [C][ld]
+  double* zV;          // [C]
+  const int* active;   // [C] or nullptr
+  int C, ld;
+};
+
+// ---- GLMs (logistic / poisson): glm.cu -------------------------------------------------------------------------
+struct GlmWorkspace {
+  double* Gp = nullptr;   // [P][C][Dp]   per row-group partial gradients
+  double* LPp = nullptr;  // [P][C]       per row-group partial log-likelihood
+  double* R = nullptr;    // [C][1 + Dp]  reduced (lp, gradient): the all-reduce payload for row sharding
+  int P = 0, C = 0, Dp = 0;
+  int variant = 0;        // 0: register-tiled DFMA kernel, 1: FP64 tensor-core (DMMA) kernel
+};
+size_t glm_workspace_bytes(int N, int D, int C, GlmWorkspace* ws);  // fills P, C, Dp; returns total bytes (3 arrays)
+void glm_workspace_bind(GlmWorkspace* ws, void* base);
+int glm_max_dim();
+// returns the number of kernels launched
+int launch_glm_grad(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, allreduce_fn ar, void* ar_user,
+                    bool add_prior, cudaStream_t stream);
+
+// ---- IRT 2PL: irt.cu -------------------------------------------------------------------------------------------
+int irt_max_items();
+int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,165 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle, same seeded inputs."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **k):
+    import cmdstan_b200 as B
+    return B.Engine(*a, **k)
+
+
+def _rel(a, b, floor=1e-12):
+    return np.max(np.abs(a - b) / np.maximum(floor, np.abs(b)))
+
+
+LPG_CASES = [
+    ("std_normal", {"D": 3}), ("std_normal", {"D": 70}), ("bernoulli", cases.BERNOULLI), ("eight_schools_nc", cases.EIGHT_SCHOOLS),
+    ("logistic", cases.logistic_data(1000, 20)), ("logistic", cases.logistic_data(777, 101)), ("logistic", cases.logistic_data(5000, 3)),
+    ("poisson_glm", cases.poisson_data(1500, 50)), ("poisson_glm", cases.poisson_data(333, 7)),
+    ("irt_2pl", cases.irt_data(100, 20)), ("irt_2pl", cases.irt_data(37, 100)),
+]
+
+
+@pytest.mark.parametrize("name,data", LPG_CASES, ids=[f"{n}-{i}" for i, (n, _) in enumerate(LPG_CASES)])
+def test_log_prob_grad_matches_oracle(name, data):
+    """north_star gate 1: lp and gradient within 1e-10 relative (abs floor 1e-12) of log_prob_grad<true,true>."""
+    m = O.Model(name, data)
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-2, 2, size=(130, m.D))
+    lp0, g0 = m.lp_grad(q)
+    e = _engine(name, data)
+    lp, g = e.log_prob_grad(q)
+    assert _rel(lp, lp0) < 1e-10
+    assert _rel(g, g0, floor=1e-9) < 1e-10
+    e.close()
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_glm_kernel_variants_agree(variant, monkeypatch):
+    """DFMA and DMMA variants of the fused GLM gradient against the oracle, ragged sizes (N not a tile multiple)."""
+    monkeypatch.setenv("B200NUTS_GLM_VARIANT", variant)
+    for name, data in [("logistic", cases.logistic_data(1234, 100)), ("poisson_glm", cases.poisson_data(999, 50)),
+                       ("logistic", cases.logistic_data(65, 1))]:
+        m = O.Model(name, data)
+        q = np.random.default_rng(6).uniform(-1, 1, size=(70, m.D))
+        lp0, g0 = m.lp_grad(q)
+        e = _engine(name, data)
+        lp, g = e.log_prob_grad(q)
+        assert _rel(lp, lp0) < 1e-10 and _rel(g, g0, floor=1e-9) < 1e-10
+        e.close()
+
+
+def test_log_prob_no_jacobian():
+    for name, data in [("bernoulli", cases.BERNOULLI), ("eight_schools_nc", cases.EIGHT_SCHOOLS)]:
+        e = _engine(name, data)
+        q = np.random.default_rng(1).uniform(-2, 2, size=(5, e.D))
+        lp1, g1 = e.log_prob_grad(q, jacobian=True)
+        lp0, g0 = e.log_prob_grad(q, jacobian=False)
+        if name == "eight_schools_nc":
+            assert np.allclose(lp1 - lp0, q[:, 1]) and np.allclose((g1 - g0)[:, 1], 1.0)
+        else:
+            au = np.abs(q[:, 0])
+            assert np.allclose(lp1 - lp0, -au - 2 * np.log1p(np.exp(-au)))
+        e.close()
+
+
+def _run(name, data, C=4, engine="auto", **kw):
+    args = dict(num_chains=C, random_seed=1234, init_chain_id=1, num_warmup=150, num_samples=100, save_warmup=True)
+    args.update(kw)
+    e = _engine(name, data, engine=engine, **args)
+    e.init_chains()
+    e.run(args["num_warmup"] + args["num_samples"])
+    err, it, ng = e.chain_status()
+    assert (err == 0).all() and (it == args["num_warmup"] + args["num_samples"]).all()
+    d = e.fetch_draws(constrained=False)
+    eps, im = e.adaptation()
+    e.close()
+    return d, eps, im
+
+
+@pytest.mark.parametrize("name", ["bernoulli", "std_normal", "eight_schools_nc"])
+def test_matched_stream_draws_vs_oracle(name):
+    """north_star gate 2: with matched RNG streams the draws agree with the reference until FP divergence.
+    Discrete columns (treedepth, n_leapfrog, divergent) must be identical and continuous ones within 1e-8 relative for
+    the first 40 transitions (device libm / reduction order differ from the host by <= 1-2 ulp)."""
+    data = cases.SMALL[name]
+    d, eps, im = _run(name, data, C=4)
+    m = O.Model(name, data)
+    for c in range(4):
+        r = O.run_chain(m, seed=1234, chain_id=1 + c, num_warmup=150, num_samples=100, save_warmup=1)
+        ref = r["draws"]
+        K = 40
+        assert np.array_equal(d[c, :K, 3:6], ref[:K, 3:6])
+        assert _rel(d[c, :K], ref[:K], floor=1e-6) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["bernoulli", "std_normal", "eight_schools_nc"])
+def test_fused_and_lockstep_engines_identical(name):
+    """Both engines run the same state machine with the same arithmetic: bit-identical draws and adaptation."""
+    data = cases.SMALL[name]
+    a = _run(name, data, C=5, engine="fused")
+    b = _run(name, data, C=5, engine="lockstep")
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_chain_output_independent_of_batch():
+    """parallel-match invariant (hmc_nuts_diag_e_adapt_parallel_match_test.cpp:73-153): chain id+c in a batch of 6
+    equals a single-chain run with id = id+c, bit for bit."""
+    data = cases.EIGHT_SCHOOLS
+    d6, eps6, im6 = _run("eight_schools_nc", data, C=6)
+    for c in (0, 3, 5):
+        d1, eps1, im1 = _run("eight_schools_nc", data, C=1, init_chain_id=1 + c)
+        assert np.array_equal(d6[c], d1[0]) and eps6[c] == eps1[0] and np.array_equal(im6[c], im1[0])
+    # same for a lock-step GLM: chain c alone vs inside a batch of 70 (crosses a 64-chain tile)
+    data = cases.logistic_data(500, 10)
+    kw = dict(num_warmup=40, num_samples=20)
+    dA, epsA, _ = _run("logistic", data, C=70, **kw)
+    for c in (0, 64, 69):
+        d1, eps1, _ = _run("logistic", data, C=1, init_chain_id=1 + c, **kw)
+        assert np.array_equal(dA[c], d1[0]) and epsA[c] == eps1[0]
+
+
+@pytest.mark.parametrize("name,data", [("logistic", cases.logistic_data(400, 6)), ("poisson_glm", cases.poisson_data(300, 4)),
+                                        ("irt_2pl", cases.irt_data(30, 8))], ids=["logistic", "poisson", "irt"])
+def test_lockstep_models_matched_stream_vs_oracle(name, data):
+    d, eps, im = _run(name, data, C=3, num_warmup=60, num_samples=40)
+    m = O.Model(name, data)
+    for c in range(3):
+        r = O.run_chain(m, seed=1234, chain_id=1 + c, num_warmup=60, num_samples=40, save_warmup=1)
+        K = 15
+        assert np.array_equal(d[c, :K, 3:6], r["draws"][:K, 3:6])
+        assert _rel(d[c, :K], r["draws"][:K], floor=1e-6) < 1e-7
+
+
+def test_run_in_pieces_equals_one_run():
+    data = cases.EIGHT_SCHOOLS
+    import cmdstan_b200 as B
+    out = []
+    for pieces in ([250], [100, 50, 100], [1] * 5 + [245]):
+        e = B.Engine("eight_schools_nc", data, num_chains=3, random_seed=9, num_warmup=150, num_samples=100, save_warmup=True)
+        e.init_chains()
+        for p in pieces:
+            e.run(p)
+        out.append(e.fetch_draws())
+        e.close()
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+
+
+def test_errors_are_loud():
+    import cmdstan_b200 as B
+    with pytest.raises(B.B200NutsError) as ei:
+        B.Engine("bernoulli", cases.BERNOULLI, num_warmup=0, adapt_engaged=True)
+    assert ei.value.code == B.USAGE
+    with pytest.raises(B.B200NutsError) as ei:
+        B.Engine("bernoulli", {"y": np.array([0, 2, 1])})
+    assert ei.value.code == B.DATAERR
+    e = B.Engine("bernoulli", cases.BERNOULLI)
+    with pytest.raises(B.B200NutsError):
+        e.run(10)  # init_chains not called
+    e.close()
