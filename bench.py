@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the NUTS (diag_e, adaptive) sampling path.
+
+Metric (BASELINE.json): min bulk-ESS / s (and gradient evaluations / s) of the SAMPLING phase, whole job over all GPUs.
+
+  step        = one NUTS transition of every chain (after the reference's windowed adaptation has finished)
+  workload    = BASELINE.json configs: c3 (default; the config the north-star target is quoted on) logistic regression
+                N=100k, D=100, 1024 chains | c2 eight schools 4096 chains | c1 bernoulli 4 chains | c4 IRT | c5 poisson
+  value       = min over (lp__, every model column) of the split rank-normalised bulk ESS of the K timed transitions,
+                summed over ranks, / device time of those K transitions (max over ranks), inputs resident in HBM
+  e2e         = same ESS / (host->device upload of the data set + the K transitions + device->host fetch of their draws),
+                all through the C ABI with host buffers
+  roofline    = dominant kernel family (gradient stage) timed live with CUDA events on the engine's stream
+  cpu_baseline= the UNMODIFIED reference (oracle/_ref/<model>, CmdStan 2.36 compiled from /root/reference) on the host
+                cores, chains in parallel, on a bounded sample of the same workload
+  --impl reference  times only that CPU arm and prints the same JSON line shape.
+
+Launch: python bench.py --gpus N --steps K --warmup W     (N > 1: torchrun, one rank per GPU; chains shard, no collectives)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "c1": dict(model="bernoulli", chains=4, desc="bernoulli N=10, 4 chains"),
+    "c2": dict(model="eight_schools_nc", chains=4096, desc="eight-schools non-centred, 4096 chains"),
+    "c3": dict(model="logistic", chains=1024, N=100000, K=100, desc="logistic regression N=100k D=100, 1024 chains"),
+    "c4": dict(model="irt_2pl", chains=8192, I=1000, J=100, desc="IRT 2PL 1000x100, 8192 chains"),
+    "c5": dict(model="poisson_glm", chains=64, N=10000000, K=50, desc="poisson GLM N=10M D=50, 64 chains (rows sharded when N>1)"),
+}
+
+
+def make_data(w, scale=1.0):
+    import cases
+    m = w["model"]
+    if m == "bernoulli":
+        return cases.BERNOULLI
+    if m == "eight_schools_nc":
+        return cases.EIGHT_SCHOOLS
+    if m == "logistic":
+        return cases.logistic_data(int(w["N"] * scale), w["K"])
+    if m == "poisson_glm":
+        return cases.poisson_data(int(w["N"] * scale), w["K"])
+    if m == "irt_2pl":
+        return cases.irt_data(int(w["I"] * scale), w["J"])
+    raise ValueError(m)
+
+
+def data_bytes(data):
+    return int(sum(np.asarray(v).nbytes for v in data.values()))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_work(w, data, model, D):
+    """Per chain-gradient algorithmic flops and bytes (restated in DESIGN.md)."""
+    if model in ("logistic", "poisson_glm"):
+        N, K = data["X"].shape
+        Dp = (K + 1 + 3) // 4 * 4
+        return dict(flops=4.0 * N * Dp, bytes_per_batch=N * Dp * 8.0 + N * 4.0, kind="tensor")
+    if model == "irt_2pl":
+        I, J = data["y"].shape
+        return dict(flops=25.0 * I * J, bytes_per_batch=None, bytes_per_chain=2 * D * 8.0, kind="fp64")
+    return dict(flops={"bernoulli": 40.0, "eight_schools_nc": 150.0}.get(model, 4.0 * D), bytes_per_chain=2 * D * 8.0, kind="latency")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(wname, w, data, cores, warm_state=None, budget_s=60.0, scale_note=""):
+    """Bounded sample of the workload through oracle/_ref/<model> (CmdStan 2.36 `sample`), chains in parallel.
+    Small models run the full adaptive path (long enough for the 1 ms timer); the GLMs are warm-started from an
+    adapted state (stepsize, inverse metric, positions) with adapt engaged=0 so that only the sampling phase is timed."""
+    from oracle import oracle as O
+    from cmdstan_b200 import analyze as A
+    import torch
+    model = w["model"]
+    if not O.have_ref(model):
+        return None
+    td = tempfile.mkdtemp(prefix="b200bench_")
+    chains = 4 if wname == "c1" else cores
+    if model in ("bernoulli", "eight_schools_nc", "std_normal"):
+        ns = 20000
+        res, wall, _ = O.ref_sample(model, data, num_chains=chains, seed=4321, num_warmup=1000, num_samples=ns, sig_figs=8, num_threads=cores, tmpdir=td)
+        sample = f"{chains} chains x (1000 warmup + {ns} draws), full adaptive run, num_threads={cores}"
+    else:
+        # warm start (adaptation on this CPU would take hours for c3): per-chain inits + metric, common stepsize
+        assert warm_state is not None
+        D = warm_state["q"].shape[1]
+        names = {"logistic": ["alpha", "beta"], "poisson_glm": ["alpha", "beta"]}.get(model)
+        for c in range(chains):
+            q = warm_state["q"][c % len(warm_state["q"])]
+            im = warm_state["inv_metric"][c % len(warm_state["inv_metric"])]
+            if model == "irt_2pl":
+                I, J = data["y"].shape
+                init = {"sigma_theta": float(np.exp(q[0])), "theta": q[1:1 + I].tolist(), "sigma_a": float(np.exp(q[1 + I])),
+                        "a": np.exp(q[2 + I:2 + I + J]).tolist(), "mu_b": float(q[2 + I + J]), "sigma_b": float(np.exp(q[3 + I + J])),
+                        "b": q[4 + I + J:].tolist()}
+            else:
+                init = {"alpha": float(q[0]), "beta": q[1:].tolist()}
+            json.dump(init, open(os.path.join(td, f"init_{c + 1}.json"), "w"))
+            json.dump({"inv_metric": im.tolist()}, open(os.path.join(td, f"metric_{c + 1}.json"), "w"))
+        eps = float(np.median(warm_state["stepsize"]))
+        # size the sample to the time budget with a 3-transition probe
+        t0 = time.time()
+        O.ref_sample(model, data, num_chains=chains, seed=4321, num_warmup=0, num_samples=3, sig_figs=8, num_threads=cores, tmpdir=td,
+                     adapt_engaged=False, stepsize=eps, metric_file=os.path.join(td, "metric.json"), init=os.path.join(td, "init.json"))
+        probe = time.time() - t0
+        res_p, _, _ = O.ref_sample(model, data, num_chains=chains, seed=4321, num_warmup=0, num_samples=1, sig_figs=8, num_threads=cores, tmpdir=td,
+                                   adapt_engaged=False, stepsize=eps, metric_file=os.path.join(td, "metric.json"), init=os.path.join(td, "init.json"))
+        ns = int(max(8, min(400, budget_s / max(probe / 3.0, 1e-3) * 0.8)))
+        res, wall, _ = O.ref_sample(model, data, num_chains=chains, seed=4321, num_warmup=0, num_samples=ns, sig_figs=8, num_threads=cores, tmpdir=td,
+                                    adapt_engaged=False, stepsize=eps, metric_file=os.path.join(td, "metric.json"), init=os.path.join(td, "init.json"))
+        sample = f"{chains} chains x {ns} sampling transitions warm-started from the adapted state (adapt engaged=0, stepsize={eps:.4g}), num_threads={cores}{scale_note}"
+    draws = np.stack([r[1] for r in res])
+    samp_s = max(r[4].get("Sampling", 0.0) for r in res)
+    if samp_s <= 0:
+        samp_s = wall
+    mess, _ = A.min_bulk_ess(torch.tensor(draws))
+    nleap = float(draws[:, :, 4].sum())
+    return dict(value=mess / samp_s, unit="min_bulk_ESS/s", cores=cores, kind="reference", sample=sample, sampling_s=samp_s, wall_s=wall,
+                grad_evals_per_s=nleap / samp_s, min_bulk_ess=mess, draws=int(draws.shape[0] * draws.shape[1]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=os.environ.get("B200_BENCH_WORKLOAD", "c3"))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--num-warmup", type=int, default=1000, help="NUTS adaptation transitions before the timed region")
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the data rows (testing only; invalidates the number)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=45.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    model = w["model"]
+    cores = os.cpu_count() or 1
+    K, W = max(args.steps, 4), max(args.warmup, 3)
+    scale_note = "" if args.scale == 1.0 else f" [rows scaled x{args.scale}]"
+    cfg_common = {"workload": args.workload + ": " + w["desc"] + scale_note, "num_warmup": args.num_warmup, "timed_transitions": K,
+                  "inputs": "data set larger than L2 for c3/c5; chain state resident in HBM", "sharding": "chains" if world > 1 else "none"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        data = make_data(w, args.scale)
+        warm = None
+        fx = os.path.join(ROOT, "tests", "golden", f"warm_{args.workload}.npz")
+        if model not in ("bernoulli", "eight_schools_nc") and os.path.exists(fx) and args.scale == 1.0:
+            z = np.load(fx)
+            warm = dict(q=z["q"], inv_metric=z["inv_metric"], stepsize=z["stepsize"])
+        elif model not in ("bernoulli", "eight_schools_nc"):
+            print(json.dumps({"impl": "reference", "unavailable": f"no warm-start fixture tests/golden/warm_{args.workload}.npz for this workload"}))
+            return
+        r = run_reference(args.workload, w, data, cores, warm, budget_s=max(20.0, 12.0 * K / 10), scale_note=scale_note)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries are missing (built from /root/reference by oracle/build_ref.sh)"}))
+            return
+        line = {"impl": "reference", "metric": "min_bulk_ESS_per_sec", "value": r["value"], "unit": "ESS/s", "n_gpus": 0, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * r["sampling_s"] / max(1, r["draws"] // max(1, (4 if args.workload == "c1" else cores))),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_common,
+                "grad_evals_per_sec": r["grad_evals_per_s"],
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "ESS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cmdstan_b200 as B
+    from cmdstan_b200 import analyze as A
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    data = make_data(w, args.scale)
+    C = args.chains or w["chains"]
+    num_samples = W + K
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- set-up (untimed): upload, initialise, run the reference's windowed adaptation
+    t_setup = time.time()
+    e = B.Engine(model, data, num_chains=C, random_seed=20241017, init_chain_id=1 + rank * C, num_warmup=args.num_warmup,
+                 num_samples=num_samples, device=local_rank)
+    e.init_chains()
+    e.run(args.num_warmup)
+    adapt_s, adapt_launches, adapt_grad_s = e.timing()
+    _, _, ng0 = e.chain_status()
+    e.run(W)
+    _, _, ng1 = e.chain_status()
+    setup_wall = time.time() - t_setup
+    # ---- timed region: K transitions of every chain
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t0 = time.time()
+    e.run(K)
+    torch.cuda.synchronize()
+    run_wall = time.time() - t0
+    barrier()
+    clk = clocks.stop()
+    run_s, launches, grad_s = e.timing()
+    err, it, ng2 = e.chain_status()
+    assert (err == 0).all(), f"chains stopped with errors: {np.unique(err)}"
+    # ---- D2H of the timed draws through the C ABI (part of e2e)
+    t0 = time.time()
+    draws = e.fetch_draws(row0=W, nrows=K, constrained=True)
+    fetch_s = time.time() - t0
+    # ---- H2D leg of e2e: a fresh engine uploads the same host data set
+    t0 = time.time()
+    e2 = B.Engine(model, data, num_chains=1, device=local_rank)
+    torch.cuda.synchronize()
+    h2d_s = time.time() - t0
+    e2.close()
+    eps, im = e.adaptation()
+
+    dt = torch.tensor(draws, device=dev)
+    _, ess_cols = A.min_bulk_ess(dt)
+    ess_cols = torch.tensor([v if v == v else float("inf") for v in ess_cols], dtype=torch.float64, device=dev)
+    nleap = torch.tensor([float(draws[:, :, 4].sum()), float((ng2 - ng1).sum())], dtype=torch.float64, device=dev)
+    times = torch.tensor([run_s, run_wall + fetch_s + h2d_s, grad_s, adapt_s], dtype=torch.float64, device=dev)
+    div = torch.tensor([float(draws[:, :, 5].sum()), float(draws[:, :, 3].mean())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ess_cols, op=dist.ReduceOp.SUM)   # ESS of independent chain sets adds
+        dist.all_reduce(nleap, op=dist.ReduceOp.SUM)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(div, op=dist.ReduceOp.SUM)
+    min_ess = float(ess_cols.min())
+    run_s, e2e_s, grad_s, adapt_s = [float(v) for v in times]
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        work = algorithmic_work(w, data, model, e.D)
+        n_grad_launch = max(1, int(np.max(ng2 - ng1)))  # lock-step: one gradient-stage launch per leapfrog of the slowest chain
+        roof = None
+        if work["kind"] == "tensor":
+            # dominant kernel: fused GLM gradient.  bound: FP64 tensor pipe; peak measured live below with a DGEMM
+            fl = work["flops"] * C
+            ach = fl / (grad_s / n_grad_launch) / 1e12 if grad_s > 0 else None
+            peak = measure_fp64_peak(dev)
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
+                    "traffic": None, "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
+                    "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                    "hbm_gbs_achieved": work["bytes_per_batch"] / (grad_s / n_grad_launch) / 1e9 if grad_s > 0 else None, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src}
+        elif work["kind"] == "fp64":
+            fl = work["flops"] * C
+            ach = fl / (grad_s / n_grad_launch) / 1e12 if grad_s > 0 else None
+            peak = measure_fp64_peak(dev)
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None, "traffic": None,
+                    "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,
+                    "note": "bound is FP64 ALU + transcendental throughput; normalised by the measured DGEMM rate"}
+        else:
+            # fused chain kernel: latency/occupancy-bound by construction (tens of flops per gradient); report HBM traffic rate
+            byt = float(nleap[1]) * (work["bytes_per_chain"] + 8 * e.D * 8.0)
+            ach = byt / run_s / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk.get("hbm_gbs"), "unit": "GB/s", "frac": ach / pk.get("hbm_gbs"), "traffic": None,
+                    "kernel": "fused_chain_kernel", "note": "latency-bound by construction (SURVEY.md 8d): state stays in L1/L2; fraction is small on purpose", "peak_source": pk_src}
+        line = {
+            "metric": "min_bulk_ESS_per_sec", "value": min_ess / run_s, "unit": "ESS/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * run_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(cfg_common, chains_per_gpu=C, l2="data set (80 MB) + chain state exceed L2 reuse between steps" if model == "logistic" else "n/a"),
+            "grad_evals_per_sec": float(nleap[0]) / run_s, "grad_evals_executed_per_sec": float(nleap[1]) / run_s,
+            "min_bulk_ess": min_ess, "timed_draws": int(C * K * world), "divergences": float(div[0]), "mean_treedepth": float(div[1]) / world,
+            "adaptation_s": adapt_s, "setup_wall_s": setup_wall, "median_stepsize": float(np.median(eps)),
+            "e2e": {"value": min_ess / e2e_s, "unit": "ESS/s", "h2d_bytes_per_step": data_bytes(data) / K, "d2h_bytes_per_step": int(draws.nbytes / K),
+                    "h2d_s": h2d_s, "run_wall_s": run_wall, "d2h_s": fetch_s},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": clk,
+        }
+        if not args.no_cpu and world >= 1:
+            try:
+                warm = dict(q=e.fetch_draws(chain0=0, nchains=min(C, cores), row0=W + K - 1, nrows=1, constrained=False)[:, 0, 7:],
+                            inv_metric=im[:min(C, cores)], stepsize=eps)
+                cb = run_reference(args.workload, w, data, cores, warm, budget_s=args.cpu_budget, scale_note=scale_note)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else {"value": None, "unit": "ESS/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
+                if cb:
+                    line["cpu_baseline"]["grad_evals_per_sec"] = cb["grad_evals_per_s"]
+            except Exception as ex:  # the CPU leg must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "ESS/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"[:300]}
+        print(json.dumps(line))
+    e.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_fp64_peak(dev):
+    """FP64 matmul rate of this GPU right now (cuBLAS DGEMM 8192^3, best of 5): the roofline denominator for the fp64
+    tensor-core kernels -- MEASURED_PEAKS.json only carries bf16 and HBM figures."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 0.0
+    for _ in range(5):
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        torch.matmul(a, b)
+        t.record()
+        torch.cuda.synchronize()
+        best = max(best, 2.0 * n ** 3 / (s.elapsed_time(t) * 1e-3) / 1e12)
+    return best
+
+
+if __name__ == "__main__":
+    main()
