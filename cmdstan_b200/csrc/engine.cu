@@ -63,7 +63,7 @@ __device__ __forceinline__ ChainView make_view(const DeviceChains& d, const Samp
 }
 
 // ---- fused engine: advance + inlined model gradient, looped until the chain is idle
-__global__ void __launch_bounds__(32 * kChainsPerBlock) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C) {
+__global__ void __launch_bounds__(32 * kChainsPerBlock, 8) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C) {
   const int c = blockIdx.x * kChainsPerBlock + (threadIdx.x >> 5);
   if (c >= C) return;
   const int lane = threadIdx.x & 31;

@@ -47,7 +47,7 @@ B200_DEV double dev_inv_logit(double u) {
 }
 
 // log_sum_exp(a, b), M/prim/fun/log_sum_exp.hpp:51-64 (NaN falls through to the last branch like the reference)
-B200_DEV double dev_log_sum_exp(double a, double b) {
+B200_DEV_CALL double dev_log_sum_exp(double a, double b) {
   if (a == -INFINITY) return b;
   if (a == INFINITY && b == INFINITY) return INFINITY;
   if (a > b) return a + dev_log1p_exp(b - a);
@@ -56,7 +56,7 @@ B200_DEV double dev_log_sum_exp(double a, double b) {
 
 // ---- kind 0: standard normal ---------------------------------------------------------------------------------
 // normal_lpdf<propto>(x, 0, 1) = -0.5 sum x^2  (M/prim/prob/normal_lpdf.hpp:83-89)
-B200_DEV double lp_grad_std_normal(const ModelData& m, const double* q, double* g, int lane) {
+B200_DEV_CALL double lp_grad_std_normal(const ModelData& m, const double* q, double* g, int lane) {
   double s = 0;
   for (int i = lane; i < m.D; i += kWarp) {
     double x = q[i];
@@ -71,7 +71,7 @@ B200_DEV double lp_grad_std_normal(const ModelData& m, const double* q, double* 
 // bernoulli_lpmf via the sufficient statistic (M/prim/prob/bernoulli_lpmf.hpp:34-114); beta_lpdf(theta|1,1) kernel
 // contributes 0*log(theta) + 0*log1m(theta) (M/prim/prob/beta_lpdf.hpp:75-92).  D = 1: every lane computes the
 // same scalars, lane 0 owns g[0].
-B200_DEV double lp_grad_bernoulli(const ModelData& m, const double* q, double* g, int lane) {
+B200_DEV_CALL double lp_grad_bernoulli(const ModelData& m, const double* q, double* g, int lane) {
   double u = q[0];
   int S = m.sum_y, N = m.N;
   double th = dev_inv_logit(u);
@@ -97,7 +97,7 @@ B200_DEV double lp_grad_bernoulli(const ModelData& m, const double* q, double* g
 // ---- kind 2: eight schools, non-centred (c2) -----------------------------------------------------------------
 // u = (mu, log tau, theta_tilde[J]).  normal_lpdf.hpp:44-105, cauchy_lpdf.hpp:80-86, lb_constrain (lp += u).
 // Element 2+j (school j) is handled by its owner lane.
-B200_DEV double lp_grad_eight_schools(const ModelData& m, const double* q, double* g, int lane) {
+B200_DEV_CALL double lp_grad_eight_schools(const ModelData& m, const double* q, double* g, int lane) {
   const int J = m.N;
   double mu = q[0], ell = q[1], tau = exp(ell);
   double ss = 0, sq = 0, sr = 0, srt = 0;

@@ -149,7 +149,7 @@ B200_DEV double leapfrog_end(const ChainView& c, const SamplerCfg& cfg, double e
 }
 
 // z := current sample (q, g, V); fresh momentum; returns H0.  (hamiltonian.sample_p + hamiltonian.init with the cached gradient)
-B200_DEV double refresh_from_current(const ChainView& c, const SamplerCfg& cfg, int lane) {
+B200_DEV_CALL double refresh_from_current(const ChainView& c, const SamplerCfg& cfg, int lane) {
   double* p = slot(c, cfg, V_P);
   const double* im = slot(c, cfg, V_IM);
   const double* cq = slot(c, cfg, V_CQ);
@@ -165,7 +165,7 @@ B200_DEV double refresh_from_current(const ChainView& c, const SamplerCfg& cfg, 
 
 // Merge of the two topmost stack entries L (level sp-2) and R (sp-1) into L: base_nuts.hpp:313-351.
 // Returns the persist criterion.
-B200_DEV bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane) {
+B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane) {
   ChainS* s = c.s;
   const int li = s->sp - 2, ri = s->sp - 1;
   double* L = slot(c, cfg, V_STACK + 5 * li);
@@ -219,7 +219,7 @@ B200_DEV bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane) {
 }
 
 // stepsize_adaptation::learn_stepsize (stepsize_adaptation.hpp:55-71)
-B200_DEV void learn_stepsize(ChainS* s, const SamplerCfg& cfg, double adapt_stat) {
+B200_DEV_CALL void learn_stepsize(ChainS* s, const SamplerCfg& cfg, double adapt_stat) {
   s->sa_counter += 1.0;
   adapt_stat = adapt_stat > 1 ? 1 : adapt_stat;
   const double eta = 1.0 / (s->sa_counter + cfg.t0);
@@ -232,7 +232,7 @@ B200_DEV void learn_stepsize(ChainS* s, const SamplerCfg& cfg, double adapt_stat
 
 // var_adaptation::learn_variance (var_adaptation.hpp:17-46) on the new sample q; returns 1 when the metric was
 // updated, -1 on numerical overflow of the metric.
-B200_DEV int learn_variance(const ChainView& c, const SamplerCfg& cfg, int lane) {
+B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int lane) {
   ChainS* s = c.s;
   const double* q = slot(c, cfg, V_CQ);
   double* im = slot(c, cfg, V_IM);

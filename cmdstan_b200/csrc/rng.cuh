@@ -52,7 +52,7 @@ B200_HD unsigned long long mm_iterate(unsigned long long* Y, unsigned long long 
 }
 
 // ---- single-lane primitives (call from lane 0 only) ---------------------------------------------------------
-B200_DEV unsigned long long rng_next(unsigned long long* st) {
+B200_DEV_CALL unsigned long long rng_next(unsigned long long* st) {
   int counter = (int)st[18];
   if (counter <= 16) {
     st[18] = (unsigned long long)(counter + 1);
@@ -78,7 +78,7 @@ B200_DEV double rng_uniform_real(unsigned long long* st, double a, double b) {
   }
 }
 
-B200_DEV double rng_unit_exponential(unsigned long long* st) {
+B200_DEV_CALL double rng_unit_exponential(unsigned long long* st) {
   using namespace tables;
   double shift = 0;
   for (;;) {
@@ -98,7 +98,7 @@ B200_DEV double rng_unit_exponential(unsigned long long* st) {
   }
 }
 
-B200_DEV double rng_normal(unsigned long long* st) {
+B200_DEV_CALL double rng_normal(unsigned long long* st) {
   using namespace tables;
   for (;;) {
     unsigned long long u = rng_next(st);
@@ -140,7 +140,7 @@ B200_DEV double warp_uniform01(unsigned long long* st, int lane) {
 // fills dst[0..n) with variates in stream order; element i is stored by its owner lane (i % warp)
 // kind 0: normal(0,1) scaled by 1/sqrt(scale[i])  (diag_e_metric::sample_p, S/mcmc/hmc/hamiltonians/diag_e_metric.hpp:44-50)
 // kind 1: uniform_real(-radius, radius)           (random_var_context, S/io/random_var_context.hpp:53-56)
-B200_DEV void warp_fill(unsigned long long* st, int lane, double* dst, int n, int kind, const double* scale, double radius) {
+B200_DEV_CALL void warp_fill(unsigned long long* st, int lane, double* dst, int n, int kind, const double* scale, double radius) {
   for (int base = 0; base < n; base += kWarp) {
     int m = n - base < kWarp ? n - base : kWarp;
     double mine = 0.0;

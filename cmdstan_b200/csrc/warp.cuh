@@ -13,6 +13,7 @@
 #ifdef B200_HOST_EMUL
 #include <cmath>
 #define B200_DEV inline
+#define B200_DEV_CALL inline
 #define B200_HD inline
 namespace b200 {
 constexpr int kWarp = 1;
@@ -25,6 +26,9 @@ inline void warp_sync() {}
 }  // namespace b200
 #else
 #define B200_DEV __device__ __forceinline__
+// out-of-line device functions: the chain kernels are branchy state machines whose warps sit at different program
+// points, so code size (instruction-cache footprint) matters more than call overhead
+#define B200_DEV_CALL static __device__ __noinline__
 #define B200_HD __host__ __device__ inline
 namespace b200 {
 constexpr int kWarp = 32;

@@ -940,3 +940,35 @@ done:
   free(s.inv_metric); free(s.wf_m); free(s.wf_m2); free(gtmp);
   return rc;
 }
+
+/* ---- state-injection entry points for the reference's adaptation KATs (ST/unit/mcmc/stepsize_adaptation_test.cpp:99-143,
+ *      var_adaptation_test.cpp) ---- */
+void oracle_learn_stepsize_kat(double counter, double s_bar, double x_bar, double mu, double delta, double gamma, double kappa,
+                               double t0, double adapt_stat, double* out /* eps, counter, s_bar, x_bar */) {
+  sampler_t s;
+  memset(&s, 0, sizeof s);
+  s.sa_counter = counter; s.s_bar = s_bar; s.x_bar = x_bar; s.mu = mu; s.delta = delta; s.gamma = gamma; s.kappa = kappa; s.t0 = t0;
+  learn_stepsize(&s, adapt_stat);
+  out[0] = s.nom_epsilon; out[1] = s.sa_counter; out[2] = s.s_bar; out[3] = s.x_bar;
+}
+
+/* feeds n_learn copies of q through learn_variance with set_window_params(num_warmup, init_buffer, term_buffer, window);
+ * returns how many times the metric was updated; var_out = final inverse metric */
+int oracle_learn_variance_kat(int D, const double* q, int n_learn, unsigned num_warmup, unsigned init_buffer, unsigned term_buffer,
+                              unsigned window, double* var_out) {
+  sampler_t s;
+  memset(&s, 0, sizeof s);
+  s.D = D;
+  s.z = pt_alloc(D);
+  memcpy(s.z.q, q, D * sizeof(double));
+  s.inv_metric = (double*)calloc(D, sizeof(double));
+  s.wf_m = (double*)calloc(D, sizeof(double));
+  s.wf_m2 = (double*)calloc(D, sizeof(double));
+  s.adapt_window_counter = 0; s.adapt_window_size = 0; s.adapt_next_window = 0u - 1u;
+  set_window_params(&s, num_warmup, init_buffer, term_buffer, window);
+  int updates = 0;
+  for (int i = 0; i < n_learn; i++) updates += learn_variance(&s);
+  memcpy(var_out, s.inv_metric, D * sizeof(double));
+  pt_free(&s.z); free(s.inv_metric); free(s.wf_m); free(s.wf_m2);
+  return updates;
+}

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.json from the UNMODIFIED reference compiled under oracle/_ref (CmdStan 2.36; see
+oracle/build_ref.sh).  Run in the build container (needs /root/reference to have built oracle/_ref):
+
+    python tests/golden/gen_golden.py
+
+Fixtures: (a) log_prob / gradient of every model at seeded random points (method=log_prob jacobian=1 sig_figs=18),
+(b) the first rows of sampling CSVs (sig_figs=18, save_warmup=1) for matched-stream checks, (c) a stansummary table.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+import cases  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+LPG = {
+    "std_normal": {"D": 3},
+    "bernoulli": cases.BERNOULLI,
+    "eight_schools_nc": cases.EIGHT_SCHOOLS,
+    "logistic": cases.logistic_data(200, 7),
+    "poisson_glm": cases.poisson_data(150, 5),
+    "irt_2pl": cases.irt_data(20, 6),
+}
+CHAINS = [
+    ("bernoulli", cases.BERNOULLI, dict(seed=1234, chain_id=1)),
+    ("bernoulli", cases.BERNOULLI, dict(seed=1234, chain_id=2)),
+    ("std_normal", {"D": 3}, dict(seed=4839294, chain_id=3)),
+    ("eight_schools_nc", cases.EIGHT_SCHOOLS, dict(seed=1234, chain_id=1)),
+    ("logistic", LPG["logistic"], dict(seed=77, chain_id=1)),
+    ("poisson_glm", LPG["poisson_glm"], dict(seed=78, chain_id=2)),
+    ("irt_2pl", LPG["irt_2pl"], dict(seed=79, chain_id=1)),
+]
+
+
+def jsonable(d):
+    return {k: np.asarray(v).tolist() for k, v in d.items()}
+
+
+def main():
+    out = {}
+    rng = np.random.default_rng(2024)
+    for name, data in LPG.items():
+        D = O.Model(name, data).D
+        q = rng.uniform(-2, 2, size=(12, D))
+        lp, g = O.ref_log_prob(name, data, q)
+        out[name] = dict(data=jsonable(data), q=q.tolist(), lp=lp.tolist(), grad=g.tolist())
+    json.dump(out, open(os.path.join(HERE, "ref_log_prob.json"), "w"))
+    chains = []
+    for name, data, kw in CHAINS:
+        res, _, _ = O.ref_sample(name, data, num_warmup=200, num_samples=100, save_warmup=True, **kw)
+        names, draws, stepsize, metric, _ = res[0]
+        chains.append(dict(model=name, data=jsonable(data), args=dict(kw, num_warmup=200, num_samples=100), columns=names,
+                           rows=draws[:80].tolist(), last_rows=draws[-3:].tolist(), stepsize=stepsize, inv_metric=metric.tolist()))
+    json.dump(chains, open(os.path.join(HERE, "ref_chains.json"), "w"))
+    # stansummary table (the metric's definition) for a 4-chain bernoulli run
+    res, _, files = O.ref_sample("bernoulli", cases.BERNOULLI, num_chains=4, seed=1234, sig_figs=18)
+    txt = subprocess.run([os.path.join(O.REF, "stansummary")] + files, capture_output=True, text=True).stdout
+    table = {}
+    for ln in txt.splitlines():
+        p = ln.split()
+        if len(p) == 11 and p[0] in ("lp__", "theta", "energy__", "accept_stat__"):
+            table[p[0]] = dict(mean=float(p[1]), sd=float(p[3]), ess_bulk=float(p[8]), ess_tail=float(p[9]), rhat=float(p[10]))
+    draws = np.stack([r[1] for r in res])
+    json.dump(dict(columns=res[0][0], draws=draws[:, :, [0, 1, 6, 7]].tolist(), kept_columns=["lp__", "accept_stat__", "energy__", "theta"],
+                   stansummary=table), open(os.path.join(HERE, "ref_stansummary_bernoulli.json"), "w"))
+    print("written:", os.listdir(HERE))
+
+
+if __name__ == "__main__":
+    main()

@@ -46,3 +46,33 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
   *n_grad = s.n_grad;
   return s.err;
 }
+
+// state-injection KAT entry points (same cases as the oracle's, against the device code)
+extern "C" void emul_learn_stepsize_kat(double counter, double s_bar, double x_bar, double mu, double delta, double gamma,
+                                        double kappa, double t0, double adapt_stat, double* out) {
+  ChainS s;
+  std::memset(&s, 0, sizeof s);
+  SamplerCfg cfg{};
+  s.sa_counter = counter; s.s_bar = s_bar; s.x_bar = x_bar; s.mu = mu;
+  cfg.delta = delta; cfg.gamma = gamma; cfg.kappa = kappa; cfg.t0 = t0;
+  learn_stepsize(&s, cfg, adapt_stat);
+  out[0] = s.eps_nom; out[1] = s.sa_counter; out[2] = s.s_bar; out[3] = s.x_bar;
+}
+
+extern "C" int emul_learn_variance_kat(int D, const double* q, int n_learn, unsigned num_warmup, unsigned init_buffer,
+                                       unsigned term_buffer, unsigned window, double* var_out) {
+  SamplerCfg cfg{};
+  cfg.D = D; cfg.ld = D;
+  resolve_window(&cfg, num_warmup, init_buffer, term_buffer, window);
+  std::vector<double> slab((size_t)num_vec_slots(1) * D, 0.0), qq(D), g(D);
+  ChainS s;
+  std::memset(&s, 0, sizeof s);
+  s.win_size = cfg.w_size0; s.win_next = cfg.w_next0;
+  double zV = 0;
+  ChainView c{&s, qq.data(), g.data(), &zV, slab.data(), nullptr, nullptr};
+  for (int i = 0; i < D; i++) slab[(size_t)V_CQ * D + i] = q[i];
+  int updates = 0;
+  for (int i = 0; i < n_learn; i++) updates += learn_variance(c, cfg, 0) > 0;
+  for (int i = 0; i < D; i++) var_out[i] = slab[(size_t)V_IM * D + i];
+  return updates;
+}

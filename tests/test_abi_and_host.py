@@ -1,0 +1,69 @@
+"""CPU suite: the C-ABI library loads without a GPU and exports every symbol include/b200nuts.h declares; the product
+fails loudly without a CUDA device (no CPU fallback); the product package never references the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_header_symbols_are_exported():
+    import cmdstan_b200 as B
+    lib = B.load_library()
+    hdr = open(os.path.join(ROOT, "include", "b200nuts.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b200nuts_[a-z0-9_]+)\s*\(", hdr)) - {"b200nuts_allreduce_fn"}
+    assert declared == set(B.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_config_struct_layout_matches_header():
+    import cmdstan_b200 as B
+    lib = B.load_library()
+    cfg = B.Config()
+    lib.b200nuts_default_config(ctypes.byref(cfg))
+    # reference defaults (src/cmdstan/arguments/arg_sample.hpp:18-29, arg_adapt.hpp:19-37, arg_nuts.hpp:15-16, arg_hmc.hpp:19-27)
+    assert (cfg.num_chains, cfg.num_warmup, cfg.num_samples, cfg.num_thin, cfg.save_warmup) == (1, 1000, 1000, 1, 0)
+    assert (cfg.delta, cfg.gamma, cfg.kappa, cfg.t0) == (0.8, 0.05, 0.75, 10.0)
+    assert (cfg.init_buffer, cfg.term_buffer, cfg.window, cfg.max_depth) == (75, 50, 25, 10)
+    assert (cfg.stepsize, cfg.stepsize_jitter, cfg.init_radius, cfg.init_chain_id, cfg.adapt_engaged) == (1.0, 0.0, 2.0, 1, 1)
+    assert (cfg.row_shards, cfg.row_shard_rank, cfg.store_draws) == (1, 0, 1)
+
+
+def test_usage_errors_before_touching_the_device():
+    import cmdstan_b200 as B
+    with pytest.raises(B.B200NutsError) as ei:
+        B.Engine("bernoulli", {"y": np.array([0, 1])}, num_chains=0)
+    assert ei.value.code == B.USAGE
+    with pytest.raises(B.B200NutsError) as ei:
+        B.Engine("bernoulli", {"y": np.array([0, 1])}, max_depth=40)
+    assert ei.value.code == B.USAGE
+    with pytest.raises(B.B200NutsError) as ei:
+        B.Engine("bernoulli", {"y": np.array([0, 1])}, num_warmup=0)  # adapting with num_warmup = 0 (command.hpp:569-574)
+    assert ei.value.code == B.USAGE
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cmdstan_b200 as B
+    with pytest.raises(B.B200NutsError) as ei:
+        B.Engine("bernoulli", {"y": np.array([0, 1])})
+    assert ei.value.code == B.SOFTWARE and "no CUDA device" in str(ei.value)
+    rc, res = B.hmc_nuts_diag_e_adapt("bernoulli", {"y": np.array([0, 1])})
+    assert rc == B.SOFTWARE and res is None
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cmdstan_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("# oracle", "").lower() or f == "analyze.py" and "oracle" not in txt.lower(), f
