@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale the data rows (testing only; invalidates the number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
+    ap.add_argument("--dump-warm", default="", help="write the adapted state (q, inv_metric, stepsize of up to 64 chains) to this .npz: "
+                    "the warm-start fixture of the reference arm (tests/golden/warm_<workload>.npz)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,7 +210,7 @@ def main():
             return
         data = make_data(w, args.scale)
         warm = None
-        fx = os.path.join(ROOT, "tests", "golden", f"warm_{args.workload}.npz")
+        fx = os.path.join(os.environ.get("B200_WARM_FIXTURE_DIR", os.path.join(ROOT, "tests", "golden")), f"warm_{args.workload}.npz")
         if model not in ("bernoulli", "eight_schools_nc") and os.path.exists(fx) and args.scale == 1.0:
             z = np.load(fx)
             warm = dict(q=z["q"], inv_metric=z["inv_metric"], stepsize=z["stepsize"])
@@ -334,6 +336,10 @@ def main():
                     "h2d_s": h2d_s, "run_wall_s": run_wall, "d2h_s": fetch_s},
             "gpu_launches": int(launches), "roofline": roof, "clocks": clk,
         }
+        if args.dump_warm:
+            nk = min(C, 64)
+            np.savez(args.dump_warm, q=e.fetch_draws(chain0=0, nchains=nk, row0=W + K - 1, nrows=1, constrained=False)[:, 0, 7:],
+                     inv_metric=im[:nk], stepsize=eps[:nk])
         if not args.no_cpu and world >= 1:
             try:
                 warm = dict(q=e.fetch_draws(chain0=0, nchains=min(C, cores), row0=W + K - 1, nrows=1, constrained=False)[:, 0, 7:],
