@@ -112,7 +112,7 @@ def algorithmic_work(w, data, model, D):
     """Per chain-gradient algorithmic flops and bytes (restated in DESIGN.md)."""
     if model in ("logistic", "poisson_glm"):
         N, K = data["X"].shape
-        Dp = (K + 1 + 3) // 4 * 4
+        Dp = (K + 1 + 7) // 8 * 8
         return dict(flops=4.0 * N * Dp, bytes_per_batch=N * Dp * 8.0 + N * 4.0, kind="tensor")
     if model == "irt_2pl":
         I, J = data["y"].shape
@@ -303,18 +303,22 @@ def main():
         work = algorithmic_work(w, data, model, e.D)
         n_grad_launch = max(1, int(np.max(ng2 - ng1)))  # lock-step: one gradient-stage launch per leapfrog of the slowest chain
         roof = None
+        n_chain_grads = float(nleap[1])  # chain-gradients actually executed in the timed region (all ranks)
         if work["kind"] == "tensor":
-            # dominant kernel: fused GLM gradient.  bound: FP64 tensor pipe; peak measured live below with a DGEMM
-            fl = work["flops"] * C
-            ach = fl / (grad_s / n_grad_launch) / 1e12 if grad_s > 0 else None
+            # dominant kernel: fused GLM gradient.  bound: FP64 tensor pipe; peak measured live below with a DGEMM.
+            # achieved = algorithmic flops of the chain-gradients actually served (requesting chains are compacted, so a
+            # launch serves fewer than C chains once trees of different depth interleave) / time in the gradient stage
+            fl = work["flops"] * n_chain_grads / world
+            ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
                     "traffic": None, "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
-                    "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                    "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "avg_chains_per_launch": n_chain_grads / world / n_grad_launch,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
                     "hbm_gbs_achieved": work["bytes_per_batch"] / (grad_s / n_grad_launch) / 1e9 if grad_s > 0 else None, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src}
         elif work["kind"] == "fp64":
-            fl = work["flops"] * C
-            ach = fl / (grad_s / n_grad_launch) / 1e12 if grad_s > 0 else None
+            fl = work["flops"] * n_chain_grads / world
+            ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None, "traffic": None,
                     "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,

@@ -42,6 +42,7 @@ std::string g_create_error;
   } while (0)
 
 constexpr int kChainsPerBlock = 4;  // 4 warps per CTA
+constexpr int kCounterRing = 16;    // lock-step engine: host checks for completion every kCounterRing steps
 
 struct DeviceChains {
   ChainS* cs;
@@ -62,12 +63,45 @@ __device__ __forceinline__ ChainView make_view(const DeviceChains& d, const Samp
   return v;
 }
 
-// ---- fused engine: advance + inlined model gradient, looped until the chain is idle
-__global__ void __launch_bounds__(32 * kChainsPerBlock, 8) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C) {
-  const int c = blockIdx.x * kChainsPerBlock + (threadIdx.x >> 5);
+// ---- copy helpers: a chain's scalar block / vectors between global and shared memory (whole warp, 8-byte words)
+__device__ __forceinline__ void warp_copy_words(void* dst, const void* src, int n_words, int lane) {
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+  for (int i = lane; i < n_words; i += 32) d[i] = s[i];
+}
+static_assert(sizeof(ChainS) % 8 == 0, "ChainS is copied as 8-byte words");
+constexpr int kChainWords = (int)(sizeof(ChainS) / 8);
+
+// ---- fused engine: advance + inlined model gradient, looped until the chain is idle.
+// SMEM = true: the chain's whole state (scalars, z.q, z.g, vector slab) lives in shared memory for the duration of the
+// launch (small models: 7 KB per chain for eight schools) and is written back at the end, so the state machine's
+// many dependent accesses cost shared-memory latency instead of L2/HBM latency.
+constexpr int kFusedMaxWarps = 7;  // 4 blocks x 7 warps = 28 resident chains per SM (4096 chains = one wave on 148 SMs)
+template <bool SMEM>
+__global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C, int warps_per_block, int chain_smem_words) {
+  extern __shared__ __align__(16) unsigned long long fused_smem[];
+  const int w = threadIdx.x >> 5;
+  const int c = blockIdx.x * warps_per_block + w;
   if (c >= C) return;
   const int lane = threadIdx.x & 31;
   ChainView v = make_view(d, cfg, c);
+  ChainView g = v;  // where the state lives between launches
+  const int slab_words = (int)d.slab_stride;
+  if (SMEM) {
+    unsigned long long* base = fused_smem + (size_t)w * chain_smem_words;
+    v.s = reinterpret_cast<ChainS*>(base);
+    double* vec = reinterpret_cast<double*>(base + kChainWords);
+    v.q = vec;
+    v.g = vec + cfg.ld;
+    v.zV = vec + 2 * cfg.ld;
+    v.v = vec + 2 * cfg.ld + 2;
+    warp_copy_words(v.s, g.s, kChainWords, lane);
+    warp_copy_words(v.q, g.q, cfg.ld, lane);
+    warp_copy_words(v.g, g.g, cfg.ld, lane);
+    warp_copy_words(v.v, g.v, slab_words, lane);
+    if (lane == 0) *v.zV = *g.zV;
+    __syncwarp();
+  }
   while (advance(v, cfg, lane) == ADV_NEED_GRAD) {
     __syncwarp();
     const double lp = lp_grad_small(md, v.q, v.g, lane);
@@ -75,20 +109,39 @@ __global__ void __launch_bounds__(32 * kChainsPerBlock, 8) fused_chain_kernel(Sa
     *v.zV = -lp;
     __syncwarp();
   }
+  if (SMEM) {
+    __syncwarp();
+    warp_copy_words(g.s, v.s, kChainWords, lane);
+    warp_copy_words(g.q, v.q, cfg.ld, lane);
+    warp_copy_words(g.g, v.g, cfg.ld, lane);
+    warp_copy_words(g.v, v.v, slab_words, lane);
+    if (lane == 0) *g.zV = *v.zV;
+  }
 }
 
 // ---- lock-step engine: advance every chain to its next gradient request
+// and collect the requesting chains: active[c] flag + compacted index list (order irrelevant: a chain's gradient
+// depends on its own q only).  The chain's scalar block is staged in shared memory for the launch (one coalesced
+// load + store instead of dozens of dependent global accesses).
 __global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCfg cfg, DeviceChains d, int C, int* active,
-                                                                          int* n_active) {
-  const int c = blockIdx.x * kChainsPerBlock + (threadIdx.x >> 5);
+                                                                          int* list, int* n_active) {
+  __shared__ __align__(16) ChainS sh[kChainsPerBlock];
+  const int w = threadIdx.x >> 5;
+  const int c = blockIdx.x * kChainsPerBlock + w;
   if (c >= C) return;
   const int lane = threadIdx.x & 31;
   ChainView v = make_view(d, cfg, c);
+  ChainS* gs = v.s;
+  warp_copy_words(&sh[w], gs, kChainWords, lane);
+  __syncwarp();
+  v.s = &sh[w];
   const int r = advance(v, cfg, lane);
+  __syncwarp();
+  warp_copy_words(gs, &sh[w], kChainWords, lane);
   if (lane == 0) {
     const int a = r == ADV_NEED_GRAD ? 1 : 0;
     active[c] = a;
-    if (a) atomicAdd(n_active, 1);
+    if (a) list[atomicAdd(n_active, 1)] = c;
   }
 }
 
@@ -204,7 +257,7 @@ struct b200nuts_engine {
   DeviceChains dc{};
   double *d_user_q0 = nullptr, *d_user_im = nullptr;
   std::vector<double> h_user_q0, h_user_im;
-  int *d_active = nullptr, *d_nactive = nullptr;
+  int *d_active = nullptr, *d_list = nullptr, *d_nactive = nullptr;  // d_nactive: ring of kCounterRing per-step counters
   int* h_nactive = nullptr;  // pinned
   void* d_glm_ws = nullptr;
   GlmWorkspace glm_ws;
@@ -297,7 +350,7 @@ void b200nuts_destroy(b200nuts_engine* e) {
   cudaSetDevice(e->cfg.device);
   free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8);
   free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws);
-  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
+  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
   for (auto ev : e->grad_events) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -416,8 +469,8 @@ static int finalize_data(b200nuts_engine* e) {
       m.N = (int)e->x_rows;
       m.K = (int)e->x_cols;
       m.D = m.K + 1;
-      if (((m.D + 3) & ~3) > glm_max_dim()) { e->err = "glm: too many covariates for this build (D <= 176)"; return B200NUTS_CONFIG; }
-      m.ldx = (m.D + 3) & ~3;
+      if (((m.D + 7) & ~7) > glm_max_dim()) { e->err = "glm: too many covariates for this build (D <= 176)"; return B200NUTS_CONFIG; }
+      m.ldx = (m.D + 7) & ~7;
       // padded design matrix [1 | X | 0]
       std::vector<double> xp((size_t)m.N * m.ldx, 0.0);
       for (int i = 0; i < m.N; i++) {
@@ -494,7 +547,7 @@ static int ensure_glm_ws(b200nuts_engine* e, int C) {
   if (e->d_glm_ws && e->glm_ws.C >= C) return B200NUTS_OK;
   free_dev(e->d_glm_ws);
   e->d_glm_ws = nullptr;
-  size_t bytes = glm_workspace_bytes(e->md.N, e->md.D, C, &e->glm_ws);
+  size_t bytes = glm_workspace_bytes(e->md.N, e->md.D, C, e->sm_count, &e->glm_ws);
   CUDA_TRY(e, cudaMalloc(&e->d_glm_ws, bytes));
   glm_workspace_bind(&e->glm_ws, e->d_glm_ws);
   const char* v = getenv("B200NUTS_GLM_VARIANT");
@@ -532,7 +585,7 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   const int C = e->C;
   DeviceChains& d = e->dc;
   free_dev(d.cs); free_dev(d.q); free_dev(d.g); free_dev(d.zV); free_dev(d.slab); free_dev(d.draws);
-  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_nactive);
+  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive);
   d = DeviceChains{};
   e->d_user_q0 = e->d_user_im = nullptr;
   d.slab_stride = (size_t)num_vec_slots(c.max_depth) * e->ld;
@@ -555,7 +608,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
     }
   }
   CUDA_TRY(e, cudaMalloc(&e->d_active, sizeof(int) * C));
-  CUDA_TRY(e, cudaMalloc(&e->d_nactive, sizeof(int)));
+  CUDA_TRY(e, cudaMalloc(&e->d_list, sizeof(int) * C));
+  CUDA_TRY(e, cudaMalloc(&e->d_nactive, sizeof(int) * kCounterRing));
   if (!e->h_nactive) CUDA_TRY(e, cudaMallocHost(&e->h_nactive, sizeof(int)));
   // per-chain scalars + seeded streams (host), then upload
   std::vector<ChainS> hs(C);
@@ -615,11 +669,26 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
   launches++;
   const int blocks = (C + kChainsPerBlock - 1) / kChainsPerBlock;
   if (e->fused) {
-    fused_chain_kernel<<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C);
+    // state in shared memory when a wave of ceil(C / #SM) chains per SM fits (<= 16 KB per chain); else global memory
+    const int chain_words = kChainWords + 2 * e->ld + 2 + (int)e->dc.slab_stride;
+    const size_t chain_bytes = (size_t)chain_words * 8;
+    const int per_sm = (C + e->sm_count - 1) / e->sm_count;
+    if (chain_bytes <= 16 * 1024) {
+      // warps per block: spread the per-SM wave over blocks of <= 8 warps so that several blocks share an SM
+      int wpb = per_sm < kFusedMaxWarps ? (per_sm < 1 ? 1 : per_sm) : kFusedMaxWarps;
+      while ((size_t)wpb * chain_bytes > 56 * 1024 && wpb > 1) wpb--;
+      const size_t smem = (size_t)wpb * chain_bytes;
+      auto k = fused_chain_kernel<true>;
+      CUDA_TRY(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<(C + wpb - 1) / wpb, 32 * wpb, smem, e->stream>>>(e->scfg, e->md, e->dc, C, wpb, chain_words);
+    } else {
+      fused_chain_kernel<false><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C, kChainsPerBlock, 0);
+    }
     launches++;
   } else {
     GradBatch b{e->dc.q, e->dc.g, e->dc.zV, e->d_active, C, e->ld};
-    const int kCheck = 16;
+    b.list = e->d_list;
+    const int kCheck = kCounterRing;
     // two CUDA events bracket every gradient stage so that the dominant kernel family is timed live (bench.py roofline)
     size_t ev_used = 0;
     auto next_event = [&]() -> cudaEvent_t {
@@ -632,11 +701,13 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
     };
     for (long long step = 0;; step++) {
       const bool check = (step % kCheck) == 0;
-      if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int), e->stream));
-      advance_kernel<<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_nactive);
+      int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
+      if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
+      advance_kernel<<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;
+      b.n_list = counter;
       if (check) {
-        CUDA_TRY(e, cudaMemcpyAsync(e->h_nactive, e->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_nactive, counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CUDA_TRY(e, cudaStreamSynchronize(e->stream));
         // harvest finished event pairs
         for (size_t i = 0; i + 1 < ev_used; i += 2) {

@@ -15,7 +15,8 @@
 // are summed in index order by glm_reduce_kernel, so chain c's (lp, grad) depends only on q_c.
 //
 // Algorithmic work per chain-gradient: 4 N Dp flop + N link evaluations (exp [+ log1p, div]).
-// variant 0 (this file, first correct path): register-tiled DFMA.  variant 1: FP64 tensor cores (mma.sync m8n8k4 DMMA).
+// variant 0 (this file; designs with more than 112 columns): register-tiled DFMA.  variant 1 (glm_dmma.cu, default): FP64
+// tensor cores (mma.sync m8n8k4 DMMA), persistent over fixed row groups, compacted chain tiles.
 #include <cstdio>
 
 #include "kernels.h"
@@ -56,8 +57,8 @@ __device__ __forceinline__ void link_eval(double eta, int yv, double& lpi, doubl
 template <int LINK, int MK>
 __global__ void __launch_bounds__(NT, 1)
 glm_partial_kernel(const double* __restrict__ X, int ldx, const int* __restrict__ y, int N, int Dp, const double* __restrict__ Q,
-                   int ldq, int D, const int* __restrict__ active, int C, int rows_per_group, double* __restrict__ Gp,
-                   double* __restrict__ LPp) {
+                   int ldq, int D, const int* __restrict__ active, int C, long long n_row_tiles, int P, int cap,
+                   double* __restrict__ Gp, double* __restrict__ LPp) {
   extern __shared__ double smem[];
   const int xs_ld = Dp + 1;
   double* Bs = smem;                        // [Dp][TC]
@@ -92,8 +93,9 @@ glm_partial_kernel(const double* __restrict__ X, int ldx, const int* __restrict_
 #pragma unroll
     for (int c = 0; c < 4; c++) gacc[m][c] = 0.0;
 
-  const long long row_begin = (long long)p * rows_per_group;
-  long long row_end = row_begin + rows_per_group;
+  // fixed row group p: row tiles [p T / P, (p+1) T / P) -- a function of N only (same partition as the DMMA kernel)
+  const long long row_begin = ((long long)p * n_row_tiles / P) * TR;
+  long long row_end = ((long long)(p + 1) * n_row_tiles / P) * TR;
   if (row_end > N) row_end = N;
   for (long long row0 = row_begin; row0 < row_end; row0 += TR) {
     __syncthreads();  // previous tile fully consumed (and Bs visible on the first pass)
@@ -167,7 +169,7 @@ glm_partial_kernel(const double* __restrict__ X, int ldx, const int* __restrict_
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const int chain = chain0 + c0 + c;
-        if (chain < C) Gp[((size_t)p * C + chain) * Dp + k] = gacc[m][c];
+        if (chain < C) Gp[((size_t)p * cap + chain) * Dp + k] = gacc[m][c];
       }
     }
   }
@@ -179,27 +181,28 @@ glm_partial_kernel(const double* __restrict__ X, int ldx, const int* __restrict_
   if (tid < TC && chain0 + tid < C) {
     double s = 0.0;
     for (int t = 0; t < 16; t++) s += red[t * TC + tid];
-    LPp[(size_t)p * C + chain0 + tid] = s;
+    LPp[(size_t)p * cap + chain0 + tid] = s;
   }
 }
 
-// R[c][0] = sum_p LPp[p][c] ; R[c][1+k] = sum_p Gp[p][c][k]   (fixed order over row groups)
-__global__ void glm_reduce_kernel(const double* __restrict__ Gp, const double* __restrict__ LPp, int P, int C, int Dp,
+// R[chain][0] = sum_p LPp[p][slot] ; R[chain][1+k] = sum_p Gp[p][slot][k]   (fixed order over row groups).
+// slot -> chain through the compacted list of requesting chains (list == nullptr: identity, `active` flags respected).
+__global__ void glm_reduce_kernel(const double* __restrict__ Gp, const double* __restrict__ LPp, int P, int cap, int Dp,
+                                  const int* __restrict__ list, const int* __restrict__ n_list, int n_fixed,
                                   const int* __restrict__ active, double* __restrict__ R) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int w = 1 + Dp;
-  if (idx >= (long long)C * w) return;
-  const int c = (int)(idx / w), j = (int)(idx - (long long)c * w);
-  if (active && !active[c]) {
-    R[idx] = 0.0;  // inactive chains contribute zeros to the all-reduce payload
-    return;
-  }
+  const int n = n_list ? *n_list : n_fixed;
+  if (idx >= (long long)n * w) return;
+  const int slot = (int)(idx / w), j = (int)(idx - (long long)slot * w);
+  const int c = list ? list[slot] : slot;
+  if (!list && active && !active[c]) return;
   double s = 0.0;
   if (j == 0)
-    for (int p = 0; p < P; p++) s += LPp[(size_t)p * C + c];
+    for (int p = 0; p < P; p++) s += LPp[(size_t)p * cap + slot];
   else
-    for (int p = 0; p < P; p++) s += Gp[((size_t)p * C + c) * Dp + (j - 1)];
-  R[idx] = s;
+    for (int p = 0; p < P; p++) s += Gp[((size_t)p * cap + slot) * Dp + (j - 1)];
+  R[(size_t)c * w + j] = s;
 }
 
 // priors + sign convention: zV = -(loglik + prior), G = -(X^T d + prior gradient).  One warp per chain.
@@ -237,13 +240,10 @@ __global__ void glm_finish_kernel(const double* __restrict__ R, int Dp, const do
   }
 }
 
-size_t glm_workspace_bytes(int N, int D, int C, GlmWorkspace* ws) {
-  const int Dp = (D + 3) & ~3;
-  const int chain_tiles = (C + TC - 1) / TC;
-  int P = 148 / chain_tiles;
-  if (P < 1) P = 1;
-  const int max_groups = (N + TR - 1) / TR;
-  if (P > max_groups) P = max_groups;
+size_t glm_workspace_bytes(int N, int D, int C, int sm_count, GlmWorkspace* ws) {
+  const int Dp = (D + 7) & ~7;
+  const long long T = ((long long)N + TR - 1) / TR;
+  int P = (int)(T < sm_count ? T : sm_count);  // one row group per SM; depends on N only (batch-independent sums)
   if (P < 1) P = 1;
   ws->P = P;
   ws->C = C;
@@ -258,34 +258,38 @@ void glm_workspace_bind(GlmWorkspace* ws, void* base) {
 }
 
 int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, cudaStream_t stream);  // glm_dmma.cu
+int glm_tc_max_dk();
 
 template <int LINK>
 static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, allreduce_fn ar, void* ar_user,
                         cudaStream_t stream) {
   const int Dp = ws.Dp, C = b.C, P = ws.P;
   int launches = 0;
-  if (ws.variant == 1 && ((m.D + 7) & ~7) <= 112) {
+  const bool tc = ws.variant == 1 && Dp <= glm_tc_max_dk();
+  if (tc) {
     launches += launch_glm_dmma(m, b, ws, stream);
   } else {
-    int rows_per_group = (m.N + P - 1) / P;
-    rows_per_group = (rows_per_group + TR - 1) / TR * TR;
+    const long long T = ((long long)m.N + TR - 1) / TR;
     const size_t smem = ((size_t)Dp * TC + (size_t)TR * (Dp + 1) + (size_t)TR * TC) * sizeof(double) + TR * sizeof(int);
     dim3 grid((C + TC - 1) / TC, P);
     if (Dp <= 112) {
       auto k = glm_partial_kernel<LINK, 7>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, NT, smem, stream>>>(m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, rows_per_group, ws.Gp, ws.LPp);
+      k<<<grid, NT, smem, stream>>>(m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, T, P, ws.C, ws.Gp, ws.LPp);
     } else {
       auto k = glm_partial_kernel<LINK, 11>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, NT, smem, stream>>>(m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, rows_per_group, ws.Gp, ws.LPp);
+      k<<<grid, NT, smem, stream>>>(m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, T, P, ws.C, ws.Gp, ws.LPp);
     }
     launches++;
   }
+  // the DMMA kernel works on the compacted list of requesting chains, the DFMA kernel on all chains + active flags
+  const int* list = tc ? b.list : nullptr;
+  const int* n_list = tc ? b.n_list : nullptr;
   const long long tot = (long long)C * (1 + Dp);
-  glm_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ws.Gp, ws.LPp, P, C, Dp, b.active, ws.R);
+  glm_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ws.Gp, ws.LPp, P, ws.C, Dp, list, n_list, C, b.active, ws.R);
   launches++;
-  if (ar) ar(ws.R, tot, (void*)stream, ar_user);
+  if (ar) ar(ws.R, (long long)ws.C * (1 + Dp), (void*)stream, ar_user);
   glm_finish_kernel<LINK><<<(C * 32 + 127) / 128, 128, 0, stream>>>(ws.R, Dp, b.Q, b.ld, m.D, b.active, C, b.G, b.zV);
   launches++;
   return launches;

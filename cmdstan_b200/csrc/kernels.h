@@ -22,17 +22,19 @@ struct GradBatch {
   double* zV;          // [C]
   const int* active;   // [C] or nullptr
   int C, ld;
+  const int* list = nullptr;    // compacted indices of the chains with active[c] != 0 (any order), or nullptr
+  const int* n_list = nullptr;  // device count of entries in `list`
 };
 
 // ---- GLMs (logistic / poisson): glm.cu -------------------------------------------------------------------------
 struct GlmWorkspace {
-  double* Gp = nullptr;   // [P][C][Dp]   per row-group partial gradients
+  double* Gp = nullptr;   // [P][C][Dp]   per row-group partial gradients (second index: slot in the chain list)
   double* LPp = nullptr;  // [P][C]       per row-group partial log-likelihood
   double* R = nullptr;    // [C][1 + Dp]  reduced (lp, gradient): the all-reduce payload for row sharding
   int P = 0, C = 0, Dp = 0;
   int variant = 0;        // 0: register-tiled DFMA kernel, 1: FP64 tensor-core (DMMA) kernel
 };
-size_t glm_workspace_bytes(int N, int D, int C, GlmWorkspace* ws);  // fills P, C, Dp; returns total bytes (3 arrays)
+size_t glm_workspace_bytes(int N, int D, int C, int sm_count, GlmWorkspace* ws);  // fills P, C, Dp (= D padded to 8); returns total bytes
 void glm_workspace_bind(GlmWorkspace* ws, void* base);
 int glm_max_dim();
 // returns the number of kernels launched
