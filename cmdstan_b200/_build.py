@@ -11,6 +11,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200nuts.so")
+HOST = os.path.join(HERE, "host")
+BIN = os.path.join(HERE, "bin")
+CLI = os.path.join(BIN, "b200stan")
+CLI_MODELS = ["std_normal", "bernoulli", "eight_schools_nc", "logistic", "irt_2pl", "poisson_glm"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 UNITS = [("engine.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", [])]
@@ -21,14 +25,36 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200nuts.h")]
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")] + [os.path.join(HERE, "..", "include", "b200nuts.h")]
+
+
+def host_sources():
+    return [os.path.join(HOST, f) for f in os.listdir(HOST)]
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in sources())
+    if any(os.path.getmtime(s) > t for s in sources()):
+        return True
+    t = os.path.getmtime(CLI)
+    return any(os.path.getmtime(s) > t for s in host_sources() + [LIB])
+
+
+def build_cli():
+    """C++ host side above the C ABI: cmdstan_b200/bin/b200stan (+ one link per model name, as CmdStan has one
+    executable per model)."""
+    os.makedirs(BIN, exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", CLI, os.path.join(HOST, "main.cpp"), "-L" + HERE, "-lb200nuts",
+           "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+    subprocess.check_call(cmd)
+    for m in CLI_MODELS:
+        link = os.path.join(BIN, m)
+        if os.path.lexists(link):
+            os.remove(link)
+        os.symlink("b200stan", link)
+    return CLI
 
 
 def build(force=False, verbose=False):
@@ -49,6 +75,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
     cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
     subprocess.check_call(cmd)
+    build_cli()
     return LIB
 
 

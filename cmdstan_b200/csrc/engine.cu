@@ -67,6 +67,7 @@ __device__ __forceinline__ ChainView make_view(const DeviceChains& d, const Samp
 __device__ __forceinline__ void warp_copy_words(void* dst, const void* src, int n_words, int lane) {
   unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
   const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+#pragma unroll 1
   for (int i = lane; i < n_words; i += 32) d[i] = s[i];
 }
 static_assert(sizeof(ChainS) % 8 == 0, "ChainS is copied as 8-byte words");

@@ -34,16 +34,16 @@ struct ModelData {
   const signed char* y8;  // IRT responses, persons x items row-major
 };
 
-B200_DEV double dev_log1p_exp(double a) { return a > 0.0 ? a + log1p(exp(-a)) : log1p(exp(a)); }
+B200_DEV double dev_log1p_exp(double a) { return a > 0.0 ? a + dev_log1p(dev_exp(-a)) : dev_log1p(dev_exp(a)); }
 
 // M/prim/fun/inv_logit.hpp:51-60
 B200_DEV double dev_inv_logit(double u) {
   if (u < 0) {
-    double e = exp(u);
+    double e = dev_exp(u);
     if (u < -36.04365338911715) return e;
     return e / (1 + e);
   }
-  return 1 / (1 + exp(-u));
+  return 1 / (1 + dev_exp(-u));
 }
 
 // log_sum_exp(a, b), M/prim/fun/log_sum_exp.hpp:51-64 (NaN falls through to the last branch like the reference)
@@ -58,7 +58,7 @@ B200_DEV_CALL double dev_log_sum_exp(double a, double b) {
 // normal_lpdf<propto>(x, 0, 1) = -0.5 sum x^2  (M/prim/prob/normal_lpdf.hpp:83-89)
 B200_DEV_CALL double lp_grad_std_normal(const ModelData& m, const double* q, double* g, int lane) {
   double s = 0;
-  for (int i = lane; i < m.D; i += kWarp) {
+  _Pragma("unroll 1") for (int i = lane; i < m.D; i += kWarp) {
     double x = q[i];
     s += x * x;
     g[i] = -x;
@@ -77,7 +77,7 @@ B200_DEV_CALL double lp_grad_bernoulli(const ModelData& m, const double* q, doub
   double th = dev_inv_logit(u);
   double au = fabs(u);
   double lp = -au - 2.0 * dev_log1p_exp(-au);
-  double lth = log(th), l1m = log1p(-th);
+  double lth = dev_log(th), l1m = dev_log1p(-th);
   lp += 0.0 * lth + 0.0 * l1m;
   double dth;
   if (S == N) {
@@ -99,9 +99,9 @@ B200_DEV_CALL double lp_grad_bernoulli(const ModelData& m, const double* q, doub
 // Element 2+j (school j) is handled by its owner lane.
 B200_DEV_CALL double lp_grad_eight_schools(const ModelData& m, const double* q, double* g, int lane) {
   const int J = m.N;
-  double mu = q[0], ell = q[1], tau = exp(ell);
+  double mu = q[0], ell = q[1], tau = dev_exp(ell);
   double ss = 0, sq = 0, sr = 0, srt = 0;
-  for (int idx = lane; idx < m.D; idx += kWarp) {
+  _Pragma("unroll 1") for (int idx = lane; idx < m.D; idx += kWarp) {
     if (idx >= 2) {
       int j = idx - 2;
       double tt = q[idx];
@@ -124,7 +124,7 @@ B200_DEV_CALL double lp_grad_eight_schools(const ModelData& m, const double* q, 
   double z = mu / 5.0, t5 = tau / 5.0;
   double lp = ell;
   lp += -0.5 * z * z;
-  lp += -log1p(t5 * t5);
+  lp += -dev_log1p(t5 * t5);
   lp += -0.5 * ss - 0.5 * sq;
   if (lane == 0) g[0] = -mu / 25.0 + sr;
   if (lane == 1 % kWarp) g[1] = 1.0 - 2.0 * t5 * t5 / (1.0 + t5 * t5) + tau * srt;

@@ -116,7 +116,7 @@ B200_DEV double* slot(const ChainView& c, const SamplerCfg& cfg, int k) { return
 // T(p) = 0.5 p . (M^-1 o p)   (diag_e_metric.hpp:20-22)
 B200_DEV double kinetic(const double* p, const double* im, int D, int lane) {
   double acc = 0;
-  for (int i = lane; i < D; i += kWarp) acc += p[i] * (im[i] * p[i]);
+  _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) acc += p[i] * (im[i] * p[i]);
   return 0.5 * warp_sum(acc);
 }
 
@@ -125,7 +125,7 @@ B200_DEV void leapfrog_begin(const ChainView& c, const SamplerCfg& cfg, double e
   const double h = 0.5 * eps;
   double* p = slot(c, cfg, V_P);
   const double* im = slot(c, cfg, V_IM);
-  for (int i = lane; i < cfg.D; i += kWarp) {
+  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     double pi = p[i] - h * c.g[i];
     p[i] = pi;
     c.q[i] += eps * (im[i] * pi);
@@ -137,7 +137,7 @@ B200_DEV double leapfrog_end(const ChainView& c, const SamplerCfg& cfg, double e
   double* p = slot(c, cfg, V_P);
   const double* im = slot(c, cfg, V_IM);
   double acc = 0;
-  for (int i = lane; i < cfg.D; i += kWarp) {
+  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     double pi = p[i] - h * c.g[i];
     p[i] = pi;
     acc += pi * (im[i] * pi);
@@ -155,7 +155,7 @@ B200_DEV_CALL double refresh_from_current(const ChainView& c, const SamplerCfg& 
   const double* cq = slot(c, cfg, V_CQ);
   const double* cg = slot(c, cfg, V_CG);
   warp_fill(c.s->rng, lane, p, cfg.D, 0, im, 0.0);
-  for (int i = lane; i < cfg.D; i += kWarp) {
+  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     c.q[i] = cq[i];
     c.g[i] = cg[i];
   }
@@ -178,11 +178,11 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
   if (lsw_r > lsw_sub) {
     take_right = true;
   } else {
-    double accept_prob = exp(lsw_r - lsw_sub);
+    double accept_prob = dev_exp(lsw_r - lsw_sub);
     take_right = warp_uniform01(s->rng, lane) < accept_prob;
   }
   double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
-  for (int i = lane; i < cfg.D; i += kWarp) {
+  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     const double m = im[i];
     const double lpb = L[i], lpe = L[ld + i], lr = L[2 * ld + i];
     const double rpb = R[i], rpe = R[ld + i], rr = R[2 * ld + i];
@@ -227,7 +227,7 @@ B200_DEV_CALL void learn_stepsize(ChainS* s, const SamplerCfg& cfg, double adapt
   const double x = s->mu - s->s_bar * sqrt(s->sa_counter) / cfg.gamma;
   const double x_eta = pow(s->sa_counter, -cfg.kappa);
   s->x_bar = (1.0 - x_eta) * s->x_bar + x_eta * x;
-  s->eps_nom = exp(x);
+  s->eps_nom = dev_exp(x);
 }
 
 // var_adaptation::learn_variance (var_adaptation.hpp:17-46) on the new sample q; returns 1 when the metric was
@@ -243,7 +243,7 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
   if (in_window) {
     s->wf_n += 1.0;
     const double n = s->wf_n;
-    for (int i = lane; i < cfg.D; i += kWarp) {
+    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
       double delta = q[i] - wm[i];
       double mi = wm[i] + delta / n;
       wm[i] = mi;
@@ -264,7 +264,7 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
     }
     const double n = s->wf_n;
     double bad = 0;
-    for (int i = lane; i < cfg.D; i += kWarp) {
+    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
       double var = im[i];
       if (n > 1) var = wm2[i] / (n - 1.0);
       var = (n / (n + 5.0)) * var + 1e-3 * (5.0 / (n + 5.0)) * 1.0;
@@ -297,9 +297,9 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_INIT_DRAW: {  // util::initialize (initialize.hpp:87-117)
         if (c.user_q0) {
-          for (int i = lane; i < D; i += kWarp) c.q[i] = c.user_q0[i];
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) c.q[i] = c.user_q0[i];
         } else if (cfg.init_radius == 0.0) {
-          for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;
         } else {
           warp_fill(s->rng, lane, c.q, D, 1, nullptr, cfg.init_radius);
         }
@@ -309,12 +309,12 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_INIT_CHECK: {  // finite lp and finite sum of the gradient (initialize.hpp:148-184)
         double gs = 0;
-        for (int i = lane; i < D; i += kWarp) gs += c.g[i];
+        _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) gs += c.g[i];
         gs = warp_sum(gs);
         if (isfinite((*c.zV)) && isfinite(gs)) {
           double* cq = slot(c, cfg, V_CQ);
           double* cg = slot(c, cfg, V_CG);
-          for (int i = lane; i < D; i += kWarp) {
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             cq[i] = c.q[i];
             cg[i] = c.g[i];
           }
@@ -384,7 +384,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_ISS_END: {  // z restored to z_init (the current sample is untouched); adapt_diag_e_nuts.hpp:35-40
         if (s->iss_after == 1) {
-          s->mu = log(10 * s->eps_nom);
+          s->mu = dev_log(10 * s->eps_nom);
           s->sa_counter = 0;
           s->s_bar = 0;
           s->x_bar = 0;
@@ -404,7 +404,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           double* fq = slot(c, cfg, V_FQ); double* fp = slot(c, cfg, V_FP); double* fg = slot(c, cfg, V_FG);
           double* bq = slot(c, cfg, V_BQ); double* bp = slot(c, cfg, V_BP); double* bg = slot(c, cfg, V_BG);
           double* pfb = slot(c, cfg, V_PFB); double* pbf = slot(c, cfg, V_PBF); double* rho = slot(c, cfg, V_RHO);
-          for (int i = lane; i < D; i += kWarp) {
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             const double qi = c.q[i], pi = p[i], gi = c.g[i];
             fq[i] = qi; fp[i] = pi; fg[i] = gi;
             bq[i] = qi; bp[i] = pi; bg[i] = gi;
@@ -433,7 +433,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           const double* ep = slot(c, cfg, fwd ? V_FP : V_BP);
           const double* eg = slot(c, cfg, fwd ? V_FG : V_BG);
           double* pmid = slot(c, cfg, fwd ? V_PBF : V_PFB);  // p_bck_fwd = p_fwd_fwd  /  p_fwd_bck = p_bck_bck
-          for (int i = lane; i < D; i += kWarp) {
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             c.q[i] = eq[i];
             p[i] = ep[i];
             c.g[i] = eg[i];
@@ -459,14 +459,14 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         if ((h - s->H0) > 1000.0) s->divergent = 1;
         const double w = s->H0 - h;
         if (w > 0) s->sum_metro += 1;
-        else s->sum_metro += exp(w);
+        else s->sum_metro += dev_exp(w);
         bool valid = !s->divergent;
         {
           const int e = s->sp;
           double* E = slot(c, cfg, V_STACK + 5 * e);
           const double* p = slot(c, cfg, V_P);
           const int ld = cfg.ld;
-          for (int i = lane; i < D; i += kWarp) {
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             const double pi = p[i];
             E[i] = pi;
             E[ld + i] = pi;
@@ -498,7 +498,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           double* eq = slot(c, cfg, fwd ? V_FQ : V_BQ);
           double* ep = slot(c, cfg, fwd ? V_FP : V_BP);
           double* eg = slot(c, cfg, fwd ? V_FG : V_BG);
-          for (int i = lane; i < D; i += kWarp) {
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             eq[i] = c.q[i];
             ep[i] = p[i];
             eg[i] = c.g[i];
@@ -514,7 +514,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         if (lsw_sub > s->lsw) {
           take = true;
         } else {
-          double accept_prob = exp(lsw_sub - s->lsw);
+          double accept_prob = dev_exp(lsw_sub - s->lsw);
           take = warp_uniform01(s->rng, lane) < accept_prob;
         }
         s->lsw = dev_log_sum_exp(s->lsw, lsw_sub);
@@ -530,7 +530,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           const double* pbb = slot(c, cfg, V_BP);  // p_bck_bck == z_bck.p
           double* cq = slot(c, cfg, V_CQ);
           double* cg = slot(c, cfg, V_CG);
-          for (int i = lane; i < D; i += kWarp) {
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             const double m = im[i];
             double rho_bck, rho_fwd;
             if (fwd) {
@@ -589,7 +589,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             r[6] = s->curH;
           }
           const double* cq = slot(c, cfg, V_CQ);
-          for (int i = lane; i < D; i += kWarp) r[7 + i] = cq[i];
+          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) r[7 + i] = cq[i];
           s->draws_row++;
         }
         s->iter++;
@@ -611,7 +611,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         break;
       }
       case ST_ITER_NEXT: {  // disengage_adaptation after the last warm-up transition (adapt_diag_e_nuts.hpp:45-48)
-        if (cfg.adapt_engaged && s->iter == cfg.num_warmup) s->eps_nom = exp(s->x_bar);
+        if (cfg.adapt_engaged && s->iter == cfg.num_warmup) s->eps_nom = dev_exp(s->x_bar);
         s->state = ST_ITER_BEGIN;
         break;
       }

@@ -93,7 +93,7 @@ B200_DEV_CALL double rng_unit_exponential(unsigned long long* st) {
       double y = kZigExpY[i] + y01 * (kZigExpY[i + 1] - kZigExpY[i]);
       double y_above_ubound = (kZigExpX[i] - kZigExpX[i + 1]) * y01 - (kZigExpX[i] - x);
       double y_above_lbound = y - (kZigExpY[i + 1] + (kZigExpX[i + 1] - x) * kZigExpY[i + 1]);
-      if (y_above_ubound < 0 && (y_above_lbound < 0 || y < exp(-x))) return x + shift;
+      if (y_above_ubound < 0 && (y_above_lbound < 0 || y < dev_exp(-x))) return x + shift;
     }
   }
 }
@@ -126,7 +126,7 @@ B200_DEV_CALL double rng_normal(unsigned long long* st) {
       y_above_lbound = (kZigNormX[i] - kZigNormX[i + 1]) * y01 - (kZigNormX[i] - x);
       y_above_ubound = y - (kZigNormY[i] + (kZigNormX[i] - x) * kZigNormY[i] * kZigNormX[i]);
     }
-    if (y_above_ubound < 0 && (y_above_lbound < 0 || y < exp(-(x * x / 2)))) return x * sign;
+    if (y_above_ubound < 0 && (y_above_lbound < 0 || y < dev_exp(-(x * x / 2)))) return x * sign;
   }
 }
 

@@ -23,6 +23,9 @@ inline double bcast0(double v) { return v; }
 inline int bcast0i(int v) { return v; }
 inline double warp_sum(double v) { return v; }
 inline void warp_sync() {}
+inline double dev_exp(double x) { return std::exp(x); }
+inline double dev_log(double x) { return std::log(x); }
+inline double dev_log1p(double x) { return std::log1p(x); }
 }  // namespace b200
 #else
 #define B200_DEV __device__ __forceinline__
@@ -36,11 +39,16 @@ constexpr unsigned kFull = 0xffffffffu;
 B200_DEV int lane_id() { return threadIdx.x & 31; }
 B200_DEV double bcast0(double v) { return __shfl_sync(kFull, v, 0); }
 B200_DEV int bcast0i(int v) { return __shfl_sync(kFull, v, 0); }
-B200_DEV double warp_sum(double v) {
+B200_DEV_CALL double warp_sum(double v) {  // out of line: ~50 call sites in the chain kernels (instruction-cache budget)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
 B200_DEV void warp_sync() { __syncwarp(); }
+// one out-of-line copy of each double-precision transcendental: the chain kernels are instruction-cache bound
+// (28 warps per SM sitting at different points of a branchy state machine), so code size is the budget
+B200_DEV_CALL double dev_exp(double x) { return exp(x); }
+B200_DEV_CALL double dev_log(double x) { return log(x); }
+B200_DEV_CALL double dev_log1p(double x) { return log1p(x); }
 }  // namespace b200
 #endif

@@ -1,0 +1,248 @@
+// CmdStan's command-line argument tree for `method=sample` (the caller of the path), restated:
+//   grammar / defaults / validity   src/cmdstan/arguments/arg_sample.hpp:18-29, arg_adapt.hpp:19-37, arg_hmc.hpp:19-27,
+//                                   arg_nuts.hpp:15-16, arg_engine.hpp:16-21, arg_metric.hpp:17-23, arg_id.hpp, arg_data.hpp,
+//                                   arg_init.hpp, arg_random.hpp, arg_seed.hpp, arg_output.hpp:19-28, arg_num_threads.hpp
+//   parsing                         src/cmdstan/arguments/argument_parser.hpp (sequential tokens; a token that is not a
+//                                   sub-argument of the current category pops back to its ancestors)
+//   echo                            argument::print: "name = value[ (Default)]", two spaces per depth, selected list
+//                                   element printed as a nested category (SURVEY.md Appendix D golden header)
+// Only `sample` is built here; the other methods are outside the hot path and are rejected by name.
+#pragma once
+#include <cmath>
+#include <cstdlib>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace b200 {
+namespace cmd {
+
+struct arg {
+  enum kind_t { CATEGORY, INT, UINT, LONG, REAL, BOOL, STRING, LIST } kind = CATEGORY;
+  std::string name, value, def;
+  std::string valid;  // description of the valid range for error messages
+  std::function<bool(const arg&)> ok;
+  std::vector<std::unique_ptr<arg>> kids;
+  arg* parent = nullptr;
+  double rval = 0.0;  // REAL: the parsed value at full precision (`value` holds the 6-digit echo)
+
+  bool is_default() const { return value == def; }
+  arg* child(const std::string& n) {
+    for (auto& k : kids)
+      if (k->name == n) return k.get();
+    return nullptr;
+  }
+  arg* add(std::unique_ptr<arg> a) {
+    a->parent = this;
+    kids.push_back(std::move(a));
+    return kids.back().get();
+  }
+  double real() const { return kind == REAL ? rval : std::strtod(value.c_str(), nullptr); }
+  long long integer() const { return std::strtoll(value.c_str(), nullptr, 10); }
+  bool boolean() const { return value == "true" || value == "1"; }
+};
+
+inline std::unique_ptr<arg> mk(arg::kind_t k, const std::string& name, const std::string& def, const std::string& valid = "",
+                               std::function<bool(const arg&)> ok = nullptr) {
+  std::unique_ptr<arg> a(new arg());
+  a->kind = k;
+  a->name = name;
+  a->value = a->def = def;
+  a->rval = std::strtod(def.c_str(), nullptr);
+  a->valid = valid;
+  a->ok = ok;
+  return a;
+}
+
+class argument_parser {
+ public:
+  argument_parser() {
+    root_.name = "";
+    // method
+    arg* method = root_.add(mk(arg::LIST, "method", "sample"));
+    arg* sample = method->add(mk(arg::CATEGORY, "sample", ""));
+    for (const char* other : {"optimize", "variational", "diagnose", "generate_quantities", "pathfinder", "log_prob", "laplace"})
+      method->add(mk(arg::CATEGORY, other, ""));
+    sample->add(mk(arg::INT, "num_samples", "1000", "0 <= num_samples", [](const arg& a) { return a.integer() >= 0; }));
+    sample->add(mk(arg::INT, "num_warmup", "1000", "0 <= num_warmup", [](const arg& a) { return a.integer() >= 0; }));
+    sample->add(mk(arg::BOOL, "save_warmup", "false"));
+    sample->add(mk(arg::INT, "thin", "1", "0 < thin", [](const arg& a) { return a.integer() > 0; }));
+    arg* adapt = sample->add(mk(arg::CATEGORY, "adapt", ""));
+    adapt->add(mk(arg::BOOL, "engaged", "true"));
+    adapt->add(mk(arg::REAL, "gamma", "0.05", "0 < gamma", [](const arg& a) { return a.real() > 0; }));
+    adapt->add(mk(arg::REAL, "delta", "0.8", "0.1 <= delta <= 1", [](const arg& a) { return a.real() >= 0.1 && a.real() <= 1; }));
+    adapt->add(mk(arg::REAL, "kappa", "0.75", "0 < kappa", [](const arg& a) { return a.real() > 0; }));
+    adapt->add(mk(arg::REAL, "t0", "10", "0 < t0", [](const arg& a) { return a.real() > 0; }));
+    adapt->add(mk(arg::UINT, "init_buffer", "75", "All", nullptr));
+    adapt->add(mk(arg::UINT, "term_buffer", "50", "All", nullptr));
+    adapt->add(mk(arg::UINT, "window", "25", "All", nullptr));
+    adapt->add(mk(arg::BOOL, "save_metric", "false"));
+    arg* algo = sample->add(mk(arg::LIST, "algorithm", "hmc"));
+    arg* hmc = algo->add(mk(arg::CATEGORY, "hmc", ""));
+    algo->add(mk(arg::CATEGORY, "fixed_param", ""));
+    arg* engine = hmc->add(mk(arg::LIST, "engine", "nuts"));
+    arg* stat = engine->add(mk(arg::CATEGORY, "static", ""));
+    stat->add(mk(arg::REAL, "int_time", "6.28319", "0 < int_time", [](const arg& a) { return a.real() > 0; }));
+    arg* nuts = engine->add(mk(arg::CATEGORY, "nuts", ""));
+    nuts->add(mk(arg::INT, "max_depth", "10", "0 < max_depth", [](const arg& a) { return a.integer() > 0; }));
+    arg* metric = hmc->add(mk(arg::LIST, "metric", "diag_e"));
+    for (const char* m : {"unit_e", "diag_e", "dense_e"}) metric->add(mk(arg::CATEGORY, m, ""));
+    hmc->add(mk(arg::STRING, "metric_file", ""));
+    hmc->add(mk(arg::REAL, "stepsize", "1", "0 < stepsize", [](const arg& a) { return a.real() > 0; }));
+    hmc->add(mk(arg::REAL, "stepsize_jitter", "0", "0 <= stepsize_jitter <= 1", [](const arg& a) { return a.real() >= 0 && a.real() <= 1; }));
+    sample->add(mk(arg::INT, "num_chains", "1", "num_chains > 0", [](const arg& a) { return a.integer() > 0; }));
+    // the rest of the top level
+    root_.add(mk(arg::INT, "id", "1", "id >= 0", [](const arg& a) { return a.integer() >= 0; }));
+    arg* data = root_.add(mk(arg::CATEGORY, "data", ""));
+    data->add(mk(arg::STRING, "file", ""));
+    root_.add(mk(arg::STRING, "init", "2"));
+    arg* random = root_.add(mk(arg::CATEGORY, "random", ""));
+    random->add(mk(arg::LONG, "seed", "-1", "non-negative integer < 4294967296  or -1",
+                   [](const arg& a) { return a.integer() == -1 || (a.integer() >= 0 && a.integer() <= 4294967295LL); }));
+    arg* output = root_.add(mk(arg::CATEGORY, "output", ""));
+    output->add(mk(arg::STRING, "file", "output.csv"));
+    output->add(mk(arg::STRING, "diagnostic_file", ""));
+    output->add(mk(arg::INT, "refresh", "100"));
+    output->add(mk(arg::INT, "sig_figs", "-1", "0 <= integer <= 18 or -1 to use the default number of significant figures",
+                   [](const arg& a) { return a.integer() >= -1 && a.integer() <= 18; }));
+    output->add(mk(arg::STRING, "profile_file", "profile.csv"));
+    output->add(mk(arg::BOOL, "save_cmdstan_config", "false"));
+    root_.add(mk(arg::INT, "num_threads", "1", "num_threads > 0 || num_threads == -1",
+                 [](const arg& a) { return a.integer() > 0 || a.integer() == -1; }));
+  }
+
+  // returns 0 or throws std::invalid_argument with CmdStan's wording
+  void parse(const std::vector<std::string>& tokens) {
+    arg* ctx = &root_;
+    bool method_seen = false;
+    for (const std::string& tok : tokens) {
+      std::string key = tok, val;
+      const size_t eq = tok.find('=');
+      const bool has_val = eq != std::string::npos;
+      if (has_val) {
+        key = tok.substr(0, eq);
+        val = tok.substr(eq + 1);
+      }
+      arg* hit = nullptr;
+      arg* scope = ctx;
+      for (; scope; scope = scope->parent) {
+        // a bare element name of a list argument in scope selects it ("sample", "hmc", "nuts")
+        if ((hit = scope->child(key))) break;
+        for (auto& k : scope->kids)
+          if (k->kind == arg::LIST && !has_val && k->child(key)) {
+            hit = k.get();
+            val = key;
+            break;
+          }
+        if (hit) break;
+      }
+      if (!hit) throw std::invalid_argument(tok + " is either mistyped or misplaced.");
+      if (hit->kind == arg::CATEGORY && hit->parent && hit->parent->kind == arg::LIST && !has_val) {  // element of a list
+        val = hit->name;
+        hit = hit->parent;
+      }
+      if (hit->kind == arg::CATEGORY) {
+        if (has_val) throw std::invalid_argument(tok + " is either mistyped or misplaced.");
+        ctx = hit;
+        continue;
+      }
+      if (hit->kind == arg::LIST) {
+        if (hit->name == "method") method_seen = true;
+        if (!has_val && val.empty()) throw std::invalid_argument("Value for " + key + " is missing");
+        arg* sel = hit->child(val);
+        if (!sel) throw std::invalid_argument(val + " is not a valid value for \"" + hit->name + "\"");
+        hit->value = val;
+        ctx = sel;
+        continue;
+      }
+      if (!has_val) throw std::invalid_argument("Value for " + key + " is missing");
+      set_value(hit, val);
+      ctx = hit->parent;
+    }
+    if (!method_seen) throw std::invalid_argument("A method must be specified!");
+  }
+
+  arg* find(std::initializer_list<const char*> path) {
+    arg* a = &root_;
+    for (const char* p : path) {
+      a = a->child(p);
+      if (!a) throw std::logic_error(std::string("no such argument: ") + p);
+    }
+    return a;
+  }
+  std::string str(std::initializer_list<const char*> p) { return find(p)->value; }
+  double real(std::initializer_list<const char*> p) { return find(p)->real(); }
+  long long integer(std::initializer_list<const char*> p) { return find(p)->integer(); }
+  bool boolean(std::initializer_list<const char*> p) { return find(p)->boolean(); }
+
+  // config echo: lines without prefix (the caller adds "# " for CSV files)
+  std::vector<std::string> echo() const {
+    std::vector<std::string> out;
+    for (auto& k : root_.kids) print(*k, 0, out);
+    return out;
+  }
+
+ private:
+  static void set_value(arg* a, const std::string& v) {
+    char* end = nullptr;
+    std::string canon = v;
+    switch (a->kind) {
+      case arg::INT:
+      case arg::UINT:
+      case arg::LONG: {
+        long long x = std::strtoll(v.c_str(), &end, 10);
+        if (v.empty() || *end) throw std::invalid_argument("Invalid numeric value for " + a->name);
+        if (a->kind == arg::UINT && x < 0) throw std::invalid_argument(v + " is not a valid value for \"" + a->name + "\"\n  Valid values: All");
+        canon = std::to_string(x);
+        break;
+      }
+      case arg::REAL: {
+        double x = std::strtod(v.c_str(), &end);
+        if (v.empty() || *end) throw std::invalid_argument("Invalid numeric value for " + a->name);
+        std::stringstream ss;
+        ss << x;  // printed the way the reference prints a double argument (operator<<, 6 significant digits)
+        canon = ss.str();
+        const double old = a->rval;
+        a->rval = x;
+        if (a->ok && !a->ok(*a)) {
+          a->rval = old;
+          throw std::invalid_argument(v + " is not a valid value for \"" + a->name + "\"\n  Valid values: " + a->valid);
+        }
+        a->value = canon;
+        return;
+      }
+      case arg::BOOL:
+        if (v == "1" || v == "true") canon = "true";
+        else if (v == "0" || v == "false") canon = "false";
+        else throw std::invalid_argument(v + " is not a valid value for \"" + a->name + "\"\n  Valid values: [0, 1, false, true]");
+        break;
+      default:
+        break;
+    }
+    a->value = canon;
+    if (a->ok && !a->ok(*a)) {
+      a->value = a->def;
+      throw std::invalid_argument(v + " is not a valid value for \"" + a->name + "\"\n  Valid values: " + a->valid);
+    }
+  }
+  static void print(const arg& a, int depth, std::vector<std::string>& out) {
+    const std::string ind(2 * depth, ' ');
+    if (a.kind == arg::CATEGORY) {
+      out.push_back(ind + a.name);
+      for (auto& k : a.kids) print(*k, depth + 1, out);
+      return;
+    }
+    out.push_back(ind + a.name + " = " + a.value + (a.is_default() ? " (Default)" : ""));
+    if (a.kind == arg::LIST)
+      for (auto& k : a.kids)
+        if (k->name == a.value && !k->kids.empty()) print(*k, depth + 1, out);
+  }
+  arg root_;
+};
+
+}  // namespace cmd
+}  // namespace b200

@@ -1,0 +1,204 @@
+// Host-side model object of the B200 engine: the part of the stan::model::model_base contract
+// (stan/src/stan/model/model_base.hpp:36-705) that the sampling service and the CSV writer use -- model_name,
+// get_param_names / get_dims, constrained_param_names / unconstrained_param_names, num_params_r, transform_inits --
+// for the hand-written device model family (include/b200nuts.h enum b200nuts_model; densities: SURVEY.md Appendix E).
+// log_prob and write_array run on the device (b200nuts_log_prob_grad, b200nuts_fetch_draws constrained=1): a C++
+// virtual cannot be called from a kernel, so "drops into model_base" means same names, dims, transforms and columns.
+// The construction hook mirrors the reference's link-time hook
+//     stan::model::model_base& new_model(stan::io::var_context&, unsigned int seed, std::ostream*)
+// (src/cmdstan/command.hpp:71-73).
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nuts.h"
+#include "json.hpp"
+
+namespace b200 {
+namespace model {
+
+enum constraint_t { FREE = 0, LOWER0 = 1, UNIT_INTERVAL = 2 };
+struct block_t {
+  std::string name;
+  int64_t size;  // -1: scalar, >= 0: vector of that length
+  constraint_t constraint;
+  int64_t count() const { return size < 0 ? 1 : size; }
+};
+
+class device_model {
+ public:
+  device_model(const std::string& name, const io::var_context& data) : short_name_(name) {
+    auto need = [&](const char* v) {
+      if (!data.contains_r(v)) throw std::invalid_argument(std::string("variable does not exist; processing stage=data initialization; variable name=") + v + "; base type=double");
+    };
+    auto scalar_int = [&](const char* v) {
+      need(v);
+      return (int64_t)data.vals_r(v)[0];
+    };
+    if (name == "std_normal") {
+      id_ = B200NUTS_STD_NORMAL;
+      D_ = data.contains_r("D") ? (int64_t)data.vals_r("D")[0] : 3;
+      params_ = {{"x", D_, FREE}};
+    } else if (name == "bernoulli") {
+      id_ = B200NUTS_BERNOULLI;
+      const int64_t N = scalar_int("N");
+      need("y");
+      yi_ = data.vals_i("y");
+      check_size("y", (int64_t)yi_.size(), N);
+      for (int v : yi_)
+        if (v < 0 || v > 1) throw std::domain_error("bernoulli_model: y is " + std::to_string(v) + ", but must be in the interval [0, 1]");
+      params_ = {{"theta", -1, UNIT_INTERVAL}};
+    } else if (name == "eight_schools_nc") {
+      id_ = B200NUTS_EIGHT_SCHOOLS_NC;
+      const int64_t J = scalar_int("J");
+      need("y");
+      need("sigma");
+      yr_ = data.vals_r("y");
+      sigma_ = data.vals_r("sigma");
+      check_size("y", (int64_t)yr_.size(), J);
+      check_size("sigma", (int64_t)sigma_.size(), J);
+      for (double s : sigma_)
+        if (!(s > 0)) throw std::domain_error("eight_schools_nc_model: sigma must be positive");
+      params_ = {{"mu", -1, FREE}, {"tau", -1, LOWER0}, {"theta_tilde", J, FREE}};
+      tparams_ = {{"theta", J, FREE}};
+    } else if (name == "logistic" || name == "poisson_glm") {
+      id_ = name == "logistic" ? B200NUTS_LOGISTIC_GLM : B200NUTS_POISSON_GLM;
+      N_ = scalar_int("N");
+      K_ = scalar_int("D");
+      need("X");
+      need("y");
+      X_ = data.vals_r("X");
+      yi_ = data.vals_i("y");
+      check_size("X", (int64_t)X_.size(), N_ * K_);
+      check_size("y", (int64_t)yi_.size(), N_);
+      params_ = {{"alpha", -1, FREE}, {"beta", K_, FREE}};
+    } else if (name == "irt_2pl") {
+      id_ = B200NUTS_IRT_2PL;
+      N_ = scalar_int("I");
+      K_ = scalar_int("J");
+      need("y");
+      std::vector<int> y = data.vals_i("y");
+      check_size("y", (int64_t)y.size(), N_ * K_);
+      y8_.assign(y.begin(), y.end());
+      params_ = {{"sigma_theta", -1, LOWER0}, {"theta", N_, FREE}, {"sigma_a", -1, LOWER0}, {"a", K_, LOWER0},
+                 {"mu_b", -1, FREE},          {"sigma_b", -1, LOWER0}, {"b", K_, FREE}};
+    } else {
+      throw std::invalid_argument("unknown model '" + name + "' (available: std_normal bernoulli eight_schools_nc logistic irt_2pl poisson_glm)");
+    }
+    num_params_r_ = 0;
+    for (auto& b : params_) num_params_r_ += b.count();
+  }
+
+  std::string model_name() const { return short_name_ + "_model"; }
+  std::vector<std::string> model_compile_info() const {
+    return {"stanc_version = b200-nuts hand-written device model (no stanc)", "stancflags = "};
+  }
+  int model_id() const { return id_; }
+  int64_t num_params_r() const { return num_params_r_; }
+
+  void get_param_names(std::vector<std::string>& names, bool emit_tparams = true, bool = true) const {
+    names.clear();
+    for (auto& b : params_) names.push_back(b.name);
+    if (emit_tparams)
+      for (auto& b : tparams_) names.push_back(b.name);
+  }
+  void get_dims(std::vector<std::vector<size_t>>& dimss, bool emit_tparams = true, bool = true) const {
+    dimss.clear();
+    auto push = [&](const block_t& b) { dimss.push_back(b.size < 0 ? std::vector<size_t>{} : std::vector<size_t>{(size_t)b.size}); };
+    for (auto& b : params_) push(b);
+    if (emit_tparams)
+      for (auto& b : tparams_) push(b);
+  }
+  // names are appended (as model_base::constrained_param_names does): "theta", "beta.1", ...
+  void constrained_param_names(std::vector<std::string>& names, bool emit_tparams = true, bool = true) const {
+    for (auto& b : params_) expand(b, names);
+    if (emit_tparams)
+      for (auto& b : tparams_) expand(b, names);
+  }
+  void unconstrained_param_names(std::vector<std::string>& names, bool = true, bool = true) const {
+    for (auto& b : params_) expand(b, names);
+  }
+
+  // constrained initial values -> unconstrained vector (model_base::transform_inits; lb_free = log,
+  // lub_free(0,1) = logit: stan/math/prim/constraint/lb_free.hpp, lub_free.hpp).  Every parameter must be present.
+  void transform_inits(const io::var_context& init, std::vector<double>& params_r) const {
+    params_r.clear();
+    for (auto& b : params_) {
+      if (!init.contains_r(b.name)) throw std::invalid_argument("variable does not exist; processing stage=parameter initialization; variable name=" + b.name + "; base type=double (partial inits are not supported by the B200 engine)");
+      const std::vector<double>& v = init.vals_r(b.name);
+      if ((int64_t)v.size() != b.count()) throw std::invalid_argument("mismatch in number dimensions declared and found in context; processing stage=parameter initialization; variable name=" + b.name);
+      for (double x : v) {
+        if (b.constraint == LOWER0) {
+          if (!(x >= 0)) throw std::domain_error("lb_free: Bounded variable is " + std::to_string(x) + ", but must be greater than or equal to 0");
+          params_r.push_back(std::log(x));
+        } else if (b.constraint == UNIT_INTERVAL) {
+          if (!(x >= 0 && x <= 1)) throw std::domain_error("lub_free: Bounded variable is " + std::to_string(x) + ", but must be in the interval [0, 1]");
+          params_r.push_back(std::log(x / (1 - x)));
+        } else {
+          params_r.push_back(x);
+        }
+      }
+    }
+  }
+
+  // hands the data to an engine through the C ABI
+  int upload(b200nuts_engine* e) const {
+    int rc = 0;
+    int64_t d1[1], d2[2];
+    switch (id_) {
+      case B200NUTS_STD_NORMAL: {
+        int32_t D = (int32_t)D_;
+        d1[0] = 1;
+        return b200nuts_set_data_i32(e, "D", &D, d1, 1);
+      }
+      case B200NUTS_BERNOULLI:
+        d1[0] = (int64_t)yi_.size();
+        return b200nuts_set_data_i32(e, "y", yi_.data(), d1, 1);
+      case B200NUTS_EIGHT_SCHOOLS_NC:
+        d1[0] = (int64_t)yr_.size();
+        if ((rc = b200nuts_set_data_f64(e, "y", yr_.data(), d1, 1))) return rc;
+        return b200nuts_set_data_f64(e, "sigma", sigma_.data(), d1, 1);
+      case B200NUTS_LOGISTIC_GLM:
+      case B200NUTS_POISSON_GLM:
+        d2[0] = N_;
+        d2[1] = K_;
+        d1[0] = N_;
+        if ((rc = b200nuts_set_data_f64(e, "X", X_.data(), d2, 2))) return rc;
+        return b200nuts_set_data_i32(e, "y", yi_.data(), d1, 1);
+      case B200NUTS_IRT_2PL:
+        d2[0] = N_;
+        d2[1] = K_;
+        return b200nuts_set_data_i8(e, "y", y8_.data(), d2, 2);
+    }
+    return B200NUTS_USAGE;
+  }
+
+ private:
+  static void expand(const block_t& b, std::vector<std::string>& names) {
+    if (b.size < 0) names.push_back(b.name);
+    else
+      for (int64_t i = 1; i <= b.size; i++) names.push_back(b.name + "." + std::to_string(i));
+  }
+  void check_size(const char* v, int64_t got, int64_t want) const {
+    if (got != want)
+      throw std::invalid_argument(std::string("mismatch in dimension declared and found in context; processing stage=data initialization; variable name=") + v +
+                                  "; dims declared=(" + std::to_string(want) + "); dims found=(" + std::to_string(got) + ")");
+  }
+  std::string short_name_;
+  int id_ = 0;
+  int64_t D_ = 0, N_ = 0, K_ = 0, num_params_r_ = 0;
+  std::vector<block_t> params_, tparams_;
+  std::vector<double> X_, yr_, sigma_;
+  std::vector<int> yi_;
+  std::vector<int8_t> y8_;
+};
+
+// the reference's link-time hook, with the model selected by name instead of by linking a stanc-generated class
+inline device_model& new_model(const std::string& name, const io::var_context& data, unsigned int /*seed*/, std::ostream* /*msg*/) {
+  return *new device_model(name, data);
+}
+
+}  // namespace model
+}  // namespace b200

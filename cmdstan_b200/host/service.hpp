@@ -1,0 +1,402 @@
+// b200::services::sample::hmc_nuts_diag_e_adapt -- host shim with the parameter list of the reference service
+//
+//   stan::services::sample::hmc_nuts_diag_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id,
+//       init_radius, num_warmup, num_samples, num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth,
+//       delta, gamma, kappa, t0, init_buffer, term_buffer, window, interrupt, logger, init_writer, sample_writer,
+//       diagnostic_writer, metric_writer)           stan/src/stan/services/sample/hmc_nuts_diag_e_adapt.hpp:328-407
+//
+// so that the call site in cmdstan::command() (src/cmdstan/command.hpp:673-688) changes by one namespace
+// (INTEGRATION.md).  Everything the reference does per chain inside that call -- create_rng, initialize, sampler
+// set-up, run_adaptive_sampler (init_stepsize, warm-up, adaptation block, sampling, timing), mcmc_writer rows -- happens
+// here for ALL chains at once: the numerical work on the GPU(s) through the C ABI (include/b200nuts.h), the text
+// output on the host in the reference's order and format:
+//
+//   header row            mcmc_writer::write_sample_names       services/util/mcmc_writer.hpp:64-78
+//   draws                 mcmc_writer::write_sample_params      :98-135   (stream precision = sig_figs)
+//   "Adaptation terminated" / "Step size = " / metric          :144-146, mcmc/hmc/base_hmc.hpp:46-65,
+//                                                                 mcmc/hmc/hamiltonians/diag_e_point.hpp:44-52
+//   timing footer         mcmc_writer::write_timing             :198-218
+//   progress messages     util::generate_transitions            services/util/generate_transitions.hpp:52-69
+//   metric JSON           base_hmc::write_sampler_state_struct  mcmc/hmc/base_hmc.hpp:67-73
+//
+// Differences, by construction: chains advance together, so rows are written after each phase rather than streamed;
+// the interrupt callback runs once per refresh interval; elapsed times are those of the batched run (identical in every
+// chain's footer); the diagnostic writer receives the same header but no per-draw momenta (they never leave the GPU).
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <iomanip>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200nuts.h"
+#include "callbacks.hpp"
+#include "json.hpp"
+#include "model.hpp"
+
+namespace b200 {
+namespace services {
+
+namespace error_codes {  // stan/src/stan/services/error_codes.hpp
+enum { OK = 0, USAGE = 64, DATAERR = 65, NOINPUT = 66, SOFTWARE = 70, CONFIG = 78 };
+}
+
+// GPU placement of the chains (no counterpart in the reference: it runs chains as TBB tasks)
+struct device_options {
+  std::vector<int> devices = {0};  // chains are split contiguously over these CUDA devices
+  int engine = B200NUTS_ENGINE_AUTO;
+  int format_threads = 8;          // host threads used to format CSV rows (per-chain files are independent)
+};
+
+// metric_writer interface: one JSON record per chain (callbacks::structured_writer's use in write_sampler_state_struct)
+class json_metric_writer {
+ public:
+  json_metric_writer() {}
+  explicit json_metric_writer(std::unique_ptr<std::ostream>&& out) : out_(std::move(out)) {}
+  void write(double stepsize, const double* inv_metric, int64_t n) {
+    if (!out_) return;
+    *out_ << "{\n  \"stepsize\" : " << stepsize << ",\n  \"metric_type\" : \"diag_e\",\n  \"inv_metric\" : [ ";
+    for (int64_t i = 0; i < n; i++) *out_ << (i ? ", " : "") << inv_metric[i];
+    *out_ << " ]\n}\n";
+    out_->flush();
+  }
+
+ private:
+  std::unique_ptr<std::ostream> out_;
+};
+
+namespace sample {
+
+namespace internal {
+
+struct engine_guard {
+  std::vector<b200nuts_engine*> e;
+  ~engine_guard() {
+    for (auto p : e) b200nuts_destroy(p);
+  }
+};
+
+// one CSV row at the stream's precision; identical to `os << v[0] << "," << ...` of unique_stream_writer::write_vector
+inline void format_row(std::string& buf, const double* v, int64_t n, int precision) {
+  char tmp[40];
+  for (int64_t i = 0; i < n; i++) {
+    int len = std::snprintf(tmp, sizeof tmp, "%.*g", precision, v[i]);
+    buf.append(tmp, (size_t)len);
+    buf.push_back(i + 1 < n ? ',' : '\n');
+  }
+}
+
+// iterations (0-based, within a phase of `n` transitions starting at global index `start` of `finish`) at which
+// generate_transitions logs a progress message
+inline std::vector<int> message_iterations(int n, int start, int finish, int refresh) {
+  std::vector<int> r;
+  if (refresh <= 0) return r;
+  for (int m = 0; m < n; ++m)
+    if (start + m + 1 == finish || m == 0 || (m + 1) % refresh == 0) r.push_back(m);
+  return r;
+}
+
+inline std::string progress_message(int m, int start, int finish, bool warmup, size_t chain_id, size_t num_chains) {
+  int it_print_width = (int)std::ceil(std::log10(static_cast<double>(finish)));
+  std::stringstream message;
+  if (num_chains != 1) message << "Chain [" << chain_id << "] ";
+  message << "Iteration: ";
+  message << std::setw(it_print_width) << m + 1 + start << " / " << finish;
+  message << " [" << std::setw(3) << static_cast<int>((100.0 * (start + m + 1)) / finish) << "%] ";
+  message << (warmup ? " (Warmup)" : " (Sampling)");
+  return message.str();
+}
+
+}  // namespace internal
+
+template <class Model, typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter,
+          typename DiagnosticWriter, typename MetricWriter>
+int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init,
+                          const std::vector<InitInvContextPtr>& init_inv_metric, unsigned int random_seed,
+                          unsigned int init_chain_id, double init_radius, int num_warmup, int num_samples, int num_thin,
+                          bool save_warmup, int refresh, double stepsize, double stepsize_jitter, int max_depth, double delta,
+                          double gamma, double kappa, double t0, unsigned int init_buffer, unsigned int term_buffer,
+                          unsigned int window, callbacks::interrupt& interrupt, callbacks::logger& logger,
+                          std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                          std::vector<DiagnosticWriter>& diagnostic_writer, std::vector<MetricWriter>& metric_writer,
+                          const device_options& opt = device_options(), bool adapt_engaged = true) {
+  using internal::engine_guard;
+  (void)init_writer;
+  const int64_t D = model.num_params_r();
+  const int C = (int)num_chains;
+  // ---- inits and metric (initialize.hpp:70-260; util::read_diag_inv_metric / validate_diag_inv_metric)
+  std::vector<double> q0, im;
+  try {
+    size_t n_user = 0;
+    for (size_t c = 0; c < num_chains && c < init.size(); c++)
+      if (init[c] && !init[c]->empty()) n_user++;
+    if (n_user != 0 && n_user != num_chains) throw std::invalid_argument("inits must be given for every chain or for none");
+    if (n_user) {
+      std::vector<double> one;
+      for (size_t c = 0; c < num_chains; c++) {
+        model.transform_inits(*init[c], one);
+        q0.insert(q0.end(), one.begin(), one.end());
+      }
+    }
+    bool any_metric = false;
+    for (size_t c = 0; c < num_chains && c < init_inv_metric.size(); c++)
+      if (init_inv_metric[c] && init_inv_metric[c]->contains_r("inv_metric")) any_metric = true;
+    if (any_metric) {
+      im.assign((size_t)C * D, 1.0);
+      for (size_t c = 0; c < num_chains && c < init_inv_metric.size(); c++) {
+        if (!init_inv_metric[c] || !init_inv_metric[c]->contains_r("inv_metric")) continue;
+        const std::vector<double>& v = init_inv_metric[c]->vals_r("inv_metric");
+        if ((int64_t)v.size() != D) throw std::domain_error("Cannot get inverse metric from input file; expected " + std::to_string(D) + " elements");
+        std::copy(v.begin(), v.end(), im.begin() + c * D);
+      }
+    }
+  } catch (const std::domain_error& e) {
+    logger.error(e.what());
+    return error_codes::CONFIG;
+  } catch (const std::exception& e) {
+    logger.error(e.what());
+    return error_codes::CONFIG;
+  }
+
+  // ---- engines: chains split contiguously over the devices
+  const int G = (int)std::max<size_t>(1, std::min<size_t>(opt.devices.size(), num_chains));
+  engine_guard eg;
+  std::vector<int> first(G + 1, 0);
+  for (int g = 0; g < G; g++) first[g + 1] = (int)((int64_t)C * (g + 1) / G);
+  for (int g = 0; g < G; g++) {
+    b200nuts_config cfg;
+    b200nuts_default_config(&cfg);
+    cfg.model = model.model_id();
+    cfg.num_chains = first[g + 1] - first[g];
+    cfg.random_seed = random_seed;
+    cfg.init_chain_id = init_chain_id + (unsigned)first[g];
+    cfg.init_radius = init_radius;
+    cfg.num_warmup = num_warmup;
+    cfg.num_samples = num_samples;
+    cfg.num_thin = num_thin;
+    cfg.save_warmup = save_warmup;
+    cfg.stepsize = stepsize;
+    cfg.stepsize_jitter = stepsize_jitter;
+    cfg.max_depth = max_depth;
+    cfg.delta = delta;
+    cfg.gamma = gamma;
+    cfg.kappa = kappa;
+    cfg.t0 = t0;
+    cfg.init_buffer = init_buffer;
+    cfg.term_buffer = term_buffer;
+    cfg.window = window;
+    cfg.adapt_engaged = adapt_engaged;
+    cfg.engine = opt.engine;
+    cfg.device = opt.devices.empty() ? 0 : opt.devices[g];
+    b200nuts_engine* e = nullptr;
+    int rc = b200nuts_create(&cfg, &e);
+    if (rc) {
+      logger.error(b200nuts_last_error(nullptr));
+      return rc;
+    }
+    eg.e.push_back(e);
+    if ((rc = model.upload(e)) || (!q0.empty() && (rc = b200nuts_set_inits(e, q0.data() + (size_t)first[g] * D))) ||
+        (!im.empty() && (rc = b200nuts_set_inv_metric(e, im.data() + (size_t)first[g] * D))) || (rc = b200nuts_init_chains(e))) {
+      logger.error(b200nuts_last_error(e));
+      return rc;
+    }
+  }
+  int64_t nu = 0, K = 0;
+  b200nuts_num_params(eg.e[0], &nu, &K);
+
+  // window fallback notice (windowed_adaptation.hpp:42-67), once -- the reference prints it per chain
+  if (adapt_engaged && num_warmup >= 20 && init_buffer + window + term_buffer > (unsigned)num_warmup) {
+    unsigned ib = (unsigned)(0.15 * num_warmup), tb = (unsigned)(0.1 * num_warmup);
+    std::stringstream m;
+    m << "WARNING: There aren't enough warmup iterations to fit the\n         three stages of adaptation as currently configured.\n"
+      << "         Reducing each adaptation stage to 15%/75%/10% of\n         the given number of warmup iterations:\n"
+      << "           init_buffer = " << ib << "\n           adapt_window = " << num_warmup - (ib + tb) << "\n           term_buffer = " << tb << "\n";
+    logger.info(m.str());
+  } else if (adapt_engaged && num_warmup < 20) {
+    logger.info("WARNING: No variance estimation is\n         performed for num_warmup < 20\n");
+  }
+
+  // ---- header rows
+  std::vector<std::string> names = {"lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"};
+  model.constrained_param_names(names, true, true);
+  for (int c = 0; c < C; c++) {
+    if ((size_t)c < sample_writer.size()) sample_writer[c](names);
+    if ((size_t)c < diagnostic_writer.size()) diagnostic_writer[c](names);
+  }
+
+  auto run_all = [&](int n_iter) -> int {
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back([&, g] { rcs[g] = b200nuts_run(eg.e[g], n_iter); });
+    rcs[0] = b200nuts_run(eg.e[0], n_iter);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++)
+      if (rcs[g]) {
+        logger.error(b200nuts_last_error(eg.e[g]));
+        return rcs[g];
+      }
+    return 0;
+  };
+  // one phase of `n` transitions with the reference's progress messages; the interrupt runs at each message point
+  auto run_phase = [&](int n, int start, bool warmup) -> int {
+    const int finish = num_warmup + num_samples;
+    std::vector<int> at = internal::message_iterations(n, start, finish, refresh);
+    int done = 0;
+    size_t k = 0;
+    while (done < n) {
+      if (k < at.size() && at[k] == done) {
+        interrupt();
+        if (C <= 16) {
+          for (int c = 0; c < C; c++) logger.info(internal::progress_message(done, start, finish, warmup, init_chain_id + c, num_chains));
+        } else {
+          std::stringstream m;
+          m << "Chains [" << init_chain_id << "-" << init_chain_id + C - 1 << "] "
+            << internal::progress_message(done, start, finish, warmup, 0, 1);
+          logger.info(m.str());
+        }
+        k++;
+      }
+      const int next = k < at.size() ? at[k] : n;
+      int rc = run_all(next - done);
+      if (rc) return rc;
+      done = next;
+    }
+    return 0;
+  };
+  // rows [row0, row0 + nrows) of every chain -> its sample writer
+  auto write_rows = [&](int64_t row0, int64_t nrows) -> int {
+    if (nrows <= 0) return 0;
+    const int64_t ncol = 7 + K;
+    for (int g = 0; g < G; g++) {
+      const int Cg = first[g + 1] - first[g];
+      // bound the host staging buffer to ~1 GiB
+      int64_t chunk = std::max<int64_t>(1, (int64_t)((1ull << 30) / (sizeof(double) * (size_t)ncol * (size_t)nrows)));
+      std::vector<double> buf;
+      for (int64_t c0 = 0; c0 < Cg; c0 += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, Cg - c0);
+        buf.resize((size_t)m * nrows * ncol);
+        int rc = b200nuts_fetch_draws(eg.e[g], c0, m, row0, nrows, 1, buf.data());
+        if (rc) {
+          logger.error(b200nuts_last_error(eg.e[g]));
+          return rc;
+        }
+        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(opt.format_threads, m));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+          th.emplace_back([&, t] {
+            std::string text;
+            for (int64_t c = t; c < m; c += nt) {
+              const size_t chain = (size_t)(first[g] + c0 + c);
+              if (chain >= sample_writer.size()) continue;
+              std::ostream* os = sample_writer[chain].stream();
+              if (!os) continue;
+              text.clear();
+              const int prec = (int)os->precision();
+              for (int64_t r = 0; r < nrows; r++) internal::format_row(text, buf.data() + ((size_t)c * nrows + r) * ncol, ncol, prec);
+              os->write(text.data(), (std::streamsize)text.size());
+            }
+          });
+        for (auto& t : th) t.join();
+      }
+    }
+    return 0;
+  };
+  auto chain_errors = [&]() -> int {
+    int code = 0;
+    for (int g = 0; g < G; g++) {
+      const int Cg = first[g + 1] - first[g];
+      std::vector<int32_t> err(Cg);
+      if (b200nuts_get_chain_status(eg.e[g], err.data(), nullptr, nullptr)) return error_codes::SOFTWARE;
+      for (int c = 0; c < Cg; c++)
+        if (err[c]) {
+          std::stringstream m;
+          if (num_chains != 1) m << "Chain [" << init_chain_id + first[g] + c << "] ";
+          m << (err[c] == error_codes::CONFIG ? "Initialization failed." : "Exception: step size or metric adaptation failed (Posterior is improper / No acceptably small step size / Numerical overflow in metric adaptation).");
+          logger.error(m.str());
+          if (!code) code = err[c];
+        }
+    }
+    return code;
+  };
+
+  const int64_t warm_rows = save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0;
+  const int64_t samp_rows = (num_samples + num_thin - 1) / num_thin;
+  int rc;
+  // ---- warm-up (generate_transitions with warmup = true)
+  auto t0w = std::chrono::steady_clock::now();
+  if ((rc = run_phase(num_warmup, 0, true))) return rc;
+  double warm_delta_t = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0w).count() / 1000.0;
+  if (num_warmup == 0 && (rc = run_all(0))) return rc;  // initialisation happens inside the first run call
+  if ((rc = chain_errors())) return rc;
+  if ((rc = write_rows(0, warm_rows))) return rc;
+  // ---- adaptation block (write_adapt_finish + write_sampler_state) and metric JSON
+  {
+    std::vector<double> eps((size_t)C), met((size_t)C * D);
+    for (int g = 0; g < G; g++)
+      if ((rc = b200nuts_get_adaptation(eg.e[g], eps.data() + first[g], met.data() + (size_t)first[g] * D))) {
+        logger.error(b200nuts_last_error(eg.e[g]));
+        return rc;
+      }
+    for (int c = 0; c < C; c++) {
+      if ((size_t)c < sample_writer.size()) {
+        auto& w = sample_writer[c];
+        if (adapt_engaged) {
+          w("Adaptation terminated");
+          std::stringstream ss;
+          ss << "Step size = " << eps[c];
+          w(ss.str());
+          w("Diagonal elements of inverse mass matrix:");
+          std::stringstream ms;
+          for (int64_t i = 0; i < D; i++) ms << (i ? ", " : "") << met[(size_t)c * D + i];
+          w(ms.str());
+        }
+      }
+      if (adapt_engaged && (size_t)c < metric_writer.size()) metric_writer[c].write(eps[c], met.data() + (size_t)c * D, D);
+    }
+  }
+  // ---- sampling
+  auto t0s = std::chrono::steady_clock::now();
+  if ((rc = run_phase(num_samples, num_warmup, false))) return rc;
+  double sample_delta_t = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0s).count() / 1000.0;
+  if ((rc = chain_errors())) return rc;
+  if ((rc = write_rows(warm_rows, samp_rows))) return rc;
+  // ---- timing footer (mcmc_writer::write_timing)
+  auto timing = [&](auto& w) {
+    const std::string title(" Elapsed Time: ");
+    w();
+    std::stringstream s1, s2, s3;
+    s1 << title << warm_delta_t << " seconds (Warm-up)";
+    s2 << std::string(title.size(), ' ') << sample_delta_t << " seconds (Sampling)";
+    s3 << std::string(title.size(), ' ') << warm_delta_t + sample_delta_t << " seconds (Total)";
+    w(s1.str());
+    w(s2.str());
+    w(s3.str());
+    w();
+  };
+  for (int c = 0; c < C; c++) {
+    if ((size_t)c < sample_writer.size()) timing(sample_writer[c]);
+    if ((size_t)c < diagnostic_writer.size()) timing(diagnostic_writer[c]);
+  }
+  {
+    const std::string title(" Elapsed Time: ");
+    std::stringstream s1, s2, s3;
+    s1 << title << warm_delta_t << " seconds (Warm-up)";
+    s2 << std::string(title.size(), ' ') << sample_delta_t << " seconds (Sampling)";
+    s3 << std::string(title.size(), ' ') << warm_delta_t + sample_delta_t << " seconds (Total)";
+    logger.info("");
+    logger.info(s1.str());
+    logger.info(s2.str());
+    logger.info(s3.str());
+    logger.info("");
+  }
+  return error_codes::OK;
+}
+
+}  // namespace sample
+}  // namespace services
+}  // namespace b200
