@@ -203,7 +203,7 @@ def main():
     K, W = max(args.steps, 4), max(args.warmup, 3)
     scale_note = "" if args.scale == 1.0 else f" [rows scaled x{args.scale}]"
     cfg_common = {"workload": args.workload + ": " + w["desc"] + scale_note, "num_warmup": args.num_warmup, "timed_transitions": K,
-                  "inputs": "data set larger than L2 for c3/c5; chain state resident in HBM", "sharding": "chains" if world > 1 else "none"}
+                  "inputs": "data set larger than L2 for c3/c5; chain state resident in HBM", "sharding": ("rows + ncclAllReduce per leapfrog" if model == "poisson_glm" else "chains") if world > 1 else "none"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -250,8 +250,14 @@ def main():
 
     # ---- set-up (untimed): upload, initialise, run the reference's windowed adaptation
     t_setup = time.time()
-    e = B.Engine(model, data, num_chains=C, random_seed=20241017, init_chain_id=1 + rank * C, num_warmup=args.num_warmup,
-                 num_samples=num_samples, device=local_rank)
+    from cmdstan_b200 import sharding as S
+    row_mode = model == "poisson_glm" and world > 1   # c5: rows data-sharded, one NCCL all-reduce per leapfrog (SURVEY 8e mode 2)
+    if row_mode:
+        e = S.row_sharded_engine(model, data, rank, world, transport=os.environ.get("B200_BENCH_TRANSPORT", "nccl"), device=local_rank,
+                                 num_chains=C, random_seed=20241017, init_chain_id=1, num_warmup=args.num_warmup, num_samples=num_samples)
+    else:   # chains shard (weak scaling): rank r runs stream ids 1 + r*C ... (no data-path collective)
+        e = B.Engine(model, data, num_chains=C, random_seed=20241017, init_chain_id=1 + rank * C, num_warmup=args.num_warmup,
+                     num_samples=num_samples, device=local_rank)
     e.init_chains()
     e.run(args.num_warmup)
     adapt_s, adapt_launches, adapt_grad_s = e.timing()
@@ -278,7 +284,7 @@ def main():
     fetch_s = time.time() - t0
     # ---- H2D leg of e2e: a fresh engine uploads the same host data set
     t0 = time.time()
-    e2 = B.Engine(model, data, num_chains=1, device=local_rank)
+    e2 = B.Engine(model, S.shard_rows(data, rank, world) if row_mode else data, num_chains=1, device=local_rank)
     torch.cuda.synchronize()
     h2d_s = time.time() - t0
     e2.close()
@@ -291,10 +297,11 @@ def main():
     times = torch.tensor([run_s, run_wall + fetch_s + h2d_s, grad_s, adapt_s], dtype=torch.float64, device=dev)
     div = torch.tensor([float(draws[:, :, 5].sum()), float(draws[:, :, 3].mean())], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(ess_cols, op=dist.ReduceOp.SUM)   # ESS of independent chain sets adds
-        dist.all_reduce(nleap, op=dist.ReduceOp.SUM)
+        if not row_mode:   # row mode: every rank holds the same chains -- nothing to add up
+            dist.all_reduce(ess_cols, op=dist.ReduceOp.SUM)   # ESS of independent chain sets adds
+            dist.all_reduce(nleap, op=dist.ReduceOp.SUM)
+            dist.all_reduce(div, op=dist.ReduceOp.SUM)
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(div, op=dist.ReduceOp.SUM)
     min_ess = float(ess_cols.min())
     run_s, e2e_s, grad_s, adapt_s = [float(v) for v in times]
 
@@ -308,7 +315,7 @@ def main():
             # dominant kernel: fused GLM gradient.  bound: FP64 tensor pipe; peak measured live below with a DGEMM.
             # achieved = algorithmic flops of the chain-gradients actually served (requesting chains are compacted, so a
             # launch serves fewer than C chains once trees of different depth interleave) / time in the gradient stage
-            fl = work["flops"] * n_chain_grads / world
+            fl = work["flops"] * n_chain_grads / world   # per rank: chains/world (chain mode) or rows/world (row mode)
             ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
@@ -331,10 +338,10 @@ def main():
                     "kernel": "fused_chain_kernel", "note": "latency-bound by construction (SURVEY.md 8d): state stays in L1/L2; fraction is small on purpose", "peak_source": pk_src}
         line = {
             "metric": "min_bulk_ESS_per_sec", "value": min_ess / run_s, "unit": "ESS/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * run_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": 1e3 * run_s / K, "higher_is_better": True, "scaling": "strong" if row_mode else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(cfg_common, chains_per_gpu=C, l2="data set (80 MB) + chain state exceed L2 reuse between steps" if model == "logistic" else "n/a"),
             "grad_evals_per_sec": float(nleap[0]) / run_s, "grad_evals_executed_per_sec": float(nleap[1]) / run_s,
-            "min_bulk_ess": min_ess, "timed_draws": int(C * K * world), "divergences": float(div[0]), "mean_treedepth": float(div[1]) / world,
+            "min_bulk_ess": min_ess, "timed_draws": int(C * K * (1 if row_mode else world)), "divergences": float(div[0]), "mean_treedepth": float(div[1]) / (1 if row_mode else world),
             "adaptation_s": adapt_s, "setup_wall_s": setup_wall, "median_stepsize": float(np.median(eps)),
             "e2e": {"value": min_ess / e2e_s, "unit": "ESS/s", "h2d_bytes_per_step": data_bytes(data) / K, "d2h_bytes_per_step": int(draws.nbytes / K),
                     "h2d_s": h2d_s, "run_wall_s": run_wall, "d2h_s": fetch_s},

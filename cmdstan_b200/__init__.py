@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS"]
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "nccl_unique_id"]
 
 MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
 ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
@@ -39,7 +39,8 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_
 EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b200nuts_last_error", "b200nuts_set_data_f64",
            "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
            "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_rows_saved",
-           "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce"]
+           "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
+           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init"]
 
 _lib = None
 
@@ -84,8 +85,36 @@ def load_library(build=True):
     lib.b200nuts_get_chain_status.argtypes = [vp, vp, vp, vp]
     lib.b200nuts_get_timing.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double)]
     lib.b200nuts_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    lib.b200nuts_nccl_get_unique_id.argtypes = [vp]
+    lib.b200nuts_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
     _lib = lib
     return lib
+
+
+def _point_at_bundled_nccl():
+    """The torch wheel bundles NCCL (site-packages/nvidia/nccl/lib/libnccl.so.2); tell the library where it is."""
+    if "B200NUTS_NCCL_LIB" in os.environ:
+        return
+    try:
+        import nvidia.nccl
+        for d in nvidia.nccl.__path__:
+            p = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                os.environ["B200NUTS_NCCL_LIB"] = p
+                return
+    except Exception:
+        pass
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and broadcasts it, e.g. with torch.distributed.broadcast_object_list)."""
+    _point_at_bundled_nccl()
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.b200nuts_nccl_get_unique_id(buf)
+    if rc:
+        raise B200NutsError(rc, lib.b200nuts_last_error(None).decode())
+    return buf.raw
 
 
 def _np(a, dt):
@@ -150,6 +179,13 @@ class Engine:
                 fn, a = self.lib.b200nuts_set_data_i8, _np(a, np.int8)
             dims = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
             self._chk(fn(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), dims, max(a.ndim, 1)))
+
+    def nccl_init(self, unique_id, nranks, rank):
+        """Row sharding: join the NCCL communicator identified by `unique_id` (128 bytes from nccl_unique_id() on rank 0);
+        from then on every gradient stage all-reduces its (lp, gradient) partials with ncclAllReduce on the engine stream."""
+        _point_at_bundled_nccl()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._chk(self.lib.b200nuts_nccl_init(self.h, buf, int(nranks), int(rank)))
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

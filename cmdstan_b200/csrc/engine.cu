@@ -14,6 +14,7 @@
 // else (parallel-match invariant, ST/unit/services/sample/hmc_nuts_diag_e_adapt_parallel_match_test.cpp:73-153), which
 // is what makes chain sharding across GPUs communication-free.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -31,6 +32,19 @@ using namespace b200;
 namespace {
 
 std::string g_create_error;
+struct ncclUniqueIdBlob {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char bytes[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, ncclUniqueIdBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+};
+NcclApi g_nccl;
 
 #define CUDA_TRY(e, call)                                                                         \
   do {                                                                                            \
@@ -267,6 +281,7 @@ struct b200nuts_engine {
   std::vector<cudaEvent_t> grad_events;
   allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
+  void* nccl_comm = nullptr;  // ncclComm_t owned by the engine (b200nuts_nccl_init)
   double last_run_s = 0, last_grad_s = 0;
   long long last_launches = 0;
 };
@@ -352,6 +367,7 @@ void b200nuts_destroy(b200nuts_engine* e) {
   free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8);
   free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws);
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
+  if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
   for (auto ev : e->grad_events) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -534,6 +550,77 @@ int b200nuts_set_inv_metric(b200nuts_engine* e, const double* im) {
   } else {
     e->h_user_im.clear();
   }
+  return B200NUTS_OK;
+}
+
+// ---- NCCL, loaded at run time (the library has no link-time dependency on NCCL; single-GPU users never touch it) --------
+namespace {
+
+bool load_nccl(std::string* err) {
+  if (g_nccl.handle) return true;
+  std::vector<std::string> names;
+  if (const char* p = getenv("B200NUTS_NCCL_LIB")) names.push_back(p);
+  names.push_back("libnccl.so.2");
+  names.push_back("libnccl.so");
+  for (const std::string& n : names) {
+    g_nccl.handle = dlopen(n.c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) {
+    *err = "cannot load NCCL (set B200NUTS_NCCL_LIB to the path of libnccl.so.2; the torch-bundled one lives in site-packages/nvidia/nccl/lib)";
+    return false;
+  }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, ncclUniqueIdBlob, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    *err = "the NCCL library lacks ncclGetUniqueId / ncclCommInitRank / ncclAllReduce / ncclCommDestroy";
+    return false;
+  }
+  return true;
+}
+
+// the per-leapfrog exchange step of row sharding: sum the (lp, gradient) partials of all row shards, in place
+int nccl_allreduce_hook(void* device_buf, int64_t count, void* cuda_stream, void* user) {
+  const int kDouble = 8, kSum = 0;  // ncclFloat64, ncclSum
+  return g_nccl.AllReduce(device_buf, device_buf, (size_t)count, kDouble, kSum, user, (cudaStream_t)cuda_stream);
+}
+}  // namespace
+
+int b200nuts_nccl_get_unique_id(void* id128) {
+  std::string err;
+  if (!load_nccl(&err)) {
+    g_create_error = err;
+    return B200NUTS_SOFTWARE;
+  }
+  int rc = g_nccl.GetUniqueId(id128);
+  if (rc) {
+    g_create_error = std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return B200NUTS_SOFTWARE;
+  }
+  return B200NUTS_OK;
+}
+
+int b200nuts_nccl_init(b200nuts_engine* e, const void* id128, int nranks, int rank) {
+  if (!load_nccl(&e->err)) return B200NUTS_SOFTWARE;
+  if (nranks != e->cfg.row_shards || rank != e->cfg.row_shard_rank) {
+    e->err = "b200nuts_nccl_init: nranks / rank must equal the engine's row_shards / row_shard_rank";
+    return B200NUTS_USAGE;
+  }
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  ncclUniqueIdBlob id;
+  std::memcpy(id.bytes, id128, sizeof id.bytes);
+  void* comm = nullptr;
+  int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (rc) {
+    e->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return B200NUTS_SOFTWARE;
+  }
+  e->nccl_comm = comm;
+  e->ar = nccl_allreduce_hook;
+  e->ar_user = comm;
   return B200NUTS_OK;
 }
 

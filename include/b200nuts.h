@@ -138,6 +138,13 @@ int b200nuts_get_timing(b200nuts_engine* e, double* run_seconds, int64_t* kernel
 typedef int (*b200nuts_allreduce_fn)(void* device_buf, int64_t count, void* cuda_stream, void* user);
 int b200nuts_set_allreduce(b200nuts_engine* e, b200nuts_allreduce_fn fn, void* user);
 
+/* Row sharding over NCCL (mode 2: "one ncclAllReduce(sum, double, (1+D) C) per leapfrog").  NCCL is
+   loaded at run time (dlopen of libnccl.so.2, or the path in the environment variable B200NUTS_NCCL_LIB).  Rank 0 obtains a
+   128-byte unique id and hands it to every rank by any channel; each rank then creates its communicator on the engine's
+   device; this installs the all-reduce hook above with ncclAllReduce on the engine's stream. */
+int b200nuts_nccl_get_unique_id(void* id128);
+int b200nuts_nccl_init(b200nuts_engine* e, const void* id128, int nranks, int rank);
+
 #ifdef __cplusplus
 }
 #endif
