@@ -8,6 +8,7 @@ GPU without going through text CSV -> stansummary):
     ess (Geyer, FFT autocov.)     stan/src/stan/analyze/mcmc/ess.hpp:28-103, autocovariance.hpp
     split_rank_normalized_ess     stan/src/stan/analyze/mcmc/split_rank_normalized_ess.hpp:28-55   (bulk)
     rhat / split_rank_normalized_rhat   stan/src/stan/analyze/mcmc/rhat.hpp, split_rank_normalized_rhat.hpp
+    mcse_mean / mcse_sd           stan/src/stan/analyze/mcmc/mcse.hpp:23-63
 
 Checked against the reference's own `stansummary` in tests/test_analyze.py (golden table under tests/golden/).
 Works on CPU or CUDA torch tensors; this is measurement code, not part of the sampling hot path.
@@ -100,6 +101,26 @@ def rhat(x):
     var_between = n * chain_mean.var(unbiased=True)
     var_within = chain_var.mean()
     return float(torch.sqrt((var_between / var_within + n - 1) / n))
+
+
+def mcse_mean(draws):
+    """stan::analyze::mcse_mean (stan/src/stan/analyze/mcmc/mcse.hpp:23-30): sqrt(sample variance / ess(chains)).  draws [chains, n]."""
+    x = torch.as_tensor(draws).to(torch.float64)
+    if x.shape[1] < 4 or not _ok(x):
+        return float("nan")
+    return math.sqrt(float(x.reshape(-1).var(unbiased=True)) / ess(x))
+
+
+def mcse_sd(draws):
+    """stan::analyze::mcse_sd (mcse.hpp:41-63): ESS of |x - mean| on split chains, Taylor expansion of sqrt(variance)."""
+    x = torch.as_tensor(draws).to(torch.float64)
+    if x.shape[1] < 4 or not _ok(x):
+        return float("nan")
+    ctr = (x - x.mean()).abs()
+    ess_mean = ess(split_chains(ctr))
+    evar = float((ctr ** 2).mean())
+    varvar = (float((ctr ** 4).mean()) - evar ** 2) / ess_mean
+    return math.sqrt(varvar / evar / 4.0)
 
 
 def _ok(s):

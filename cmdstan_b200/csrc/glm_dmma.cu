@@ -23,6 +23,7 @@
 //
 // Fragment layout of mma.m8n8k4.f64 (PTX ISA): A a0 = A[lane>>2][lane&3]; B b0 = B[lane&3][lane>>2];
 // C c0,c1 = C[lane>>2][2*(lane&3) + {0,1}].
+#include "fastmath.cuh"
 #include "kernels.h"
 
 namespace b200 {
@@ -39,99 +40,6 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 }
 
 __host__ __device__ inline int xs_ld_for(int Dk) { return Dk + 4; }  // Dk % 8 == 0  =>  ld % 8 == 4
-
-// ---- branch-free double-precision building blocks -----------------------------------------------------------------
-// exp(x) for |x| <= 700 (callers clamp): x = k ln2 + r, |r| <= ln2/2, Taylor degree 12 (remainder 1.7e-16), 2^k applied
-// to the exponent field with integer arithmetic.
-__device__ __forceinline__ double fast_exp(double x) {
-  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
-  const double t = fma(x, 1.4426950408889634074, kMagic);
-  const double kf = t - kMagic;
-  const int k = __double2loint(t);
-  double r = fma(kf, -6.93147180369123816490e-01, x);   // ln2 high part (fdlibm split)
-  r = fma(kf, -1.90821492927058770002e-10, r);          // ln2 low part
-  double p = 1.0 / 479001600.0;                         // 1/12!
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-
-// 1/x for x in [1, 16]: hardware seed (20 bits) + two Newton steps
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-
-// per-observation log-likelihood term and d(term)/d(eta).  `yd` is 2y-1 (logistic) or y (poisson) as a double.
-//   logistic: bernoulli_logit_glm_lpmf.hpp:121-126 (lp), :137-142 (derivative), cutoffs +-20
-//   poisson : poisson_log_glm_lpmf.hpp:117-118, :127-132
-template <int LINK>
-__device__ __forceinline__ void link_eval(double eta, double yd, double& lpi, double& d) {
-  if (LINK == 0) {
-    const double t = yd * eta;
-    const double a = fabs(t);
-    const double em = fast_exp(-fmin(a, 700.0));  // exp(-|t|) in (0, 1]
-    // log1p(em) = kln2 + 2 atanh(z), z = (f-1)/(f+1), f = (1+em) / (big ? 2 : 1)  =>  |z| <= 0.1716
-    const bool big = em > 0.41421356237309503;
-    const double num = em - (big ? 1.0 : 0.0);
-    const double den = em + (big ? 3.0 : 2.0);
-    const double f1 = 1.0 + em;
-    const double R = fast_rcp(den * f1);
-    const double z = num * (R * f1);
-    const double s = R * den;  // 1 / (1 + em)
-    const double w = z * z;
-    double p = 2.0 / 19.0;  // truncation: w^10 * 2/21 <= 2.4e-17 relative
-    p = fma(p, w, 2.0 / 17.0);
-    p = fma(p, w, 2.0 / 15.0);
-    p = fma(p, w, 2.0 / 13.0);
-    p = fma(p, w, 2.0 / 11.0);
-    p = fma(p, w, 2.0 / 9.0);
-    p = fma(p, w, 2.0 / 7.0);
-    p = fma(p, w, 2.0 / 5.0);
-    p = fma(p, w, 2.0 / 3.0);
-    p = fma(p, w, 2.0);
-    const double l1p = fma(z, p, big ? 0.69314718055994530942 : 0.0);
-    const bool neg = t < 0.0;
-    double lp_v = -((neg ? a : 0.0) + l1p);   // -log1p(exp(-t))
-    double d_v = yd * (neg ? s : em * s);     // sign * e / (e + 1), e = exp(-t)
-    if (t > 20.0) {
-      lp_v = -em;
-      d_v = -em;
-    }
-    if (t < -20.0) {
-      lp_v = t;
-      d_v = yd;
-    }
-    if (t != t) {
-      lp_v = t;
-      d_v = t;
-    }
-    lpi = lp_v;
-    d = d_v;
-  } else {
-    const double xc = fmin(fmax(eta, -700.0), 700.0);
-    double ee = fast_exp(xc);
-    if (eta > 709.78) ee = INFINITY;
-    if (eta != eta) ee = eta;
-    lpi = yd * eta - ee;
-    d = yd - ee;
-  }
-}
 
 struct GlmTcArgs {
   const double* X;       // [N][ldx], ldx == Dk (multiple of 8), column 0 = 1, zero padded
@@ -172,6 +80,42 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// phase A of one warp: acc[4 row blocks][NB column blocks] += X tile rows . q columns   (NB = column blocks in use)
+template <int NB>
+__device__ __forceinline__ void phase_a(double (&acc)[4][2][2], const double* xa, const double* ba, int Dk, int xs_ld) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < Dk; k0 += 4) {
+    double av[4], bv[NB];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) av[mi] = xa[mi * 8 * xs_ld + k0];
+#pragma unroll
+    for (int ni = 0; ni < NB; ni++) bv[ni] = ba[ni * 8 * xs_ld + k0];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NB; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+  }
+}
+
+// phase B of one warp: gacc[MB design-column blocks][NB chain blocks] += X tile^T . Dm tile
+template <int NB, int MB>
+__device__ __forceinline__ void phase_b(double (&gacc)[MB][2][2], const double* xb, const double* db, int b_mh, int Dk, int xs_ld) {
+#pragma unroll 2
+  for (int r0 = 0; r0 < TR; r0 += 4) {
+    double bv[NB];
+#pragma unroll
+    for (int ni = 0; ni < NB; ni++) bv[ni] = db[r0 * DS_LD + ni * 8];
+#pragma unroll
+    for (int m = 0; m < MB; m++) {
+      if ((b_mh + m) * 8 < Dk) {  // warp-uniform
+        const double av = xb[r0 * xs_ld + m * 8];
+#pragma unroll
+        for (int ni = 0; ni < NB; ni++) dmma(gacc[m][ni][0], gacc[m][ni][1], av, bv[ni]);
+      }
+    }
+  }
+}
 
 // MB: 8-row blocks of G per warp half (Dk <= 16*MB)
 template <int LINK, int MB>
@@ -284,6 +228,10 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
     const double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
     const double* ys = ys0 + buf * TR;
     const long long row0 = row_begin + (long long)rt * TR;
+    // 8-chain column blocks of this warp's 16 chains that hold requesting chains (warp-uniform; an underfilled tile --
+    // few requesting chains, or the last tile -- skips the tensor and link work of its empty blocks)
+    const int in_tile = n_list - ct * TC;
+    const int nb = in_tile - a_cb >= 16 ? 2 : (in_tile - a_cb > 8 ? 2 : (in_tile - a_cb > 0 ? 1 : 0));
     // ---- phase A
     double acc[4][2][2];
 #pragma unroll
@@ -293,18 +241,8 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
     {
       const double* xa = Xs + (a_rb + gid) * xs_ld + tig;
       const double* ba = Bs + (a_cb + gid) * xs_ld + tig;
-#pragma unroll 2
-      for (int k0 = 0; k0 < Dk; k0 += 4) {
-        double av[4], bv[2];
-#pragma unroll
-        for (int mi = 0; mi < 4; mi++) av[mi] = xa[mi * 8 * xs_ld + k0];
-#pragma unroll
-        for (int ni = 0; ni < 2; ni++) bv[ni] = ba[ni * 8 * xs_ld + k0];
-#pragma unroll
-        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-          for (int ni = 0; ni < 2; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
-      }
+      if (nb == 2) phase_a<2>(acc, xa, ba, Dk, xs_ld);
+      else if (nb == 1) phase_a<1>(acc, xa, ba, Dk, xs_ld);
     }
     if (rt == n_rt - 1 && ct + 1 < n_ct) {  // last row tile of this chain tile: the B tile is free after phase A
       __syncthreads();
@@ -318,6 +256,7 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
       const double yd = ys[r];
 #pragma unroll
       for (int ni = 0; ni < 2; ni++) {
+        if (ni >= nb) continue;
         double lv[2], dv[2];
 #pragma unroll
         for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
@@ -331,20 +270,8 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
     {
       const double* xb = Xs + tig * xs_ld + b_mh * 8 + gid;
       const double* db = Ds + tig * DS_LD + b_cb + gid;
-#pragma unroll 2
-      for (int r0 = 0; r0 < TR; r0 += 4) {
-        double bv[2];
-#pragma unroll
-        for (int ni = 0; ni < 2; ni++) bv[ni] = db[r0 * DS_LD + ni * 8];
-#pragma unroll
-        for (int m = 0; m < MB; m++) {
-          if ((b_mh + m) * 8 < Dk) {  // warp-uniform
-            const double av = xb[r0 * xs_ld + m * 8];
-#pragma unroll
-            for (int ni = 0; ni < 2; ni++) dmma(gacc[m][ni][0], gacc[m][ni][1], av, bv[ni]);
-          }
-        }
-      }
+      if (nb == 2) phase_b<2, MB>(gacc, xb, db, b_mh, Dk, xs_ld);
+      else if (nb == 1) phase_b<1, MB>(gacc, xb, db, b_mh, Dk, xs_ld);
     }
     if (rt == n_rt - 1) {
       const int slot0 = ct * TC;

