@@ -26,7 +26,11 @@ import tempfile
 import threading
 import time
 
+import warnings
+
 import numpy as np
+
+warnings.filterwarnings("ignore")   # stdout carries exactly one JSON line
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

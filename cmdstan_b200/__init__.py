@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "nccl_unique_id"]
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "nccl_unique_id"]
 
 MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
 ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
@@ -31,7 +31,7 @@ class Config(C.Structure):
                 ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double), ("t0", C.c_double),
                 ("init_buffer", C.c_uint32), ("term_buffer", C.c_uint32), ("window", C.c_uint32), ("adapt_engaged", C.c_int32),
                 ("engine", C.c_int32), ("device", C.c_int32), ("store_draws", C.c_int32), ("row_shards", C.c_int32),
-                ("row_shard_rank", C.c_int32)]
+                ("row_shard_rank", C.c_int32), ("metric", C.c_int32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
@@ -127,7 +127,7 @@ class Engine:
     def __init__(self, model, data, num_chains=1, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
                  num_samples=1000, num_thin=1, save_warmup=False, stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8,
                  gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50, window=25, adapt_engaged=True, engine="auto",
-                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None):
+                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None, metric="diag_e"):
         self.lib = load_library()
         cfg = Config()
         self.lib.b200nuts_default_config(C.byref(cfg))
@@ -139,6 +139,7 @@ class Engine:
         cfg.init_buffer, cfg.term_buffer, cfg.window = int(init_buffer), int(term_buffer), int(window)
         cfg.adapt_engaged, cfg.engine, cfg.device, cfg.store_draws = int(bool(adapt_engaged)), ENGINES[engine], int(device), int(bool(store_draws))
         cfg.row_shards, cfg.row_shard_rank = int(row_shards), int(row_shard_rank)
+        cfg.metric = {"diag_e": 0, "unit_e": 1}[metric]
         self.cfg = cfg
         self.model = model
         self.h = C.c_void_p()
@@ -253,25 +254,34 @@ class Engine:
         return s.value, n.value, g.value
 
 
-def hmc_nuts_diag_e_adapt(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1,
-                          init_radius=2.0, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=False, refresh=100,
-                          stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0,
-                          init_buffer=75, term_buffer=50, window=25, logger=None, device=0, engine="auto"):
-    """Mirror of stan::services::sample::hmc_nuts_diag_e_adapt (multi-chain overload,
-    stan/src/stan/services/sample/hmc_nuts_diag_e_adapt.hpp:331-407).
+def param_names(model, data):
+    """constrained_param_names(include_tparams=True) of the device model family (host mirror: cmdstan_b200/host/model.hpp)."""
+    vec = lambda n, k: [f"{n}.{i}" for i in range(1, k + 1)]
+    if model == "std_normal":
+        return vec("x", int(np.asarray(data.get("D", 3)).ravel()[0]))
+    if model == "bernoulli":
+        return ["theta"]
+    if model == "eight_schools_nc":
+        J = len(data["y"])
+        return ["mu", "tau"] + vec("theta_tilde", J) + vec("theta", J)
+    if model in ("logistic", "poisson_glm"):
+        return ["alpha"] + vec("beta", np.asarray(data["X"]).shape[1])
+    if model == "irt_2pl":
+        I, J = np.asarray(data["y"]).shape
+        return ["sigma_theta"] + vec("theta", I) + ["sigma_a"] + vec("a", J) + ["mu_b", "sigma_b"] + vec("b", J)
+    raise KeyError(model)
 
-    Returns (return_code, result) with return_code in stan::services::error_codes; result is a dict with
-    `draws` [num_chains, rows, 7 + K], `columns`, `stepsize` [num_chains], `inv_metric` [num_chains, D], `timing`.
-    `init` are unconstrained initial values [num_chains, D] (None: uniform(-init_radius, init_radius) from each chain's
-    own stream, like util::initialize); `init_inv_metric` [num_chains, D] (None: ones).
-    """
+
+def _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                 num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, init_buffer, term_buffer,
+                 window, logger, device, engine, adapt_engaged, metric):
     log = logger or (lambda msg: None)
     try:
         e = Engine(model, data, num_chains=num_chains, random_seed=random_seed, init_chain_id=init_chain_id,
                    init_radius=init_radius, num_warmup=num_warmup, num_samples=num_samples, num_thin=num_thin,
                    save_warmup=save_warmup, stepsize=stepsize, stepsize_jitter=stepsize_jitter, max_depth=max_depth, delta=delta,
                    gamma=gamma, kappa=kappa, t0=t0, init_buffer=init_buffer, term_buffer=term_buffer, window=window,
-                   adapt_engaged=True, engine=engine, device=device)
+                   adapt_engaged=adapt_engaged, engine=engine, device=device, metric=metric)
     except B200NutsError as ex:
         log(str(ex))
         return ex.code, None
@@ -292,10 +302,59 @@ def hmc_nuts_diag_e_adapt(model, data, num_chains=1, init=None, init_inv_metric=
             return code, None
         eps, im = e.adaptation()
         draws = e.fetch_draws()
-        names = SAMPLER_COLUMNS + [f"v{i + 1}" for i in range(e.K)]
+        try:
+            names = SAMPLER_COLUMNS + param_names(model, data)
+        except KeyError:
+            names = SAMPLER_COLUMNS + [f"v{i + 1}" for i in range(e.K)]
         return OK, dict(draws=draws, columns=names, stepsize=eps, inv_metric=im, timing=dict(warmup=warm_s, sampling=samp_s), n_grad=ng)
     except B200NutsError as ex:
         log(str(ex))
         return ex.code, None
     finally:
         e.close()
+
+
+def hmc_nuts_diag_e_adapt(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1,
+                          init_radius=2.0, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=False, refresh=100,
+                          stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0,
+                          init_buffer=75, term_buffer=50, window=25, logger=None, device=0, engine="auto"):
+    """Mirror of stan::services::sample::hmc_nuts_diag_e_adapt (multi-chain overload,
+    stan/src/stan/services/sample/hmc_nuts_diag_e_adapt.hpp:331-407).
+
+    Returns (return_code, result) with return_code in stan::services::error_codes; result is a dict with
+    `draws` [num_chains, rows, 7 + K], `columns`, `stepsize` [num_chains], `inv_metric` [num_chains, D], `timing`.
+    `init` are unconstrained initial values [num_chains, D] (None: uniform(-init_radius, init_radius) from each chain's
+    own stream, like util::initialize); `init_inv_metric` [num_chains, D] (None: ones).
+    """
+    return _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                        num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, init_buffer, term_buffer,
+                        window, logger, device, engine, True, "diag_e")
+
+
+def hmc_nuts_diag_e(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1, init_radius=2.0,
+                    num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=False, refresh=100, stepsize=1.0,
+                    stepsize_jitter=0.0, max_depth=10, logger=None, device=0, engine="auto"):
+    """stan::services::sample::hmc_nuts_diag_e (stan/src/stan/services/sample/hmc_nuts_diag_e.hpp): fixed step size and
+    metric, no adaptation (util::run_sampler: warm-up transitions are ordinary transitions, no init_stepsize)."""
+    return _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                        num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75, 50, 25, logger, device,
+                        engine, False, "diag_e")
+
+
+def hmc_nuts_unit_e_adapt(model, data, num_chains=1, init=None, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
+                          num_samples=1000, num_thin=1, save_warmup=False, refresh=100, stepsize=1.0, stepsize_jitter=0.0,
+                          max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0, logger=None, device=0, engine="auto"):
+    """stan::services::sample::hmc_nuts_unit_e_adapt (stan/src/stan/services/sample/hmc_nuts_unit_e_adapt.hpp): identity
+    metric, step-size adaptation only (adapt_unit_e_nuts.hpp:24-35)."""
+    return _run_service(model, data, num_chains, init, None, random_seed, init_chain_id, init_radius, num_warmup, num_samples, num_thin,
+                        save_warmup, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, 75, 50, 25, logger, device, engine,
+                        True, "unit_e")
+
+
+def hmc_nuts_unit_e(model, data, num_chains=1, init=None, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
+                    num_samples=1000, num_thin=1, save_warmup=False, refresh=100, stepsize=1.0, stepsize_jitter=0.0, max_depth=10,
+                    logger=None, device=0, engine="auto"):
+    """stan::services::sample::hmc_nuts_unit_e (stan/src/stan/services/sample/hmc_nuts_unit_e.hpp): identity metric, no adaptation."""
+    return _run_service(model, data, num_chains, init, None, random_seed, init_chain_id, init_radius, num_warmup, num_samples, num_thin,
+                        save_warmup, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75, 50, 25, logger, device, engine,
+                        False, "unit_e")

@@ -315,6 +315,7 @@ void b200nuts_default_config(b200nuts_config* c) {
   c->store_draws = 1;
   c->row_shards = 1;
   c->row_shard_rank = 0;
+  c->metric = 0;
 }
 
 const char* b200nuts_last_error(const b200nuts_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
@@ -334,6 +335,7 @@ int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
   if (!(cfg->stepsize > 0) || !(cfg->gamma > 0) || !(cfg->kappa > 0) || !(cfg->t0 > 0)) { g_create_error = "stepsize, gamma, kappa, t0 must be > 0"; return B200NUTS_USAGE; }
   if (cfg->stepsize_jitter < 0 || cfg->stepsize_jitter > 1) { g_create_error = "stepsize_jitter must be in [0, 1]"; return B200NUTS_USAGE; }
   if (cfg->init_radius < 0) { g_create_error = "init radius must be >= 0"; return B200NUTS_USAGE; }
+  if (cfg->metric != 0 && cfg->metric != 1) { g_create_error = "metric must be 0 (diag_e) or 1 (unit_e)"; return B200NUTS_USAGE; }
   if (cfg->row_shards < 1 || cfg->row_shard_rank < 0 || cfg->row_shard_rank >= cfg->row_shards) { g_create_error = "bad row shard configuration"; return B200NUTS_USAGE; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -543,6 +545,7 @@ int b200nuts_set_inits(b200nuts_engine* e, const double* q0) {
 int b200nuts_set_inv_metric(b200nuts_engine* e, const double* im) {
   int rc = finalize_data(e);
   if (rc) return rc;
+  if (im && e->cfg.metric == 1) { e->err = "unit_e has no free metric parameters"; return B200NUTS_USAGE; }
   if (im) {
     for (size_t i = 0; i < (size_t)e->C * e->D; i++)
       if (!(im[i] > 0) || !std::isfinite(im[i])) { e->err = "Inverse Euclidean metric not positive definite."; return B200NUTS_CONFIG; }  // validate_diag_inv_metric
@@ -666,7 +669,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   s.kappa = c.kappa;
   s.t0 = c.t0;
   s.init_radius = c.init_radius;
-  resolve_window(&s, c.adapt_engaged ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
+  // unit_e: no variance windows at all (adapt_unit_e_nuts::transition only learns the step size)
+  resolve_window(&s, (c.adapt_engaged && c.metric == 0) ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
   s.ncol = 7 + e->D;
   s.rows_per_chain = c.store_draws ? (c.save_warmup ? (c.num_warmup + c.num_thin - 1) / c.num_thin : 0) + (c.num_samples + c.num_thin - 1) / c.num_thin : 0;
 

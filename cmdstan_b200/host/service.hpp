@@ -51,6 +51,7 @@ struct device_options {
   std::vector<int> devices = {0};  // chains are split contiguously over these CUDA devices
   int engine = B200NUTS_ENGINE_AUTO;
   int format_threads = 8;          // host threads used to format CSV rows (per-chain files are independent)
+  bool unit_e = false;             // identity metric (the hmc_nuts_unit_e* services below set it)
 };
 
 // metric_writer interface: one JSON record per chain (callbacks::structured_writer's use in write_sampler_state_struct)
@@ -191,6 +192,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     cfg.term_buffer = term_buffer;
     cfg.window = window;
     cfg.adapt_engaged = adapt_engaged;
+    cfg.metric = opt.unit_e ? 1 : 0;
     cfg.engine = opt.engine;
     cfg.device = opt.devices.empty() ? 0 : opt.devices[g];
     b200nuts_engine* e = nullptr;
@@ -210,14 +212,14 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   b200nuts_num_params(eg.e[0], &nu, &K);
 
   // window fallback notice (windowed_adaptation.hpp:42-67), once -- the reference prints it per chain
-  if (adapt_engaged && num_warmup >= 20 && init_buffer + window + term_buffer > (unsigned)num_warmup) {
+  if (adapt_engaged && !opt.unit_e && num_warmup >= 20 && init_buffer + window + term_buffer > (unsigned)num_warmup) {
     unsigned ib = (unsigned)(0.15 * num_warmup), tb = (unsigned)(0.1 * num_warmup);
     std::stringstream m;
     m << "WARNING: There aren't enough warmup iterations to fit the\n         three stages of adaptation as currently configured.\n"
       << "         Reducing each adaptation stage to 15%/75%/10% of\n         the given number of warmup iterations:\n"
       << "           init_buffer = " << ib << "\n           adapt_window = " << num_warmup - (ib + tb) << "\n           term_buffer = " << tb << "\n";
     logger.info(m.str());
-  } else if (adapt_engaged && num_warmup < 20) {
+  } else if (adapt_engaged && !opt.unit_e && num_warmup < 20) {
     logger.info("WARNING: No variance estimation is\n         performed for num_warmup < 20\n");
   }
 
@@ -350,10 +352,14 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
           std::stringstream ss;
           ss << "Step size = " << eps[c];
           w(ss.str());
-          w("Diagonal elements of inverse mass matrix:");
-          std::stringstream ms;
-          for (int64_t i = 0; i < D; i++) ms << (i ? ", " : "") << met[(size_t)c * D + i];
-          w(ms.str());
+          if (opt.unit_e) {
+            w("No free parameters for unit metric");  // unit_e_point::write_metric (mcmc/hmc/hamiltonians/unit_e_point.hpp)
+          } else {
+            w("Diagonal elements of inverse mass matrix:");
+            std::stringstream ms;
+            for (int64_t i = 0; i < D; i++) ms << (i ? ", " : "") << met[(size_t)c * D + i];
+            w(ms.str());
+          }
         }
       }
       if (adapt_engaged && (size_t)c < metric_writer.size()) metric_writer[c].write(eps[c], met.data() + (size_t)c * D, D);
@@ -395,6 +401,53 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     logger.info("");
   }
   return error_codes::OK;
+}
+
+// ---- sibling services: same engine, fewer knobs; parameter lists as in the reference ----------
+
+// stan::services::sample::hmc_nuts_diag_e (services/sample/hmc_nuts_diag_e.hpp): no adaptation
+template <class Model, typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter,
+          typename DiagnosticWriter>
+int hmc_nuts_diag_e(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init,
+                    const std::vector<InitInvContextPtr>& init_inv_metric, unsigned int random_seed, unsigned int init_chain_id,
+                    double init_radius, int num_warmup, int num_samples, int num_thin, bool save_warmup, int refresh, double stepsize,
+                    double stepsize_jitter, int max_depth, callbacks::interrupt& interrupt, callbacks::logger& logger,
+                    std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                    std::vector<DiagnosticWriter>& diagnostic_writer, const device_options& opt = device_options()) {
+  std::vector<json_metric_writer> none;
+  return hmc_nuts_diag_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                               num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75u, 50u, 25u,
+                               interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, false);
+}
+
+// stan::services::sample::hmc_nuts_unit_e_adapt (services/sample/hmc_nuts_unit_e_adapt.hpp): identity metric, step size adapted
+template <class Model, typename InitContextPtr, typename InitWriter, typename SampleWriter, typename DiagnosticWriter,
+          typename MetricWriter>
+int hmc_nuts_unit_e_adapt(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init, unsigned int random_seed,
+                          unsigned int init_chain_id, double init_radius, int num_warmup, int num_samples, int num_thin,
+                          bool save_warmup, int refresh, double stepsize, double stepsize_jitter, int max_depth, double delta,
+                          double gamma, double kappa, double t0, callbacks::interrupt& interrupt, callbacks::logger& logger,
+                          std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                          std::vector<DiagnosticWriter>& diagnostic_writer, std::vector<MetricWriter>& metric_writer,
+                          device_options opt = device_options(), bool adapt_engaged = true) {
+  opt.unit_e = true;
+  std::vector<std::shared_ptr<io::var_context>> no_metric;
+  return hmc_nuts_diag_e_adapt(model, num_chains, init, no_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples, num_thin,
+                               save_warmup, refresh, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, 75u, 50u, 25u, interrupt,
+                               logger, init_writer, sample_writer, diagnostic_writer, metric_writer, opt, adapt_engaged);
+}
+
+// stan::services::sample::hmc_nuts_unit_e (services/sample/hmc_nuts_unit_e.hpp): identity metric, no adaptation
+template <class Model, typename InitContextPtr, typename InitWriter, typename SampleWriter, typename DiagnosticWriter>
+int hmc_nuts_unit_e(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init, unsigned int random_seed,
+                    unsigned int init_chain_id, double init_radius, int num_warmup, int num_samples, int num_thin, bool save_warmup,
+                    int refresh, double stepsize, double stepsize_jitter, int max_depth, callbacks::interrupt& interrupt,
+                    callbacks::logger& logger, std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                    std::vector<DiagnosticWriter>& diagnostic_writer, const device_options& opt = device_options()) {
+  std::vector<json_metric_writer> none;
+  return hmc_nuts_unit_e_adapt(model, num_chains, init, random_seed, init_chain_id, init_radius, num_warmup, num_samples, num_thin,
+                               save_warmup, refresh, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, interrupt, logger,
+                               init_writer, sample_writer, diagnostic_writer, none, opt, false);
 }
 
 }  // namespace sample

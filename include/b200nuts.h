@@ -81,6 +81,8 @@ typedef struct b200nuts_config {
      partial (lp, gradient) sums are combined across `row_shards` engines by the all-reduce hook below. */
   int32_t row_shards;       /* default 1 */
   int32_t row_shard_rank;   /* default 0 */
+  int32_t metric;           /* 0 diag_e (default): hmc_nuts_diag_e[_adapt]; 1 unit_e: hmc_nuts_unit_e[_adapt]
+                               (stan/src/stan/services/sample/hmc_nuts_unit_e_adapt.hpp; the metric stays the identity) */
 } b200nuts_config;
 
 typedef struct b200nuts_engine b200nuts_engine;

@@ -509,6 +509,8 @@ typedef struct {
   unsigned init_buffer, term_buffer, window;
   double init_radius;
   int adapt_engaged;
+  int unit_e; /* 1: adapt_unit_e_nuts / unit_e_nuts (S/mcmc/hmc/nuts/adapt_unit_e_nuts.hpp:24-35): metric frozen at the identity,
+                 step-size adaptation only -- arithmetically diag_e with M^-1 = 1 and no variance windows */
 } oracle_config_t;
 
 typedef struct {
@@ -900,7 +902,7 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   if (c->kappa > 0) s.kappa = c->kappa;
   if (c->t0 > 0) s.t0 = c->t0;
   s.adapt_window_counter = 0; s.adapt_window_size = 0; s.adapt_next_window = 0u - 1u;
-  if (c->adapt_engaged) set_window_params(&s, c->num_warmup, c->init_buffer, c->term_buffer, c->window);
+  if (c->adapt_engaged && !c->unit_e) set_window_params(&s, c->num_warmup, c->init_buffer, c->term_buffer, c->window);
   /* ---- run_adaptive_sampler ---- */
   int adapt_flag = c->adapt_engaged;
   update_potential_gradient(&s, &s.z); /* z.V, z.g at q0 (init_stepsize / transition re-evaluate them anyway) */

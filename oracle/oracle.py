@@ -28,7 +28,7 @@ class ConfigT(C.Structure):
                 ("num_thin", C.c_int), ("save_warmup", C.c_int), ("stepsize", C.c_double), ("stepsize_jitter", C.c_double),
                 ("max_depth", C.c_int), ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double),
                 ("t0", C.c_double), ("init_buffer", C.c_uint), ("term_buffer", C.c_uint), ("window", C.c_uint),
-                ("init_radius", C.c_double), ("adapt_engaged", C.c_int)]
+                ("init_radius", C.c_double), ("adapt_engaged", C.c_int), ("unit_e", C.c_int)]
 
 
 _lib = None
@@ -118,7 +118,7 @@ class Model:
 
 DEFAULTS = dict(seed=0, chain_id=1, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=0, stepsize=1.0,
                 stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75,
-                term_buffer=50, window=25, init_radius=2.0, adapt_engaged=1)
+                term_buffer=50, window=25, init_radius=2.0, adapt_engaged=1, unit_e=0)
 
 
 def run_chain(model, q0=None, inv_metric=None, **kw):
@@ -216,7 +216,7 @@ def read_stan_csv(path):
 
 def ref_sample(name, data, num_chains=1, seed=0, chain_id=1, num_warmup=1000, num_samples=1000, sig_figs=18, num_threads=None,
                extra_args=(), tmpdir=None, keep=False, save_warmup=False, delta=0.8, max_depth=10, init=None,
-               adapt_engaged=True, stepsize=None, metric_file=None):
+               adapt_engaged=True, stepsize=None, metric_file=None, metric=None):
     """Run the unmodified reference `sample` method; returns list (per chain) of read_stan_csv tuples + wall seconds."""
     import time
     own = tmpdir is None
@@ -228,6 +228,8 @@ def ref_sample(name, data, num_chains=1, seed=0, chain_id=1, num_warmup=1000, nu
     cmd = [os.path.join(REF, name), "sample", f"num_samples={num_samples}", f"num_warmup={num_warmup}",
            f"save_warmup={int(save_warmup)}", "adapt", f"engaged={int(adapt_engaged)}", f"delta={delta}", "algorithm=hmc", "engine=nuts",
            f"max_depth={max_depth}"]
+    if metric is not None:
+        cmd += [f"metric={metric}"]
     if metric_file is not None:
         cmd += [f"metric_file={metric_file}"]
     if stepsize is not None:

@@ -74,5 +74,23 @@ def main():
     print("written:", os.listdir(HERE))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--unit-e" not in sys.argv:
     main()
+
+
+def gen_unit_e():
+    """metric=unit_e goldens (hmc_nuts_unit_e_adapt / hmc_nuts_unit_e of the compiled reference): first rows at sig_figs=18."""
+    out = []
+    for name, data, kw in (("bernoulli", cases.BERNOULLI, dict(seed=21, chain_id=1)), ("eight_schools_nc", cases.EIGHT_SCHOOLS, dict(seed=22, chain_id=2))):
+        for adapt in (True, False):
+            res, _, _ = O.ref_sample(name, data, num_warmup=150, num_samples=50, save_warmup=True, metric="unit_e", adapt_engaged=adapt,
+                                     stepsize=None if adapt else 0.25, **kw)
+            names, draws, stepsize, metric, _ = res[0]
+            out.append(dict(model=name, data=jsonable(data), args=dict(kw, num_warmup=150, num_samples=50, adapt_engaged=int(adapt),
+                                                                        stepsize=1.0 if adapt else 0.25), rows=draws[:60].tolist(),
+                            last_rows=draws[-3:].tolist(), stepsize=stepsize))
+    json.dump(out, open(os.path.join(HERE, "ref_chains_unit_e.json"), "w"))
+
+
+if __name__ == "__main__" and "--unit-e" in sys.argv:
+    gen_unit_e()

@@ -14,7 +14,8 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
                               unsigned seed, unsigned chain_id, int num_warmup, int num_samples, int num_thin, int save_warmup,
                               double stepsize, double jitter, int max_depth, double delta, double gamma, double kappa, double t0,
                               unsigned init_buffer, unsigned term_buffer, unsigned window, double init_radius, int adapt_engaged,
-                              const double* q0, const double* inv_metric0, double* draws, double* adapt_out, long long* n_grad) {
+                              const double* q0, const double* inv_metric0, double* draws, double* adapt_out, long long* n_grad,
+                              int unit_e) {
   ModelData m{};
   m.kind = kind; m.D = D; m.N = N; m.yr = yr; m.sigma = sigma; m.sum_y = sum_y;
   SamplerCfg cfg{};
@@ -24,7 +25,7 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
   cfg.stepsize = stepsize; cfg.stepsize_jitter = (jitter > 0 && jitter < 1) ? jitter : 0.0;
   cfg.delta = (delta > 0 && delta < 1) ? delta : 0.5; cfg.gamma = gamma > 0 ? gamma : 0.05;
   cfg.kappa = kappa > 0 ? kappa : 0.75; cfg.t0 = t0 > 0 ? t0 : 10; cfg.init_radius = init_radius;
-  resolve_window(&cfg, adapt_engaged ? num_warmup : 0, init_buffer, term_buffer, window);
+  resolve_window(&cfg, (adapt_engaged && !unit_e) ? num_warmup : 0, init_buffer, term_buffer, window);
   cfg.ncol = 7 + D;
   cfg.rows_per_chain = (save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0) + (num_samples + num_thin - 1) / num_thin;
   std::vector<double> slab((size_t)num_vec_slots(max_depth) * D, 0.0), q(D), g(D);

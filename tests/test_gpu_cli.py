@@ -140,6 +140,25 @@ def test_cli_init_and_metric_files(tmp_path):
     assert np.array_equal(draws[:, 3:6], want[:, 3:6]) and np.allclose(draws, want, rtol=1e-9)
 
 
+@pytest.mark.skipif(not O.have_ref("bernoulli"), reason="oracle/_ref not built")
+def test_cli_metric_unit_e_vs_reference(tmp_path):
+    dj = _bernoulli_json(tmp_path)
+    args = ["sample", "num_samples=40", "num_warmup=60", "save_warmup=1", "algorithm=hmc", "metric=unit_e", "data", f"file={dj}", "random", "seed=3",
+            "output", "sig_figs=12"]
+    r = _cli("bernoulli", args + ["file=u.csv"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rr = subprocess.run([os.path.join(O.REF, "bernoulli")] + args + ["file=ur.csv"], cwd=tmp_path, capture_output=True, text=True)
+    assert rr.returncode == 0, rr.stdout + rr.stderr
+    mine = _strip((tmp_path / "u.csv").read_text().splitlines())
+    ref = _strip((tmp_path / "ur.csv").read_text().splitlines())
+    assert len(mine) == len(ref) and "# No free parameters for unit metric" in mine and "#         metric = unit_e" in mine
+    cm, cr = [x for x in mine if x.startswith("#")], [x for x in ref if x.startswith("#")]
+    assert [x for x in cm if "Step size" not in x] == [x for x in cr if "Step size" not in x]
+    dm = np.array([x.split(",") for x in mine if not x.startswith("#")][1:], dtype=float)
+    dr = np.array([x.split(",") for x in ref if not x.startswith("#")][1:], dtype=float)
+    assert np.array_equal(dm[:, 3:6], dr[:, 3:6]) and np.allclose(dm[:30], dr[:30], rtol=1e-9) and np.allclose(dm, dr, rtol=1e-4)
+
+
 def test_cli_errors(tmp_path):
     dj = _bernoulli_json(tmp_path)
     assert _cli("bernoulli", ["sample", "adapt", "delta=1.5"], tmp_path).returncode == 64

@@ -142,6 +142,29 @@ def test_lockstep_models_matched_stream_vs_oracle(name, data):
         assert _rel(d[c, :K], r["draws"][:K], floor=1e-6) < 1e-5
 
 
+def test_sibling_services_vs_oracle():
+    """hmc_nuts_unit_e_adapt / hmc_nuts_unit_e / hmc_nuts_diag_e (Python mirrors of the reference services) against the
+    oracle configured the same way (the oracle's unit_e / no-adapt paths are pinned to the compiled reference's
+    metric=unit_e and adapt engaged=0 output in tests/test_oracle.py)."""
+    import cmdstan_b200 as B
+    data = cases.EIGHT_SCHOOLS
+    m = O.Model("eight_schools_nc", data)
+    kw = dict(num_chains=2, random_seed=31, init_chain_id=4, num_warmup=100, num_samples=40, save_warmup=True)
+    for fn, okw in ((B.hmc_nuts_unit_e_adapt, dict(unit_e=1)), (B.hmc_nuts_unit_e, dict(unit_e=1, adapt_engaged=0, stepsize=0.2)),
+                    (B.hmc_nuts_diag_e, dict(adapt_engaged=0, stepsize=0.2))):
+        extra = {} if fn is B.hmc_nuts_unit_e_adapt else dict(stepsize=0.2)
+        rc, res = fn("eight_schools_nc", data, **kw, **extra)
+        assert rc == 0 and res["columns"][7:9] == ["mu", "tau"]
+        for c in range(2):
+            r = O.run_chain(m, seed=31, chain_id=4 + c, num_warmup=100, num_samples=40, save_warmup=1, **okw)
+            ref = np.concatenate([r["draws"][:, :7], m.write_array(r["draws"][:, 7:])], axis=1)
+            assert np.array_equal(res["draws"][c, :10, 3:6], ref[:10, 3:6]) and _rel(res["draws"][c, :10], ref[:10], floor=1e-6) < 1e-8
+            if okw.get("unit_e"):
+                assert (res["inv_metric"][c] == 1.0).all()
+            if not okw.get("adapt_engaged", 1):
+                assert (res["draws"][c, :, 2] == 0.2).all()
+
+
 def test_run_in_pieces_equals_one_run():
     data = cases.EIGHT_SCHOOLS
     import cmdstan_b200 as B

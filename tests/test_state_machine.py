@@ -21,6 +21,8 @@ OPTS = [
     dict(seed=11, chain_id=4, num_warmup=0, num_samples=40, adapt_engaged=0, stepsize=0.3),
     dict(seed=12, chain_id=2, num_warmup=100, num_samples=20, init_radius=0.0),
     dict(seed=13, chain_id=2, num_warmup=100, num_samples=20, term_buffer=0, init_buffer=50, window=50),
+    dict(seed=14, chain_id=3, num_warmup=200, num_samples=50, unit_e=1, save_warmup=1),            # hmc_nuts_unit_e_adapt
+    dict(seed=15, chain_id=1, num_warmup=20, num_samples=50, unit_e=1, adapt_engaged=0, stepsize=0.2),  # hmc_nuts_unit_e
 ]
 
 
