@@ -14,10 +14,11 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "nccl_unique_id"]
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id"]
 
 MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
 ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
+SUMMARY_COLUMNS = ["Mean", "MCSE", "StdDev", "MAD", "5%", "50%", "95%", "ESS_bulk", "ESS_tail", "R_hat"]
 SAMPLER_COLUMNS = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
 
 # stan::services::error_codes (stan/src/stan/services/error_codes.hpp)
@@ -40,7 +41,7 @@ EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b2
            "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
            "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_rows_saved",
            "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
-           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init"]
+           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws"]
 
 _lib = None
 
@@ -87,6 +88,8 @@ def load_library(build=True):
     lib.b200nuts_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     lib.b200nuts_nccl_get_unique_id.argtypes = [vp]
     lib.b200nuts_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.b200nuts_summary.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp]
+    lib.b200nuts_summarize_draws.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_char_p, C.c_int]
     _lib = lib
     return lib
 
@@ -115,6 +118,20 @@ def nccl_unique_id():
     if rc:
         raise B200NutsError(rc, lib.b200nuts_last_error(None).decode())
     return buf.raw
+
+
+def summarize_draws(draws, device=0):
+    """stansummary's table (columns SUMMARY_COLUMNS) of host draws [chains, rows, ncols], computed on the GPU."""
+    lib = load_library()
+    a = np.ascontiguousarray(draws, dtype=np.float64)
+    assert a.ndim == 3
+    out = np.empty((a.shape[2], lib.b200nuts_summary_num_stats()))
+    err = C.create_string_buffer(512)
+    rc = lib.b200nuts_summarize_draws(a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], a.shape[2], int(device),
+                                      out.ctypes.data_as(C.c_void_p), err, 512)
+    if rc:
+        raise B200NutsError(rc, err.value.decode())
+    return out
 
 
 def _np(a, dt):
@@ -233,6 +250,14 @@ class Engine:
         if out is None:
             out = np.empty((nchains, nrows, 7 + k))
         self._chk(self.lib.b200nuts_fetch_draws(self.h, chain0, nchains, row0, nrows, int(constrained), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def summary(self, row0=0, nrows=None, constrained=True):
+        """stansummary's table computed on the device from the stored draws: [7 + K, 10] with columns SUMMARY_COLUMNS."""
+        nrows = self.rows_saved() - row0 if nrows is None else nrows
+        k = self.K if constrained else self.D
+        out = np.empty((7 + k, self.lib.b200nuts_summary_num_stats()))
+        self._chk(self.lib.b200nuts_summary(self.h, row0, nrows, int(constrained), out.ctypes.data_as(C.c_void_p)))
         return out
 
     def adaptation(self):

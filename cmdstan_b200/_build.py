@@ -17,7 +17,7 @@ CLI = os.path.join(BIN, "b200stan")
 CLI_MODELS = ["std_normal", "bernoulli", "eight_schools_nc", "logistic", "irt_2pl", "poisson_glm"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-UNITS = [("engine.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", [])]
+UNITS = [("engine.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", []), ("summary.cu", [])]
 
 
 def _nvcc():

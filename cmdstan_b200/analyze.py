@@ -51,8 +51,11 @@ def autocovariance(x):
     while m < 2 * n:
         m *= 2
     f = torch.fft.rfft(xc, n=m, dim=1)
-    ac = torch.fft.irfft(f * torch.conj(f), n=m, dim=1)[:, :n]
-    return ac / n
+    ac = torch.fft.irfft(f * torch.conj(f), n=m, dim=1)[:, :n] / n
+    # the reference normalises by ac(0) before scaling by the variance (autocovariance.hpp:52-53): a chain without
+    # variance yields NaN at every lag (this is what makes ess() of a one-sided tail indicator come out as S/2)
+    const = (xc == 0).all(dim=1)
+    return torch.where(const[:, None], torch.full_like(ac, float("nan")), ac)
 
 
 def ess(x):
@@ -123,8 +126,22 @@ def mcse_sd(draws):
     return math.sqrt(varvar / evar / 4.0)
 
 
+def _approx_const(x, val):
+    """Eigen isApproxToConstant(val, 1e-12): |x - val| <= min(|x|, |val|) * 1e-12 for every coefficient."""
+    return bool(((x - val).abs() <= torch.minimum(x.abs(), val.abs()) * 1e-12).all())
+
+
 def _ok(s):
-    return bool(torch.isfinite(s).all()) and bool((s != s.reshape(-1)[0]).any())
+    """is_finite_and_varies (stan/src/stan/analyze/mcmc/check_chains.hpp:27-48): every draw finite, no chain constant,
+    and (more than one chain) the chains' first draws not all equal.  s [chains, draws]."""
+    if not bool(torch.isfinite(s).all()):
+        return False
+    for c in range(s.shape[0]):
+        if _approx_const(s[c], s[c, 0]):
+            return False
+    if s.shape[0] > 1 and _approx_const(s[:, 0], s[0, 0]):
+        return False
+    return True
 
 
 def ess_bulk(draws):
@@ -144,7 +161,7 @@ def ess_tail(draws):
     for prob, op in ((0.05, torch.le), (0.95, torch.ge)):
         qv = torch.quantile(flat, prob)
         ind = op(s, qv).to(torch.float64)
-        out.append(ess(ind) if _ok(ind) else float("nan"))
+        out.append(ess(ind))
     out = [v for v in out if not math.isnan(v)]
     return min(out) if out else float("nan")
 
@@ -155,9 +172,30 @@ def split_rhat(draws):
     if s.shape[1] < 4 or not _ok(s):
         return float("nan")
     bulk = rhat(rank_transform(s))
-    med = torch.median(s.reshape(-1))
+    med = torch.quantile(s.reshape(-1), 0.5)   # math::quantile (interpolating), not the lower median
     tail = rhat(rank_transform(torch.abs(s - med)))
     return max(bulk, tail)
+
+
+def mad(draws):
+    """chainset::med_abs_deviation (stan/src/stan/mcmc/chainset.hpp:266-276): 1.4826 * median(|x - median(x)|), pooled."""
+    x = torch.as_tensor(draws).to(torch.float64).reshape(-1)
+    return 1.4826 * float(torch.quantile((x - torch.quantile(x, 0.5)).abs(), 0.5))
+
+
+def stansummary_table(draws):
+    """draws [chains, rows, ncols] -> [ncols, 10] table in stansummary's column order (Mean, MCSE, StdDev, MAD, 5%, 50%,
+    95%, ESS_bulk, ESS_tail, R_hat; src/cmdstan/stansummary_helper.hpp:405-428).  CPU/torch restatement used to check the
+    on-device b200nuts_summary; pinned to the compiled reference by tests/golden/ref_stansummary_full.npz."""
+    t = torch.as_tensor(draws).to(torch.float64)
+    rows = []
+    for k in range(t.shape[2]):
+        x = t[:, :, k]
+        flat = x.reshape(-1)
+        q = torch.quantile(flat, torch.tensor([0.05, 0.5, 0.95], dtype=torch.float64))
+        rows.append([float(flat.mean()), mcse_mean(x), float(flat.std(unbiased=True)), mad(x), float(q[0]), float(q[1]), float(q[2]),
+                     ess_bulk(x), ess_tail(x), split_rhat(x)])
+    return torch.tensor(rows, dtype=torch.float64).numpy()
 
 
 def summarize(draws, columns=None, device=None):

@@ -26,6 +26,7 @@
 #include "host_seed.h"
 #include "kernels.h"
 #include "nuts.cuh"
+#include "summary.h"
 
 using namespace b200;
 
@@ -980,6 +981,74 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
   }
   cudaFree(d_out);
   return B200NUTS_OK;
+}
+
+int b200nuts_summary_num_stats(void) { return kSummaryStats; }
+
+int b200nuts_summary(b200nuts_engine* e, int64_t row0, int64_t nrows, int constrained, double* out) {
+  if (!e->chains_ready || !e->dc.draws) { e->err = "no draws are stored (store_draws=0 or chains not initialised)"; return B200NUTS_USAGE; }
+  if (row0 < 0 || nrows < 0 || row0 + nrows > e->scfg.rows_per_chain) { e->err = "summary: range out of bounds"; return B200NUTS_USAGE; }
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  SummaryArgs a;
+  a.draws = e->dc.draws;
+  a.draws_stride = e->dc.draws_stride;
+  a.ncol = e->scfg.ncol;
+  a.kind = e->md.kind;
+  a.D = e->D;
+  a.N = e->md.N;
+  a.K = e->md.K;
+  a.K_out = e->K_out;
+  a.constrained = constrained;
+  a.C = e->C;
+  a.row0 = row0;
+  a.n = nrows;
+  a.stream = e->stream;
+  return summary_run(a, out, &e->err);
+}
+
+int b200nuts_summarize_draws(const double* draws, int64_t chains, int64_t rows, int64_t ncols, int device, double* out, char* errbuf,
+                             int errlen) {
+  std::string err;
+  int rc = B200NUTS_OK;
+  double* d = nullptr;
+  cudaStream_t st = nullptr;
+  auto fail = [&](const std::string& m, int code) {
+    err = m;
+    rc = code;
+  };
+  int ndev = 0;
+  if (chains < 1 || rows < 2 || ncols < 1) fail("summarize_draws: chains >= 1, rows >= 2, ncols >= 1 required", B200NUTS_USAGE);
+  else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail("no CUDA device available (libb200nuts has no CPU path)", B200NUTS_SOFTWARE);
+  else if (device < 0 || device >= ndev) fail("device ordinal out of range", B200NUTS_USAGE);
+  else if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) fail("cudaSetDevice / cudaStreamCreate failed", B200NUTS_SOFTWARE);
+  else {
+    const size_t bytes = sizeof(double) * (size_t)chains * rows * ncols;
+    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemcpyAsync(d, draws, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      fail("summarize_draws: cannot upload the draws", B200NUTS_SOFTWARE);
+    } else {
+      SummaryArgs a;
+      a.draws = d;
+      a.draws_stride = (size_t)rows * ncols;
+      a.ncol = (int)ncols;
+      a.kind = MODEL_STD_NORMAL;
+      a.D = (int)ncols - 7;
+      a.N = a.K = 0;
+      a.K_out = a.D;
+      a.constrained = 0;
+      a.C = chains;
+      a.row0 = 0;
+      a.n = rows;
+      a.stream = st;
+      rc = summary_run(a, out, &err);
+    }
+  }
+  if (d) cudaFree(d);
+  if (st) cudaStreamDestroy(st);
+  if (rc && errbuf && errlen > 0) {
+    std::strncpy(errbuf, err.c_str(), (size_t)errlen - 1);
+    errbuf[errlen - 1] = 0;
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -180,4 +180,29 @@ B200_HD void model_write_array(int kind, int D, int N, int K, const double* q, d
   }
 }
 
+// one column of write_array (same arithmetic as model_write_array): lets the on-device posterior summary read a
+// constrained output column straight from the stored unconstrained draw without materialising the whole row
+B200_HD double model_output_column(int kind, int D, int N, int K, const double* q, int k) {
+  switch (kind) {
+    case MODEL_BERNOULLI: {
+      double out;
+      model_write_array(kind, D, N, K, q, &out);
+      return out;
+    }
+    case MODEL_EIGHT_SCHOOLS: {
+      const int J = N;
+      if (k == 1) return exp(q[1]);
+      if (k < 2 + J) return q[k];
+      return q[0] + exp(q[1]) * q[k - J];
+    }
+    case MODEL_IRT2PL: {
+      const int I = N, J = K;
+      const bool positive = k == 0 || k == 1 + I || (k >= 2 + I && k < 2 + I + J) || k == 3 + I + J;
+      return positive ? exp(q[k]) : q[k];
+    }
+    default:
+      return q[k];
+  }
+}
+
 }  // namespace b200

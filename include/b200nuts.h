@@ -125,6 +125,18 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
                          double* out);
 int64_t b200nuts_rows_saved(const b200nuts_engine* e); /* rows every chain has saved so far (min over chains) */
 
+/* On-device posterior summary of the saved rows [row0, row0+nrows) of all chains of this engine: the table the reference's
+   `stansummary` prints (src/cmdstan/stansummary_helper.hpp:405-428), computed from the draws where they live in HBM
+   (stan/src/stan/analyze/mcmc/{split_chains,rank_normalization,autocovariance,ess,rhat,mcse}.hpp, stan/mcmc/chainset.hpp).
+   out[7 + K][b200nuts_summary_num_stats()] row-major, one row per output column (the 7 sampler columns first), columns
+   Mean, MCSE, StdDev, MAD, 5%, 50%, 95%, ESS_bulk, ESS_tail, R_hat. */
+int b200nuts_summary_num_stats(void);
+int b200nuts_summary(b200nuts_engine* e, int64_t row0, int64_t nrows, int constrained, double* out);
+/* the same table for draws held by the caller (e.g. read back from Stan CSV files, as bin/stansummary does):
+   draws[chains][rows][ncols] row-major host memory -> out[ncols][num_stats]; the message of a failure is copied to errbuf */
+int b200nuts_summarize_draws(const double* draws, int64_t chains, int64_t rows, int64_t ncols, int device, double* out,
+                             char* errbuf, int errlen);
+
 /* adapted step size [num_chains] and inverse metric [num_chains][D] ("# Step size", "# Diagonal elements ...") */
 int b200nuts_get_adaptation(b200nuts_engine* e, double* stepsize, double* inv_metric);
 /* per-chain status: error code (0 ok, 78 init failed, 70 step-size / metric failure), iterations done, leapfrog

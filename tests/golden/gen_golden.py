@@ -74,7 +74,7 @@ def main():
     print("written:", os.listdir(HERE))
 
 
-if __name__ == "__main__" and "--unit-e" not in sys.argv:
+if __name__ == "__main__" and "--unit-e" not in sys.argv and "--summary" not in sys.argv:
     main()
 
 
@@ -94,3 +94,31 @@ def gen_unit_e():
 
 if __name__ == "__main__" and "--unit-e" in sys.argv:
     gen_unit_e()
+
+
+def gen_summary():
+    """Full-precision stansummary tables (stansummary -s 12 -c table.csv) of the compiled reference, with the draws they
+    were computed from: golden input/output of the posterior-summary restatements (cmdstan_b200/analyze.py and the
+    on-device b200nuts_summary).  One case with an even and one with an odd number of draws per chain."""
+    import csv
+    import tempfile
+    out = {}
+    for tag, name, data, kw in (("bernoulli_even", "bernoulli", cases.BERNOULLI, dict(num_chains=4, seed=1234, num_warmup=300, num_samples=400)),
+                                ("eight_schools_odd", "eight_schools_nc", cases.EIGHT_SCHOOLS, dict(num_chains=5, seed=77, num_warmup=300, num_samples=201))):
+        res, _, files = O.ref_sample(name, data, sig_figs=18, **kw)
+        td = tempfile.mkdtemp()
+        tab = os.path.join(td, "table.csv")
+        subprocess.run([os.path.join(O.REF, "stansummary"), "-s", "12", "-c", tab] + files, capture_output=True, text=True, check=True)
+        rows = [r for r in csv.reader(l for l in open(tab) if not l.startswith("#"))]
+        hdr, body = rows[0], rows[1:]
+        out[tag + "_columns"] = np.array(res[0][0])
+        out[tag + "_draws"] = np.stack([r[1] for r in res])
+        out[tag + "_stat_names"] = np.array(hdr[1:])
+        out[tag + "_row_names"] = np.array([r[0] for r in body])
+        out[tag + "_table"] = np.array([[float(v) if v not in ("nan", "-nan", "") else np.nan for v in r[1:]] for r in body])
+    np.savez_compressed(os.path.join(HERE, "ref_stansummary_full.npz"), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__" and "--summary" in sys.argv:
+    gen_summary()
