@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id"]
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id", "load_model_library", "find_model"]
 
 MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
 ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
@@ -41,7 +41,9 @@ EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b2
            "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
            "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_rows_saved",
            "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
-           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws"]
+           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
+           # include/b200nuts_model.h
+           "b200nuts_register_model", "b200nuts_load_model_library", "b200nuts_find_model", "b200nuts_output_name"]
 
 _lib = None
 
@@ -90,8 +92,31 @@ def load_library(build=True):
     lib.b200nuts_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.b200nuts_summary.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp]
     lib.b200nuts_summarize_draws.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_char_p, C.c_int]
+    lib.b200nuts_register_model.argtypes = [vp]
+    lib.b200nuts_load_model_library.argtypes = [C.c_char_p]
+    lib.b200nuts_find_model.argtypes = [C.c_char_p]
+    lib.b200nuts_output_name.argtypes = [vp, C.c_int64, C.c_char_p, C.c_int]
     _lib = lib
     return lib
+
+
+def load_model_library(path):
+    """Registers the device models of a plug-in library (include/b200nuts_model.h: a .so built with nvcc that exports
+    b200nuts_model_entry) and returns the id of its first model.  The device-side counterpart of linking a stanc-generated
+    model into CmdStan (new_model, src/cmdstan/command.hpp:71-73)."""
+    lib = load_library()
+    rc = lib.b200nuts_load_model_library(os.fsencode(path))
+    if rc < 0:
+        raise B200NutsError(-rc, lib.b200nuts_last_error(None).decode())
+    return rc
+
+
+def find_model(name):
+    """id of a built-in or registered plug-in model by model_name(); raises KeyError when unknown."""
+    rc = load_library().b200nuts_find_model(name.encode())
+    if rc < 0:
+        raise KeyError(name)
+    return rc
 
 
 def _point_at_bundled_nccl():
@@ -148,7 +173,7 @@ class Engine:
         self.lib = load_library()
         cfg = Config()
         self.lib.b200nuts_default_config(C.byref(cfg))
-        cfg.model = MODELS[model] if isinstance(model, str) else int(model)
+        cfg.model = (MODELS[model] if model in MODELS else find_model(model)) if isinstance(model, str) else int(model)
         cfg.num_chains, cfg.random_seed, cfg.init_chain_id = int(num_chains), int(random_seed), int(init_chain_id)
         cfg.init_radius, cfg.num_warmup, cfg.num_samples, cfg.num_thin = float(init_radius), int(num_warmup), int(num_samples), int(num_thin)
         cfg.save_warmup, cfg.stepsize, cfg.stepsize_jitter, cfg.max_depth = int(bool(save_warmup)), float(stepsize), float(stepsize_jitter), int(max_depth)
@@ -260,6 +285,15 @@ class Engine:
         self._chk(self.lib.b200nuts_summary(self.h, row0, nrows, int(constrained), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def output_names(self):
+        """constrained_param_names() of the engine's model (built-in or plug-in)."""
+        buf = C.create_string_buffer(256)
+        names = []
+        for k in range(self.K):
+            self._chk(self.lib.b200nuts_output_name(self.h, k, buf, 256))
+            names.append(buf.value.decode())
+        return names
+
     def adaptation(self):
         eps = np.empty(self.num_chains)
         im = np.empty((self.num_chains, self.D))
@@ -327,10 +361,7 @@ def _run_service(model, data, num_chains, init, init_inv_metric, random_seed, in
             return code, None
         eps, im = e.adaptation()
         draws = e.fetch_draws()
-        try:
-            names = SAMPLER_COLUMNS + param_names(model, data)
-        except KeyError:
-            names = SAMPLER_COLUMNS + [f"v{i + 1}" for i in range(e.K)]
+        names = SAMPLER_COLUMNS + e.output_names()
         return OK, dict(draws=draws, columns=names, stepsize=eps, inv_metric=im, timing=dict(warmup=warm_s, sampling=samp_s), n_grad=ng)
     except B200NutsError as ex:
         log(str(ex))

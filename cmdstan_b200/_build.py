@@ -17,6 +17,8 @@ CLI = os.path.join(BIN, "b200stan")
 CLI_MODELS = ["std_normal", "bernoulli", "eight_schools_nc", "logistic", "irt_2pl", "poisson_glm"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+EXAMPLES = os.path.join(HERE, "..", "examples", "plugin_models")
+EXAMPLE_PLUGIN = os.path.join(EXAMPLES, "libb200models_example.so")
 UNITS = [("engine.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", []), ("summary.cu", [])]
 
 
@@ -25,7 +27,8 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")] + [os.path.join(HERE, "..", "include", "b200nuts.h")]
+    inc = os.path.join(HERE, "..", "include")
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")] + [os.path.join(inc, "b200nuts.h"), os.path.join(inc, "b200nuts_model.h")]
 
 
 def host_sources():
@@ -57,6 +60,19 @@ def build_cli():
     return CLI
 
 
+def build_example_plugins(force=False):
+    """examples/plugin_models/libb200models_example.so: user-written device models behind include/b200nuts_model.h
+    (also the fixture of tests/test_gpu_plugin.py).  --fmad=false like the sampler TU (the eight-schools twin must round
+    like the built-in)."""
+    src = os.path.join(EXAMPLES, "example_models.cu")
+    deps = [src, os.path.join(CSRC, "models.cuh"), os.path.join(CSRC, "warp.cuh"), os.path.join(HERE, "..", "include", "b200nuts_model.h")]
+    if not force and os.path.exists(EXAMPLE_PLUGIN) and all(os.path.getmtime(d) <= os.path.getmtime(EXAMPLE_PLUGIN) for d in deps):
+        return EXAMPLE_PLUGIN
+    cmd = [_nvcc()] + ARCH + COMMON + ["--fmad=false", "-shared", src, "-o", EXAMPLE_PLUGIN]
+    subprocess.check_call(cmd)
+    return EXAMPLE_PLUGIN
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
@@ -76,6 +92,7 @@ def build(force=False, verbose=False):
     cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
     subprocess.check_call(cmd)
     build_cli()
+    build_example_plugins(force)
     return LIB
 
 

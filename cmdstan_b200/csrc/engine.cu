@@ -19,10 +19,12 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/b200nuts.h"
+#include "../../include/b200nuts_model.h"
 #include "host_seed.h"
 #include "kernels.h"
 #include "nuts.cuh"
@@ -33,6 +35,26 @@ using namespace b200;
 namespace {
 
 std::string g_create_error;
+
+// ---- plug-in models (include/b200nuts_model.h): registry shared by all engines of the process
+constexpr int MODEL_PLUGIN = B200NUTS_MODEL_PLUGIN_BASE;  // ModelData::kind of every plug-in model
+std::mutex g_plugin_mutex;
+std::vector<const b200nuts_model_vtable*> g_plugins;       // id = B200NUTS_MODEL_PLUGIN_BASE + index
+const char* const kBuiltinNames[] = {"std_normal", "bernoulli", "eight_schools_nc", "logistic", "irt_2pl", "poisson_glm"};
+
+const b200nuts_model_vtable* plugin_by_id(int id) {
+  std::lock_guard<std::mutex> lk(g_plugin_mutex);
+  const int i = id - B200NUTS_MODEL_PLUGIN_BASE;
+  return (i >= 0 && i < (int)g_plugins.size()) ? g_plugins[i] : nullptr;
+}
+
+struct PluginVar {  // one data variable of a plug-in model, kept on the host until the model is created
+  std::string name;
+  int dtype;
+  std::vector<int64_t> dims;
+  std::vector<unsigned char> bytes;
+};
+
 struct ncclUniqueIdBlob {  // ncclUniqueId: 128 opaque bytes, passed by value
   char bytes[128];
 };
@@ -200,6 +222,7 @@ __global__ void fetch_kernel(const double* draws, size_t draws_stride, int ncol,
   const int kout = constrained ? K_out : D;
   double* dst = out + (size_t)idx * (7 + kout);
   for (int i = 0; i < 7; i++) dst[i] = src[i];
+  if (constrained && kind < 0) return;  // plug-in model: its write_array is launched by the host
   if (constrained) model_write_array(kind, D, N, K, src + 7, dst + 7);
   else for (int i = 0; i < D; i++) dst[7 + i] = src[7 + i];
 }
@@ -266,6 +289,10 @@ struct b200nuts_engine {
   std::vector<int8_t> h_y8;
   int64_t x_rows = 0, x_cols = 0, y8_rows = 0, y8_cols = 0;
   int std_normal_D = 3;
+  // plug-in model (cfg.model >= B200NUTS_MODEL_PLUGIN_BASE)
+  const b200nuts_model_vtable* plug = nullptr;
+  void* plug_model = nullptr;
+  std::vector<PluginVar> plug_data;
   // device
   double *d_X = nullptr, *d_yr = nullptr, *d_sigma = nullptr;
   int* d_yi = nullptr;
@@ -325,7 +352,10 @@ int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
   *out = nullptr;
   // argument validation mirrors the reference's argument tree (src/cmdstan/arguments/arg_*.hpp is_valid)
   if (cfg->num_chains < 1) { g_create_error = "num_chains must be >= 1"; return B200NUTS_USAGE; }
-  if (cfg->model < 0 || cfg->model > 5) { g_create_error = "unknown model"; return B200NUTS_USAGE; }
+  const b200nuts_model_vtable* plug = cfg->model >= B200NUTS_MODEL_PLUGIN_BASE ? plugin_by_id(cfg->model) : nullptr;
+  if (cfg->model < 0 || (cfg->model > 5 && !plug)) { g_create_error = "unknown model"; return B200NUTS_USAGE; }
+  if (plug && cfg->engine == B200NUTS_ENGINE_FUSED) { g_create_error = "plug-in models run in the lock-step engine"; return B200NUTS_CONFIG; }
+  if (plug && cfg->row_shards > 1) { g_create_error = "row sharding is available for the built-in GLMs only"; return B200NUTS_CONFIG; }
   if (cfg->num_warmup < 0 || cfg->num_samples < 0 || cfg->num_thin < 1) { g_create_error = "num_warmup/num_samples must be >= 0 and thin >= 1"; return B200NUTS_USAGE; }
   if (cfg->max_depth < 1 || cfg->max_depth > kMaxDepthCap) { g_create_error = "max_depth must be in 1..16"; return B200NUTS_USAGE; }
   if (cfg->adapt_engaged && cfg->num_warmup == 0) {  // command.hpp:569-574
@@ -348,6 +378,7 @@ int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
   auto* e = new b200nuts_engine();
   e->cfg = *cfg;
   e->C = cfg->num_chains;
+  e->plug = plug;
   if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
     g_create_error = "cudaSetDevice / cudaStreamCreate failed";
     delete e;
@@ -357,7 +388,7 @@ int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
   cudaEventCreate(&e->ev1);
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   std::memset(&e->md, 0, sizeof e->md);
-  e->md.kind = cfg->model;
+  e->md.kind = plug ? MODEL_PLUGIN : cfg->model;
   *out = e;
   return B200NUTS_OK;
 }
@@ -367,6 +398,7 @@ static void free_dev(void* p) { if (p) cudaFree(p); }
 void b200nuts_destroy(b200nuts_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
+  if (e->plug && e->plug_model && e->plug->destroy) e->plug->destroy(e->plug_model);
   free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8);
   free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws);
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
@@ -385,7 +417,25 @@ static int64_t prod(const int64_t* dims, int nd) {
   return p;
 }
 
+// plug-in models: keep the variable as given; the model's create() validates and uploads it
+static int plugin_set_data(b200nuts_engine* e, const char* name, int dtype, const void* host, const int64_t* dims, int nd) {
+  static const size_t kSize[3] = {8, 4, 1};
+  if (nd < 0 || nd > 8) { e->err = "set_data: 0 <= nd <= 8 required"; return B200NUTS_DATAERR; }
+  PluginVar v;
+  v.name = name;
+  v.dtype = dtype;
+  v.dims.assign(dims, dims + nd);
+  const size_t bytes = (size_t)prod(dims, nd) * kSize[dtype];
+  v.bytes.assign((const unsigned char*)host, (const unsigned char*)host + bytes);
+  for (auto& o : e->plug_data)
+    if (o.name == v.name) { o = std::move(v); e->data_ready = false; return B200NUTS_OK; }
+  e->plug_data.push_back(std::move(v));
+  e->data_ready = false;
+  return B200NUTS_OK;
+}
+
 int b200nuts_set_data_f64(b200nuts_engine* e, const char* name, const double* host, const int64_t* dims, int nd) {
+  if (e->plug) return plugin_set_data(e, name, B200NUTS_F64, host, dims, nd);
   const std::string n(name);
   const int64_t cnt = prod(dims, nd);
   if (n == "X" && nd == 2) {
@@ -407,6 +457,7 @@ int b200nuts_set_data_f64(b200nuts_engine* e, const char* name, const double* ho
 }
 
 int b200nuts_set_data_i32(b200nuts_engine* e, const char* name, const int32_t* host, const int64_t* dims, int nd) {
+  if (e->plug) return plugin_set_data(e, name, B200NUTS_I32, host, dims, nd);
   const std::string n(name);
   const int64_t cnt = prod(dims, nd);
   if (n == "y") {
@@ -429,6 +480,7 @@ int b200nuts_set_data_i32(b200nuts_engine* e, const char* name, const int32_t* h
 }
 
 int b200nuts_set_data_i8(b200nuts_engine* e, const char* name, const int8_t* host, const int64_t* dims, int nd) {
+  if (e->plug) return plugin_set_data(e, name, B200NUTS_I8, host, dims, nd);
   const std::string n(name);
   if (n == "y" && nd == 2 && e->cfg.model == B200NUTS_IRT_2PL) {
     const int64_t cnt = prod(dims, nd);
@@ -449,6 +501,29 @@ static int finalize_data(b200nuts_engine* e) {
   if (e->data_ready) return B200NUTS_OK;
   CUDA_TRY(e, cudaSetDevice(e->cfg.device));
   ModelData& m = e->md;
+  if (e->plug) {  // new_model() of a plug-in: it validates + uploads its own data
+    if (e->plug_model && e->plug->destroy) e->plug->destroy(e->plug_model);
+    e->plug_model = nullptr;
+    std::vector<b200nuts_data_view> views;
+    for (auto& v : e->plug_data) views.push_back(b200nuts_data_view{v.name.c_str(), v.dtype, (int32_t)v.dims.size(), v.dims.data(), v.bytes.data()});
+    int64_t D = 0, K_out = 0;
+    char msg[512] = {0};
+    const int rc = e->plug->create(views.data(), (int)views.size(), e->cfg.device, &e->plug_model, &D, &K_out, msg, (int)sizeof msg);
+    if (rc != B200NUTS_OK) {
+      e->err = std::string(e->plug->name) + ": " + (msg[0] ? msg : "model construction failed");
+      e->plug_model = nullptr;
+      return rc > 0 ? rc : B200NUTS_DATAERR;
+    }
+    if (D < 1 || K_out < 0 || (!e->plug->write_array && K_out != D)) { e->err = std::string(e->plug->name) + ": bad num_params_r / num_outputs"; return B200NUTS_CONFIG; }
+    m.kind = MODEL_PLUGIN;
+    m.D = (int)D;
+    e->D = m.D;
+    e->ld = (m.D + 3) & ~3;
+    e->K_out = (int)K_out;
+    e->fused = false;
+    e->data_ready = true;
+    return B200NUTS_OK;
+  }
   const int kind = e->cfg.model;
   m.kind = kind;
   auto upload = [&](void** dptr, const void* src, size_t bytes) -> cudaError_t {
@@ -736,7 +811,11 @@ int b200nuts_init_chains(b200nuts_engine* e) {
 }
 
 // gradient stage of the lock-step engine; returns the number of kernels launched
-static int launch_gradient(b200nuts_engine* e, const GradBatch& b) {
+static int launch_gradient(b200nuts_engine* e, const GradBatch& b, int jacobian = 1) {
+  if (e->plug) {
+    const int n = e->plug->log_prob_grad(e->plug_model, b.Q, b.G, b.zV, b.list, b.n_list, b.C, b.ld, jacobian, (void*)e->stream);
+    return n > 0 ? n : 0;
+  }
   switch (e->md.kind) {
     case MODEL_LOGISTIC:
     case MODEL_POISSON:
@@ -855,8 +934,8 @@ int b200nuts_log_prob_grad(b200nuts_engine* e, const double* q, int64_t n, int j
     for (int i = 0; i < m; i++) std::memcpy(hq.data() + (size_t)i * ld, q + (size_t)(off + i) * D, sizeof(double) * D);
     cudaMemcpyAsync(dQ, hq.data(), sizeof(double) * m * ld, cudaMemcpyHostToDevice, e->stream);
     GradBatch b{dQ, dG, dV, nullptr, m, ld};
-    launch_gradient(e, b);
-    if (!jacobian) remove_jacobian_kernel<<<(m + 127) / 128, 128, 0, e->stream>>>(e->md.kind, D, e->md.N, e->md.K, dQ, dG, dV, m, ld);
+    launch_gradient(e, b, jacobian);
+    if (!jacobian && !e->plug) remove_jacobian_kernel<<<(m + 127) / 128, 128, 0, e->stream>>>(e->md.kind, D, e->md.N, e->md.K, dQ, dG, dV, m, ld);
     cudaMemcpyAsync(hg.data(), dG, sizeof(double) * m * ld, cudaMemcpyDeviceToHost, e->stream);
     cudaMemcpyAsync(hv.data(), dV, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream);
     cudaError_t r = cudaStreamSynchronize(e->stream);
@@ -967,9 +1046,17 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
   for (int64_t off = 0; off < nchains; off += chunk) {
     const int64_t m = std::min(chunk, nchains - off);
     const long long tot = m * nrows;
-    fetch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, e->stream>>>(e->dc.draws, e->dc.draws_stride, e->scfg.ncol, e->md.kind, e->D,
+    const bool plug_wa = constrained && e->plug && e->plug->write_array;
+    fetch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, e->stream>>>(e->dc.draws, e->dc.draws_stride, e->scfg.ncol, plug_wa ? -1 : e->md.kind, e->D,
                                                                        e->md.N, e->md.K, e->K_out, constrained, chain0 + off, m, row0,
                                                                        nrows, d_out);
+    if (plug_wa) {  // sampler columns are in place; the model's own write_array fills the rest (one call per chain: the
+                    // rows of a chain are contiguous in the draws buffer, rows of different chains are not)
+      for (int64_t c = 0; c < m; c++) {
+        const double* q = e->dc.draws + (size_t)(chain0 + off + c) * e->dc.draws_stride + (size_t)row0 * e->scfg.ncol + 7;
+        e->plug->write_array(e->plug_model, q, nrows, e->scfg.ncol, d_out + (size_t)c * nrows * (7 + kout) + 7, 7 + kout, (void*)e->stream);
+      }
+    }
     cudaMemcpyAsync(out + (size_t)off * nrows * (7 + kout), d_out, row_bytes * nrows * m, cudaMemcpyDeviceToHost, e->stream);
     cudaError_t r = cudaStreamSynchronize(e->stream);
     if (r == cudaSuccess) r = cudaGetLastError();
@@ -989,6 +1076,33 @@ int b200nuts_summary(b200nuts_engine* e, int64_t row0, int64_t nrows, int constr
   if (!e->chains_ready || !e->dc.draws) { e->err = "no draws are stored (store_draws=0 or chains not initialised)"; return B200NUTS_USAGE; }
   if (row0 < 0 || nrows < 0 || row0 + nrows > e->scfg.rows_per_chain) { e->err = "summary: range out of bounds"; return B200NUTS_USAGE; }
   CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  if (constrained && e->plug && e->plug->write_array) {
+    // plug-in model: materialise its write_array outputs next to the sampler columns (device to device), then summarise
+    const int ncol = 7 + e->K_out;
+    double* tmp = nullptr;
+    CUDA_TRY(e, cudaMalloc(&tmp, sizeof(double) * (size_t)e->C * nrows * ncol));
+    const long long tot = (long long)e->C * nrows;
+    fetch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, e->stream>>>(e->dc.draws, e->dc.draws_stride, e->scfg.ncol, -1, e->D, 0, 0, e->K_out, 1,
+                                                                       0, e->C, row0, nrows, tmp);
+    for (int64_t c = 0; c < e->C; c++)
+      e->plug->write_array(e->plug_model, e->dc.draws + (size_t)c * e->dc.draws_stride + (size_t)row0 * e->scfg.ncol + 7, nrows, e->scfg.ncol,
+                           tmp + (size_t)c * nrows * ncol + 7, ncol, (void*)e->stream);
+    SummaryArgs a;
+    a.draws = tmp;
+    a.draws_stride = (size_t)nrows * ncol;
+    a.ncol = ncol;
+    a.kind = MODEL_STD_NORMAL;
+    a.D = a.K_out = e->K_out;
+    a.N = a.K = 0;
+    a.constrained = 0;
+    a.C = e->C;
+    a.row0 = 0;
+    a.n = nrows;
+    a.stream = e->stream;
+    const int rc = summary_run(a, out, &e->err);
+    cudaFree(tmp);
+    return rc;
+  }
   SummaryArgs a;
   a.draws = e->dc.draws;
   a.draws_stride = e->dc.draws_stride;
@@ -1004,6 +1118,85 @@ int b200nuts_summary(b200nuts_engine* e, int64_t row0, int64_t nrows, int constr
   a.n = nrows;
   a.stream = e->stream;
   return summary_run(a, out, &e->err);
+}
+
+// ---- plug-in registry (include/b200nuts_model.h) -----------------------------------------------------------------------
+int b200nuts_register_model(const b200nuts_model_vtable* vt) {
+  if (!vt || vt->abi != B200NUTS_MODEL_ABI || !vt->name || !vt->create || !vt->log_prob_grad) {
+    g_create_error = "register_model: bad vtable (abi, name, create and log_prob_grad are required)";
+    return -B200NUTS_USAGE;
+  }
+  std::lock_guard<std::mutex> lk(g_plugin_mutex);
+  for (size_t i = 0; i < g_plugins.size(); i++)
+    if (std::strcmp(g_plugins[i]->name, vt->name) == 0) return B200NUTS_MODEL_PLUGIN_BASE + (int)i;
+  for (const char* b : kBuiltinNames)
+    if (std::strcmp(b, vt->name) == 0) { g_create_error = std::string("register_model: '") + vt->name + "' is a built-in model name"; return -B200NUTS_USAGE; }
+  g_plugins.push_back(vt);
+  return B200NUTS_MODEL_PLUGIN_BASE + (int)g_plugins.size() - 1;
+}
+
+int b200nuts_load_model_library(const char* path) {
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) {
+    const char* m = dlerror();
+    g_create_error = std::string("load_model_library: ") + (m ? m : path);
+    return -B200NUTS_NOINPUT;
+  }
+  auto entry = (b200nuts_model_entry_fn)dlsym(h, "b200nuts_model_entry");
+  if (!entry) { g_create_error = std::string("load_model_library: ") + path + " does not export b200nuts_model_entry"; return -B200NUTS_USAGE; }
+  int first = -1;
+  for (int i = 0;; i++) {
+    const b200nuts_model_vtable* vt = entry(i);
+    if (!vt) break;
+    const int id = b200nuts_register_model(vt);
+    if (id < 0) return id;
+    if (first < 0) first = id;
+  }
+  if (first < 0) { g_create_error = std::string("load_model_library: ") + path + " exports no models"; return -B200NUTS_USAGE; }
+  return first;  // the library stays loaded for the life of the process (its vtables are referenced by the registry)
+}
+
+int b200nuts_find_model(const char* name) {
+  for (int i = 0; i < 6; i++)
+    if (std::strcmp(kBuiltinNames[i], name) == 0) return i;
+  std::lock_guard<std::mutex> lk(g_plugin_mutex);
+  for (size_t i = 0; i < g_plugins.size(); i++)
+    if (std::strcmp(g_plugins[i]->name, name) == 0) return B200NUTS_MODEL_PLUGIN_BASE + (int)i;
+  return -1;
+}
+
+// constrained_param_names (include_tparams = true) of the built-in family: same names as the host model objects
+// (cmdstan_b200/host/model.hpp, cmdstan_b200.param_names)
+int b200nuts_output_name(b200nuts_engine* e, int64_t k, char* buf, int buflen) {
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  if (k < 0 || k >= e->K_out || !buf || buflen < 2) { e->err = "output_name: index out of range"; return B200NUTS_USAGE; }
+  if (e->plug) {
+    if (e->plug->output_name) return e->plug->output_name(e->plug_model, k, buf, buflen);
+    std::snprintf(buf, (size_t)buflen, "v%lld", (long long)k + 1);
+    return B200NUTS_OK;
+  }
+  const long long N = e->md.N, K = e->md.K, i = k;
+  auto vec = [&](const char* n, long long j) { std::snprintf(buf, (size_t)buflen, "%s.%lld", n, j + 1); };
+  auto sc = [&](const char* n) { std::snprintf(buf, (size_t)buflen, "%s", n); };
+  switch (e->md.kind) {
+    case MODEL_STD_NORMAL: vec("x", i); break;
+    case MODEL_BERNOULLI: sc("theta"); break;
+    case MODEL_EIGHT_SCHOOLS:
+      if (i == 0) sc("mu"); else if (i == 1) sc("tau"); else if (i < 2 + N) vec("theta_tilde", i - 2); else vec("theta", i - 2 - N);
+      break;
+    case MODEL_LOGISTIC:
+    case MODEL_POISSON:
+      if (i == 0) sc("alpha"); else vec("beta", i - 1);
+      break;
+    case MODEL_IRT2PL:
+      if (i == 0) sc("sigma_theta"); else if (i < 1 + N) vec("theta", i - 1); else if (i == 1 + N) sc("sigma_a");
+      else if (i < 2 + N + K) vec("a", i - 2 - N); else if (i == 2 + N + K) sc("mu_b"); else if (i == 3 + N + K) sc("sigma_b");
+      else vec("b", i - 4 - N - K);
+      break;
+    default: vec("v", i);
+  }
+  return B200NUTS_OK;
 }
 
 int b200nuts_summarize_draws(const double* draws, int64_t chains, int64_t rows, int64_t ncols, int device, double* out, char* errbuf,

@@ -14,9 +14,9 @@ ROOT = os.path.dirname(HERE)
 def test_header_symbols_are_exported():
     import cmdstan_b200 as B
     lib = B.load_library()
-    hdr = open(os.path.join(ROOT, "include", "b200nuts.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "b200nuts.h")).read() + open(os.path.join(ROOT, "include", "b200nuts_model.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(b200nuts_[a-z0-9_]+)\s*\(", hdr)) - {"b200nuts_allreduce_fn"}
+    declared = set(re.findall(r"\b(b200nuts_[a-z0-9_]+)\s*\(", hdr)) - {"b200nuts_allreduce_fn", "b200nuts_model_entry", "b200nuts_model_entry_fn"}
     assert declared == set(B.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
@@ -58,6 +58,34 @@ def test_no_cpu_fallback():
     assert ei.value.code == B.SOFTWARE and "no CUDA device" in str(ei.value)
     rc, res = B.hmc_nuts_diag_e_adapt("bernoulli", {"y": np.array([0, 1])})
     assert rc == B.SOFTWARE and res is None
+
+
+def test_plugin_registry_without_a_gpu():
+    """include/b200nuts_model.h: a plug-in library registers its models by name; ids start at 100; built-in names are kept;
+    a malformed vtable is refused; constructing an engine for a plug-in model still fails loudly without a device."""
+    import cmdstan_b200 as B
+    from cmdstan_b200 import _build
+    lib = B.load_library()
+    first = B.load_model_library(_build.build_example_plugins())
+    assert first >= 100 and B.find_model("linreg") == first and B.find_model("eight_schools_plugin") == first + 1
+    assert B.load_model_library(_build.EXAMPLE_PLUGIN) == first          # idempotent
+    assert [B.find_model(n) for n in B.MODELS] == list(B.MODELS.values())  # built-ins by name
+    with pytest.raises(KeyError):
+        B.find_model("no_such_model")
+    with pytest.raises(B.B200NutsError) as ei:
+        B.load_model_library("/nonexistent/libmodel.so")
+    assert ei.value.code == B.NOINPUT
+    with pytest.raises(B.B200NutsError) as ei:
+        B.load_model_library(_build.LIB)   # a library without b200nuts_model_entry
+    assert ei.value.code == B.USAGE
+    bad = (ctypes.c_uint32 * 16)(99)  # wrong abi
+    assert lib.b200nuts_register_model(ctypes.cast(bad, ctypes.c_void_p)) == -B.USAGE
+    assert lib.b200nuts_register_model(None) == -B.USAGE
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(B.B200NutsError) as ei:
+            B.Engine("linreg", {"X": np.zeros((3, 1)), "y": np.zeros(3)})
+        assert ei.value.code == B.SOFTWARE
 
 
 def test_product_never_imports_the_oracle():
