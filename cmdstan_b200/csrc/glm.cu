@@ -265,7 +265,7 @@ static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspa
                         cudaStream_t stream) {
   const int Dp = ws.Dp, C = b.C, P = ws.P;
   int launches = 0;
-  const bool tc = ws.variant == 1 && Dp <= glm_tc_max_dk();
+  const bool tc = ws.variant >= 1 && Dp <= glm_tc_max_dk();
   if (tc) {
     launches += launch_glm_dmma(m, b, ws, stream);
   } else {

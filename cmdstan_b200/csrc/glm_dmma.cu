@@ -318,6 +318,242 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
   }
 }
 
+
+// =====================================================================================================================
+// v3: the same fused product, with NO block-wide barrier in steady state (profiles/README.md r01c: with three
+// __syncthreads per tile all eight warps run the same phase at the same time, the link phase cannot saturate the shared
+// FP64 pipe on its own, and 24 % of its cycles idle).
+//
+//  * warp w (8 of them) owns the 8 chains [8w, 8w+8) of the chain tile for ALL 64 rows of the row tile: phase A 8 row
+//    blocks x 1 chain block, link on its own accumulators, derivative tile Dw[64][8] in its private slice of shared
+//    memory, phase B Dk/8 design-column blocks x 1 chain block.  Its phase-B operand is produced by itself, so a
+//    __syncwarp replaces the __syncthreads; the log-likelihood partial needs only shuffles;
+//  * nobody waits to refill a buffer: a warp that is done with X buffer `buf` bumps a shared counter, and the LAST warp to
+//    do so issues the TMA bulk copies of the tile two iterations ahead into that buffer (same for the q tile of the next
+//    chain tile after phase A of the last row tile).  Consumers only ever wait on the "full" mbarriers;
+//  * warps therefore drift apart by up to one tile: while one warp of an SM sub-partition evaluates the link function
+//    (latency-bound scalar FP64), the other one issues DMMAs.
+// Row groups, partial buffers and summation order per chain are unchanged (fixed order; independent of the batch).
+// =====================================================================================================================
+constexpr int NCW = 8;                 // warps per CTA
+constexpr int NT3 = 32 * NCW;
+constexpr int DW_LD = 12;              // leading dimension of a warp's derivative tile [TR][8] (== 4 mod 8: conflict-free fragments)
+
+// one arrival per warp on a shared counter; returns true (to the whole warp) in the warp that arrived last, after
+// resetting the counter.  Orders the warp's earlier shared-memory reads before the refill the last arriver issues.
+__device__ __forceinline__ bool warp_arrive_is_last(int* cnt, int lane) {
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(cnt, 1) == NCW - 1;
+    if (last) {
+      *cnt = 0;
+      __threadfence_block();
+    }
+  }
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+template <int LINK, int MB>
+__global__ void __launch_bounds__(NT3, 1) glm_dmma3_kernel(const GlmTcArgs a) {
+  extern __shared__ __align__(128) double smem[];
+  const int Dk = a.Dk;
+  const int xs_ld = xs_ld_for(Dk);
+  double* Bs = smem;                                // [TC][xs_ld]
+  double* Xs0 = Bs + (size_t)TC * xs_ld;            // [2][TR][xs_ld]
+  double* Dw0 = Xs0 + (size_t)2 * TR * xs_ld;       // [NCW][TR][DW_LD]
+  double* ys0 = Dw0 + (size_t)NCW * TR * DW_LD;     // [2][TR]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ys0 + 2 * TR);
+  unsigned long long* fullX = bars;        // [2]
+  unsigned long long* fullB = bars + 2;
+  int* doneX = reinterpret_cast<int*>(bars + 3);  // [2] warps done with X buffer b;  [2]: warps done with the q tile
+  int* doneB = doneX + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int p = blockIdx.x;
+  const int n_list = a.n_list ? *a.n_list : a.n_fixed;
+  const int n_ct = (n_list + TC - 1) / TC;
+
+  const long long t_begin = (long long)p * a.n_row_tiles / a.P, t_end = (long long)(p + 1) * a.n_row_tiles / a.P;
+  const long long row_begin = t_begin * TR;
+  long long row_end = t_end * TR;
+  if (row_end > a.N) row_end = a.N;
+  const int n_rt = (int)(t_end - t_begin);
+  const long long n_it = (long long)n_ct * n_rt;
+  if (n_it == 0) return;
+
+  if (tid == 0) {
+    mbar_init(&fullX[0], 1);
+    mbar_init(&fullX[1], 1);
+    mbar_init(fullB, 1);
+    doneX[0] = doneX[1] = doneB[0] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = tid; e < TC * (Dk - a.ldq); e += NT3) {  // columns [ldq, Dk) of the q tile are never written by the bulk copies
+    const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
+    Bs[c * xs_ld + k] = 0.0;
+  }
+  fence_proxy_async();
+  __syncthreads();  // the only block-wide barrier of the kernel
+
+  const unsigned row_bytes = (unsigned)Dk * 8u, q_bytes = (unsigned)a.ldq * 8u;
+  // issued by one whole warp: X tile + y slice of iteration `it2` into its buffer
+  auto load_x = [&](long long it2) {
+    const int buf = (int)(it2 & 1);
+    const int rt2 = (int)(it2 % n_rt);
+    double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const long long row0 = row_begin + (long long)rt2 * TR;
+    const int valid = (int)((row_end - row0) < TR ? (row_end - row0) : TR);
+    // generic-proxy part of the tile first (y slice, zero rows past the end of the group): released by the arrive below
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      const int yv = r < valid ? a.y[row0 + r] : 0;
+      ys0[buf * TR + r] = LINK == 0 ? 2.0 * yv - 1.0 : (double)yv;
+      if (r >= valid)
+        for (int k = 0; k < Dk; k += 2) *reinterpret_cast<double2*>(Xs + r * xs_ld + k) = make_double2(0.0, 0.0);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&fullX[buf], (unsigned)valid * row_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      if (r < valid) tma_load_1d(Xs + r * xs_ld, a.X + (size_t)(row0 + r) * a.ldx, row_bytes, &fullX[buf]);
+    }
+  };
+  auto load_b = [&](int ct2) {  // one whole warp: q rows of chain tile ct2
+    const int nb = n_list - ct2 * TC < TC ? n_list - ct2 * TC : TC;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(fullB, (unsigned)nb * q_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TC / 32; h++) {
+      const int c = lane + 32 * h;
+      if (c < nb) {
+        const int slot = ct2 * TC + c;
+        tma_load_1d(Bs + c * xs_ld, a.Q + (size_t)(a.list ? a.list[slot] : slot) * a.ldq, q_bytes, fullB);
+      }
+    }
+  };
+  if (warp == 0) {
+    load_b(0);
+    load_x(0);
+    if (n_it > 1) load_x(1);
+  }
+
+  const int cb = warp * 8;  // this warp's chains inside the chain tile
+  double* Dw = Dw0 + (size_t)warp * TR * DW_LD;
+  double gacc[MB][2];
+  double lpacc[2];
+  int ct = 0, rt = 0;
+  for (long long it = 0; it < n_it; it++) {
+    const int buf = (int)(it & 1);
+    const bool have = n_list - ct * TC > cb;  // warp-uniform: does this warp's block hold requesting chains?
+    if (rt == 0) {
+#pragma unroll
+      for (int m = 0; m < MB; m++) gacc[m][0] = gacc[m][1] = 0.0;
+      lpacc[0] = lpacc[1] = 0.0;
+      mbar_wait(fullB, (unsigned)(ct & 1));
+    }
+    mbar_wait(&fullX[buf], (unsigned)((it >> 1) & 1));
+    const double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const double* ys = ys0 + buf * TR;
+    const long long row0 = row_begin + (long long)rt * TR;
+    double acc[8][2];
+    if (have) {
+      // ---- phase A: Eta[64 rows][8 chains]
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) acc[mi][0] = acc[mi][1] = 0.0;
+      const double* xa = Xs + gid * xs_ld + tig;
+      const double* ba = Bs + (cb + gid) * xs_ld + tig;
+#pragma unroll 2
+      for (int k0 = 0; k0 < Dk; k0 += 4) {
+        double av[8];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) av[mi] = xa[mi * 8 * xs_ld + k0];
+        const double bv = ba[k0];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) dmma(acc[mi][0], acc[mi][1], av[mi], bv);
+      }
+    }
+    if (rt == n_rt - 1 && ct + 1 < n_ct) {  // last row tile of this chain tile: this warp is done with the q tile
+      if (warp_arrive_is_last(doneB, lane)) load_b(ct + 1);
+    }
+    if (have) {
+      // ---- link on the accumulator fragments: element (row = mi*8 + gid, chain = cb + 2*tig + j)
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int r = mi * 8 + gid;
+        const bool valid = row0 + r < row_end;
+        const double yd = ys[r];
+        double lv[2], dv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][j], yd, lv[j], dv[j]);
+#pragma unroll
+        for (int j = 0; j < 2; j++) lpacc[j] += valid ? lv[j] : 0.0;
+        *reinterpret_cast<double2*>(&Dw[r * DW_LD + 2 * tig]) = make_double2(dv[0], dv[1]);
+      }
+      __syncwarp();
+      // ---- phase B: G[Dk][8 chains] += X tile^T . Dw
+      const double* xb = Xs + tig * xs_ld + gid;
+      const double* db = Dw + tig * DW_LD + gid;
+#pragma unroll 2
+      for (int r0 = 0; r0 < TR; r0 += 4) {
+        const double bv = db[r0 * DW_LD];
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          if (m * 8 < Dk) {  // warp-uniform
+            const double av = xb[r0 * xs_ld + m * 8];
+            dmma(gacc[m][0], gacc[m][1], av, bv);
+          }
+        }
+      }
+    }
+    // this warp is done with Xs[buf] (and with its Dw): the last warp to get here refills the buffer for iteration it + 2
+    if (it + 2 < n_it) {
+      if (warp_arrive_is_last(&doneX[buf], lane)) load_x(it + 2);
+    } else {
+      __syncwarp();
+    }
+    if (rt == n_rt - 1) {
+      if (have) {
+        const int slot0 = ct * TC + cb;
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          const int k = m * 8 + gid;
+          if (k < Dk) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int slot = slot0 + 2 * tig + j;
+              if (slot < n_list) a.Gp[((size_t)p * a.cap + slot) * Dk + k] = gacc[m][j];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {  // sum over the 8 row lanes (gid) in a fixed order
+          double v = lpacc[j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          const int slot = slot0 + 2 * tig + j;
+          if (gid == 0 && slot < n_list) a.LPp[(size_t)p * a.cap + slot] = v;
+        }
+      }
+      rt = 0;
+      ct++;
+    } else {
+      rt++;
+    }
+  }
+}
+
+size_t glm_tc3_smem_bytes(int Dk) {
+  return ((size_t)TC * xs_ld_for(Dk) + (size_t)2 * TR * xs_ld_for(Dk) + (size_t)NCW * TR * DW_LD + 2 * TR + 8) * sizeof(double);
+}
+
 }  // namespace
 
 int glm_tc_max_dk() { return 112; }
@@ -344,6 +580,27 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
   a.n_fixed = b.C;
   a.cap = ws.C;
   a.P = ws.P;
+  const bool logistic = m.kind == MODEL_LOGISTIC;
+  if (ws.variant == 2) {
+    const size_t smem3 = glm_tc3_smem_bytes(a.Dk);
+#define LAUNCH3(LINK, MB)                                                                     \
+  {                                                                                           \
+    auto k = glm_dmma3_kernel<LINK, MB>;                                                      \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);         \
+    k<<<ws.P, NT3, smem3, stream>>>(a);                                                       \
+  }
+    if (a.Dk <= 16) {
+      if (logistic) LAUNCH3(0, 2) else LAUNCH3(1, 2)
+    } else if (a.Dk <= 32) {
+      if (logistic) LAUNCH3(0, 4) else LAUNCH3(1, 4)
+    } else if (a.Dk <= 64) {
+      if (logistic) LAUNCH3(0, 8) else LAUNCH3(1, 8)
+    } else {
+      if (logistic) LAUNCH3(0, 14) else LAUNCH3(1, 14)
+    }
+#undef LAUNCH3
+    return 1;
+  }
   const size_t smem = glm_tc_smem_bytes(a.Dk);
 #define LAUNCH(LINK, MB)                                                                     \
   {                                                                                          \
@@ -351,7 +608,6 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     k<<<ws.P, NT, smem, stream>>>(a);                                                        \
   }
-  const bool logistic = m.kind == MODEL_LOGISTIC;
   if (a.Dk <= 16) {
     if (logistic) LAUNCH(0, 1) else LAUNCH(1, 1)
   } else if (a.Dk <= 32) {

@@ -14,6 +14,8 @@
 // FP64 pipe: ~51 FP64 instructions per response, 2 I J of them transcendental-class).  y is shared by all chains (int8,
 // L2-resident); per chain the kernel reads q (D doubles) and writes g (D doubles).  All sums run in a fixed order
 // (shuffle trees, then warp order) => deterministic and independent of the batch.
+#include <cstdlib>
+
 #include "fastmath.cuh"
 #include "kernels.h"
 
@@ -26,8 +28,11 @@ constexpr int IRT_MAX_IPL = 16;     // items per lane
 
 int irt_max_items() { return IRT_G * IRT_MAX_IPL; }
 
-template <int IPL>
-__global__ void __launch_bounds__(IRT_NT, 1) irt_grad_kernel(const signed char* __restrict__ y, int I, int J, int D,
+// OCC = 1: item parameters in registers, one CTA per SM (254 registers).  OCC = 2: exp(a), b in shared memory and a 128-register
+// budget, two CTAs (16 warps) per SM: the r01c capture showed the one-CTA form latency-bound (FP64 pipe 47 % busy, 45 % of
+// the samples in fixed-latency dependency stalls at 2 warps per sub-partition).
+template <int IPL, int OCC>
+__global__ void __launch_bounds__(IRT_NT, OCC) irt_grad_kernel(const signed char* __restrict__ y, int I, int J, int D,
                                                              const double* __restrict__ Q, double* __restrict__ G,
                                                              double* __restrict__ zV, const int* __restrict__ active,
                                                              const int* __restrict__ list, const int* __restrict__ n_list, int ld) {
@@ -58,12 +63,22 @@ __global__ void __launch_bounds__(IRT_NT, 1) irt_grad_kernel(const signed char* 
   const double* bq = q + 4 + I + J;
   const double st = exp(u_st), sa = exp(u_sa), sb = exp(u_sb);
 
-  double a[IPL], b[IPL], ga[IPL], gb[IPL];
+  __shared__ double s_a[OCC == 2 ? IRT_G * IRT_MAX_IPL : 1], s_b[OCC == 2 ? IRT_G * IRT_MAX_IPL : 1];
+  double a[OCC == 2 ? 1 : IPL], b[OCC == 2 ? 1 : IPL], ga[IPL], gb[IPL];
+  if (OCC == 2) {
+    if (tid < IRT_G * IRT_MAX_IPL) {
+      s_a[tid] = tid < J ? exp(u_a[tid]) : 0.0;   // a = 0 for padding items: no gradient contribution by construction
+      s_b[tid] = tid < J ? bq[tid] : 0.0;
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int t = 0; t < IPL; t++) {
     const int j = sub + IRT_G * t;
-    a[t] = j < J ? exp(u_a[j]) : 0.0;   // a = 0 for padding items: no gradient contribution by construction
-    b[t] = j < J ? bq[j] : 0.0;
+    if (OCC != 2) {
+      a[t] = j < J ? exp(u_a[j]) : 0.0;
+      b[t] = j < J ? bq[j] : 0.0;
+    }
     ga[t] = 0.0;
     gb[t] = 0.0;
   }
@@ -80,11 +95,12 @@ __global__ void __launch_bounds__(IRT_NT, 1) irt_grad_kernel(const signed char* 
       const int j = sub + IRT_G * t;
       const bool valid = j < J;
       const double sgn = valid ? 2.0 * yrow[j] - 1.0 : 1.0;
-      const double diff = th - b[t];
+      const double at = OCC == 2 ? s_a[j] : a[t], bt = OCC == 2 ? s_b[j] : b[t];
+      const double diff = th - bt;
       double lpi, d;
-      link_eval<0>(a[t] * diff, sgn, lpi, d);
+      link_eval<0>(at * diff, sgn, lpi, d);
       lp += valid ? lpi : 0.0;
-      const double da = d * a[t];
+      const double da = d * at;
       gth += da;
       gb[t] -= da;
       ga[t] += d * diff;
@@ -196,14 +212,19 @@ __global__ void __launch_bounds__(IRT_NT, 1) irt_grad_kernel(const signed char* 
 
 int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream) {
   const int ipl = (m.K + IRT_G - 1) / IRT_G;
-#define IRT_LAUNCH(IPL) \
-  irt_grad_kernel<IPL><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld)
-  if (ipl <= 2) IRT_LAUNCH(2);
-  else if (ipl <= 4) IRT_LAUNCH(4);
-  else if (ipl <= 7) IRT_LAUNCH(7);
-  else if (ipl <= 10) IRT_LAUNCH(10);
-  else if (ipl <= 13) IRT_LAUNCH(13);
-  else IRT_LAUNCH(16);
+  const char* var = getenv("B200NUTS_IRT_VARIANT");  // read per launch (a handful of ns next to a >100 us kernel): tests switch it
+  const int occ = var ? atoi(var) : 1;
+#define IRT_LAUNCH(IPL)                                                                                                                     \
+  {                                                                                                                                         \
+    if (occ == 2) irt_grad_kernel<IPL, 2><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld); \
+    else irt_grad_kernel<IPL, 1><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);          \
+  }
+  if (ipl <= 2) IRT_LAUNCH(2)
+  else if (ipl <= 4) IRT_LAUNCH(4)
+  else if (ipl <= 7) IRT_LAUNCH(7)
+  else if (ipl <= 10) IRT_LAUNCH(10)
+  else if (ipl <= 13) IRT_LAUNCH(13)
+  else IRT_LAUNCH(16)
 #undef IRT_LAUNCH
   return 1;
 }

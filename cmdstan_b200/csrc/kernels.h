@@ -32,7 +32,7 @@ struct GlmWorkspace {
   double* LPp = nullptr;  // [P][C]       per row-group partial log-likelihood
   double* R = nullptr;    // [C][1 + Dp]  reduced (lp, gradient): the all-reduce payload for row sharding
   int P = 0, C = 0, Dp = 0;
-  int variant = 0;        // 0: register-tiled DFMA kernel, 1: FP64 tensor-core (DMMA) kernel
+  int variant = 0;        // 0: register-tiled DFMA kernel, 1: DMMA kernel v2 (block-synchronous), 2: DMMA kernel v3 (warp-asynchronous)
 };
 size_t glm_workspace_bytes(int N, int D, int C, int sm_count, GlmWorkspace* ws);  // fills P, C, Dp (= D padded to 8); returns total bytes
 void glm_workspace_bind(GlmWorkspace* ws, void* base);

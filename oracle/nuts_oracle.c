@@ -511,6 +511,9 @@ typedef struct {
   int adapt_engaged;
   int unit_e; /* 1: adapt_unit_e_nuts / unit_e_nuts (S/mcmc/hmc/nuts/adapt_unit_e_nuts.hpp:24-35): metric frozen at the identity,
                  step-size adaptation only -- arithmetically diag_e with M^-1 = 1 and no variance windows */
+  int dense_e; /* 1: adapt_dense_e_nuts / dense_e_nuts (S/mcmc/hmc/nuts/adapt_dense_e_nuts.hpp:20-50): dense inverse metric
+                  (S/mcmc/hmc/hamiltonians/dense_e_metric.hpp:21-58, dense_e_point.hpp), covariance windows
+                  (S/mcmc/covar_adaptation.hpp:17-45, M/prim/fun/welford_covar_estimator.hpp:10-50) */
 } oracle_config_t;
 
 typedef struct {
@@ -539,7 +542,10 @@ typedef struct {
   mixmax_t rng;
   int D;
   point_t z;
-  double* inv_metric;
+  double* inv_metric; /* diag_e: [D]; dense_e: [D][D] column-major like Eigen::MatrixXd, element (i,j) at j*D + i */
+  int dense;          /* dense_e metric */
+  double* chol;       /* dense_e: lower Cholesky factor L of inv_metric (L L^T = M^-1), column-major */
+  double* tmpv;       /* dense_e: scratch vector [D] */
   double nom_epsilon, epsilon, epsilon_jitter;
   int max_depth;
   double max_deltaH;
@@ -560,19 +566,76 @@ static void update_potential_gradient(sampler_t* s, point_t* z) { /* base_hamilt
   z->V = -lp;
   for (int i = 0; i < s->D; i++) z->g[i] = -z->g[i];
 }
-static double kinetic(const sampler_t* s, const point_t* z) { /* diag_e_metric.hpp:20-22 */
+/* dtau_dp = M^-1 p.  diag_e_metric.hpp:36-38; dense_e_metric.hpp:38 (Eigen's column-major gemv accumulates each output
+ * row sequentially over the columns -- the order used here) */
+static void sharp(const sampler_t* s, const double* p, double* out) {
+  const int D = s->D;
+  if (!s->dense) {
+    for (int i = 0; i < D; i++) out[i] = s->inv_metric[i] * p[i];
+    return;
+  }
+  for (int i = 0; i < D; i++) {
+    double acc = 0;
+    for (int j = 0; j < D; j++) acc += s->inv_metric[(size_t)j * D + i] * p[j];
+    out[i] = acc;
+  }
+}
+/* lower Cholesky factor of the dense inverse metric (the reference re-factorises in every sample_p, dense_e_metric.hpp:55:
+ * z.inv_e_metric_.llt(); the factor only changes when the metric does, so it is cached).  Only the lower triangle is
+ * read, as Eigen::LLT<Lower> does.  Returns 0 when the matrix is not positive definite. */
+static int dense_factor(sampler_t* s) {
+  const int D = s->D;
+  const double* A = s->inv_metric;
+  double* L = s->chol;
+  for (size_t k = 0; k < (size_t)D * D; k++) L[k] = 0;
+  for (int j = 0; j < D; j++) {
+    double d = A[(size_t)j * D + j];
+    for (int k = 0; k < j; k++) d -= L[(size_t)k * D + j] * L[(size_t)k * D + j];
+    if (!(d > 0)) return 0;
+    const double ljj = sqrt(d);
+    L[(size_t)j * D + j] = ljj;
+    for (int i = j + 1; i < D; i++) {
+      double v = A[(size_t)j * D + i];
+      for (int k = 0; k < j; k++) v -= L[(size_t)k * D + i] * L[(size_t)k * D + j];
+      L[(size_t)j * D + i] = v / ljj;
+    }
+  }
+  return 1;
+}
+static double kinetic(const sampler_t* s, const point_t* z) { /* diag_e_metric.hpp:20-22; dense_e_metric.hpp:21-23 */
   double acc = 0;
+  if (s->dense) {
+    sharp(s, z->p, s->tmpv);
+    for (int i = 0; i < s->D; i++) acc += z->p[i] * s->tmpv[i];
+    return 0.5 * acc;
+  }
   for (int i = 0; i < s->D; i++) acc += z->p[i] * (s->inv_metric[i] * z->p[i]);
   return 0.5 * acc;
 }
 static double hamiltonian(const sampler_t* s, const point_t* z) { return kinetic(s, z) + z->V; }
-static void sample_p(sampler_t* s, point_t* z) { /* diag_e_metric.hpp:44-50 */
-  for (int i = 0; i < s->D; i++) z->p[i] = oracle_normal(&s->rng) / sqrt(s->inv_metric[i]);
+static void sample_p(sampler_t* s, point_t* z) { /* diag_e_metric.hpp:44-50; dense_e_metric.hpp:44-56 */
+  const int D = s->D;
+  if (s->dense) { /* u ~ N(0, I) in index order; p = L^-T u  (matrixU().solve(u): back substitution on L^T) */
+    for (int i = 0; i < D; i++) s->tmpv[i] = oracle_normal(&s->rng);
+    const double* L = s->chol;
+    for (int i = D - 1; i >= 0; i--) {
+      double acc = 0;
+      for (int k = i + 1; k < D; k++) acc += L[(size_t)i * D + k] * z->p[k];
+      z->p[i] = (s->tmpv[i] - acc) / L[(size_t)i * D + i];
+    }
+    return;
+  }
+  for (int i = 0; i < D; i++) z->p[i] = oracle_normal(&s->rng) / sqrt(s->inv_metric[i]);
 }
 static void evolve(sampler_t* s, point_t* z, double eps) { /* base_leapfrog.hpp:17-22 + expl_leapfrog.hpp:16-32 */
   double h = 0.5 * eps;
   for (int i = 0; i < s->D; i++) z->p[i] -= h * z->g[i];
-  for (int i = 0; i < s->D; i++) z->q[i] += eps * (s->inv_metric[i] * z->p[i]);
+  if (s->dense) {
+    sharp(s, z->p, s->tmpv);
+    for (int i = 0; i < s->D; i++) z->q[i] += eps * s->tmpv[i];
+  } else {
+    for (int i = 0; i < s->D; i++) z->q[i] += eps * (s->inv_metric[i] * z->p[i]);
+  }
   update_potential_gradient(s, z);
   for (int i = 0; i < s->D; i++) z->p[i] -= h * z->g[i];
 }
@@ -643,8 +706,8 @@ static int build_tree(sampler_t* s, int depth, point_t* z_propose, double* p_sha
     if (H0 - h > 0) *sum_metro_prob += 1;
     else *sum_metro_prob += exp(H0 - h);
     pt_copy(z_propose, &s->z);
+    sharp(s, s->z.p, p_sharp_beg);
     for (int i = 0; i < D; i++) {
-      p_sharp_beg[i] = s->inv_metric[i] * s->z.p[i];
       p_sharp_end[i] = p_sharp_beg[i];
       rho[i] += s->z.p[i];
       p_beg[i] = s->z.p[i];
@@ -710,8 +773,9 @@ static double transition(sampler_t* s, double* lp_out) {
   double *p_fwd_fwd = buf, *p_sharp_fwd_fwd = buf + D, *p_fwd_bck = buf + 2 * D, *p_sharp_fwd_bck = buf + 3 * D;
   double *p_bck_fwd = buf + 4 * D, *p_sharp_bck_fwd = buf + 5 * D, *p_bck_bck = buf + 6 * D, *p_sharp_bck_bck = buf + 7 * D;
   double *rho = buf + 8 * D, *rho_fwd = buf + 9 * D, *rho_bck = buf + 10 * D, *rho_ext = buf + 11 * D;
+  sharp(s, s->z.p, p_sharp_fwd_fwd);
   for (int i = 0; i < D; i++) {
-    double ps = s->inv_metric[i] * s->z.p[i];
+    double ps = p_sharp_fwd_fwd[i];
     p_fwd_fwd[i] = p_fwd_bck[i] = p_bck_fwd[i] = p_bck_bck[i] = s->z.p[i];
     p_sharp_fwd_fwd[i] = p_sharp_fwd_bck[i] = p_sharp_bck_fwd[i] = p_sharp_bck_bck[i] = ps;
     rho[i] = s->z.p[i];
@@ -815,7 +879,16 @@ static int learn_variance(sampler_t* s) { /* var_adaptation.hpp:17-46 */
   int in_window = (s->adapt_window_counter >= s->adapt_init_buffer) &&
                   (s->adapt_window_counter < s->num_warmup - s->adapt_term_buffer) &&
                   (s->adapt_window_counter != s->num_warmup);
-  if (in_window) {
+  if (in_window && s->dense) { /* welford_covar_estimator::add_sample: m2 += (q - m_new) delta^T */
+    ++s->wf_n;
+    double* delta = s->tmpv;
+    for (int i = 0; i < D; i++) {
+      delta[i] = q[i] - s->wf_m[i];
+      s->wf_m[i] += delta[i] / s->wf_n;
+    }
+    for (int j = 0; j < D; j++)
+      for (int i = 0; i < D; i++) s->wf_m2[(size_t)j * D + i] += (q[i] - s->wf_m[i]) * delta[j];
+  } else if (in_window) {
     ++s->wf_n;
     for (int i = 0; i < D; i++) {
       double delta = q[i] - s->wf_m[i];
@@ -836,6 +909,20 @@ static int learn_variance(sampler_t* s) { /* var_adaptation.hpp:17-46 */
       }
     }
     double n = s->wf_n;
+    if (s->dense) { /* covar_adaptation.hpp:24-31 */
+      for (int j = 0; j < D; j++)
+        for (int i = 0; i < D; i++) {
+          const size_t e = (size_t)j * D + i;
+          double cov = s->inv_metric[e];
+          if (n > 1) cov = s->wf_m2[e] / (n - 1.0);
+          s->inv_metric[e] = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * (i == j ? 1.0 : 0.0);
+          s->wf_m2[e] = 0;
+        }
+      for (int i = 0; i < D; i++) s->wf_m[i] = 0;
+      s->wf_n = 0;
+      ++s->adapt_window_counter;
+      return dense_factor(s) ? 1 : -1;
+    }
     for (int i = 0; i < D; i++) {
       double var = s->inv_metric[i];
       if (n > 1) var = s->wf_m2[i] / (n - 1.0);
@@ -855,7 +942,8 @@ static int learn_variance(sampler_t* s) { /* var_adaptation.hpp:17-46 */
  * run_adaptive_sampler.hpp:47-103).  q0 != NULL: user-specified unconstrained inits (no RNG consumed, one try).
  * draws: [(save_warmup? W:0 + S)/thin rows][7 + D] =
  *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, q (unconstrained).
- * adapt_out: [1 + D] = final step size, inverse metric.  Returns 0 ok, 78 init failure, 70 stepsize failure.
+ * adapt_out: [1 + D] = final step size, inverse metric ([1 + D*D], row-major, for dense_e).  inv_metric0 likewise [D] or
+ * [D][D].  Returns 0 ok, 78 init failure, 70 stepsize failure.
  */
 int oracle_run_chain(const model_t* model, const oracle_config_t* c, const double* q0, const double* inv_metric0,
                      double* draws, double* adapt_out, double* q_init_out, long* grad_evals_out) {
@@ -865,9 +953,13 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   s.model = model;
   s.D = D;
   s.z = pt_alloc(D);
-  s.inv_metric = (double*)malloc(D * sizeof(double));
+  s.dense = c->dense_e;
+  const size_t msz = s.dense ? (size_t)D * D : (size_t)D;
+  s.inv_metric = (double*)malloc(msz * sizeof(double));
   s.wf_m = (double*)calloc(D, sizeof(double));
-  s.wf_m2 = (double*)calloc(D, sizeof(double));
+  s.wf_m2 = (double*)calloc(msz, sizeof(double));
+  s.chol = s.dense ? (double*)calloc(msz, sizeof(double)) : NULL;
+  s.tmpv = (double*)calloc(D, sizeof(double));
   double* gtmp = (double*)malloc(D * sizeof(double));
   int rc = 0;
   oracle_rng_seed(&s.rng, c->seed, c->chain_id);
@@ -887,7 +979,13 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   if (!ok) { rc = 78; goto done; }
   if (q_init_out) memcpy(q_init_out, s.z.q, D * sizeof(double));
   /* ---- sampler configuration, hmc_nuts_diag_e_adapt.hpp:84-98 ---- */
-  for (int i = 0; i < D; i++) s.inv_metric[i] = inv_metric0 ? inv_metric0[i] : 1.0;
+  if (s.dense) {
+    for (int i = 0; i < D; i++)
+      for (int j = 0; j < D; j++) s.inv_metric[(size_t)j * D + i] = inv_metric0 ? inv_metric0[(size_t)i * D + j] : (i == j ? 1.0 : 0.0);
+    if (!dense_factor(&s)) { rc = 78; goto done; }
+  } else {
+    for (int i = 0; i < D; i++) s.inv_metric[i] = inv_metric0 ? inv_metric0[i] : 1.0;
+  }
   s.nom_epsilon = 0.1;
   if (c->stepsize > 0) s.nom_epsilon = c->stepsize;
   s.epsilon = s.nom_epsilon;
@@ -916,7 +1014,9 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
     double eps_used = s.epsilon;
     if (adapt_flag && warm) {
       learn_stepsize(&s, accept);
-      if (learn_variance(&s)) {
+      int upd = learn_variance(&s);
+      if (upd < 0) { rc = 70; goto done; }
+      if (upd) {
         if (init_stepsize(&s)) { rc = 70; goto done; }
         s.mu = log(10 * s.nom_epsilon);
         sa_restart(&s);
@@ -934,12 +1034,17 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   }
   if (adapt_out) {
     adapt_out[0] = s.nom_epsilon;
-    memcpy(adapt_out + 1, s.inv_metric, D * sizeof(double));
+    if (s.dense) {
+      for (int i = 0; i < D; i++)
+        for (int j = 0; j < D; j++) adapt_out[1 + (size_t)i * D + j] = s.inv_metric[(size_t)j * D + i];
+    } else {
+      memcpy(adapt_out + 1, s.inv_metric, D * sizeof(double));
+    }
   }
 done:
   if (grad_evals_out) *grad_evals_out = s.grad_evals;
   pt_free(&s.z);
-  free(s.inv_metric); free(s.wf_m); free(s.wf_m2); free(gtmp);
+  free(s.inv_metric); free(s.wf_m); free(s.wf_m2); free(s.chol); free(s.tmpv); free(gtmp);
   return rc;
 }
 

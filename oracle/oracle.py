@@ -28,7 +28,7 @@ class ConfigT(C.Structure):
                 ("num_thin", C.c_int), ("save_warmup", C.c_int), ("stepsize", C.c_double), ("stepsize_jitter", C.c_double),
                 ("max_depth", C.c_int), ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double),
                 ("t0", C.c_double), ("init_buffer", C.c_uint), ("term_buffer", C.c_uint), ("window", C.c_uint),
-                ("init_radius", C.c_double), ("adapt_engaged", C.c_int), ("unit_e", C.c_int)]
+                ("init_radius", C.c_double), ("adapt_engaged", C.c_int), ("unit_e", C.c_int), ("dense_e", C.c_int)]
 
 
 _lib = None
@@ -118,7 +118,7 @@ class Model:
 
 DEFAULTS = dict(seed=0, chain_id=1, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=0, stepsize=1.0,
                 stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75,
-                term_buffer=50, window=25, init_radius=2.0, adapt_engaged=1, unit_e=0)
+                term_buffer=50, window=25, init_radius=2.0, adapt_engaged=1, unit_e=0, dense_e=0)
 
 
 def run_chain(model, q0=None, inv_metric=None, **kw):
@@ -130,14 +130,15 @@ def run_chain(model, q0=None, inv_metric=None, **kw):
     nrow = ((cfg.num_warmup + cfg.num_thin - 1) // cfg.num_thin if cfg.save_warmup else 0) + (
         cfg.num_samples + cfg.num_thin - 1) // cfg.num_thin
     draws = np.zeros((nrow, 7 + D))
-    adapt = np.zeros(1 + D)
+    adapt = np.zeros(1 + (D * D if cfg.dense_e else D))
     qinit = np.zeros(D)
     ge = C.c_long(0)
     q0a = None if q0 is None else np.ascontiguousarray(q0, dtype=np.float64)
     ima = None if inv_metric is None else np.ascontiguousarray(inv_metric, dtype=np.float64)
     rc = lib().oracle_run_chain(C.byref(model.c), C.byref(cfg), _ptr(q0a), _ptr(ima), _ptr(draws), _ptr(adapt), _ptr(qinit),
                                 C.byref(ge))
-    return dict(draws=draws, stepsize=adapt[0], inv_metric=adapt[1:].copy(), q_init=qinit, grad_evals=ge.value, rc=rc)
+    im = adapt[1:].copy().reshape(D, D) if cfg.dense_e else adapt[1:].copy()
+    return dict(draws=draws, stepsize=adapt[0], inv_metric=im, q_init=qinit, grad_evals=ge.value, rc=rc)
 
 
 def rng_kat(seed, chain, kind, n):
@@ -201,6 +202,10 @@ def read_stan_csv(path):
             elif ln.startswith("# Diagonal elements of inverse mass matrix:"):
                 metric = np.array([float(v) for v in lines[i + 1][1:].split(",")])
                 i += 1
+            elif ln.startswith("# Elements of inverse mass matrix:"):  # dense_e_point::write_metric: D rows of D values
+                first = [float(v) for v in lines[i + 1][1:].split(",")]
+                metric = np.array([first] + [[float(v) for v in lines[i + 1 + k][1:].split(",")] for k in range(1, len(first))])
+                i += len(first)
             elif "seconds (" in ln:
                 val = float(ln[1:].replace("Elapsed Time:", "").split("seconds")[0])
                 timing[ln.split("(")[1].rstrip(")")] = val

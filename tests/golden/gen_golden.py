@@ -74,7 +74,7 @@ def main():
     print("written:", os.listdir(HERE))
 
 
-if __name__ == "__main__" and "--unit-e" not in sys.argv and "--summary" not in sys.argv:
+if __name__ == "__main__" and "--unit-e" not in sys.argv and "--summary" not in sys.argv and "--dense-e" not in sys.argv:
     main()
 
 
@@ -94,6 +94,26 @@ def gen_unit_e():
 
 if __name__ == "__main__" and "--unit-e" in sys.argv:
     gen_unit_e()
+
+
+def gen_dense_e():
+    """metric=dense_e goldens (hmc_nuts_dense_e_adapt / hmc_nuts_dense_e of the compiled reference) at sig_figs=18: every
+    saved row + the adapted step size and inverse metric as printed (6 significant digits) in the adaptation block."""
+    out = []
+    for name, data, kw in (("bernoulli", cases.BERNOULLI, dict(seed=31, chain_id=1)), ("std_normal", {"D": 3}, dict(seed=32, chain_id=2)),
+                           ("eight_schools_nc", cases.EIGHT_SCHOOLS, dict(seed=33, chain_id=1))):
+        for adapt in (True, False):
+            res, _, _ = O.ref_sample(name, data, num_warmup=200, num_samples=100, save_warmup=True, metric="dense_e", adapt_engaged=adapt,
+                                     stepsize=None if adapt else 0.25, **kw)
+            names, draws, stepsize, metric, _ = res[0]
+            out.append(dict(model=name, data=jsonable(data), args=dict(kw, num_warmup=200, num_samples=100, adapt_engaged=int(adapt),
+                                                                        stepsize=1.0 if adapt else 0.25), rows=draws.tolist(), stepsize=stepsize,
+                            inv_metric=None if metric is None else np.asarray(metric).tolist()))
+    json.dump(out, open(os.path.join(HERE, "ref_chains_dense_e.json"), "w"))
+
+
+if __name__ == "__main__" and "--dense-e" in sys.argv:
+    gen_dense_e()
 
 
 def gen_summary():

@@ -39,16 +39,44 @@ def test_log_prob_grad_matches_oracle(name, data):
     e.close()
 
 
-@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
 def test_glm_kernel_variants_agree(variant, monkeypatch):
-    """DFMA and DMMA variants of the fused GLM gradient against the oracle, ragged sizes (N not a tile multiple)."""
+    """DFMA (0), block-synchronous DMMA (1) and warp-asynchronous DMMA (2) variants of the fused GLM gradient against the
+    oracle: ragged sizes (N not a tile multiple, several row tiles per row group, chain counts that leave tiles underfilled)."""
     monkeypatch.setenv("B200NUTS_GLM_VARIANT", variant)
-    for name, data in [("logistic", cases.logistic_data(1234, 100)), ("poisson_glm", cases.poisson_data(999, 50)),
-                       ("logistic", cases.logistic_data(65, 1))]:
+    for name, data, nq in [("logistic", cases.logistic_data(1234, 100), 70), ("poisson_glm", cases.poisson_data(999, 50), 70),
+                           ("logistic", cases.logistic_data(65, 1), 70), ("logistic", cases.logistic_data(30011, 37), 131),
+                           ("poisson_glm", cases.poisson_data(20000, 12), 5)]:
         m = O.Model(name, data)
-        q = np.random.default_rng(6).uniform(-1, 1, size=(70, m.D))
+        q = np.random.default_rng(6).uniform(-1, 1, size=(nq, m.D))
         lp0, g0 = m.lp_grad(q)
         e = _engine(name, data)
+        lp, g = e.log_prob_grad(q)
+        assert _rel(lp, lp0) < 1e-10 and _rel(g, g0, floor=1e-9) < 1e-10
+        e.close()
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_glm_tensor_variants_batch_independent(variant, monkeypatch):
+    """a chain's draws do not depend on which slot of which chain tile serves it (fixed summation order per chain)."""
+    monkeypatch.setenv("B200NUTS_GLM_VARIANT", variant)
+    data = cases.logistic_data(9000, 10)   # 141 row tiles: one per row group on 148 SMs, some groups empty
+    kw = dict(num_warmup=40, num_samples=20)
+    dA, epsA, _ = _run("logistic", data, C=70, **kw)
+    for c in (0, 64, 69):
+        d1, eps1, _ = _run("logistic", data, C=1, init_chain_id=1 + c, **kw)
+        assert np.array_equal(dA[c], d1[0]) and epsA[c] == eps1[0]
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_irt_kernel_variants_agree(variant, monkeypatch):
+    """one-CTA-per-SM (1) and two-CTAs-per-SM (2) forms of the IRT gradient kernel against the oracle."""
+    monkeypatch.setenv("B200NUTS_IRT_VARIANT", variant)
+    for data in (cases.irt_data(100, 20), cases.irt_data(37, 100), cases.irt_data(300, 128)):
+        m = O.Model("irt_2pl", data)
+        q = np.random.default_rng(8).uniform(-1.5, 1.5, size=(33, m.D))
+        lp0, g0 = m.lp_grad(q)
+        e = _engine("irt_2pl", data)
         lp, g = e.log_prob_grad(q)
         assert _rel(lp, lp0) < 1e-10 and _rel(g, g0, floor=1e-9) < 1e-10
         e.close()
