@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id", "load_model_library", "find_model"]
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "hmc_nuts_dense_e_adapt", "hmc_nuts_dense_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id", "load_model_library", "find_model"]
 
 MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
 ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
@@ -181,7 +181,8 @@ class Engine:
         cfg.init_buffer, cfg.term_buffer, cfg.window = int(init_buffer), int(term_buffer), int(window)
         cfg.adapt_engaged, cfg.engine, cfg.device, cfg.store_draws = int(bool(adapt_engaged)), ENGINES[engine], int(device), int(bool(store_draws))
         cfg.row_shards, cfg.row_shard_rank = int(row_shards), int(row_shard_rank)
-        cfg.metric = {"diag_e": 0, "unit_e": 1}[metric]
+        cfg.metric = {"diag_e": 0, "unit_e": 1, "dense_e": 2}[metric]
+        self.metric = metric
         self.cfg = cfg
         self.model = model
         self.h = C.c_void_p()
@@ -247,7 +248,8 @@ class Engine:
         self._chk(self.lib.b200nuts_set_inits(self.h, None if a is None else a.ctypes.data_as(C.c_void_p)))
 
     def set_inv_metric(self, im):
-        a = None if im is None else _np(im, np.float64).reshape(self.num_chains, self.D)
+        shape = (self.num_chains, self.D, self.D) if self.metric == "dense_e" else (self.num_chains, self.D)
+        a = None if im is None else _np(im, np.float64).reshape(shape)
         self._chk(self.lib.b200nuts_set_inv_metric(self.h, None if a is None else a.ctypes.data_as(C.c_void_p)))
 
     def init_chains(self):
@@ -296,7 +298,7 @@ class Engine:
 
     def adaptation(self):
         eps = np.empty(self.num_chains)
-        im = np.empty((self.num_chains, self.D))
+        im = np.empty((self.num_chains, self.D, self.D) if self.metric == "dense_e" else (self.num_chains, self.D))
         self._chk(self.lib.b200nuts_get_adaptation(self.h, eps.ctypes.data_as(C.c_void_p), im.ctypes.data_as(C.c_void_p)))
         return eps, im
 
@@ -414,3 +416,25 @@ def hmc_nuts_unit_e(model, data, num_chains=1, init=None, random_seed=0, init_ch
     return _run_service(model, data, num_chains, init, None, random_seed, init_chain_id, init_radius, num_warmup, num_samples, num_thin,
                         save_warmup, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75, 50, 25, logger, device, engine,
                         False, "unit_e")
+
+
+def hmc_nuts_dense_e_adapt(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1,
+                           init_radius=2.0, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=False, refresh=100,
+                           stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0,
+                           init_buffer=75, term_buffer=50, window=25, logger=None, device=0, engine="auto"):
+    """stan::services::sample::hmc_nuts_dense_e_adapt (stan/src/stan/services/sample/hmc_nuts_dense_e_adapt.hpp): dense
+    Euclidean metric, step size and covariance adapted in windows (adapt_dense_e_nuts.hpp:25-44).  `init_inv_metric` is
+    [num_chains, D, D] (None: identity); the result's `inv_metric` has the same shape."""
+    return _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                        num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, init_buffer, term_buffer,
+                        window, logger, device, engine, True, "dense_e")
+
+
+def hmc_nuts_dense_e(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1, init_radius=2.0,
+                     num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=False, refresh=100, stepsize=1.0,
+                     stepsize_jitter=0.0, max_depth=10, logger=None, device=0, engine="auto"):
+    """stan::services::sample::hmc_nuts_dense_e (stan/src/stan/services/sample/hmc_nuts_dense_e.hpp): fixed step size and
+    dense metric, no adaptation."""
+    return _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                        num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75, 50, 25, logger, device,
+                        engine, False, "dense_e")

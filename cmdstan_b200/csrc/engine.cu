@@ -86,6 +86,8 @@ struct DeviceChains {
   double *q, *g, *zV, *slab, *draws;
   const double* user_q0;
   size_t slab_stride, draws_stride;
+  double* mat;        // dense metric: [C][3][D][D] (inverse metric, its Cholesky factor, Welford m2), else nullptr
+  size_t mat_stride;  // 3 D D
 };
 
 __device__ __forceinline__ ChainView make_view(const DeviceChains& d, const SamplerCfg& cfg, int c) {
@@ -97,6 +99,7 @@ __device__ __forceinline__ ChainView make_view(const DeviceChains& d, const Samp
   v.v = d.slab + (size_t)c * d.slab_stride;
   v.draws = d.draws ? d.draws + (size_t)c * d.draws_stride : nullptr;
   v.user_q0 = d.user_q0 ? d.user_q0 + (size_t)c * cfg.ld : nullptr;
+  v.mat = d.mat ? d.mat + (size_t)c * d.mat_stride : nullptr;
   return v;
 }
 
@@ -237,6 +240,24 @@ __global__ void gather_status_kernel(const ChainS* cs, int C, int* err, int* ite
   rows[c] = cs[c].draws_row;
 }
 
+// dense metric: mat[c][0] (column-major) <- identity or the user's [C][D][D] (row-major); and the way back
+__global__ void init_dense_metric_kernel(double* mat, size_t mat_stride, int D, int C, const double* user_im) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long DD = (long long)D * D;
+  if (idx >= (long long)C * DD) return;
+  const int c = (int)(idx / DD);
+  const int e = (int)(idx - (long long)c * DD), i = e / D, j = e - i * D;
+  mat[(size_t)c * mat_stride + (size_t)j * D + i] = user_im ? user_im[idx] : (i == j ? 1.0 : 0.0);
+}
+__global__ void gather_dense_metric_kernel(const double* mat, size_t mat_stride, int D, int C, double* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long DD = (long long)D * D;
+  if (idx >= (long long)C * DD) return;
+  const int c = (int)(idx / DD);
+  const int e = (int)(idx - (long long)c * DD), i = e / D, j = e - i * D;
+  out[idx] = mat[(size_t)c * mat_stride + (size_t)j * D + i];
+}
+
 __global__ void gather_metric_kernel(const double* slab, size_t slab_stride, int ld, int D, int C, double* out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)C * D) return;
@@ -366,7 +387,7 @@ int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
   if (!(cfg->stepsize > 0) || !(cfg->gamma > 0) || !(cfg->kappa > 0) || !(cfg->t0 > 0)) { g_create_error = "stepsize, gamma, kappa, t0 must be > 0"; return B200NUTS_USAGE; }
   if (cfg->stepsize_jitter < 0 || cfg->stepsize_jitter > 1) { g_create_error = "stepsize_jitter must be in [0, 1]"; return B200NUTS_USAGE; }
   if (cfg->init_radius < 0) { g_create_error = "init radius must be >= 0"; return B200NUTS_USAGE; }
-  if (cfg->metric != 0 && cfg->metric != 1) { g_create_error = "metric must be 0 (diag_e) or 1 (unit_e)"; return B200NUTS_USAGE; }
+  if (cfg->metric < 0 || cfg->metric > 2) { g_create_error = "metric must be 0 (diag_e), 1 (unit_e) or 2 (dense_e)"; return B200NUTS_USAGE; }
   if (cfg->row_shards < 1 || cfg->row_shard_rank < 0 || cfg->row_shard_rank >= cfg->row_shards) { g_create_error = "bad row shard configuration"; return B200NUTS_USAGE; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -400,7 +421,7 @@ void b200nuts_destroy(b200nuts_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->plug && e->plug_model && e->plug->destroy) e->plug->destroy(e->plug_model);
   free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8);
-  free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws);
+  free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws); free_dev(e->dc.mat);
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
@@ -622,7 +643,31 @@ int b200nuts_set_inv_metric(b200nuts_engine* e, const double* im) {
   int rc = finalize_data(e);
   if (rc) return rc;
   if (im && e->cfg.metric == 1) { e->err = "unit_e has no free metric parameters"; return B200NUTS_USAGE; }
-  if (im) {
+  if (im && e->cfg.metric == 2) {
+    // validate_dense_inv_metric (S/services/util/validate_dense_inv_metric.hpp): check_pos_definite = symmetric + LDLT positive
+    const size_t D = (size_t)e->D;
+    std::vector<double> L(D * D);
+    for (int c = 0; c < e->C; c++) {
+      const double* A = im + (size_t)c * D * D;
+      bool ok = true;
+      for (size_t i = 0; i < D && ok; i++)
+        for (size_t j = 0; j < i; j++)
+          if (!(std::fabs(A[i * D + j] - A[j * D + i]) <= 1e-8)) { ok = false; break; }  // check_symmetric: CONSTRAINT_TOLERANCE 1e-8
+      for (size_t j = 0; j < D && ok; j++) {  // Cholesky of the lower triangle
+        double d = A[j * D + j];
+        for (size_t k = 0; k < j; k++) d -= L[j * D + k] * L[j * D + k];
+        if (!(d > 0) || !std::isfinite(d)) { ok = false; break; }
+        L[j * D + j] = std::sqrt(d);
+        for (size_t i = j + 1; i < D; i++) {
+          double v = A[i * D + j];
+          for (size_t k = 0; k < j; k++) v -= L[i * D + k] * L[j * D + k];
+          L[i * D + j] = v / L[j * D + j];
+        }
+      }
+      if (!ok) { e->err = "Inverse Euclidean metric not positive definite."; return B200NUTS_CONFIG; }
+    }
+    e->h_user_im.assign(im, im + (size_t)e->C * D * D);
+  } else if (im) {
     for (size_t i = 0; i < (size_t)e->C * e->D; i++)
       if (!(im[i] > 0) || !std::isfinite(im[i])) { e->err = "Inverse Euclidean metric not positive definite."; return B200NUTS_CONFIG; }  // validate_diag_inv_metric
     e->h_user_im.assign(im, im + (size_t)e->C * e->D);
@@ -746,17 +791,19 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   s.t0 = c.t0;
   s.init_radius = c.init_radius;
   // unit_e: no variance windows at all (adapt_unit_e_nuts::transition only learns the step size)
-  resolve_window(&s, (c.adapt_engaged && c.metric == 0) ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
+  s.dense = c.metric == 2;
+  resolve_window(&s, (c.adapt_engaged && c.metric != 1) ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
   s.ncol = 7 + e->D;
   s.rows_per_chain = c.store_draws ? (c.save_warmup ? (c.num_warmup + c.num_thin - 1) / c.num_thin : 0) + (c.num_samples + c.num_thin - 1) / c.num_thin : 0;
 
   const int C = e->C;
   DeviceChains& d = e->dc;
-  free_dev(d.cs); free_dev(d.q); free_dev(d.g); free_dev(d.zV); free_dev(d.slab); free_dev(d.draws);
+  free_dev(d.cs); free_dev(d.q); free_dev(d.g); free_dev(d.zV); free_dev(d.slab); free_dev(d.draws); free_dev(d.mat);
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive);
   d = DeviceChains{};
   e->d_user_q0 = e->d_user_im = nullptr;
-  d.slab_stride = (size_t)num_vec_slots(c.max_depth) * e->ld;
+  d.slab_stride = (size_t)num_vec_slots(c.max_depth, s.dense) * e->ld;
+  d.mat_stride = s.dense ? 3 * (size_t)e->D * e->D : 0;
   d.draws_stride = (size_t)s.rows_per_chain * s.ncol;
   CUDA_TRY(e, cudaMalloc(&d.cs, sizeof(ChainS) * C));
   CUDA_TRY(e, cudaMalloc(&d.q, sizeof(double) * C * e->ld));
@@ -767,6 +814,15 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   CUDA_TRY(e, cudaMemset(d.g, 0, sizeof(double) * C * e->ld));
   CUDA_TRY(e, cudaMemset(d.zV, 0, sizeof(double) * C));
   CUDA_TRY(e, cudaMemset(d.slab, 0, sizeof(double) * C * d.slab_stride));
+  if (s.dense) {
+    cudaError_t r = cudaMalloc(&d.mat, sizeof(double) * C * d.mat_stride);
+    if (r != cudaSuccess) {
+      e->err = "cannot allocate the dense metric (" + std::to_string(sizeof(double) * C * d.mat_stride >> 20) + " MiB): " + cudaGetErrorString(r);
+      d.mat = nullptr;
+      return B200NUTS_SOFTWARE;
+    }
+    CUDA_TRY(e, cudaMemset(d.mat, 0, sizeof(double) * C * d.mat_stride));
+  }
   if (d.draws_stride) {
     cudaError_t r = cudaMalloc(&d.draws, sizeof(double) * C * d.draws_stride);
     if (r != cudaSuccess) {
@@ -798,8 +854,13 @@ int b200nuts_init_chains(b200nuts_engine* e) {
     CUDA_TRY(e, cudaMalloc(&e->d_user_im, sizeof(double) * e->h_user_im.size()));
     CUDA_TRY(e, cudaMemcpy(e->d_user_im, e->h_user_im.data(), sizeof(double) * e->h_user_im.size(), cudaMemcpyHostToDevice));
   }
-  {
+  if (s.dense) {
+    const long long tot = (long long)C * e->D * e->D;
+    if (!e->h_user_im.empty() && (long long)e->h_user_im.size() != tot) { e->err = "dense_e: the inverse metric must be [num_chains][D][D]"; return B200NUTS_USAGE; }
+    init_dense_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(d.mat, d.mat_stride, e->D, C, e->d_user_im);
+  } else {
     const long long tot = (long long)C * e->D;
+    if (!e->h_user_im.empty() && (long long)e->h_user_im.size() != tot) { e->err = "diag_e: the inverse metric must be [num_chains][D]"; return B200NUTS_USAGE; }
     init_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(d.slab, d.slab_stride, e->ld, e->D, C, e->d_user_im);
   }
   rc = ensure_glm_ws(e, C);
@@ -1016,9 +1077,11 @@ int b200nuts_get_adaptation(b200nuts_engine* e, double* stepsize, double* inv_me
   if (stepsize) std::memcpy(stepsize, veps.data(), sizeof(double) * e->C);
   if (inv_metric) {
     double* d_out;
-    const long long tot = (long long)e->C * e->D;
+    const bool dense = e->scfg.dense != 0;
+    const long long tot = (long long)e->C * e->D * (dense ? e->D : 1);
     CUDA_TRY(e, cudaMalloc(&d_out, sizeof(double) * tot));
-    gather_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->dc.slab, e->dc.slab_stride, e->ld, e->D, e->C, d_out);
+    if (dense) gather_dense_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->dc.mat, e->dc.mat_stride, e->D, e->C, d_out);
+    else gather_metric_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->dc.slab, e->dc.slab_stride, e->ld, e->D, e->C, d_out);
     cudaMemcpyAsync(inv_metric, d_out, sizeof(double) * tot, cudaMemcpyDeviceToHost, e->stream);
     cudaError_t r = cudaStreamSynchronize(e->stream);
     cudaFree(d_out);

@@ -9,6 +9,8 @@
 //   base_hmc::init_stepsize / sample_stepsize S/mcmc/hmc/base_hmc.hpp:93-161, :195-200
 //   expl_leapfrog                             S/mcmc/hmc/integrators/expl_leapfrog.hpp:16-32
 //   diag_e_metric                             S/mcmc/hmc/hamiltonians/diag_e_metric.hpp:20-50
+//   dense_e_metric / covar_adaptation         S/mcmc/hmc/hamiltonians/dense_e_metric.hpp:21-58, S/mcmc/covar_adaptation.hpp:17-45,
+//                                             M/prim/fun/welford_covar_estimator.hpp:10-50 (metric = dense_e, cfg.dense)
 //   stepsize_adaptation / var_adaptation      S/mcmc/stepsize_adaptation.hpp:49-73, S/mcmc/var_adaptation.hpp:17-46,
 //   windowed_adaptation / welford             S/mcmc/windowed_adaptation.hpp:23-110, M/prim/fun/welford_var_estimator.hpp
 //
@@ -48,7 +50,8 @@ enum VecSlot {
   V_WM, V_WM2, // Welford accumulators
   V_STACK      // + 5*level + {0: p_beg, 1: p_end, 2: rho, 3: proposal q, 4: proposal g}
 };
-B200_HD int num_vec_slots(int max_depth) { return V_STACK + 5 * max_depth; }
+// dense metric: 4 more scratch vectors after the tree stack (sharp momenta M^-1 p are recomputed where the reference stores them)
+B200_HD int num_vec_slots(int max_depth, int dense = 0) { return V_STACK + 5 * max_depth + (dense ? 4 : 0); }
 
 enum ChainState {
   ST_START = 0,
@@ -75,6 +78,7 @@ struct SamplerCfg {
   int D, ld, max_depth;
   int num_warmup, num_samples, num_thin, save_warmup;
   int adapt_engaged, user_inits;
+  int dense;             // 1: dense_e metric (per-chain D x D inverse metric, covariance windows); 0: diag_e / unit_e
   double stepsize, stepsize_jitter, delta, gamma, kappa, t0, init_radius;
   // resolved window schedule (windowed_adaptation::set_window_params)
   unsigned w_num_warmup, w_init_buffer, w_term_buffer, w_base_window, w_next0, w_size0;
@@ -109,9 +113,61 @@ struct ChainView {
   double* v;      // vector slab, slot k at v + k*ld
   double* draws;  // this chain's rows [rows_per_chain][ncol] or nullptr
   const double* user_q0;  // [ld] or nullptr
+  double* mat = nullptr;  // dense metric only: three D x D column-major matrices (element (i,j) at j*D + i, like
+                          // Eigen::MatrixXd): [0] inverse metric M^-1, [1] its lower Cholesky factor L, [2] Welford m2
 };
 
 B200_DEV double* slot(const ChainView& c, const SamplerCfg& cfg, int k) { return c.v + (size_t)k * cfg.ld; }
+
+B200_DEV double* scratch(const ChainView& c, const SamplerCfg& cfg, int k) { return slot(c, cfg, V_STACK + 5 * cfg.max_depth + k); }
+
+// ---- dense metric -----------------------------------------------------------------------------------------------------
+// out = M^-1 p  (dense_e_metric::dtau_dp, dense_e_metric.hpp:38).  Lane l owns rows l, l+32, ...; the matrix is column-major
+// so the 32 lanes read consecutive addresses; each row is accumulated over the columns in index order (the order of Eigen's
+// column-major gemv kernel).
+B200_DEV_CALL void dense_sharp(const double* M, const double* p, double* out, int D, int lane) {
+  warp_sync();  // p was written by its owner lanes
+  _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+    double acc = 0;
+    _Pragma("unroll 4") for (int j = 0; j < D; j++) acc += M[(size_t)j * D + i] * p[j];
+    out[i] = acc;
+  }
+}
+// lower Cholesky factor L of M^-1 into mat[1] (the reference factorises inside every sample_p, dense_e_metric.hpp:55
+// `inv_e_metric_.llt()`; the factor only changes with the metric, so it is computed once per metric).  Reads the lower
+// triangle only, like Eigen::LLT<Lower>.  Returns false when the matrix is not positive definite.
+B200_DEV_CALL bool dense_factor(double* mat, int D, int lane) {
+  const double* A = mat;
+  double* L = mat + (size_t)D * D;
+  _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp)
+    for (int j = 0; j < D; j++) L[(size_t)j * D + i] = 0.0;
+  warp_sync();
+  for (int j = 0; j < D; j++) {
+    double d = A[(size_t)j * D + j];  // every lane forms the pivot itself (same values, same order)
+    for (int k = 0; k < j; k++) d -= L[(size_t)k * D + j] * L[(size_t)k * D + j];
+    if (!(d > 0)) return false;
+    const double ljj = sqrt(d);
+    _Pragma("unroll 1") for (int i = j + 1 + ((lane - (j + 1)) % kWarp + kWarp) % kWarp; i < D; i += kWarp) {  // rows i > j owned by this lane
+      double v = A[(size_t)j * D + i];
+      for (int k = 0; k < j; k++) v -= L[(size_t)k * D + i] * L[(size_t)k * D + j];
+      L[(size_t)j * D + i] = v / ljj;
+    }
+    if (lane == j % kWarp) L[(size_t)j * D + j] = ljj;
+    warp_sync();
+  }
+  return true;
+}
+// p = L^-T u  (dense_e_metric::sample_p, dense_e_metric.hpp:44-56: matrixU().solve(u)): back substitution on L^T
+B200_DEV_CALL void dense_solve_upper(const double* L, const double* u, double* p, int D, int lane) {
+  warp_sync();
+  for (int i = D - 1; i >= 0; i--) {
+    double acc = 0;
+    _Pragma("unroll 1") for (int k = i + 1 + lane; k < D; k += kWarp) acc += L[(size_t)i * D + k] * p[k];
+    acc = warp_sum(acc);
+    if (lane == i % kWarp) p[i] = (u[i] - acc) / L[(size_t)i * D + i];
+    warp_sync();
+  }
+}
 
 // T(p) = 0.5 p . (M^-1 o p)   (diag_e_metric.hpp:20-22)
 B200_DEV double kinetic(const double* p, const double* im, int D, int lane) {
@@ -120,10 +176,26 @@ B200_DEV double kinetic(const double* p, const double* im, int D, int lane) {
   return 0.5 * warp_sum(acc);
 }
 
+// dense_e_metric::T (dense_e_metric.hpp:21-23): 0.5 p^T (M^-1 p)
+B200_DEV_CALL double kinetic_dense(const ChainView& c, const SamplerCfg& cfg, const double* p, int lane) {
+  double* s0 = scratch(c, cfg, 0);
+  dense_sharp(c.mat, p, s0, cfg.D, lane);
+  double acc = 0;
+  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) acc += p[i] * s0[i];
+  return 0.5 * warp_sum(acc);
+}
+
 // first two thirds of expl_leapfrog::evolve: p -= (eps/2) g ; q += eps (M^-1 o p); then the gradient is wanted
 B200_DEV void leapfrog_begin(const ChainView& c, const SamplerCfg& cfg, double eps, int lane) {
   const double h = 0.5 * eps;
   double* p = slot(c, cfg, V_P);
+  if (cfg.dense) {
+    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
+    double* s0 = scratch(c, cfg, 0);
+    dense_sharp(c.mat, p, s0, cfg.D, lane);
+    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) c.q[i] += eps * s0[i];
+    return;
+  }
   const double* im = slot(c, cfg, V_IM);
   _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     double pi = p[i] - h * c.g[i];
@@ -137,12 +209,18 @@ B200_DEV double leapfrog_end(const ChainView& c, const SamplerCfg& cfg, double e
   double* p = slot(c, cfg, V_P);
   const double* im = slot(c, cfg, V_IM);
   double acc = 0;
-  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
-    double pi = p[i] - h * c.g[i];
-    p[i] = pi;
-    acc += pi * (im[i] * pi);
+  double H;
+  if (cfg.dense) {
+    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
+    H = kinetic_dense(c, cfg, p, lane) + (*c.zV);
+  } else {
+    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+      double pi = p[i] - h * c.g[i];
+      p[i] = pi;
+      acc += pi * (im[i] * pi);
+    }
+    H = 0.5 * warp_sum(acc) + (*c.zV);
   }
-  double H = 0.5 * warp_sum(acc) + (*c.zV);
   *h_raw = H;
   if (isnan(H)) H = INFINITY;
   return H;
@@ -154,12 +232,19 @@ B200_DEV_CALL double refresh_from_current(const ChainView& c, const SamplerCfg& 
   const double* im = slot(c, cfg, V_IM);
   const double* cq = slot(c, cfg, V_CQ);
   const double* cg = slot(c, cfg, V_CG);
-  warp_fill(c.s->rng, lane, p, cfg.D, 0, im, 0.0);
+  if (cfg.dense) {  // u ~ N(0, I) in index order, p = L^-T u
+    double* u = scratch(c, cfg, 1);
+    warp_fill(c.s->rng, lane, u, cfg.D, 0, nullptr, 0.0);
+    dense_solve_upper(c.mat + (size_t)cfg.D * cfg.D, u, p, cfg.D, lane);
+  } else {
+    warp_fill(c.s->rng, lane, p, cfg.D, 0, im, 0.0);
+  }
   _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     c.q[i] = cq[i];
     c.g[i] = cg[i];
   }
   (*c.zV) = c.s->curV;
+  if (cfg.dense) return kinetic_dense(c, cfg, p, lane) + c.s->curV;
   return kinetic(p, im, cfg.D, lane) + c.s->curV;
 }
 
@@ -182,11 +267,21 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
     take_right = warp_uniform01(s->rng, lane) < accept_prob;
   }
   double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
+  const bool dense = cfg.dense != 0;
+  const double *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
+  if (dense) {  // sharp momenta of the four boundary momenta (the reference keeps them; here they are recomputed)
+    dense_sharp(c.mat, L, scratch(c, cfg, 0), cfg.D, lane);
+    dense_sharp(c.mat, L + ld, scratch(c, cfg, 1), cfg.D, lane);
+    dense_sharp(c.mat, R, scratch(c, cfg, 2), cfg.D, lane);
+    dense_sharp(c.mat, R + ld, scratch(c, cfg, 3), cfg.D, lane);
+    s0 = scratch(c, cfg, 0); s1 = scratch(c, cfg, 1); s2 = scratch(c, cfg, 2); s3 = scratch(c, cfg, 3);
+  }
   _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
     const double m = im[i];
     const double lpb = L[i], lpe = L[ld + i], lr = L[2 * ld + i];
     const double rpb = R[i], rpe = R[ld + i], rr = R[2 * ld + i];
-    const double sh_lpb = m * lpb, sh_lpe = m * lpe, sh_rpb = m * rpb, sh_rpe = m * rpe;
+    const double sh_lpb = dense ? s0[i] : m * lpb, sh_lpe = dense ? s1[i] : m * lpe, sh_rpb = dense ? s2[i] : m * rpb,
+                 sh_rpe = dense ? s3[i] : m * rpe;
     const double rs = lr + rr;   // rho_subtree = rho_init + rho_final
     a1 += sh_rpe * rs;           // compute_criterion(p_sharp_beg, p_sharp_end, rho_subtree)
     a2 += sh_lpb * rs;
@@ -240,7 +335,23 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
   double* wm2 = slot(c, cfg, V_WM2);
   const unsigned cnt = s->win_counter;
   const bool in_window = (cnt >= cfg.w_init_buffer) && (cnt < cfg.w_num_warmup - cfg.w_term_buffer) && (cnt != cfg.w_num_warmup);
-  if (in_window) {
+  const int D = cfg.D;
+  if (in_window && cfg.dense) {  // welford_covar_estimator::add_sample: m2 += (q - m_new) delta^T
+    s->wf_n += 1.0;
+    const double n = s->wf_n;
+    double* delta = scratch(c, cfg, 0);
+    double* W = c.mat + 2 * (size_t)D * D;
+    _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+      const double dl = q[i] - wm[i];
+      delta[i] = dl;
+      wm[i] += dl / n;
+    }
+    warp_sync();
+    _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+      const double r = q[i] - wm[i];
+      for (int j = 0; j < D; j++) W[(size_t)j * D + i] += r * delta[j];
+    }
+  } else if (in_window) {
     s->wf_n += 1.0;
     const double n = s->wf_n;
     _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
@@ -264,6 +375,27 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
     }
     const double n = s->wf_n;
     double bad = 0;
+    if (cfg.dense) {  // covar_adaptation::learn_covariance, covar_adaptation.hpp:24-38
+      double* M = c.mat;
+      double* W = c.mat + 2 * (size_t)D * D;
+      _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+        for (int j = 0; j < D; j++) {
+          const size_t e = (size_t)j * D + i;
+          double cov = M[e];
+          if (n > 1) cov = W[e] / (n - 1.0);
+          cov = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * (i == j ? 1.0 : 0.0);
+          M[e] = cov;
+          if (!isfinite(cov)) bad = 1;
+          W[e] = 0;
+        }
+        wm[i] = 0;
+      }
+      bad = warp_sum(bad);
+      s->wf_n = 0;
+      s->win_counter = cnt + 1;
+      if (bad > 0) return -1;
+      return dense_factor(c.mat, D, lane) ? 1 : -1;
+    }
     _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
       double var = im[i];
       if (n > 1) var = wm2[i] / (n - 1.0);
@@ -293,6 +425,10 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       case ST_START: {
         s->init_tries = 0;
         s->state = ST_INIT_DRAW;
+        if (cfg.dense && !dense_factor(c.mat, D, lane)) {  // "Inverse Euclidean metric not positive definite."
+          s->err = 78;
+          s->state = ST_DONE;
+        }
         break;
       }
       case ST_INIT_DRAW: {  // util::initialize (initialize.hpp:87-117)
@@ -530,6 +666,17 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           const double* pbb = slot(c, cfg, V_BP);  // p_bck_bck == z_bck.p
           double* cq = slot(c, cfg, V_CQ);
           double* cg = slot(c, cfg, V_CG);
+          const bool dense = cfg.dense != 0;
+          const double *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
+          if (dense) {  // boundary momentum of the new subtree first, then the four sharp momenta
+            double* dst = fwd ? pfb : pbf;
+            _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) dst[i] = S[i];
+            dense_sharp(c.mat, pff, scratch(c, cfg, 0), D, lane);
+            dense_sharp(c.mat, pbb, scratch(c, cfg, 1), D, lane);
+            dense_sharp(c.mat, pfb, scratch(c, cfg, 2), D, lane);
+            dense_sharp(c.mat, pbf, scratch(c, cfg, 3), D, lane);
+            s0 = scratch(c, cfg, 0); s1 = scratch(c, cfg, 1); s2 = scratch(c, cfg, 2); s3 = scratch(c, cfg, 3);
+          }
           _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
             const double m = im[i];
             double rho_bck, rho_fwd;
@@ -543,15 +690,17 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
               pbf[i] = S[i];
             }
             const double v_pfb = pfb[i], v_pbf = pbf[i], v_pff = pff[i], v_pbb = pbb[i];
+            const double sh_pff = dense ? s0[i] : m * v_pff, sh_pbb = dense ? s1[i] : m * v_pbb, sh_pfb = dense ? s2[i] : m * v_pfb,
+                         sh_pbf = dense ? s3[i] : m * v_pbf;
             const double r = rho_bck + rho_fwd;
-            a1 += (m * v_pff) * r;  // compute_criterion(p_sharp_bck_bck, p_sharp_fwd_fwd, rho)
-            a2 += (m * v_pbb) * r;
+            a1 += sh_pff * r;  // compute_criterion(p_sharp_bck_bck, p_sharp_fwd_fwd, rho)
+            a2 += sh_pbb * r;
             const double re = rho_bck + v_pfb;
-            b1 += (m * v_pfb) * re; // compute_criterion(p_sharp_bck_bck, p_sharp_fwd_bck, rho_bck + p_fwd_bck)
-            b2 += (m * v_pbb) * re;
+            b1 += sh_pfb * re; // compute_criterion(p_sharp_bck_bck, p_sharp_fwd_bck, rho_bck + p_fwd_bck)
+            b2 += sh_pbb * re;
             const double rf = rho_fwd + v_pbf;
-            c1 += (m * v_pff) * rf; // compute_criterion(p_sharp_bck_fwd, p_sharp_fwd_fwd, rho_fwd + p_bck_fwd)
-            c2 += (m * v_pbf) * rf;
+            c1 += sh_pff * rf; // compute_criterion(p_sharp_bck_fwd, p_sharp_fwd_fwd, rho_fwd + p_bck_fwd)
+            c2 += sh_pbf * rf;
             rho[i] = r;
             if (take) {
               cq[i] = S[3 * ld + i];

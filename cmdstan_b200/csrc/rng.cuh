@@ -138,7 +138,8 @@ B200_DEV double warp_uniform01(unsigned long long* st, int lane) {
 }
 
 // fills dst[0..n) with variates in stream order; element i is stored by its owner lane (i % warp)
-// kind 0: normal(0,1) scaled by 1/sqrt(scale[i])  (diag_e_metric::sample_p, S/mcmc/hmc/hamiltonians/diag_e_metric.hpp:44-50)
+// kind 0: normal(0,1) scaled by 1/sqrt(scale[i])  (diag_e_metric::sample_p, S/mcmc/hmc/hamiltonians/diag_e_metric.hpp:44-50);
+//         scale == nullptr: unscaled (the u of dense_e_metric::sample_p)
 // kind 1: uniform_real(-radius, radius)           (random_var_context, S/io/random_var_context.hpp:53-56)
 B200_DEV_CALL void warp_fill(unsigned long long* st, int lane, double* dst, int n, int kind, const double* scale, double radius) {
   for (int base = 0; base < n; base += kWarp) {
@@ -150,7 +151,7 @@ B200_DEV_CALL void warp_fill(unsigned long long* st, int lane, double* dst, int 
       v = bcast0(v);
       if (lane == j) mine = v;
     }
-    if (lane < m) dst[base + lane] = kind == 0 ? mine / sqrt(scale[base + lane]) : mine;
+    if (lane < m) dst[base + lane] = (kind == 0 && scale) ? mine / sqrt(scale[base + lane]) : mine;
   }
 }
 

@@ -71,9 +71,10 @@ class json_parser {
       expect(':');
       var v;
       std::vector<int64_t> dims;
+      skip_ = false;
       value(v, dims, 0);
       v.dims = dims;
-      ctx.add(key, std::move(v));
+      if (!skip_) ctx.add(key, std::move(v));  // a top-level string (e.g. "metric_type" : "dense_e" of a saved metric file) is not data
       ws();
       if (peek() == ',') { p_++; continue; }
       expect('}');
@@ -130,6 +131,7 @@ class json_parser {
       if (t == "NaN") v.vals.push_back(std::numeric_limits<double>::quiet_NaN());
       else if (t == "Infinity" || t == "Inf") v.vals.push_back(std::numeric_limits<double>::infinity());
       else if (t == "-Infinity" || t == "-Inf") v.vals.push_back(-std::numeric_limits<double>::infinity());
+      else if (depth == 0) skip_ = true;
       else fail("string values are not allowed: " + t);
       v.is_int = false;
       return;
@@ -143,6 +145,7 @@ class json_parser {
   }
   std::string s_;
   size_t p_;
+  bool skip_ = false;
 };
 
 inline var_context read_json_file(const std::string& path) {

@@ -75,13 +75,13 @@ int main(int argc, char** argv) {
     return services::error_codes::USAGE;
   }
   if (parser.str({"method"}) != "sample") {
-    std::cerr << "method=" << parser.str({"method"}) << " is not available in the B200 engine (only `sample` with algorithm=hmc engine=nuts metric=diag_e)" << std::endl;
+    std::cerr << "method=" << parser.str({"method"}) << " is not available in the B200 engine (only `sample` with algorithm=hmc engine=nuts metric=diag_e|unit_e|dense_e)" << std::endl;
     return services::error_codes::USAGE;
   }
   const std::string metric = parser.str({"method", "sample", "algorithm", "hmc", "metric"});
   if (parser.str({"method", "sample", "algorithm"}) != "hmc" || parser.str({"method", "sample", "algorithm", "hmc", "engine"}) != "nuts" ||
-      (metric != "diag_e" && metric != "unit_e")) {
-    std::cerr << "only algorithm=hmc engine=nuts metric=diag_e|unit_e is available in the B200 engine" << std::endl;
+      (metric != "diag_e" && metric != "unit_e" && metric != "dense_e")) {
+    std::cerr << "only algorithm=hmc engine=nuts metric=diag_e|unit_e|dense_e is available in the B200 engine" << std::endl;
     return services::error_codes::USAGE;
   }
   const unsigned num_chains = (unsigned)parser.integer({"method", "sample", "num_chains"});
@@ -177,6 +177,7 @@ int main(int argc, char** argv) {
 
     services::device_options opt;
     opt.unit_e = metric == "unit_e";  // command.hpp dispatches to hmc_nuts_unit_e[_adapt]; same call below with the identity metric
+    opt.dense_e = metric == "dense_e";  // ... and to hmc_nuts_dense_e[_adapt] (command.hpp:620-660)
     if (const char* dv = std::getenv("B200_DEVICES")) {
       opt.devices.clear();
       std::stringstream ss(dv);

@@ -52,6 +52,7 @@ struct device_options {
   int engine = B200NUTS_ENGINE_AUTO;
   int format_threads = 8;          // host threads used to format CSV rows (per-chain files are independent)
   bool unit_e = false;             // identity metric (the hmc_nuts_unit_e* services below set it)
+  bool dense_e = false;            // dense metric (the hmc_nuts_dense_e* services below set it)
 };
 
 // metric_writer interface: one JSON record per chain (callbacks::structured_writer's use in write_sampler_state_struct)
@@ -59,10 +60,18 @@ class json_metric_writer {
  public:
   json_metric_writer() {}
   explicit json_metric_writer(std::unique_ptr<std::ostream>&& out) : out_(std::move(out)) {}
-  void write(double stepsize, const double* inv_metric, int64_t n) {
+  void write(double stepsize, const double* inv_metric, int64_t n, bool dense = false) {
     if (!out_) return;
-    *out_ << "{\n  \"stepsize\" : " << stepsize << ",\n  \"metric_type\" : \"diag_e\",\n  \"inv_metric\" : [ ";
-    for (int64_t i = 0; i < n; i++) *out_ << (i ? ", " : "") << inv_metric[i];
+    *out_ << "{\n  \"stepsize\" : " << stepsize << ",\n  \"metric_type\" : \"" << (dense ? "dense_e" : "diag_e") << "\",\n  \"inv_metric\" : [ ";
+    if (dense) {  // json_writer::write(key, Eigen::MatrixXd), callbacks/json_writer.hpp:484-500: one bracketed row per matrix row
+      for (int64_t i = 0; i < n; i++) {
+        *out_ << (i ? ", " : "") << "[ ";
+        for (int64_t j = 0; j < n; j++) *out_ << (j ? ", " : "") << inv_metric[i * n + j];
+        *out_ << " ]";
+      }
+    } else {
+      for (int64_t i = 0; i < n; i++) *out_ << (i ? ", " : "") << inv_metric[i];
+    }
     *out_ << " ]\n}\n";
     out_->flush();
   }
@@ -148,12 +157,18 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     for (size_t c = 0; c < num_chains && c < init_inv_metric.size(); c++)
       if (init_inv_metric[c] && init_inv_metric[c]->contains_r("inv_metric")) any_metric = true;
     if (any_metric) {
-      im.assign((size_t)C * D, 1.0);
+      // util::read_diag_inv_metric / read_dense_inv_metric (services/util/read_*_inv_metric.hpp); a dense matrix is symmetric,
+      // so the flattening order of the context does not matter
+      const int64_t MD = opt.dense_e ? D * D : D;
+      im.assign((size_t)C * MD, opt.dense_e ? 0.0 : 1.0);
+      if (opt.dense_e)
+        for (int c = 0; c < C; c++)
+          for (int64_t i = 0; i < D; i++) im[(size_t)c * MD + i * D + i] = 1.0;
       for (size_t c = 0; c < num_chains && c < init_inv_metric.size(); c++) {
         if (!init_inv_metric[c] || !init_inv_metric[c]->contains_r("inv_metric")) continue;
         const std::vector<double>& v = init_inv_metric[c]->vals_r("inv_metric");
-        if ((int64_t)v.size() != D) throw std::domain_error("Cannot get inverse metric from input file; expected " + std::to_string(D) + " elements");
-        std::copy(v.begin(), v.end(), im.begin() + c * D);
+        if ((int64_t)v.size() != MD) throw std::domain_error("Cannot get inverse metric from input file; expected " + std::to_string(MD) + " elements");
+        std::copy(v.begin(), v.end(), im.begin() + c * MD);
       }
     }
   } catch (const std::domain_error& e) {
@@ -192,7 +207,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     cfg.term_buffer = term_buffer;
     cfg.window = window;
     cfg.adapt_engaged = adapt_engaged;
-    cfg.metric = opt.unit_e ? 1 : 0;
+    cfg.metric = opt.dense_e ? 2 : (opt.unit_e ? 1 : 0);
     cfg.engine = opt.engine;
     cfg.device = opt.devices.empty() ? 0 : opt.devices[g];
     b200nuts_engine* e = nullptr;
@@ -203,7 +218,8 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     }
     eg.e.push_back(e);
     if ((rc = model.upload(e)) || (!q0.empty() && (rc = b200nuts_set_inits(e, q0.data() + (size_t)first[g] * D))) ||
-        (!im.empty() && (rc = b200nuts_set_inv_metric(e, im.data() + (size_t)first[g] * D))) || (rc = b200nuts_init_chains(e))) {
+        (!im.empty() && (rc = b200nuts_set_inv_metric(e, im.data() + (size_t)first[g] * D * (opt.dense_e ? D : 1)))) ||
+        (rc = b200nuts_init_chains(e))) {
       logger.error(b200nuts_last_error(e));
       return rc;
     }
@@ -338,9 +354,10 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   if ((rc = write_rows(0, warm_rows))) return rc;
   // ---- adaptation block (write_adapt_finish + write_sampler_state) and metric JSON
   {
-    std::vector<double> eps((size_t)C), met((size_t)C * D);
+    const int64_t MD = opt.dense_e ? D * D : D;
+    std::vector<double> eps((size_t)C), met((size_t)C * MD);
     for (int g = 0; g < G; g++)
-      if ((rc = b200nuts_get_adaptation(eg.e[g], eps.data() + first[g], met.data() + (size_t)first[g] * D))) {
+      if ((rc = b200nuts_get_adaptation(eg.e[g], eps.data() + first[g], met.data() + (size_t)first[g] * MD))) {
         logger.error(b200nuts_last_error(eg.e[g]));
         return rc;
       }
@@ -354,6 +371,13 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
           w(ss.str());
           if (opt.unit_e) {
             w("No free parameters for unit metric");  // unit_e_point::write_metric (mcmc/hmc/hamiltonians/unit_e_point.hpp)
+          } else if (opt.dense_e) {  // dense_e_point::write_metric (mcmc/hmc/hamiltonians/dense_e_point.hpp:46-56): one row per line
+            w("Elements of inverse mass matrix:");
+            for (int64_t i = 0; i < D; i++) {
+              std::stringstream ms;
+              for (int64_t j = 0; j < D; j++) ms << (j ? ", " : "") << met[(size_t)c * MD + i * D + j];
+              w(ms.str());
+            }
           } else {
             w("Diagonal elements of inverse mass matrix:");
             std::stringstream ms;
@@ -362,7 +386,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
           }
         }
       }
-      if (adapt_engaged && (size_t)c < metric_writer.size()) metric_writer[c].write(eps[c], met.data() + (size_t)c * D, D);
+      if (adapt_engaged && (size_t)c < metric_writer.size()) metric_writer[c].write(eps[c], met.data() + (size_t)c * MD, D, opt.dense_e);
     }
   }
   // ---- sampling
@@ -418,6 +442,42 @@ int hmc_nuts_diag_e(Model& model, size_t num_chains, const std::vector<InitConte
   return hmc_nuts_diag_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
                                num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75u, 50u, 25u,
                                interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, false);
+}
+
+// stan::services::sample::hmc_nuts_dense_e_adapt (services/sample/hmc_nuts_dense_e_adapt.hpp:331-407 multi-chain): dense
+// Euclidean metric; step size and covariance adapted in windows (adapt_dense_e_nuts.hpp:25-44, covar_adaptation.hpp:17-45).
+// init_inv_metric contexts hold "inv_metric" as a D x D matrix (util::read_dense_inv_metric).
+template <class Model, typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter,
+          typename DiagnosticWriter, typename MetricWriter>
+int hmc_nuts_dense_e_adapt(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init,
+                           const std::vector<InitInvContextPtr>& init_inv_metric, unsigned int random_seed, unsigned int init_chain_id,
+                           double init_radius, int num_warmup, int num_samples, int num_thin, bool save_warmup, int refresh,
+                           double stepsize, double stepsize_jitter, int max_depth, double delta, double gamma, double kappa, double t0,
+                           unsigned int init_buffer, unsigned int term_buffer, unsigned int window, callbacks::interrupt& interrupt,
+                           callbacks::logger& logger, std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                           std::vector<DiagnosticWriter>& diagnostic_writer, std::vector<MetricWriter>& metric_writer,
+                           device_options opt = device_options(), bool adapt_engaged = true) {
+  opt.dense_e = true;
+  opt.unit_e = false;
+  return hmc_nuts_diag_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                               num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, init_buffer,
+                               term_buffer, window, interrupt, logger, init_writer, sample_writer, diagnostic_writer, metric_writer, opt,
+                               adapt_engaged);
+}
+
+// stan::services::sample::hmc_nuts_dense_e (services/sample/hmc_nuts_dense_e.hpp): dense metric, no adaptation
+template <class Model, typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter,
+          typename DiagnosticWriter>
+int hmc_nuts_dense_e(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init,
+                     const std::vector<InitInvContextPtr>& init_inv_metric, unsigned int random_seed, unsigned int init_chain_id,
+                     double init_radius, int num_warmup, int num_samples, int num_thin, bool save_warmup, int refresh, double stepsize,
+                     double stepsize_jitter, int max_depth, callbacks::interrupt& interrupt, callbacks::logger& logger,
+                     std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                     std::vector<DiagnosticWriter>& diagnostic_writer, const device_options& opt = device_options()) {
+  std::vector<json_metric_writer> none;
+  return hmc_nuts_dense_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
+                                num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75u, 50u, 25u,
+                                interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, false);
 }
 
 // stan::services::sample::hmc_nuts_unit_e_adapt (services/sample/hmc_nuts_unit_e_adapt.hpp): identity metric, step size adapted

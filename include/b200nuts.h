@@ -82,7 +82,10 @@ typedef struct b200nuts_config {
   int32_t row_shards;       /* default 1 */
   int32_t row_shard_rank;   /* default 0 */
   int32_t metric;           /* 0 diag_e (default): hmc_nuts_diag_e[_adapt]; 1 unit_e: hmc_nuts_unit_e[_adapt]
-                               (stan/src/stan/services/sample/hmc_nuts_unit_e_adapt.hpp; the metric stays the identity) */
+                               (stan/src/stan/services/sample/hmc_nuts_unit_e_adapt.hpp; the metric stays the identity);
+                               2 dense_e: hmc_nuts_dense_e[_adapt] (stan/src/stan/services/sample/hmc_nuts_dense_e_adapt.hpp,
+                               stan/mcmc/hmc/hamiltonians/dense_e_metric.hpp, stan/mcmc/covar_adaptation.hpp): a D x D
+                               inverse metric per chain, covariance learned in the adaptation windows */
 } b200nuts_config;
 
 typedef struct b200nuts_engine b200nuts_engine;
@@ -103,8 +106,9 @@ int b200nuts_set_data_i8(b200nuts_engine* e, const char* name, const int8_t* hos
 /* dimension of the unconstrained space / number of write_array output columns (valid after the data is set) */
 int b200nuts_num_params(const b200nuts_engine* e, int64_t* num_unconstrained, int64_t* num_outputs);
 
-/* optional user inits q0[num_chains][D] (unconstrained scale) and inverse metric [num_chains][D]; NULL => reference
-   behaviour (uniform(-R,R) draws from each chain's own stream; unit metric) */
+/* optional user inits q0[num_chains][D] (unconstrained scale) and inverse metric [num_chains][D] (dense_e:
+   [num_chains][D][D], symmetric positive definite, else CONFIG "Inverse Euclidean metric not positive definite.");
+   NULL => reference behaviour (uniform(-R,R) draws from each chain's own stream; unit metric) */
 int b200nuts_set_inits(b200nuts_engine* e, const double* q0);
 int b200nuts_set_inv_metric(b200nuts_engine* e, const double* inv_metric);
 
@@ -137,7 +141,8 @@ int b200nuts_summary(b200nuts_engine* e, int64_t row0, int64_t nrows, int constr
 int b200nuts_summarize_draws(const double* draws, int64_t chains, int64_t rows, int64_t ncols, int device, double* out,
                              char* errbuf, int errlen);
 
-/* adapted step size [num_chains] and inverse metric [num_chains][D] ("# Step size", "# Diagonal elements ...") */
+/* adapted step size [num_chains] and inverse metric [num_chains][D] ("# Step size", "# Diagonal elements ...");
+   dense_e: [num_chains][D][D] ("# Elements of inverse mass matrix:") */
 int b200nuts_get_adaptation(b200nuts_engine* e, double* stepsize, double* inv_metric);
 /* per-chain status: error code (0 ok, 78 init failed, 70 step-size / metric failure), iterations done, leapfrog
    gradients consumed; any pointer may be NULL */

@@ -15,7 +15,7 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
                               double stepsize, double jitter, int max_depth, double delta, double gamma, double kappa, double t0,
                               unsigned init_buffer, unsigned term_buffer, unsigned window, double init_radius, int adapt_engaged,
                               const double* q0, const double* inv_metric0, double* draws, double* adapt_out, long long* n_grad,
-                              int unit_e) {
+                              int unit_e, int dense_e) {
   ModelData m{};
   m.kind = kind; m.D = D; m.N = N; m.yr = yr; m.sigma = sigma; m.sum_y = sum_y;
   SamplerCfg cfg{};
@@ -25,17 +25,24 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
   cfg.stepsize = stepsize; cfg.stepsize_jitter = (jitter > 0 && jitter < 1) ? jitter : 0.0;
   cfg.delta = (delta > 0 && delta < 1) ? delta : 0.5; cfg.gamma = gamma > 0 ? gamma : 0.05;
   cfg.kappa = kappa > 0 ? kappa : 0.75; cfg.t0 = t0 > 0 ? t0 : 10; cfg.init_radius = init_radius;
+  cfg.dense = dense_e;
   resolve_window(&cfg, (adapt_engaged && !unit_e) ? num_warmup : 0, init_buffer, term_buffer, window);
   cfg.ncol = 7 + D;
   cfg.rows_per_chain = (save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0) + (num_samples + num_thin - 1) / num_thin;
-  std::vector<double> slab((size_t)num_vec_slots(max_depth) * D, 0.0), q(D), g(D);
+  std::vector<double> slab((size_t)num_vec_slots(max_depth, dense_e) * D, 0.0), q(D), g(D), mat(dense_e ? 3 * (size_t)D * D : 1, 0.0);
   ChainS s;
   std::memset(&s, 0, sizeof s);
   chain_init_scalars(&s, cfg);
   seed_stream(s.rng, seed, chain_id);
   double zV = 0;
   ChainView c{&s, q.data(), g.data(), &zV, slab.data(), draws, q0};
-  for (int i = 0; i < D; i++) slab[(size_t)V_IM * D + i] = inv_metric0 ? inv_metric0[i] : 1.0;
+  if (dense_e) {  // inv_metric0: [D][D] row-major -> column-major
+    c.mat = mat.data();
+    for (int i = 0; i < D; i++)
+      for (int j = 0; j < D; j++) mat[(size_t)j * D + i] = inv_metric0 ? inv_metric0[(size_t)i * D + j] : (i == j ? 1.0 : 0.0);
+  } else {
+    for (int i = 0; i < D; i++) slab[(size_t)V_IM * D + i] = inv_metric0 ? inv_metric0[i] : 1.0;
+  }
   s.iter_end = num_warmup + num_samples;
   while (advance(c, cfg, 0) == ADV_NEED_GRAD) {
     double lp = lp_grad_small(m, q.data(), g.data(), 0);
@@ -43,7 +50,12 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
     zV = -lp;
   }
   adapt_out[0] = s.eps_nom;
-  for (int i = 0; i < D; i++) adapt_out[1 + i] = slab[(size_t)V_IM * D + i];
+  if (dense_e) {
+    for (int i = 0; i < D; i++)
+      for (int j = 0; j < D; j++) adapt_out[1 + (size_t)i * D + j] = mat[(size_t)j * D + i];
+  } else {
+    for (int i = 0; i < D; i++) adapt_out[1 + i] = slab[(size_t)V_IM * D + i];
+  }
   *n_grad = s.n_grad;
   return s.err;
 }

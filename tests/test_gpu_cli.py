@@ -159,6 +159,43 @@ def test_cli_metric_unit_e_vs_reference(tmp_path):
     assert np.array_equal(dm[:, 3:6], dr[:, 3:6]) and np.allclose(dm[:30], dr[:30], rtol=1e-9) and np.allclose(dm, dr, rtol=1e-4)
 
 
+@pytest.mark.skipif(not O.have_ref("eight_schools_nc"), reason="oracle/_ref not built")
+def test_cli_metric_dense_e_vs_reference(tmp_path):
+    """`model sample algorithm=hmc metric=dense_e` (hmc_nuts_dense_e_adapt): same comment skeleton as the unmodified reference
+    (config echo with metric = dense_e, "# Elements of inverse mass matrix:" followed by D rows of D values), first
+    transitions equal, save_metric JSON with metric_type dense_e and a D x D inv_metric; then the written metric is fed back
+    through metric_file= with adapt engaged=0 (hmc_nuts_dense_e)."""
+    dj = tmp_path / "es.json"
+    dj.write_text(json.dumps({"J": 8, "y": [28, 8, -3, 7, -1, 1, 18, 12], "sigma": [15, 10, 16, 11, 9, 11, 10, 18]}))
+    args = ["sample", "num_samples=30", "num_warmup=150", "save_warmup=1", "adapt", "save_metric=1", "algorithm=hmc", "metric=dense_e", "data",
+            f"file={dj}", "random", "seed=5", "output", "sig_figs=12"]
+    r = _cli("eight_schools_nc", args + ["file=d.csv"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rr = subprocess.run([os.path.join(O.REF, "eight_schools_nc")] + args + ["file=dr.csv"], cwd=tmp_path, capture_output=True, text=True)
+    assert rr.returncode == 0, rr.stdout + rr.stderr
+    mine = _strip((tmp_path / "d.csv").read_text().splitlines())
+    ref = _strip((tmp_path / "dr.csv").read_text().splitlines())
+    assert len(mine) == len(ref) and "#         metric = dense_e" in mine
+    i = mine.index("# Elements of inverse mass matrix:")
+    assert ref.index("# Elements of inverse mass matrix:") == i
+    M = np.array([ln[1:].split(",") for ln in mine[i + 1:i + 11]], dtype=float)
+    assert M.shape == (10, 10) and np.allclose(M, M.T, rtol=1e-5) and np.all(np.linalg.eigvalsh(M) > 0)
+    dm = np.array([x.split(",") for x in mine if not x.startswith("#")][1:], dtype=float)
+    dr = np.array([x.split(",") for x in ref if not x.startswith("#")][1:], dtype=float)
+    assert np.array_equal(dm[:10, 3:6], dr[:10, 3:6]) and np.allclose(dm[:10], dr[:10], rtol=1e-7, atol=1e-9)
+    mj = json.loads((tmp_path / "d_metric.json").read_text())
+    rj = json.loads((tmp_path / "dr_metric.json").read_text())
+    assert mj["metric_type"] == rj["metric_type"] == "dense_e" and np.array(mj["inv_metric"]).shape == np.array(rj["inv_metric"]).shape == (10, 10)
+    # the adapted metric read back from the JSON file, no adaptation: stepsize__ column constant, no adaptation block
+    args2 = ["sample", "num_samples=40", "num_warmup=0", "adapt", "engaged=0", "algorithm=hmc", "metric=dense_e", f"metric_file={tmp_path / 'd_metric.json'}",
+             "stepsize=0.3", "data", f"file={dj}", "random", "seed=6", "output", "file=f.csv"]
+    r = _cli("eight_schools_nc", args2, tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = (tmp_path / "f.csv").read_text().splitlines()
+    rows = np.array([x.split(",") for x in lines if x and not x.startswith("#")][1:], dtype=float)
+    assert rows.shape[0] == 40 and (rows[:, 2] == 0.3).all() and not any("Adaptation terminated" in x for x in lines)
+
+
 def test_cli_errors(tmp_path):
     dj = _bernoulli_json(tmp_path)
     assert _cli("bernoulli", ["sample", "adapt", "delta=1.5"], tmp_path).returncode == 64

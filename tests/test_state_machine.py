@@ -23,6 +23,9 @@ OPTS = [
     dict(seed=13, chain_id=2, num_warmup=100, num_samples=20, term_buffer=0, init_buffer=50, window=50),
     dict(seed=14, chain_id=3, num_warmup=200, num_samples=50, unit_e=1, save_warmup=1),            # hmc_nuts_unit_e_adapt
     dict(seed=15, chain_id=1, num_warmup=20, num_samples=50, unit_e=1, adapt_engaged=0, stepsize=0.2),  # hmc_nuts_unit_e
+    dict(seed=16, chain_id=2, num_warmup=200, num_samples=60, dense_e=1, save_warmup=1),           # hmc_nuts_dense_e_adapt
+    dict(seed=17, chain_id=1, num_warmup=60, num_samples=30, dense_e=1, stepsize_jitter=0.2),      # fallback windows, jitter
+    dict(seed=18, chain_id=5, num_warmup=10, num_samples=40, dense_e=1, adapt_engaged=0, stepsize=0.3),  # hmc_nuts_dense_e
 ]
 
 
@@ -47,6 +50,25 @@ def test_user_inits_and_metric():
     a = O.run_chain(O.Model(name, data), q0=q0, inv_metric=im, **kw)
     b = E.run_chain(kind, D, data, q0=q0, inv_metric=im, **kw)
     assert np.array_equal(a["draws"], b["draws"])
+
+
+def test_user_dense_metric():
+    """user-supplied dense inverse metric (metric_file of hmc_nuts_dense_e[_adapt]): a correlated SPD matrix."""
+    name, kind, D, data = MODELS[2]
+    rng = np.random.default_rng(4)
+    A = rng.normal(size=(D, D))
+    im = A @ A.T / D + np.eye(D)
+    for kw in (dict(seed=3, chain_id=1, num_warmup=120, num_samples=40, save_warmup=1, dense_e=1),
+               dict(seed=4, chain_id=2, num_warmup=0, num_samples=60, adapt_engaged=0, stepsize=0.15, dense_e=1)):
+        a = O.run_chain(O.Model(name, data), inv_metric=im, **kw)
+        b = E.run_chain(kind, D, data, inv_metric=im, **kw)
+        assert a["rc"] == b["rc"] == 0
+        assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["inv_metric"], b["inv_metric"])
+    # not positive definite: refused (error_codes::CONFIG) by both
+    bad = np.eye(D)
+    bad[0, 0] = -1.0
+    assert O.run_chain(O.Model(name, data), inv_metric=bad, seed=1, num_warmup=20, num_samples=5, dense_e=1)["rc"] == 78
+    assert E.run_chain(kind, D, data, inv_metric=bad, seed=1, num_warmup=20, num_samples=5, dense_e=1)["rc"] == 78
 
 
 def test_init_failure_code():
