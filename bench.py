@@ -200,6 +200,11 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    t_start = time.time()
+
+    def note(msg):   # progress on stderr (stdout carries exactly one JSON line)
+        if os.environ.get("B200_BENCH_VERBOSE"):
+            print(f"[bench +{time.time() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     w = WORKLOADS[args.workload]
     model = w["model"]
@@ -263,8 +268,18 @@ def main():
         e = B.Engine(model, data, num_chains=C, random_seed=20241017, init_chain_id=1 + rank * C, num_warmup=args.num_warmup,
                      num_samples=num_samples, device=local_rank)
     e.init_chains()
-    e.run(args.num_warmup)
-    adapt_s, adapt_launches, adapt_grad_s = e.timing()
+    note("engine ready, data uploaded")
+    if os.environ.get("B200_BENCH_VERBOSE") and args.num_warmup > 20:   # adaptation in pieces, to see where the time goes
+        done, adapt_s, adapt_launches, adapt_grad_s = 0, 0.0, 0, 0.0
+        while done < args.num_warmup:
+            n = min(max(10, args.num_warmup // 10), args.num_warmup - done)
+            e.run(n)
+            s_, l_, g_ = e.timing()
+            adapt_s, adapt_launches, adapt_grad_s, done = adapt_s + s_, adapt_launches + l_, adapt_grad_s + g_, done + n
+            note(f"warm-up {done}/{args.num_warmup}: last {n} transitions {s_:.2f} s device, {l_} launches, gradient stage {g_:.2f} s")
+    else:
+        e.run(args.num_warmup)
+        adapt_s, adapt_launches, adapt_grad_s = e.timing()
     _, _, ng0 = e.chain_status()
     e.run(W)
     _, _, ng1 = e.chain_status()
@@ -280,6 +295,7 @@ def main():
     barrier()
     clk = clocks.stop()
     run_s, launches, grad_s = e.timing()
+    note(f"timed region: {run_s:.3f} s device, {launches} launches, gradient stage {grad_s:.3f} s")
     err, it, ng2 = e.chain_status()
     assert (err == 0).all(), f"chains stopped with errors: {np.unique(err)}"
     # ---- D2H of the timed draws through the C ABI (part of e2e)

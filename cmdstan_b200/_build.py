@@ -3,6 +3,8 @@
 The sampler translation unit is compiled with --fmad=false: the reference host build is x86-64 baseline (no FMA
 contraction), and matched-stream parity of the trajectory arithmetic needs the same roundings.
 The data-heavy gradient kernels (GLM, IRT) keep FMA contraction: their reductions are re-associated anyway.
+summary.cu is also built without contraction so that the write_array arithmetic it applies on the fly (model_output_column)
+rounds exactly like the write_array of b200nuts_fetch_draws (engine.cu).
 """
 import os
 import shutil
@@ -19,7 +21,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 EXAMPLES = os.path.join(HERE, "..", "examples", "plugin_models")
 EXAMPLE_PLUGIN = os.path.join(EXAMPLES, "libb200models_example.so")
-UNITS = [("engine.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", []), ("summary.cu", [])]
+UNITS = [("engine.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", []), ("summary.cu", ["--fmad=false"])]
 
 
 def _nvcc():
