@@ -112,6 +112,17 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(model):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json);
+    None when this workload has no capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(model)
+        return None if not t else {"bytes": t["read_bytes"] + t["write_bytes"], "kernel": t["kernel"], "chains_in_launch": t["chains_in_launch"],
+                                   "source": t["capture"]}
+    except Exception:
+        return None
+
+
 def algorithmic_work(w, data, model, D):
     """Per chain-gradient algorithmic flops and bytes (restated in DESIGN.md)."""
     if model in ("logistic", "poisson_glm"):
@@ -338,8 +349,10 @@ def main():
             fl = work["flops"] * n_chain_grads / world   # per rank: chains/world (chain mode) or rows/world (row mode)
             ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
+            tr = ncu_traffic(model) if args.scale == 1.0 and world == 1 else None
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
-                    "traffic": None, "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
+                    "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "algorithmic_bytes_per_launch": work["bytes_per_batch"],
+                    "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
                     "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "avg_chains_per_launch": n_chain_grads / world / n_grad_launch,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
                     "hbm_gbs_achieved": work["bytes_per_batch"] / (grad_s / n_grad_launch) / 1e9 if grad_s > 0 else None, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src}
@@ -347,8 +360,9 @@ def main():
             fl = work["flops"] * n_chain_grads / world
             ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None, "traffic": None,
-                    "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,
+            tr = ncu_traffic(model) if args.scale == 1.0 else None
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
+                    "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,
                     "note": "bound is FP64 ALU + transcendental throughput; normalised by the measured DGEMM rate"}
         else:
             # fused chain kernel: latency/occupancy-bound by construction (tens of flops per gradient); report HBM traffic rate

@@ -59,7 +59,8 @@ int main(int argc, char** argv) {
   int first = 1;
   if (model_name == "b200stan") {
     if (argc < 2) {
-      std::cerr << "usage: b200stan <model> sample [arguments]   (models: std_normal bernoulli eight_schools_nc logistic irt_2pl poisson_glm)" << std::endl;
+      std::cerr << "usage: b200stan <model> sample [arguments]   (models: std_normal bernoulli eight_schools_nc logistic irt_2pl poisson_glm,\n"
+                   "        or a plug-in model of the libraries named in B200NUTS_MODEL_LIBRARY -- include/b200nuts_model.h)" << std::endl;
       return services::error_codes::USAGE;
     }
     model_name = argv[1];

@@ -9,11 +9,15 @@
 // (src/cmdstan/command.hpp:71-73).
 #pragma once
 #include <cmath>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "../../include/b200nuts.h"
+#include "../../include/b200nuts_model.h"
 #include "json.hpp"
 
 namespace b200 {
@@ -84,12 +88,16 @@ class device_model {
       y8_.assign(y.begin(), y.end());
       params_ = {{"sigma_theta", -1, LOWER0}, {"theta", N_, FREE}, {"sigma_a", -1, LOWER0}, {"a", K_, LOWER0},
                  {"mu_b", -1, FREE},          {"sigma_b", -1, LOWER0}, {"b", K_, FREE}};
+    } else if (init_plugin(name, data)) {
+      return;
     } else {
-      throw std::invalid_argument("unknown model '" + name + "' (available: std_normal bernoulli eight_schools_nc logistic irt_2pl poisson_glm)");
+      throw std::invalid_argument("unknown model '" + name + "' (built in: std_normal bernoulli eight_schools_nc logistic irt_2pl poisson_glm; "
+                                  "plug-in libraries are named in the environment variable B200NUTS_MODEL_LIBRARY)");
     }
     num_params_r_ = 0;
     for (auto& b : params_) num_params_r_ += b.count();
   }
+  bool is_plugin() const { return id_ >= B200NUTS_MODEL_PLUGIN_BASE; }
 
   std::string model_name() const { return short_name_ + "_model"; }
   std::vector<std::string> model_compile_info() const {
@@ -100,12 +108,30 @@ class device_model {
 
   void get_param_names(std::vector<std::string>& names, bool emit_tparams = true, bool = true) const {
     names.clear();
+    if (is_plugin()) {  // base names of the output columns ("beta.3" -> "beta"), in order of first appearance
+      for (const std::string& n : plugin_outputs_) {
+        const std::string b = n.substr(0, n.find('.'));
+        if (names.empty() || names.back() != b) names.push_back(b);
+      }
+      return;
+    }
     for (auto& b : params_) names.push_back(b.name);
     if (emit_tparams)
       for (auto& b : tparams_) names.push_back(b.name);
   }
   void get_dims(std::vector<std::vector<size_t>>& dimss, bool emit_tparams = true, bool = true) const {
     dimss.clear();
+    if (is_plugin()) {  // run lengths of equal base names (a plug-in reports flat output names only)
+      std::string last;
+      for (const std::string& n : plugin_outputs_) {
+        const std::string b = n.substr(0, n.find('.'));
+        const bool indexed = n.find('.') != std::string::npos;
+        if (dimss.empty() || b != last) dimss.push_back(indexed ? std::vector<size_t>{1} : std::vector<size_t>{});
+        else dimss.back()[0]++;
+        last = b;
+      }
+      return;
+    }
     auto push = [&](const block_t& b) { dimss.push_back(b.size < 0 ? std::vector<size_t>{} : std::vector<size_t>{(size_t)b.size}); };
     for (auto& b : params_) push(b);
     if (emit_tparams)
@@ -113,11 +139,19 @@ class device_model {
   }
   // names are appended (as model_base::constrained_param_names does): "theta", "beta.1", ...
   void constrained_param_names(std::vector<std::string>& names, bool emit_tparams = true, bool = true) const {
+    if (is_plugin()) {
+      names.insert(names.end(), plugin_outputs_.begin(), plugin_outputs_.end());
+      return;
+    }
     for (auto& b : params_) expand(b, names);
     if (emit_tparams)
       for (auto& b : tparams_) expand(b, names);
   }
   void unconstrained_param_names(std::vector<std::string>& names, bool = true, bool = true) const {
+    if (is_plugin()) {
+      for (int64_t i = 0; i < num_params_r_; i++) names.push_back("u." + std::to_string(i + 1));
+      return;
+    }
     for (auto& b : params_) expand(b, names);
   }
 
@@ -125,6 +159,8 @@ class device_model {
   // lub_free(0,1) = logit: stan/math/prim/constraint/lb_free.hpp, lub_free.hpp).  Every parameter must be present.
   void transform_inits(const io::var_context& init, std::vector<double>& params_r) const {
     params_r.clear();
+    if (is_plugin())  // the plug-in interface has no unconstraining transform: only random inits (init=<radius>)
+      throw std::invalid_argument("user-specified initial values are not available for plug-in models (use init=<radius>)");
     for (auto& b : params_) {
       if (!init.contains_r(b.name)) throw std::invalid_argument("variable does not exist; processing stage=parameter initialization; variable name=" + b.name + "; base type=double (partial inits are not supported by the B200 engine)");
       const std::vector<double>& v = init.vals_r(b.name);
@@ -147,6 +183,7 @@ class device_model {
   int upload(b200nuts_engine* e) const {
     int rc = 0;
     int64_t d1[1], d2[2];
+    if (is_plugin()) return upload_all(e, plugin_data_);
     switch (id_) {
       case B200NUTS_STD_NORMAL: {
         int32_t D = (int32_t)D_;
@@ -176,6 +213,60 @@ class device_model {
   }
 
  private:
+  // every variable of the data context, as given: integer-valued ones as i32, the rest as f64 (the model's create() validates)
+  static int upload_all(b200nuts_engine* e, const io::var_context& data) {
+    for (const std::string& n : data.names()) {
+      const std::vector<int64_t>& dims = data.dims_r(n);
+      const int64_t one = 1;
+      const int64_t* dp = dims.empty() ? &one : dims.data();
+      const int nd = dims.empty() ? 1 : (int)dims.size();
+      int rc;
+      if (data.contains_i(n)) {
+        std::vector<int> v = data.vals_i(n);
+        rc = b200nuts_set_data_i32(e, n.c_str(), v.data(), dp, nd);
+      } else {
+        rc = b200nuts_set_data_f64(e, n.c_str(), data.vals_r(n).data(), dp, nd);
+      }
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  // A model that is not built in: look it up among the plug-in libraries of B200NUTS_MODEL_LIBRARY (':'-separated paths,
+  // include/b200nuts_model.h), construct it once on device 0 to learn its dimensions and output names.
+  bool init_plugin(const std::string& name, const io::var_context& data) {
+    if (const char* libs = std::getenv("B200NUTS_MODEL_LIBRARY")) {
+      std::stringstream ss(libs);
+      std::string path;
+      while (std::getline(ss, path, ':'))
+        if (!path.empty() && b200nuts_load_model_library(path.c_str()) < 0) throw std::invalid_argument(b200nuts_last_error(nullptr));
+    }
+    const int id = b200nuts_find_model(name.c_str());
+    if (id < B200NUTS_MODEL_PLUGIN_BASE) return false;
+    id_ = id;
+    plugin_data_ = data;
+    b200nuts_config cfg;
+    b200nuts_default_config(&cfg);
+    cfg.model = id;
+    b200nuts_engine* e = nullptr;
+    if (b200nuts_create(&cfg, &e)) throw std::runtime_error(b200nuts_last_error(nullptr));
+    int64_t D = 0, K = 0;
+    int rc = upload_all(e, data);
+    if (!rc) rc = b200nuts_num_params(e, &D, &K);
+    if (rc) {
+      const std::string msg = b200nuts_last_error(e);
+      b200nuts_destroy(e);
+      if (rc == B200NUTS_DATAERR) throw std::domain_error(msg);
+      throw std::invalid_argument(msg);
+    }
+    char buf[256];
+    for (int64_t k = 0; k < K; k++) {
+      b200nuts_output_name(e, k, buf, (int)sizeof buf);
+      plugin_outputs_.push_back(buf);
+    }
+    b200nuts_destroy(e);
+    num_params_r_ = D;
+    return true;
+  }
   static void expand(const block_t& b, std::vector<std::string>& names) {
     if (b.size < 0) names.push_back(b.name);
     else
@@ -193,6 +284,8 @@ class device_model {
   std::vector<double> X_, yr_, sigma_;
   std::vector<int> yi_;
   std::vector<int8_t> y8_;
+  io::var_context plugin_data_;
+  std::vector<std::string> plugin_outputs_;
 };
 
 // the reference's link-time hook, with the model selected by name instead of by linking a stanc-generated class

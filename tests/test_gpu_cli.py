@@ -207,3 +207,41 @@ def test_cli_errors(tmp_path):
     assert r.returncode != 0 and "must be in the interval [0, 1]" in r.stderr
     r = _cli("bernoulli", ["sample", "data", "file=/nonexistent.json"], tmp_path)
     assert r.returncode != 0
+
+
+def test_cli_plugin_model(tmp_path):
+    """a model that is not built in, reached from the command line through a plug-in library (B200NUTS_MODEL_LIBRARY,
+    include/b200nuts_model.h): Stan-CSV columns come from the model's output_name, the reference's stansummary reads the files."""
+    from cmdstan_b200 import _build
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(400, 3))
+    y = 1.0 + X @ np.array([0.5, -1.0, 2.0]) + 0.3 * rng.normal(size=400)
+    dj = tmp_path / "linreg.json"
+    dj.write_text(json.dumps({"N": 400, "K": 3, "X": X.tolist(), "y": y.tolist()}))
+    env = dict(os.environ, B200NUTS_MODEL_LIBRARY=_build.build_example_plugins())
+    r = _cli("linreg", ["sample", "num_samples=200", "num_warmup=200", "num_chains=4", "data", f"file={dj}", "random", "seed=11", "output", "file=lr.csv"],
+             tmp_path, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    files = [tmp_path / f"lr_{i}.csv" for i in range(1, 5)]
+    draws = []
+    for f in files:
+        lines = f.read_text().splitlines()
+        assert "# model = linreg_model" in lines
+        body = [x for x in lines if x and not x.startswith("#")]
+        assert body[0].split(",") == ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__", "alpha",
+                                      "beta.1", "beta.2", "beta.3", "sigma"]
+        draws.append(np.array([x.split(",") for x in body[1:]], dtype=float))
+    d = np.stack(draws)
+    assert d.shape == (4, 200, 12)
+    assert np.all(np.abs(d[:, :, 7:].mean(axis=(0, 1)) - np.array([1.0, 0.5, -1.0, 2.0, 0.3])) < 0.08)
+    if O.have_ref("bernoulli"):
+        s = subprocess.run([os.path.join(O.REF, "stansummary")] + [str(f) for f in files], capture_output=True, text=True)
+        assert s.returncode == 0 and "beta[3]" in s.stdout and "sigma" in s.stdout
+    # unknown model name, with and without a library
+    r = _cli("no_such_model", ["sample", "data", f"file={dj}"], tmp_path, env=env)
+    assert r.returncode != 0 and "unknown model" in (r.stdout + r.stderr)
+    # user inits are refused for plug-ins (no unconstraining transform in the interface)
+    ini = tmp_path / "init.json"
+    ini.write_text(json.dumps({"alpha": 0.0}))
+    r = _cli("linreg", ["sample", "data", f"file={dj}", f"init={ini}"], tmp_path, env=env)
+    assert r.returncode != 0 and "plug-in" in (r.stdout + r.stderr)
