@@ -1,0 +1,77 @@
+// Device-side chain storage of the engine and the lock-step engine's advance kernel (shared by engine.cu and
+// advance_big.cu, which builds the same kernel with the vector loops unrolled for long parameter vectors).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "nuts.cuh"
+
+namespace b200 {
+
+constexpr int kChainsPerBlock = 4;  // 4 warps per CTA
+constexpr int kCounterRing = 16;    // lock-step engine: host checks for completion every kCounterRing steps
+constexpr int kAdvanceBigD = 64;    // parameter vectors at least this long use the unrolled advance kernel (advance_big.cu)
+
+struct DeviceChains {
+  ChainS* cs;
+  double *q, *g, *zV, *slab, *draws;
+  const double* user_q0;
+  size_t slab_stride, draws_stride;
+  double* mat;        // dense metric: [C][3][D][D] (inverse metric, its Cholesky factor, Welford m2), else nullptr
+  size_t mat_stride;  // 3 D D
+};
+
+__device__ __forceinline__ ChainView make_view(const DeviceChains& d, const SamplerCfg& cfg, int c) {
+  ChainView v;
+  v.s = d.cs + c;
+  v.q = d.q + (size_t)c * cfg.ld;
+  v.g = d.g + (size_t)c * cfg.ld;
+  v.zV = d.zV + c;
+  v.v = d.slab + (size_t)c * d.slab_stride;
+  v.draws = d.draws ? d.draws + (size_t)c * d.draws_stride : nullptr;
+  v.user_q0 = d.user_q0 ? d.user_q0 + (size_t)c * cfg.ld : nullptr;
+  v.mat = d.mat ? d.mat + (size_t)c * d.mat_stride : nullptr;
+  return v;
+}
+
+// ---- copy helpers: a chain's scalar block / vectors between global and shared memory (whole warp, 8-byte words)
+__device__ __forceinline__ void warp_copy_words(void* dst, const void* src, int n_words, int lane) {
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+#pragma unroll 1
+  for (int i = lane; i < n_words; i += 32) d[i] = s[i];
+}
+static_assert(sizeof(ChainS) % 8 == 0, "ChainS is copied as 8-byte words");
+constexpr int kChainWords = (int)(sizeof(ChainS) / 8);
+
+// ---- lock-step engine: advance every chain to its next gradient request
+// and collect the requesting chains: active[c] flag + compacted index list (order irrelevant: a chain's gradient
+// depends on its own q only).  The chain's scalar block is staged in shared memory for the launch (one coalesced
+// load + store instead of dozens of dependent global accesses).
+template <int TAG>
+__global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCfg cfg, DeviceChains d, int C, int* active,
+                                                                          int* list, int* n_active) {
+  __shared__ __align__(16) ChainS sh[kChainsPerBlock];
+  const int w = threadIdx.x >> 5;
+  const int c = blockIdx.x * kChainsPerBlock + w;
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  ChainView v = make_view(d, cfg, c);
+  ChainS* gs = v.s;
+  warp_copy_words(&sh[w], gs, kChainWords, lane);
+  __syncwarp();
+  v.s = &sh[w];
+  const int r = advance(v, cfg, lane);
+  __syncwarp();
+  warp_copy_words(gs, &sh[w], kChainWords, lane);
+  if (lane == 0) {
+    const int a = r == ADV_NEED_GRAD ? 1 : 0;
+    active[c] = a;
+    if (a) list[atomicAdd(n_active, 1)] = c;
+  }
+}
+
+
+// advance_big.cu: the same kernel built with B200_VEC_UNROLL = 8 (bit-identical results)
+void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
+
+}  // namespace b200

@@ -27,6 +27,7 @@
 #include "../../include/b200nuts_model.h"
 #include "host_seed.h"
 #include "kernels.h"
+#include "chains.cuh"
 #include "nuts.cuh"
 #include "summary.h"
 
@@ -78,41 +79,6 @@ NcclApi g_nccl;
     }                                                                                             \
   } while (0)
 
-constexpr int kChainsPerBlock = 4;  // 4 warps per CTA
-constexpr int kCounterRing = 16;    // lock-step engine: host checks for completion every kCounterRing steps
-
-struct DeviceChains {
-  ChainS* cs;
-  double *q, *g, *zV, *slab, *draws;
-  const double* user_q0;
-  size_t slab_stride, draws_stride;
-  double* mat;        // dense metric: [C][3][D][D] (inverse metric, its Cholesky factor, Welford m2), else nullptr
-  size_t mat_stride;  // 3 D D
-};
-
-__device__ __forceinline__ ChainView make_view(const DeviceChains& d, const SamplerCfg& cfg, int c) {
-  ChainView v;
-  v.s = d.cs + c;
-  v.q = d.q + (size_t)c * cfg.ld;
-  v.g = d.g + (size_t)c * cfg.ld;
-  v.zV = d.zV + c;
-  v.v = d.slab + (size_t)c * d.slab_stride;
-  v.draws = d.draws ? d.draws + (size_t)c * d.draws_stride : nullptr;
-  v.user_q0 = d.user_q0 ? d.user_q0 + (size_t)c * cfg.ld : nullptr;
-  v.mat = d.mat ? d.mat + (size_t)c * d.mat_stride : nullptr;
-  return v;
-}
-
-// ---- copy helpers: a chain's scalar block / vectors between global and shared memory (whole warp, 8-byte words)
-__device__ __forceinline__ void warp_copy_words(void* dst, const void* src, int n_words, int lane) {
-  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
-  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
-#pragma unroll 1
-  for (int i = lane; i < n_words; i += 32) d[i] = s[i];
-}
-static_assert(sizeof(ChainS) % 8 == 0, "ChainS is copied as 8-byte words");
-constexpr int kChainWords = (int)(sizeof(ChainS) / 8);
-
 // ---- fused engine: advance + inlined model gradient, looped until the chain is idle.
 // SMEM = true: the chain's whole state (scalars, z.q, z.g, vector slab) lives in shared memory for the duration of the
 // launch (small models: 7 KB per chain for eight schools) and is written back at the end, so the state machine's
@@ -157,32 +123,6 @@ __global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(Sam
     warp_copy_words(g.g, v.g, cfg.ld, lane);
     warp_copy_words(g.v, v.v, slab_words, lane);
     if (lane == 0) *g.zV = *v.zV;
-  }
-}
-
-// ---- lock-step engine: advance every chain to its next gradient request
-// and collect the requesting chains: active[c] flag + compacted index list (order irrelevant: a chain's gradient
-// depends on its own q only).  The chain's scalar block is staged in shared memory for the launch (one coalesced
-// load + store instead of dozens of dependent global accesses).
-__global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCfg cfg, DeviceChains d, int C, int* active,
-                                                                          int* list, int* n_active) {
-  __shared__ __align__(16) ChainS sh[kChainsPerBlock];
-  const int w = threadIdx.x >> 5;
-  const int c = blockIdx.x * kChainsPerBlock + w;
-  if (c >= C) return;
-  const int lane = threadIdx.x & 31;
-  ChainView v = make_view(d, cfg, c);
-  ChainS* gs = v.s;
-  warp_copy_words(&sh[w], gs, kChainWords, lane);
-  __syncwarp();
-  v.s = &sh[w];
-  const int r = advance(v, cfg, lane);
-  __syncwarp();
-  warp_copy_words(gs, &sh[w], kChainWords, lane);
-  if (lane == 0) {
-    const int a = r == ADV_NEED_GRAD ? 1 : 0;
-    active[c] = a;
-    if (a) list[atomicAdd(n_active, 1)] = c;
   }
 }
 
@@ -936,7 +876,8 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       const bool check = (step % kCheck) == 0;
       int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
       if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
-      advance_kernel<<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
+      if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
+      else advance_kernel<0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;
       b.n_list = counter;
       if (check) {

@@ -31,6 +31,18 @@
 #include "models.cuh"
 #include "rng.cuh"
 
+// Unroll factor of the per-lane loops over a chain's vector elements (i = lane, lane + 32, ...).  1 (default) keeps the
+// state machine small: the fused chain kernels of the small models are instruction-cache bound.  The lock-step engine's
+// advance kernel for long vectors (advance_big.cu, D >= 64) is built with 8: one warp per chain is latency-bound on its
+// dependent global loads (profiles r01e: 895 us per step at D = 1204), and unrolling puts 8 elements per lane in flight.
+// Unrolling does not reorder any floating-point sum.
+#ifndef B200_VEC_UNROLL
+#define B200_VEC_UNROLL 1
+#endif
+#define B200_PRAGMA_(x) _Pragma(#x)
+#define B200_PRAGMA(x) B200_PRAGMA_(x)
+#define B200_VEC_LOOP B200_PRAGMA(unroll B200_VEC_UNROLL)
+
 namespace b200 {
 
 constexpr int kMaxDepthCap = 16;  // stack scalars are sized for trees of up to 2^16 leapfrogs
@@ -127,7 +139,7 @@ B200_DEV double* scratch(const ChainView& c, const SamplerCfg& cfg, int k) { ret
 // column-major gemv kernel).
 B200_DEV_CALL void dense_sharp(const double* M, const double* p, double* out, int D, int lane) {
   warp_sync();  // p was written by its owner lanes
-  _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+  B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
     double acc = 0;
     _Pragma("unroll 4") for (int j = 0; j < D; j++) acc += M[(size_t)j * D + i] * p[j];
     out[i] = acc;
@@ -139,7 +151,7 @@ B200_DEV_CALL void dense_sharp(const double* M, const double* p, double* out, in
 B200_DEV_CALL bool dense_factor(double* mat, int D, int lane) {
   const double* A = mat;
   double* L = mat + (size_t)D * D;
-  _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp)
+  B200_VEC_LOOP for (int i = lane; i < D; i += kWarp)
     for (int j = 0; j < D; j++) L[(size_t)j * D + i] = 0.0;
   warp_sync();
   for (int j = 0; j < D; j++) {
@@ -147,7 +159,7 @@ B200_DEV_CALL bool dense_factor(double* mat, int D, int lane) {
     for (int k = 0; k < j; k++) d -= L[(size_t)k * D + j] * L[(size_t)k * D + j];
     if (!(d > 0)) return false;
     const double ljj = sqrt(d);
-    _Pragma("unroll 1") for (int i = j + 1 + ((lane - (j + 1)) % kWarp + kWarp) % kWarp; i < D; i += kWarp) {  // rows i > j owned by this lane
+    B200_VEC_LOOP for (int i = j + 1 + ((lane - (j + 1)) % kWarp + kWarp) % kWarp; i < D; i += kWarp) {  // rows i > j owned by this lane
       double v = A[(size_t)j * D + i];
       for (int k = 0; k < j; k++) v -= L[(size_t)k * D + i] * L[(size_t)k * D + j];
       L[(size_t)j * D + i] = v / ljj;
@@ -162,7 +174,7 @@ B200_DEV_CALL void dense_solve_upper(const double* L, const double* u, double* p
   warp_sync();
   for (int i = D - 1; i >= 0; i--) {
     double acc = 0;
-    _Pragma("unroll 1") for (int k = i + 1 + lane; k < D; k += kWarp) acc += L[(size_t)i * D + k] * p[k];
+    B200_VEC_LOOP for (int k = i + 1 + lane; k < D; k += kWarp) acc += L[(size_t)i * D + k] * p[k];
     acc = warp_sum(acc);
     if (lane == i % kWarp) p[i] = (u[i] - acc) / L[(size_t)i * D + i];
     warp_sync();
@@ -172,7 +184,7 @@ B200_DEV_CALL void dense_solve_upper(const double* L, const double* u, double* p
 // T(p) = 0.5 p . (M^-1 o p)   (diag_e_metric.hpp:20-22)
 B200_DEV double kinetic(const double* p, const double* im, int D, int lane) {
   double acc = 0;
-  _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) acc += p[i] * (im[i] * p[i]);
+  B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) acc += p[i] * (im[i] * p[i]);
   return 0.5 * warp_sum(acc);
 }
 
@@ -181,7 +193,7 @@ B200_DEV_CALL double kinetic_dense(const ChainView& c, const SamplerCfg& cfg, co
   double* s0 = scratch(c, cfg, 0);
   dense_sharp(c.mat, p, s0, cfg.D, lane);
   double acc = 0;
-  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) acc += p[i] * s0[i];
+  B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) acc += p[i] * s0[i];
   return 0.5 * warp_sum(acc);
 }
 
@@ -190,14 +202,14 @@ B200_DEV void leapfrog_begin(const ChainView& c, const SamplerCfg& cfg, double e
   const double h = 0.5 * eps;
   double* p = slot(c, cfg, V_P);
   if (cfg.dense) {
-    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
+    B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
     double* s0 = scratch(c, cfg, 0);
     dense_sharp(c.mat, p, s0, cfg.D, lane);
-    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) c.q[i] += eps * s0[i];
+    B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) c.q[i] += eps * s0[i];
     return;
   }
   const double* im = slot(c, cfg, V_IM);
-  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+  B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) {
     double pi = p[i] - h * c.g[i];
     p[i] = pi;
     c.q[i] += eps * (im[i] * pi);
@@ -211,10 +223,10 @@ B200_DEV double leapfrog_end(const ChainView& c, const SamplerCfg& cfg, double e
   double acc = 0;
   double H;
   if (cfg.dense) {
-    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
+    B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
     H = kinetic_dense(c, cfg, p, lane) + (*c.zV);
   } else {
-    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+    B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) {
       double pi = p[i] - h * c.g[i];
       p[i] = pi;
       acc += pi * (im[i] * pi);
@@ -239,7 +251,7 @@ B200_DEV_CALL double refresh_from_current(const ChainView& c, const SamplerCfg& 
   } else {
     warp_fill(c.s->rng, lane, p, cfg.D, 0, im, 0.0);
   }
-  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+  B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) {
     c.q[i] = cq[i];
     c.g[i] = cg[i];
   }
@@ -276,7 +288,7 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
     dense_sharp(c.mat, R + ld, scratch(c, cfg, 3), cfg.D, lane);
     s0 = scratch(c, cfg, 0); s1 = scratch(c, cfg, 1); s2 = scratch(c, cfg, 2); s3 = scratch(c, cfg, 3);
   }
-  _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+  B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) {
     const double m = im[i];
     const double lpb = L[i], lpe = L[ld + i], lr = L[2 * ld + i];
     const double rpb = R[i], rpe = R[ld + i], rr = R[2 * ld + i];
@@ -341,20 +353,20 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
     const double n = s->wf_n;
     double* delta = scratch(c, cfg, 0);
     double* W = c.mat + 2 * (size_t)D * D;
-    _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+    B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
       const double dl = q[i] - wm[i];
       delta[i] = dl;
       wm[i] += dl / n;
     }
     warp_sync();
-    _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+    B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
       const double r = q[i] - wm[i];
       for (int j = 0; j < D; j++) W[(size_t)j * D + i] += r * delta[j];
     }
   } else if (in_window) {
     s->wf_n += 1.0;
     const double n = s->wf_n;
-    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+    B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) {
       double delta = q[i] - wm[i];
       double mi = wm[i] + delta / n;
       wm[i] = mi;
@@ -378,7 +390,7 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
     if (cfg.dense) {  // covar_adaptation::learn_covariance, covar_adaptation.hpp:24-38
       double* M = c.mat;
       double* W = c.mat + 2 * (size_t)D * D;
-      _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+      B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
         for (int j = 0; j < D; j++) {
           const size_t e = (size_t)j * D + i;
           double cov = M[e];
@@ -396,7 +408,7 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
       if (bad > 0) return -1;
       return dense_factor(c.mat, D, lane) ? 1 : -1;
     }
-    _Pragma("unroll 1") for (int i = lane; i < cfg.D; i += kWarp) {
+    B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) {
       double var = im[i];
       if (n > 1) var = wm2[i] / (n - 1.0);
       var = (n / (n + 5.0)) * var + 1e-3 * (5.0 / (n + 5.0)) * 1.0;
@@ -433,9 +445,9 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_INIT_DRAW: {  // util::initialize (initialize.hpp:87-117)
         if (c.user_q0) {
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) c.q[i] = c.user_q0[i];
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = c.user_q0[i];
         } else if (cfg.init_radius == 0.0) {
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;
         } else {
           warp_fill(s->rng, lane, c.q, D, 1, nullptr, cfg.init_radius);
         }
@@ -445,12 +457,12 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_INIT_CHECK: {  // finite lp and finite sum of the gradient (initialize.hpp:148-184)
         double gs = 0;
-        _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) gs += c.g[i];
+        B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) gs += c.g[i];
         gs = warp_sum(gs);
         if (isfinite((*c.zV)) && isfinite(gs)) {
           double* cq = slot(c, cfg, V_CQ);
           double* cg = slot(c, cfg, V_CG);
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
             cq[i] = c.q[i];
             cg[i] = c.g[i];
           }
@@ -540,7 +552,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           double* fq = slot(c, cfg, V_FQ); double* fp = slot(c, cfg, V_FP); double* fg = slot(c, cfg, V_FG);
           double* bq = slot(c, cfg, V_BQ); double* bp = slot(c, cfg, V_BP); double* bg = slot(c, cfg, V_BG);
           double* pfb = slot(c, cfg, V_PFB); double* pbf = slot(c, cfg, V_PBF); double* rho = slot(c, cfg, V_RHO);
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
             const double qi = c.q[i], pi = p[i], gi = c.g[i];
             fq[i] = qi; fp[i] = pi; fg[i] = gi;
             bq[i] = qi; bp[i] = pi; bg[i] = gi;
@@ -569,7 +581,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           const double* ep = slot(c, cfg, fwd ? V_FP : V_BP);
           const double* eg = slot(c, cfg, fwd ? V_FG : V_BG);
           double* pmid = slot(c, cfg, fwd ? V_PBF : V_PFB);  // p_bck_fwd = p_fwd_fwd  /  p_fwd_bck = p_bck_bck
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
             c.q[i] = eq[i];
             p[i] = ep[i];
             c.g[i] = eg[i];
@@ -602,7 +614,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           double* E = slot(c, cfg, V_STACK + 5 * e);
           const double* p = slot(c, cfg, V_P);
           const int ld = cfg.ld;
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
             const double pi = p[i];
             E[i] = pi;
             E[ld + i] = pi;
@@ -634,7 +646,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           double* eq = slot(c, cfg, fwd ? V_FQ : V_BQ);
           double* ep = slot(c, cfg, fwd ? V_FP : V_BP);
           double* eg = slot(c, cfg, fwd ? V_FG : V_BG);
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
             eq[i] = c.q[i];
             ep[i] = p[i];
             eg[i] = c.g[i];
@@ -670,14 +682,14 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           const double *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
           if (dense) {  // boundary momentum of the new subtree first, then the four sharp momenta
             double* dst = fwd ? pfb : pbf;
-            _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) dst[i] = S[i];
+            B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) dst[i] = S[i];
             dense_sharp(c.mat, pff, scratch(c, cfg, 0), D, lane);
             dense_sharp(c.mat, pbb, scratch(c, cfg, 1), D, lane);
             dense_sharp(c.mat, pfb, scratch(c, cfg, 2), D, lane);
             dense_sharp(c.mat, pbf, scratch(c, cfg, 3), D, lane);
             s0 = scratch(c, cfg, 0); s1 = scratch(c, cfg, 1); s2 = scratch(c, cfg, 2); s3 = scratch(c, cfg, 3);
           }
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) {
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
             const double m = im[i];
             double rho_bck, rho_fwd;
             if (fwd) {
@@ -738,7 +750,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             r[6] = s->curH;
           }
           const double* cq = slot(c, cfg, V_CQ);
-          _Pragma("unroll 1") for (int i = lane; i < D; i += kWarp) r[7 + i] = cq[i];
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) r[7 + i] = cq[i];
           s->draws_row++;
         }
         s->iter++;
