@@ -1079,3 +1079,28 @@ int oracle_learn_variance_kat(int D, const double* q, int n_learn, unsigned num_
   pt_free(&s.z); free(s.inv_metric); free(s.wf_m); free(s.wf_m2);
   return updates;
 }
+
+/* one expl_leapfrog::evolve on z = (q, p, g, V) of `model` with step eps and a diagonal inverse metric
+ * (ST/unit/mcmc/hmc/integrators/expl_leapfrog_test.cpp:156-370: evolve_1 .. evolve_7); out = q[D], p[D], g[D], V */
+void oracle_evolve_kat(const model_t* model, const double* q, const double* p, const double* inv_metric, double eps, double* out) {
+  sampler_t s;
+  memset(&s, 0, sizeof s);
+  const int D = model->D;
+  s.model = model;
+  s.D = D;
+  s.z = pt_alloc(D);
+  s.inv_metric = (double*)malloc(D * sizeof(double));
+  for (int i = 0; i < D; i++) {
+    s.inv_metric[i] = inv_metric ? inv_metric[i] : 1.0;
+    s.z.q[i] = q[i];
+    s.z.p[i] = p[i];
+  }
+  update_potential_gradient(&s, &s.z);
+  evolve(&s, &s.z, eps);
+  memcpy(out, s.z.q, D * sizeof(double));
+  memcpy(out + D, s.z.p, D * sizeof(double));
+  memcpy(out + 2 * D, s.z.g, D * sizeof(double));
+  out[3 * D] = s.z.V;
+  pt_free(&s.z);
+  free(s.inv_metric);
+}

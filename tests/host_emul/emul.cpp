@@ -89,3 +89,38 @@ extern "C" int emul_learn_variance_kat(int D, const double* q, int n_learn, unsi
   for (int i = 0; i < D; i++) var_out[i] = slab[(size_t)V_IM * D + i];
   return updates;
 }
+
+// expl_leapfrog::evolve through the DEVICE code path (leapfrog_begin, model gradient, leapfrog_end) for the std-normal model:
+// same KATs as the oracle's oracle_evolve_kat.  out = q[D], p[D], g[D], V, H
+extern "C" void emul_evolve_kat(int D, const double* q, const double* p, const double* inv_metric, double eps, double* out) {
+  ModelData m{};
+  m.kind = MODEL_STD_NORMAL; m.D = D;
+  SamplerCfg cfg{};
+  cfg.D = D; cfg.ld = D; cfg.max_depth = 1;
+  std::vector<double> slab((size_t)num_vec_slots(1) * D, 0.0), qq(q, q + D), g(D);
+  ChainS s;
+  std::memset(&s, 0, sizeof s);
+  double zV = 0;
+  ChainView c{&s, qq.data(), g.data(), &zV, slab.data(), nullptr, nullptr};
+  for (int i = 0; i < D; i++) {
+    slab[(size_t)V_IM * D + i] = inv_metric ? inv_metric[i] : 1.0;
+    slab[(size_t)V_P * D + i] = p[i];
+  }
+  auto grad = [&]() {
+    double lp = lp_grad_small(m, qq.data(), g.data(), 0);
+    for (int i = 0; i < D; i++) g[i] = -g[i];
+    zV = -lp;
+  };
+  grad();
+  leapfrog_begin(c, cfg, eps, 0);
+  grad();
+  double hraw;
+  const double H = leapfrog_end(c, cfg, eps, 0, &hraw);
+  for (int i = 0; i < D; i++) {
+    out[i] = qq[i];
+    out[D + i] = slab[(size_t)V_P * D + i];
+    out[2 * D + i] = g[i];
+  }
+  out[3 * D] = zV;
+  out[3 * D + 1] = H;
+}
