@@ -321,9 +321,13 @@ def main():
     e2.close()
     eps, im = e.adaptation()
 
-    dt = torch.tensor(draws, device=dev)
-    _, ess_cols = A.min_bulk_ess(dt)
+    # bulk ESS of lp__ and every model column of the timed draws, pooled over this rank's chains: stansummary's table computed
+    # on the device from the HBM-resident draws (b200nuts_summary; the torch restatement in cmdstan_b200/analyze.py gives the
+    # same numbers but loops over columns in Python -- minutes at c4's 1211 columns x 8192 chains)
+    tab = e.summary(row0=W, nrows=K, constrained=True)
+    ess_cols = tab[[0] + list(range(7, tab.shape[0])), B.SUMMARY_COLUMNS.index("ESS_bulk")]
     ess_cols = torch.tensor([v if v == v else float("inf") for v in ess_cols], dtype=torch.float64, device=dev)
+    note("summary done")
     nleap = torch.tensor([float(draws[:, :, 4].sum()), float((ng2 - ng1).sum())], dtype=torch.float64, device=dev)
     times = torch.tensor([run_s, run_wall + fetch_s + h2d_s, grad_s, adapt_s], dtype=torch.float64, device=dev)
     div = torch.tensor([float(draws[:, :, 5].sum()), float(draws[:, :, 3].mean())], dtype=torch.float64, device=dev)
