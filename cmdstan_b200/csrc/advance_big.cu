@@ -2,6 +2,7 @@
 // the per-lane vector loops unrolled 8x so that a warp keeps 8 elements per lane in flight (see nuts.cuh B200_VEC_UNROLL).
 // Built with --fmad=false like engine.cu: the two kernels must round identically.
 #define B200_VEC_UNROLL 8
+#define B200_WITH_DENSE 0
 #include "chains.cuh"
 
 namespace b200 {

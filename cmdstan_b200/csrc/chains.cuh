@@ -71,7 +71,58 @@ __global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCf
 }
 
 
+// ---- fused engine: advance + inlined model gradient, looped until the chain is idle.
+// SMEM = true: the chain's whole state (scalars, z.q, z.g, vector slab) lives in shared memory for the duration of the
+// launch (small models: 7 KB per chain for eight schools) and is written back at the end, so the state machine's
+// many dependent accesses cost shared-memory latency instead of L2/HBM latency.
+constexpr int kFusedMaxWarps = 7;  // 4 blocks x 7 warps = 28 resident chains per SM (4096 chains = one wave on 148 SMs)
+template <bool SMEM, int TAG>
+__global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C, int warps_per_block, int chain_smem_words) {
+  extern __shared__ __align__(16) unsigned long long fused_smem[];
+  const int w = threadIdx.x >> 5;
+  const int c = blockIdx.x * warps_per_block + w;
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  ChainView v = make_view(d, cfg, c);
+  ChainView g = v;  // where the state lives between launches
+  const int slab_words = (int)d.slab_stride;
+  if (SMEM) {
+    unsigned long long* base = fused_smem + (size_t)w * chain_smem_words;
+    v.s = reinterpret_cast<ChainS*>(base);
+    double* vec = reinterpret_cast<double*>(base + kChainWords);
+    v.q = vec;
+    v.g = vec + cfg.ld;
+    v.zV = vec + 2 * cfg.ld;
+    v.v = vec + 2 * cfg.ld + 2;
+    warp_copy_words(v.s, g.s, kChainWords, lane);
+    warp_copy_words(v.q, g.q, cfg.ld, lane);
+    warp_copy_words(v.g, g.g, cfg.ld, lane);
+    warp_copy_words(v.v, g.v, slab_words, lane);
+    if (lane == 0) *v.zV = *g.zV;
+    __syncwarp();
+  }
+  while (advance(v, cfg, lane) == ADV_NEED_GRAD) {
+    __syncwarp();
+    const double lp = lp_grad_small(md, v.q, v.g, lane);
+    for (int i = lane; i < cfg.D; i += 32) v.g[i] = -v.g[i];
+    *v.zV = -lp;
+    __syncwarp();
+  }
+  if (SMEM) {
+    __syncwarp();
+    warp_copy_words(g.s, v.s, kChainWords, lane);
+    warp_copy_words(g.q, v.q, cfg.ld, lane);
+    warp_copy_words(g.g, v.g, cfg.ld, lane);
+    warp_copy_words(g.v, v.v, slab_words, lane);
+    if (lane == 0) *g.zV = *v.zV;
+  }
+}
+
 // advance_big.cu: the same kernel built with B200_VEC_UNROLL = 8 (bit-identical results)
 void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
+// dense.cu: the kernels built with B200_WITH_DENSE = 1 (metric = dense_e)
+void launch_advance_dense(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
+cudaError_t launch_fused_dense(const SamplerCfg& cfg, const ModelData& md, const DeviceChains& d, int C, bool smem_state, int warps_per_block,
+                               int chain_words, size_t smem_bytes, cudaStream_t stream);
 
 }  // namespace b200

@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 
+#define B200_WITH_DENSE 0  // dense-metric chains run the kernels of dense.cu
 #include "../../include/b200nuts.h"
 #include "../../include/b200nuts_model.h"
 #include "host_seed.h"
@@ -78,53 +79,6 @@ NcclApi g_nccl;
       return B200NUTS_SOFTWARE;                                                                   \
     }                                                                                             \
   } while (0)
-
-// ---- fused engine: advance + inlined model gradient, looped until the chain is idle.
-// SMEM = true: the chain's whole state (scalars, z.q, z.g, vector slab) lives in shared memory for the duration of the
-// launch (small models: 7 KB per chain for eight schools) and is written back at the end, so the state machine's
-// many dependent accesses cost shared-memory latency instead of L2/HBM latency.
-constexpr int kFusedMaxWarps = 7;  // 4 blocks x 7 warps = 28 resident chains per SM (4096 chains = one wave on 148 SMs)
-template <bool SMEM>
-__global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C, int warps_per_block, int chain_smem_words) {
-  extern __shared__ __align__(16) unsigned long long fused_smem[];
-  const int w = threadIdx.x >> 5;
-  const int c = blockIdx.x * warps_per_block + w;
-  if (c >= C) return;
-  const int lane = threadIdx.x & 31;
-  ChainView v = make_view(d, cfg, c);
-  ChainView g = v;  // where the state lives between launches
-  const int slab_words = (int)d.slab_stride;
-  if (SMEM) {
-    unsigned long long* base = fused_smem + (size_t)w * chain_smem_words;
-    v.s = reinterpret_cast<ChainS*>(base);
-    double* vec = reinterpret_cast<double*>(base + kChainWords);
-    v.q = vec;
-    v.g = vec + cfg.ld;
-    v.zV = vec + 2 * cfg.ld;
-    v.v = vec + 2 * cfg.ld + 2;
-    warp_copy_words(v.s, g.s, kChainWords, lane);
-    warp_copy_words(v.q, g.q, cfg.ld, lane);
-    warp_copy_words(v.g, g.g, cfg.ld, lane);
-    warp_copy_words(v.v, g.v, slab_words, lane);
-    if (lane == 0) *v.zV = *g.zV;
-    __syncwarp();
-  }
-  while (advance(v, cfg, lane) == ADV_NEED_GRAD) {
-    __syncwarp();
-    const double lp = lp_grad_small(md, v.q, v.g, lane);
-    for (int i = lane; i < cfg.D; i += 32) v.g[i] = -v.g[i];
-    *v.zV = -lp;
-    __syncwarp();
-  }
-  if (SMEM) {
-    __syncwarp();
-    warp_copy_words(g.s, v.s, kChainWords, lane);
-    warp_copy_words(g.q, v.q, cfg.ld, lane);
-    warp_copy_words(g.g, v.g, cfg.ld, lane);
-    warp_copy_words(g.v, v.v, slab_words, lane);
-    if (lane == 0) *g.zV = *v.zV;
-  }
-}
 
 // gradient stage of the lock-step engine for the small models (used for engine-equivalence tests)
 __global__ void __launch_bounds__(128) grad_small_kernel(ModelData md, const double* Q, double* G, double* zV, const int* active,
@@ -851,11 +805,17 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       int wpb = per_sm < kFusedMaxWarps ? (per_sm < 1 ? 1 : per_sm) : kFusedMaxWarps;
       while ((size_t)wpb * chain_bytes > 56 * 1024 && wpb > 1) wpb--;
       const size_t smem = (size_t)wpb * chain_bytes;
-      auto k = fused_chain_kernel<true>;
-      CUDA_TRY(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<(C + wpb - 1) / wpb, 32 * wpb, smem, e->stream>>>(e->scfg, e->md, e->dc, C, wpb, chain_words);
+      if (e->scfg.dense) {
+        CUDA_TRY(e, launch_fused_dense(e->scfg, e->md, e->dc, C, true, wpb, chain_words, smem, e->stream));
+      } else {
+        auto k = fused_chain_kernel<true, 0>;
+        CUDA_TRY(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(C + wpb - 1) / wpb, 32 * wpb, smem, e->stream>>>(e->scfg, e->md, e->dc, C, wpb, chain_words);
+      }
+    } else if (e->scfg.dense) {
+      CUDA_TRY(e, launch_fused_dense(e->scfg, e->md, e->dc, C, false, kChainsPerBlock, 0, 0, e->stream));
     } else {
-      fused_chain_kernel<false><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C, kChainsPerBlock, 0);
+      fused_chain_kernel<false, 0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C, kChainsPerBlock, 0);
     }
     launches++;
   } else {
@@ -876,7 +836,8 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       const bool check = (step % kCheck) == 0;
       int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
       if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
-      if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
+      if (e->scfg.dense) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
+      else if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else advance_kernel<0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;
       b.n_list = counter;

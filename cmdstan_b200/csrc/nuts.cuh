@@ -43,6 +43,13 @@
 #define B200_PRAGMA(x) B200_PRAGMA_(x)
 #define B200_VEC_LOOP B200_PRAGMA(unroll B200_VEC_UNROLL)
 
+// The dense-metric code paths are compiled only where B200_WITH_DENSE is 1 (dense.cu, the host emulation): the fused chain
+// kernels of the small models are instruction-cache bound, and carrying the dense branches cost c2 15 % (profiles r01i).
+#ifndef B200_WITH_DENSE
+#define B200_WITH_DENSE 1
+#endif
+#define B200_DENSE(cfg) (B200_WITH_DENSE && (cfg).dense)
+
 namespace b200 {
 
 constexpr int kMaxDepthCap = 16;  // stack scalars are sized for trees of up to 2^16 leapfrogs
@@ -201,7 +208,7 @@ B200_DEV_CALL double kinetic_dense(const ChainView& c, const SamplerCfg& cfg, co
 B200_DEV void leapfrog_begin(const ChainView& c, const SamplerCfg& cfg, double eps, int lane) {
   const double h = 0.5 * eps;
   double* p = slot(c, cfg, V_P);
-  if (cfg.dense) {
+  if (B200_DENSE(cfg)) {
     B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
     double* s0 = scratch(c, cfg, 0);
     dense_sharp(c.mat, p, s0, cfg.D, lane);
@@ -222,7 +229,7 @@ B200_DEV double leapfrog_end(const ChainView& c, const SamplerCfg& cfg, double e
   const double* im = slot(c, cfg, V_IM);
   double acc = 0;
   double H;
-  if (cfg.dense) {
+  if (B200_DENSE(cfg)) {
     B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) p[i] -= h * c.g[i];
     H = kinetic_dense(c, cfg, p, lane) + (*c.zV);
   } else {
@@ -244,7 +251,7 @@ B200_DEV_CALL double refresh_from_current(const ChainView& c, const SamplerCfg& 
   const double* im = slot(c, cfg, V_IM);
   const double* cq = slot(c, cfg, V_CQ);
   const double* cg = slot(c, cfg, V_CG);
-  if (cfg.dense) {  // u ~ N(0, I) in index order, p = L^-T u
+  if (B200_DENSE(cfg)) {  // u ~ N(0, I) in index order, p = L^-T u
     double* u = scratch(c, cfg, 1);
     warp_fill(c.s->rng, lane, u, cfg.D, 0, nullptr, 0.0);
     dense_solve_upper(c.mat + (size_t)cfg.D * cfg.D, u, p, cfg.D, lane);
@@ -256,7 +263,7 @@ B200_DEV_CALL double refresh_from_current(const ChainView& c, const SamplerCfg& 
     c.g[i] = cg[i];
   }
   (*c.zV) = c.s->curV;
-  if (cfg.dense) return kinetic_dense(c, cfg, p, lane) + c.s->curV;
+  if (B200_DENSE(cfg)) return kinetic_dense(c, cfg, p, lane) + c.s->curV;
   return kinetic(p, im, cfg.D, lane) + c.s->curV;
 }
 
@@ -279,7 +286,7 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
     take_right = warp_uniform01(s->rng, lane) < accept_prob;
   }
   double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
-  const bool dense = cfg.dense != 0;
+  const bool dense = B200_DENSE(cfg);
   const double *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
   if (dense) {  // sharp momenta of the four boundary momenta (the reference keeps them; here they are recomputed)
     dense_sharp(c.mat, L, scratch(c, cfg, 0), cfg.D, lane);
@@ -348,7 +355,7 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
   const unsigned cnt = s->win_counter;
   const bool in_window = (cnt >= cfg.w_init_buffer) && (cnt < cfg.w_num_warmup - cfg.w_term_buffer) && (cnt != cfg.w_num_warmup);
   const int D = cfg.D;
-  if (in_window && cfg.dense) {  // welford_covar_estimator::add_sample: m2 += (q - m_new) delta^T
+  if (in_window && B200_DENSE(cfg)) {  // welford_covar_estimator::add_sample: m2 += (q - m_new) delta^T
     s->wf_n += 1.0;
     const double n = s->wf_n;
     double* delta = scratch(c, cfg, 0);
@@ -387,7 +394,7 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
     }
     const double n = s->wf_n;
     double bad = 0;
-    if (cfg.dense) {  // covar_adaptation::learn_covariance, covar_adaptation.hpp:24-38
+    if (B200_DENSE(cfg)) {  // covar_adaptation::learn_covariance, covar_adaptation.hpp:24-38
       double* M = c.mat;
       double* W = c.mat + 2 * (size_t)D * D;
       B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
@@ -437,7 +444,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       case ST_START: {
         s->init_tries = 0;
         s->state = ST_INIT_DRAW;
-        if (cfg.dense && !dense_factor(c.mat, D, lane)) {  // "Inverse Euclidean metric not positive definite."
+        if (B200_DENSE(cfg) && !dense_factor(c.mat, D, lane)) {  // "Inverse Euclidean metric not positive definite."
           s->err = 78;
           s->state = ST_DONE;
         }
@@ -678,7 +685,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           const double* pbb = slot(c, cfg, V_BP);  // p_bck_bck == z_bck.p
           double* cq = slot(c, cfg, V_CQ);
           double* cg = slot(c, cfg, V_CG);
-          const bool dense = cfg.dense != 0;
+          const bool dense = B200_DENSE(cfg);
           const double *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
           if (dense) {  // boundary momentum of the new subtree first, then the four sharp momenta
             double* dst = fwd ? pfb : pbf;
