@@ -381,6 +381,9 @@ def main():
             "grad_evals_per_sec": float(nleap[0]) / run_s, "grad_evals_executed_per_sec": float(nleap[1]) / run_s,
             "min_bulk_ess": min_ess, "timed_draws": int(C * K * (1 if row_mode else world)), "divergences": float(div[0]), "mean_treedepth": float(div[1]) / (1 if row_mode else world),
             "adaptation_s": adapt_s, "setup_wall_s": setup_wall, "median_stepsize": float(np.median(eps)),
+            # also per (warm-up + sampling) second -- the timed ESS scaled to the reference's 1000 sampling transitions,
+            # over the device time of the adaptation actually run plus 1000 transitions at the timed rate
+            "ess_per_sec_incl_warmup_1000_draws": (min_ess * 1000.0 / K) / (adapt_s + run_s * 1000.0 / K) if K > 0 else None,
             "e2e": {"value": min_ess / e2e_s, "unit": "ESS/s", "h2d_bytes_per_step": data_bytes(data) / K, "d2h_bytes_per_step": int(draws.nbytes / K),
                     "h2d_s": h2d_s, "run_wall_s": run_wall, "d2h_s": fetch_s},
             "gpu_launches": int(launches), "roofline": roof, "clocks": clk,
