@@ -550,6 +550,220 @@ __global__ void __launch_bounds__(NT3, 1) glm_dmma3_kernel(const GlmTcArgs a) {
   }
 }
 
+
+// =====================================================================================================================
+// v4 (EXPERIMENTAL, not validated on hardware yet: selected only by B200NUTS_GLM_VARIANT=3, covered by the GPU tests only
+// when B200_TEST_EXPERIMENTAL=1): v3 with the two changes its r01d profile asked for.
+//  * the derivative tile never touches shared memory: after the link a lane holds D[row mi*8+gid][chain 2*tig+j] in its
+//    accumulator registers; the phase-B operand fragment b0 = D[row r0+tig][chain gid] is fetched from the owning lane with
+//    two 64-bit shuffles (one per j, the destination selects) -- 64 shuffles per warp and tile in place of 49 KB of smem;
+//  * the freed shared memory holds a THIRD X stage (Dk <= 104): the refill of a buffer is still issued by the last warp to
+//    release it, but it is needed two tiles later instead of one, so warp drift no longer turns into mbarrier spinning.
+// Summation order per chain is that of v3.
+// =====================================================================================================================
+template <int LINK, int MB, int NST>
+__global__ void __launch_bounds__(NT3, 1) glm_dmma4_kernel(const GlmTcArgs a) {
+  extern __shared__ __align__(128) double smem[];
+  const int Dk = a.Dk;
+  const int xs_ld = xs_ld_for(Dk);
+  double* Bs = smem;                                  // [TC][xs_ld]
+  double* Xs0 = Bs + (size_t)TC * xs_ld;              // [NST][TR][xs_ld]
+  double* ys0 = Xs0 + (size_t)NST * TR * xs_ld;       // [NST][TR]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ys0 + NST * TR);
+  unsigned long long* fullX = bars;                   // [NST]
+  unsigned long long* fullB = bars + NST;
+  int* doneX = reinterpret_cast<int*>(bars + NST + 1);  // [NST] warps done with X buffer b
+  int* doneB = doneX + NST;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int p = blockIdx.x;
+  const int n_list = a.n_list ? *a.n_list : a.n_fixed;
+  const int n_ct = (n_list + TC - 1) / TC;
+
+  const long long t_begin = (long long)p * a.n_row_tiles / a.P, t_end = (long long)(p + 1) * a.n_row_tiles / a.P;
+  const long long row_begin = t_begin * TR;
+  long long row_end = t_end * TR;
+  if (row_end > a.N) row_end = a.N;
+  const int n_rt = (int)(t_end - t_begin);
+  const long long n_it = (long long)n_ct * n_rt;
+  if (n_it == 0) return;
+
+  if (tid == 0) {
+    for (int b = 0; b < NST; b++) {
+      mbar_init(&fullX[b], 1);
+      doneX[b] = 0;
+    }
+    mbar_init(fullB, 1);
+    doneB[0] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = tid; e < TC * (Dk - a.ldq); e += NT3) {
+    const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
+    Bs[c * xs_ld + k] = 0.0;
+  }
+  fence_proxy_async();
+  __syncthreads();  // the only block-wide barrier of the kernel
+
+  const unsigned row_bytes = (unsigned)Dk * 8u, q_bytes = (unsigned)a.ldq * 8u;
+  auto load_x = [&](long long it2) {  // one whole warp: X tile + y slice of iteration it2 into buffer it2 % NST
+    const int buf = (int)(it2 % NST);
+    const int rt2 = (int)(it2 % n_rt);
+    double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const long long row0 = row_begin + (long long)rt2 * TR;
+    const int valid = (int)((row_end - row0) < TR ? (row_end - row0) : TR);
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      const int yv = r < valid ? a.y[row0 + r] : 0;
+      ys0[buf * TR + r] = LINK == 0 ? 2.0 * yv - 1.0 : (double)yv;
+      if (r >= valid)
+        for (int k = 0; k < Dk; k += 2) *reinterpret_cast<double2*>(Xs + r * xs_ld + k) = make_double2(0.0, 0.0);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&fullX[buf], (unsigned)valid * row_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      if (r < valid) tma_load_1d(Xs + r * xs_ld, a.X + (size_t)(row0 + r) * a.ldx, row_bytes, &fullX[buf]);
+    }
+  };
+  auto load_b = [&](int ct2) {  // one whole warp: q rows of chain tile ct2
+    const int nb = n_list - ct2 * TC < TC ? n_list - ct2 * TC : TC;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(fullB, (unsigned)nb * q_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TC / 32; h++) {
+      const int c = lane + 32 * h;
+      if (c < nb) {
+        const int slot = ct2 * TC + c;
+        tma_load_1d(Bs + c * xs_ld, a.Q + (size_t)(a.list ? a.list[slot] : slot) * a.ldq, q_bytes, fullB);
+      }
+    }
+  };
+  if (warp == 0) {
+    load_b(0);
+    for (int b = 0; b < NST; b++)
+      if (b < n_it) load_x(b);
+  }
+
+  const int cb = warp * 8;
+  double gacc[MB][2];
+  double lpacc[2];
+  int ct = 0, rt = 0;
+  int buf = 0;           // it % NST
+  unsigned xphase = 0;   // bit b: parity of the next phase of fullX[b] this warp waits for
+  for (long long it = 0; it < n_it; it++) {
+    const bool have = n_list - ct * TC > cb;
+    if (rt == 0) {
+#pragma unroll
+      for (int m = 0; m < MB; m++) gacc[m][0] = gacc[m][1] = 0.0;
+      lpacc[0] = lpacc[1] = 0.0;
+      mbar_wait(fullB, (unsigned)(ct & 1));
+    }
+    mbar_wait(&fullX[buf], (xphase >> buf) & 1u);
+    xphase ^= 1u << buf;
+    const double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const double* ys = ys0 + buf * TR;
+    const long long row0 = row_begin + (long long)rt * TR;
+    double acc[8][2];  // Eta, then the derivative tile
+    if (have) {
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) acc[mi][0] = acc[mi][1] = 0.0;
+      const double* xa = Xs + gid * xs_ld + tig;
+      const double* ba = Bs + (cb + gid) * xs_ld + tig;
+#pragma unroll 2
+      for (int k0 = 0; k0 < Dk; k0 += 4) {
+        double av[8];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) av[mi] = xa[mi * 8 * xs_ld + k0];
+        const double bv = ba[k0];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) dmma(acc[mi][0], acc[mi][1], av[mi], bv);
+      }
+    }
+    if (rt == n_rt - 1 && ct + 1 < n_ct) {
+      if (warp_arrive_is_last(doneB, lane)) load_b(ct + 1);
+    }
+    if (have) {
+      // ---- link in place: acc[mi][j] becomes D[row mi*8 + gid][chain cb + 2*tig + j]
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int r = mi * 8 + gid;
+        const bool valid = row0 + r < row_end;
+        const double yd = ys[r];
+        double lv[2], dv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][j], yd, lv[j], dv[j]);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          lpacc[j] += valid ? lv[j] : 0.0;
+          acc[mi][j] = dv[j];
+        }
+      }
+      // ---- phase B: G[Dk][8 chains] += X tile^T . D, the D fragment fetched from its owner lane by shuffles
+      const double* xb = Xs + tig * xs_ld + gid;
+      const int sel = gid & 1;
+#pragma unroll
+      for (int s = 0; s < TR / 4; s++) {   // rows r0 = 4 s .. 4 s + 3 = 8 (s >> 1) + 4 (s & 1) + tig
+        const int src = (((s & 1) * 4 + tig) << 2) | (gid >> 1);
+        const double v0 = __shfl_sync(0xffffffffu, acc[s >> 1][0], src);
+        const double v1 = __shfl_sync(0xffffffffu, acc[s >> 1][1], src);
+        const double bv = sel ? v1 : v0;
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          if (m * 8 < Dk) {  // warp-uniform
+            const double av = xb[(4 * s) * xs_ld + m * 8];
+            dmma(gacc[m][0], gacc[m][1], av, bv);
+          }
+        }
+      }
+    }
+    // this warp is done with X buffer `buf`: the last warp to get here refills it for iteration it + NST
+    if (it + NST < n_it) {
+      if (warp_arrive_is_last(&doneX[buf], lane)) load_x(it + NST);
+    } else {
+      __syncwarp();
+    }
+    if (rt == n_rt - 1) {
+      if (have) {
+        const int slot0 = ct * TC + cb;
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          const int k = m * 8 + gid;
+          if (k < Dk) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int slot = slot0 + 2 * tig + j;
+              if (slot < n_list) a.Gp[((size_t)p * a.cap + slot) * Dk + k] = gacc[m][j];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          double v = lpacc[j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          const int slot = slot0 + 2 * tig + j;
+          if (gid == 0 && slot < n_list) a.LPp[(size_t)p * a.cap + slot] = v;
+        }
+      }
+      rt = 0;
+      ct++;
+    } else {
+      rt++;
+    }
+    buf = buf + 1 == NST ? 0 : buf + 1;
+  }
+}
+
+size_t glm_tc4_smem_bytes(int Dk, int nst) {
+  return ((size_t)TC * xs_ld_for(Dk) + (size_t)nst * TR * xs_ld_for(Dk) + (size_t)nst * TR + 2 * nst + 4) * sizeof(double);
+}
+
 size_t glm_tc3_smem_bytes(int Dk) {
   return ((size_t)TC * xs_ld_for(Dk) + (size_t)2 * TR * xs_ld_for(Dk) + (size_t)NCW * TR * DW_LD + 2 * TR + 8) * sizeof(double);
 }
@@ -581,6 +795,33 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
   a.cap = ws.C;
   a.P = ws.P;
   const bool logistic = m.kind == MODEL_LOGISTIC;
+  if (ws.variant == 3) {  // experimental v4: three X stages when they fit in 227 KB, else two
+    const int nst = glm_tc4_smem_bytes(a.Dk, 3) <= 232448 ? 3 : 2;
+    const size_t smem4 = glm_tc4_smem_bytes(a.Dk, nst);
+#define LAUNCH4(LINK, MB)                                                                          \
+  {                                                                                                \
+    if (nst == 3) {                                                                                \
+      auto k = glm_dmma4_kernel<LINK, MB, 3>;                                                      \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);            \
+      k<<<ws.P, NT3, smem4, stream>>>(a);                                                          \
+    } else {                                                                                       \
+      auto k = glm_dmma4_kernel<LINK, MB, 2>;                                                      \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);            \
+      k<<<ws.P, NT3, smem4, stream>>>(a);                                                          \
+    }                                                                                              \
+  }
+    if (a.Dk <= 16) {
+      if (logistic) LAUNCH4(0, 2) else LAUNCH4(1, 2)
+    } else if (a.Dk <= 32) {
+      if (logistic) LAUNCH4(0, 4) else LAUNCH4(1, 4)
+    } else if (a.Dk <= 64) {
+      if (logistic) LAUNCH4(0, 8) else LAUNCH4(1, 8)
+    } else {
+      if (logistic) LAUNCH4(0, 14) else LAUNCH4(1, 14)
+    }
+#undef LAUNCH4
+    return 1;
+  }
   if (ws.variant == 2) {
     const size_t smem3 = glm_tc3_smem_bytes(a.Dk);
 #define LAUNCH3(LINK, MB)                                                                     \
