@@ -78,3 +78,37 @@ def test_init_failure_code():
     a = O.run_chain(O.Model(name, data), q0=[np.inf], seed=1, num_warmup=20, num_samples=5)
     b = E.run_chain(kind, D, data, q0=[np.inf], seed=1, num_warmup=20, num_samples=5)
     assert a["rc"] == 78 and b["rc"] == 78
+
+
+def _random_config(rng):
+    nw = int(rng.choice([0, 5, 19, 20, 37, 60, 150, 151, 260]))
+    adapt = int(nw > 0 and rng.uniform() < 0.8)
+    kw = dict(seed=int(rng.integers(0, 2 ** 31)), chain_id=int(rng.integers(0, 50)), num_warmup=nw, num_samples=int(rng.integers(1, 60)),
+              num_thin=int(rng.choice([1, 1, 2, 5])), save_warmup=int(rng.uniform() < 0.5), stepsize=float(rng.choice([1.0, 0.1, 2.5])),
+              stepsize_jitter=float(rng.choice([0.0, 0.0, 0.4])), max_depth=int(rng.choice([1, 3, 6, 10])), delta=float(rng.choice([0.6, 0.8, 0.95])),
+              gamma=float(rng.choice([0.05, 0.1])), kappa=float(rng.choice([0.75, 0.6])), t0=float(rng.choice([10.0, 3.0])),
+              init_buffer=int(rng.choice([75, 10, 0])), term_buffer=int(rng.choice([50, 5, 0])), window=int(rng.choice([25, 7])),
+              init_radius=float(rng.choice([2.0, 0.5, 0.0])), adapt_engaged=adapt)
+    metric = rng.choice(["diag", "unit", "dense"])
+    if metric == "unit":
+        kw["unit_e"] = 1
+    elif metric == "dense":
+        kw["dense_e"] = 1
+    return kw
+
+
+@pytest.mark.parametrize("case", range(36))
+def test_device_state_machine_equals_oracle_random_configs(case):
+    """randomised option matrix (every argument of the service that changes control flow or RNG consumption: window
+    parameters incl. degenerate ones, thinning, jitter, depth caps, all three metrics, adaptation on/off): the device
+    state machine and the oracle must agree bit for bit on every draw, the adapted step size and the metric."""
+    rng = np.random.default_rng(1000 + case)
+    name, kind, D, data = MODELS[case % len(MODELS)]
+    kw = _random_config(rng)
+    a = O.run_chain(O.Model(name, data), **kw)
+    b = E.run_chain(kind, D, data, **kw)
+    assert a["rc"] == b["rc"]
+    if a["rc"] == 0:
+        assert np.array_equal(a["draws"], b["draws"], equal_nan=True)
+        assert (a["stepsize"] == b["stepsize"] or (np.isnan(a["stepsize"]) and np.isnan(b["stepsize"])))
+        assert np.array_equal(a["inv_metric"], b["inv_metric"], equal_nan=True)
