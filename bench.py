@@ -40,8 +40,9 @@ WORKLOADS = {
     "c1": dict(model="bernoulli", chains=4, desc="bernoulli N=10, 4 chains"),
     "c2": dict(model="eight_schools_nc", chains=4096, desc="eight-schools non-centred, 4096 chains"),
     "c3": dict(model="logistic", chains=1024, N=100000, K=100, desc="logistic regression N=100k D=100, 1024 chains"),
-    "c4": dict(model="irt_2pl", chains=8192, I=1000, J=100, desc="IRT 2PL 1000x100, 8192 chains"),
-    "c5": dict(model="poisson_glm", chains=64, N=10000000, K=50, desc="poisson GLM N=10M D=50, 64 chains (rows sharded when N>1)"),
+    # c4 / c5 defaults are sized so that the line finishes in ~2 minutes on one B200 (profiles r01h / r01c)
+    "c4": dict(model="irt_2pl", chains=8192, I=1000, J=100, desc="IRT 2PL 1000x100, 8192 chains", num_warmup=150, steps=30),
+    "c5": dict(model="poisson_glm", chains=64, N=10000000, K=50, desc="poisson GLM N=10M D=50, 64 chains (rows sharded when N>1)", num_warmup=150, steps=30),
 }
 
 
@@ -196,12 +197,12 @@ def run_reference(wname, w, data, cores, warm_state=None, budget_s=60.0, scale_n
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=0, help="timed transitions (default: 200; 30 for c4 / c5)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=os.environ.get("B200_BENCH_WORKLOAD", "c3"))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--num-warmup", type=int, default=1000, help="NUTS adaptation transitions before the timed region")
+    ap.add_argument("--num-warmup", type=int, default=-1, help="NUTS adaptation transitions before the timed region (default: 1000; 150 for c4 / c5)")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the data rows (testing only; invalidates the number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
@@ -218,6 +219,10 @@ def main():
             print(f"[bench +{time.time() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     w = WORKLOADS[args.workload]
+    if args.steps <= 0:
+        args.steps = w.get("steps", 200)
+    if args.num_warmup < 0:
+        args.num_warmup = w.get("num_warmup", 1000)
     model = w["model"]
     cores = os.cpu_count() or 1
     K, W = max(args.steps, 4), max(args.warmup, 3)
