@@ -852,6 +852,7 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
         }
         ev_used = 0;
         if (*e->h_nactive == 0) break;
+        b.hint_active = *e->h_nactive;
       }
       cudaEvent_t a = next_event(), bb = next_event();
       cudaEventRecord(a, e->stream);

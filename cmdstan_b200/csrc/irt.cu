@@ -212,8 +212,13 @@ __global__ void __launch_bounds__(IRT_NT, OCC) irt_grad_kernel(const signed char
 
 int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream) {
   const int ipl = (m.K + IRT_G - 1) / IRT_G;
-  const char* var = getenv("B200NUTS_IRT_VARIANT");  // read per launch (a handful of ns next to a >100 us kernel): tests switch it
-  const int occ = var ? atoi(var) : 1;
+  // B200NUTS_IRT_VARIANT: 1 (default) one CTA per SM; 2 two CTAs per SM; "auto" (EXPERIMENTAL: needs the two forms to be
+  // bit-identical, tests/test_gpu_parity.py with B200_TEST_EXPERIMENTAL=1) picks 2 when the launch is known to be dense
+  // (faster at full batch, profiles r01d) and 1 when only stragglers are left (lower single-CTA latency, profiles r01e).
+  // Read per launch (a handful of ns next to a > 100 us kernel): tests switch it.
+  const char* var = getenv("B200NUTS_IRT_VARIANT");
+  int occ = var ? atoi(var) : 1;
+  if (var && var[0] == 'a') occ = (b.hint_active < 0 ? b.C : b.hint_active) >= 296 ? 2 : 1;
 #define IRT_LAUNCH(IPL)                                                                                                                     \
   {                                                                                                                                         \
     if (occ == 2) irt_grad_kernel<IPL, 2><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld); \

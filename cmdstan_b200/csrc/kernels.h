@@ -24,6 +24,7 @@ struct GradBatch {
   int C, ld;
   const int* list = nullptr;    // compacted indices of the chains with active[c] != 0 (any order), or nullptr
   const int* n_list = nullptr;  // device count of entries in `list`
+  int hint_active = -1;         // host's last known number of requesting chains (-1: unknown); only a scheduling hint
 };
 
 // ---- GLMs (logistic / poisson): glm.cu -------------------------------------------------------------------------

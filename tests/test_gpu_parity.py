@@ -288,3 +288,18 @@ def test_advance_kernel_builds_agree():
         b = _run("std_normal", {"D": D}, C=5, engine="lockstep", num_warmup=60, num_samples=30)
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.skipif(not os.environ.get("B200_TEST_EXPERIMENTAL"), reason="experimental: set B200_TEST_EXPERIMENTAL=1")
+def test_irt_kernel_forms_bit_identical(monkeypatch):
+    """precondition of B200NUTS_IRT_VARIANT=auto (a chain may be served by either form of the kernel from one leapfrog to
+    the next): the one-CTA and the two-CTA form must agree bit for bit."""
+    data = cases.irt_data(211, 100)
+    q = np.random.default_rng(8).uniform(-1.5, 1.5, size=(40, 4 + 211 + 200))
+    out = []
+    for v in ("1", "2"):
+        monkeypatch.setenv("B200NUTS_IRT_VARIANT", v)
+        e = _engine("irt_2pl", data)
+        out.append(e.log_prob_grad(q))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
