@@ -225,6 +225,7 @@ struct b200nuts_engine {
   allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
   void* nccl_comm = nullptr;  // ncclComm_t owned by the engine (b200nuts_nccl_init)
+  int irt_tail = 0;           // EXPERIMENTAL (B200NUTS_IRT_TAIL): 0 off; 1 "nf": irt_tail.cu's gradient kernel; 2: + straggler kernel
   double last_run_s = 0, last_grad_s = 0;
   long long last_launches = 0;
 };
@@ -759,6 +760,10 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   }
   rc = ensure_glm_ws(e, C);
   if (rc) return rc;
+  {
+    const char* t = getenv("B200NUTS_IRT_TAIL");
+    e->irt_tail = !t || !t[0] || t[0] == '0' ? 0 : (t[0] == 'n' ? 1 : 2);
+  }
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   CUDA_TRY(e, cudaGetLastError());
   e->chains_ready = true;
@@ -776,6 +781,7 @@ static int launch_gradient(b200nuts_engine* e, const GradBatch& b, int jacobian 
     case MODEL_POISSON:
       return launch_glm_grad(e->md, b, e->glm_ws, e->cfg.row_shards > 1 ? e->ar : nullptr, e->ar_user, true, e->stream);
     case MODEL_IRT2PL:
+      if (e->irt_tail) return launch_irt_grad_nf(e->md, b, e->stream);
       return launch_irt_grad(e->md, b, e->stream);
     default:
       grad_small_kernel<<<(b.C + 3) / 4, 128, 0, e->stream>>>(e->md, b.Q, b.G, b.zV, b.active, b.C, b.ld);
@@ -853,6 +859,19 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
         ev_used = 0;
         if (*e->h_nactive == 0) break;
         b.hint_active = *e->h_nactive;
+        if (e->irt_tail == 2 && e->md.kind == MODEL_IRT2PL && !e->scfg.dense && *e->h_nactive <= 2 * e->sm_count) {
+          // only stragglers are left: one CTA per remaining chain runs it to the end of this call on the device (irt_tail.cu)
+          cudaEvent_t a = next_event(), bb = next_event();
+          cudaEventRecord(a, e->stream);
+          launch_irt_tail(e->scfg, e->dc, e->md, e->d_list, counter, *e->h_nactive, e->stream);
+          cudaEventRecord(bb, e->stream);
+          launches++;
+          CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+          float tail_ms = 0;
+          cudaEventElapsedTime(&tail_ms, a, bb);
+          grad_ms += tail_ms;  // gradient + the stragglers' own advance work
+          break;
+        }
       }
       cudaEvent_t a = next_event(), bb = next_event();
       cudaEventRecord(a, e->stream);

@@ -303,3 +303,30 @@ def test_irt_kernel_forms_bit_identical(monkeypatch):
         out.append(e.log_prob_grad(q))
         e.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.skipif(not os.environ.get("B200_TEST_EXPERIMENTAL"), reason="experimental: set B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("C", [5, 400])
+def test_irt_straggler_kernel_bit_identical(C, monkeypatch):
+    """B200NUTS_IRT_TAIL=1 (irt_tail.cu: once at most 2 chains per SM still request gradients, one CTA per chain runs it to the
+    end of the call on the device) against the same gradient kernel driven step by step from the host (=nf): identical draws,
+    step sizes, metrics and gradient counts.  C = 5: the whole run happens in the straggler kernel; C = 400: it takes over
+    when the faster chains have finished."""
+    data = cases.irt_data(60, 12)
+    out = []
+    for mode in ("nf", "1"):
+        monkeypatch.setenv("B200NUTS_IRT_TAIL", mode)
+        e = _engine("irt_2pl", data, num_chains=C, random_seed=77, num_warmup=60, num_samples=25, save_warmup=True)
+        e.init_chains()
+        for n in (40, 45):   # two calls: the straggler kernel must leave every chain resumable
+            e.run(n)
+        err, it, ng = e.chain_status()
+        assert (err == 0).all() and (it == 85).all()
+        out.append((e.fetch_draws(constrained=False), e.adaptation(), ng))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
+    assert np.array_equal(out[0][2], out[1][2])
+    m = O.Model("irt_2pl", data)
+    r = O.run_chain(m, seed=77, chain_id=1, num_warmup=60, num_samples=25, save_warmup=1)
+    assert np.array_equal(out[1][0][0, :6, 3:6], r["draws"][:6, 3:6]) and _rel(out[1][0][0, :6], r["draws"][:6], floor=1e-6) < 1e-8
