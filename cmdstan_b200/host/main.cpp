@@ -111,7 +111,7 @@ int main(int argc, char** argv) {
   unsigned int random_seed = seed_arg < 0 ? (unsigned int)(std::time(nullptr) % 4294967296ULL) : (unsigned int)seed_arg;
   if (seed_arg < 0) {
     parser.find({"random", "seed"})->value = std::to_string(random_seed);
-    parser.find({"random", "seed"})->def = std::to_string(random_seed) + "*";  // echoed without "(Default)", like the reference
+    parser.find({"random", "seed"})->def = std::to_string(random_seed);  // echoed as "seed = <time-based value> (Default)", like the reference
   }
 
   // echo to the console (parser.print(info))
