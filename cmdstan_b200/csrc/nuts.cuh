@@ -452,6 +452,9 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_INIT_DRAW: {  // util::initialize (initialize.hpp:87-117)
         if (c.user_q0) {
+          // initialize.hpp:93-101: the random_var_context is constructed (and draws its D uniforms) on every try, also when
+          // every value then comes from the user's context
+          if (cfg.init_radius != 0.0) warp_fill(s->rng, lane, c.q, D, 1, nullptr, cfg.init_radius);
           B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = c.user_q0[i];
         } else if (cfg.init_radius == 0.0) {
           B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;

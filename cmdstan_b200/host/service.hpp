@@ -364,7 +364,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     for (int c = 0; c < C; c++) {
       if ((size_t)c < sample_writer.size()) {
         auto& w = sample_writer[c];
-        if (adapt_engaged) {
+        {  // util::run_sampler (no adaptation) writes the same block: run_sampler.hpp:66-67, run_adaptive_sampler.hpp:88-89
           w("Adaptation terminated");
           std::stringstream ss;
           ss << "Step size = " << eps[c];

@@ -203,19 +203,8 @@ void oracle_rng_kat(uint32_t seed, uint32_t chain, int kind, int n, double* out_
 }
 
 /* ------------------------------------------------------------------ models ------------------------- */
-enum { M_STD_NORMAL = 0, M_BERNOULLI = 1, M_EIGHT_SCHOOLS = 2, M_LOGISTIC = 3, M_IRT2PL = 4, M_POISSON = 5 };
+#include "nuts_oracle.h"
 
-typedef struct {
-  int kind;
-  int D;              /* unconstrained dimension */
-  int N;              /* rows / observations (bernoulli N, eight schools J, GLM N, IRT persons I) */
-  int K;              /* covariates (GLM) / items J (IRT) */
-  const double* X;    /* GLM: N x K row-major */
-  const int* yi;      /* bernoulli / GLM outcomes */
-  const double* yr;   /* eight schools y */
-  const double* sigma;/* eight schools sigma */
-  const signed char* y8; /* IRT: I x J row-major 0/1 */
-} model_t;
 
 static inline double log1p_exp(double a) { return a > 0.0 ? a + log1p(exp(-a)) : log1p(exp(a)); }
 
@@ -500,21 +489,7 @@ void oracle_write_array(const model_t* m, const double* q, double* out) {
 }
 
 /* ------------------------------------------------------------------ sampler ------------------------ */
-typedef struct {
-  uint32_t seed, chain_id;
-  int num_warmup, num_samples, num_thin, save_warmup;
-  double stepsize, stepsize_jitter;
-  int max_depth;
-  double delta, gamma, kappa, t0;
-  unsigned init_buffer, term_buffer, window;
-  double init_radius;
-  int adapt_engaged;
-  int unit_e; /* 1: adapt_unit_e_nuts / unit_e_nuts (S/mcmc/hmc/nuts/adapt_unit_e_nuts.hpp:24-35): metric frozen at the identity,
-                 step-size adaptation only -- arithmetically diag_e with M^-1 = 1 and no variance windows */
-  int dense_e; /* 1: adapt_dense_e_nuts / dense_e_nuts (S/mcmc/hmc/nuts/adapt_dense_e_nuts.hpp:20-50): dense inverse metric
-                  (S/mcmc/hmc/hamiltonians/dense_e_metric.hpp:21-58, dense_e_point.hpp), covariance windows
-                  (S/mcmc/covar_adaptation.hpp:17-45, M/prim/fun/welford_covar_estimator.hpp:10-50) */
-} oracle_config_t;
+
 
 typedef struct {
   int D;
@@ -939,7 +914,8 @@ static int learn_variance(sampler_t* s) { /* var_adaptation.hpp:17-46 */
 
 /*
  * Runs one chain exactly as services::sample::hmc_nuts_diag_e_adapt would (hmc_nuts_diag_e_adapt.hpp:58-112,
- * run_adaptive_sampler.hpp:47-103).  q0 != NULL: user-specified unconstrained inits (no RNG consumed, one try).
+ * run_adaptive_sampler.hpp:47-103).  q0 != NULL: user-specified unconstrained inits (one try; the D uniforms of the unused
+ * random context are still drawn when init_radius > 0).
  * draws: [(save_warmup? W:0 + S)/thin rows][7 + D] =
  *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, q (unconstrained).
  * adapt_out: [1 + D] = final step size, inverse metric ([1 + D*D], row-major, for dense_e).  inv_metric0 likewise [D] or
@@ -967,7 +943,13 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   int ok = 0;
   int max_tries = (q0 || c->init_radius == 0.0) ? 1 : 100;
   for (int t = 0; t < max_tries && !ok; t++) {
-    if (q0) memcpy(s.z.q, q0, D * sizeof(double));
+    if (q0) {
+      /* initialize.hpp:93-101: the random_var_context is constructed -- and draws its D uniforms (random_var_context.hpp:43-66)
+       * -- on every try, also when every value then comes from the user's context through the chained_var_context */
+      if (c->init_radius != 0.0)
+        for (int i = 0; i < D; i++) (void)oracle_uniform_real(&s.rng, -c->init_radius, c->init_radius);
+      memcpy(s.z.q, q0, D * sizeof(double));
+    }
     else if (c->init_radius == 0.0) memset(s.z.q, 0, D * sizeof(double));
     else for (int i = 0; i < D; i++) s.z.q[i] = oracle_uniform_real(&s.rng, -c->init_radius, c->init_radius);
     double lp = oracle_lp_grad(model, s.z.q, gtmp);

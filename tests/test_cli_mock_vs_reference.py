@@ -1,0 +1,106 @@
+"""CPU suite: the whole C++ host side above the C ABI (cmdstan_b200/host: argument tree -> service shim -> Stan-CSV writer,
+adaptation block, metric JSON, per-chain file naming, thinning, save_warmup, progress messages), run END TO END without a
+GPU against a test-only mock of libb200nuts.so that serves the ABI from the CPU oracle (tests/host_emul/mock_b200nuts.cpp),
+and compared with the files the UNMODIFIED reference writes for the same randomised command lines.  The oracle is bit-exact
+for bernoulli, so every byte of every output file must agree except the lines that carry wall-clock times, the start date,
+the output file name and the stanc version.  (On the GPU the same host code runs over the real engine: tests/test_gpu_cli.py.)"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from test_cli_args_vs_reference import CLI, _random_args
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+MOCK_DIR = os.path.join(HERE, "host_emul", "mock")
+
+pytestmark = [pytest.mark.ref, pytest.mark.skipif(not O.have_ref("bernoulli"), reason="oracle/_ref not built")]
+
+
+@pytest.fixture(scope="module")
+def mock_env():
+    import cmdstan_b200
+    cmdstan_b200.load_library()   # builds the CLI if needed
+    O.lib()                       # builds liboracle.so if needed
+    os.makedirs(MOCK_DIR, exist_ok=True)
+    so = os.path.join(MOCK_DIR, "libb200nuts.so")
+    src = os.path.join(HERE, "host_emul", "mock_b200nuts.cpp")
+    deps = [src, os.path.join(ROOT, "include", "b200nuts.h"), os.path.join(ROOT, "oracle", "nuts_oracle.h"), os.path.join(ROOT, "oracle", "liboracle.so")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src, "-L" + os.path.join(ROOT, "oracle"),
+                               "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    return dict(os.environ, LD_LIBRARY_PATH=MOCK_DIR + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
+def _strip(text):
+    keep = []
+    for ln in text.splitlines():
+        if "seconds (" in ln or ln.startswith("# start_datetime") or ln.startswith("#   file = ") or ln.startswith("# stanc_version") or ln.startswith("# stancflags"):
+            continue
+        keep.append(ln)
+    return keep
+
+
+@pytest.mark.parametrize("case", range(30))
+def test_output_files_identical_to_reference(case, tmp_path, mock_env):
+    rng = np.random.default_rng(700 + case)
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    args = _random_args(rng, str(dj))
+    if "random" not in args:   # a defaulted seed is time based
+        k = args.index("output")
+        args[k:k] = ["random", f"seed={int(rng.integers(0, 100000))}"]
+    nch = int(rng.choice([1, 1, 2, 4]))
+    if nch > 1:
+        k = args.index("data") if "id=" not in " ".join(args) else next(i for i, a in enumerate(args) if a.startswith("id="))
+        args[k:k] = [f"num_chains={nch}"]
+    mine_dir, ref_dir = tmp_path / "mine", tmp_path / "ref"
+    mine_dir.mkdir()
+    ref_dir.mkdir()
+    ref = subprocess.run([os.path.join(O.REF, "bernoulli")] + args + ["file=out.csv"], cwd=ref_dir, capture_output=True, text=True)
+    mine = subprocess.run([CLI, "bernoulli"] + args + ["file=out.csv"], cwd=mine_dir, capture_output=True, text=True, env=mock_env)
+    assert ref.returncode == 0, " ".join(args) + "\n" + ref.stdout[-800:] + ref.stderr[-800:]
+    assert mine.returncode == 0, " ".join(args) + "\n" + mine.stdout[-800:] + mine.stderr[-800:]
+    ref_files, mine_files = sorted(os.listdir(ref_dir)), sorted(os.listdir(mine_dir))
+    assert mine_files == ref_files, " ".join(args)
+    for f in ref_files:
+        a, b = (mine_dir / f).read_text(), (ref_dir / f).read_text()
+        if f.endswith(".json"):
+            ja, jb = json.loads(a), json.loads(b)
+            assert ja.keys() == jb.keys() and ja["metric_type"] == jb["metric_type"], f
+            assert np.allclose(np.array(ja["inv_metric"], dtype=float), np.array(jb["inv_metric"], dtype=float), rtol=1e-5) and abs(ja["stepsize"] - jb["stepsize"]) <= 1e-5 * jb["stepsize"], f
+        else:
+            assert _strip(a) == _strip(b), f + ": " + " ".join(args)
+    # progress messages on the console (the reference's chains are threads: their lines interleave, so compare as a multiset)
+    it = lambda s: sorted(ln.strip() for ln in s.splitlines() if "Iteration:" in ln)
+    assert it(mine.stdout) == it(ref.stdout), " ".join(args)
+
+
+@pytest.mark.parametrize("metric,adapt", [("diag_e", 1), ("diag_e", 0), ("dense_e", 1), ("dense_e", 0), ("unit_e", 0)])
+def test_user_inits_and_metric_file_identical_to_reference(metric, adapt, tmp_path, mock_env):
+    """init=<file> (constrained values -> transform_inits) and metric_file=<file> (read_diag_inv_metric / read_dense_inv_metric),
+    with and without adaptation, for each metric: files identical to the reference's."""
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    ini = tmp_path / "init.json"
+    ini.write_text(json.dumps({"theta": 0.3}))
+    args = ["sample", "num_samples=25", "num_warmup=40", "save_warmup=1", "adapt", f"engaged={adapt}", "algorithm=hmc", f"metric={metric}"]
+    if metric != "unit_e":
+        mf = tmp_path / "metric.json"
+        mf.write_text(json.dumps({"inv_metric": [0.7] if metric == "diag_e" else [[0.7]]}))
+        args.append(f"metric_file={mf}")
+    args += ["stepsize=0.8", "data", f"file={dj}", f"init={ini}", "random", "seed=99", "output", "sig_figs=10"]
+    mine_dir, ref_dir = tmp_path / "mine", tmp_path / "ref"
+    mine_dir.mkdir()
+    ref_dir.mkdir()
+    ref = subprocess.run([os.path.join(O.REF, "bernoulli")] + args + ["file=out.csv"], cwd=ref_dir, capture_output=True, text=True)
+    mine = subprocess.run([CLI, "bernoulli"] + args + ["file=out.csv"], cwd=mine_dir, capture_output=True, text=True, env=mock_env)
+    assert ref.returncode == 0, ref.stdout[-800:] + ref.stderr[-800:]
+    assert mine.returncode == 0, mine.stdout[-800:] + mine.stderr[-800:]
+    a, b = _strip((mine_dir / "out.csv").read_text()), _strip((ref_dir / "out.csv").read_text())
+    drop = lambda ls: [x for x in ls if not x.startswith("#     metric_file = ") and not x.startswith("# init = ")]
+    assert drop(a) == drop(b)

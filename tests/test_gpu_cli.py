@@ -132,7 +132,8 @@ def test_cli_init_and_metric_files(tmp_path):
                            "data", f"file={dj}", "init=init.json", "random", "seed=9", "output", "file=fix.csv", "sig_figs=18"], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     names, draws, stepsize, metric, _ = O.read_stan_csv(str(tmp_path / "fix.csv"))
-    assert stepsize is None and (draws[:, 2] == 0.7).all() and draws.shape[0] == 30   # no adaptation block, fixed step size
+    # fixed step size and metric; util::run_sampler still writes the sampler-state block (run_sampler.hpp:66-67)
+    assert stepsize == 0.7 and metric is not None and metric[0] == 0.5 and (draws[:, 2] == 0.7).all() and draws.shape[0] == 30
     ref = O.run_chain(O.Model("bernoulli", cases.BERNOULLI), q0=[np.log(0.3 / 0.7)], inv_metric=[0.5], seed=9, chain_id=1, num_warmup=30, num_samples=30,
                       adapt_engaged=0, stepsize=0.7)
     m = O.Model("bernoulli", cases.BERNOULLI)
@@ -164,7 +165,7 @@ def test_cli_metric_dense_e_vs_reference(tmp_path):
     """`model sample algorithm=hmc metric=dense_e` (hmc_nuts_dense_e_adapt): same comment skeleton as the unmodified reference
     (config echo with metric = dense_e, "# Elements of inverse mass matrix:" followed by D rows of D values), first
     transitions equal, save_metric JSON with metric_type dense_e and a D x D inv_metric; then the written metric is fed back
-    through metric_file= with adapt engaged=0 (hmc_nuts_dense_e)."""
+    through metric_file= with adapt engaged=0 (hmc_nuts_dense_e: no adaptation, but the sampler state is still written)."""
     dj = tmp_path / "es.json"
     dj.write_text(json.dumps({"J": 8, "y": [28, 8, -3, 7, -1, 1, 18, 12], "sigma": [15, 10, 16, 11, 9, 11, 10, 18]}))
     args = ["sample", "num_samples=30", "num_warmup=150", "save_warmup=1", "adapt", "save_metric=1", "algorithm=hmc", "metric=dense_e", "data",
@@ -193,7 +194,10 @@ def test_cli_metric_dense_e_vs_reference(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     lines = (tmp_path / "f.csv").read_text().splitlines()
     rows = np.array([x.split(",") for x in lines if x and not x.startswith("#")][1:], dtype=float)
-    assert rows.shape[0] == 40 and (rows[:, 2] == 0.3).all() and not any("Adaptation terminated" in x for x in lines)
+    # util::run_sampler writes the sampler state too (run_sampler.hpp:66-67): the step size given and the metric read back
+    assert rows.shape[0] == 40 and (rows[:, 2] == 0.3).all()
+    k = lines.index("# Adaptation terminated")
+    assert lines[k + 1] == "# Step size = 0.3" and lines[k + 2] == "# Elements of inverse mass matrix:"
 
 
 def test_cli_errors(tmp_path):
