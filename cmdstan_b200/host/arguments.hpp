@@ -186,6 +186,14 @@ class argument_parser {
     return out;
   }
 
+  // the same tree as members of a JSON object (argument_parser::print(structured_writer&), used by write_config for
+  // `output save_cmdstan_config=1`, src/cmdstan/write_config.hpp:31-47): list arguments become {"value": v, v: {...}},
+  // categories become objects, scalars JSON scalars.  Lines are appended to `out` at `depth` levels of two-space indentation,
+  // each entry ending with a comma.
+  void echo_json(std::string& out, int depth) const {
+    for (auto& k : root_.kids) print_json(*k, depth, out);
+  }
+
  private:
   static void set_value(arg* a, const std::string& v) {
     char* end = nullptr;
@@ -240,6 +248,47 @@ class argument_parser {
     if (a.kind == arg::LIST)
       for (auto& k : a.kids)
         if (k->name == a.value && !k->kids.empty()) print(*k, depth + 1, out);
+  }
+  static std::string json_string(const std::string& v) {
+    std::string r = "\"";
+    for (char ch : v) {
+      if (ch == '"' || ch == '\\' || ch == '/') r += '\\';  // stan::callbacks::json_writer escapes the solidus too
+      r += ch;
+    }
+    return r + "\"";
+  }
+  static void print_json(const arg& a, int depth, std::string& out) {
+    const std::string ind(2 * depth, ' ');
+    auto kids_of = [&](const arg& parent, int d) {
+      for (auto& k : parent.kids) print_json(*k, d, out);
+    };
+    if (a.kind == arg::CATEGORY) {
+      out += ind + "\"" + a.name + "\" : {\n";
+      kids_of(a, depth + 1);
+      close(out, ind);
+      return;
+    }
+    if (a.kind == arg::LIST) {
+      out += ind + "\"" + a.name + "\" : {\n" + ind + "  \"value\" : " + json_string(a.value) + ",\n";
+      for (auto& k : a.kids)
+        if (k->name == a.value && !k->kids.empty()) {
+          out += ind + "  \"" + k->name + "\" : {\n";
+          kids_of(*k, depth + 2);
+          close(out, ind + "  ");
+        }
+      close(out, ind);
+      return;
+    }
+    std::string v;
+    if (a.kind == arg::BOOL) v = a.boolean() ? "true" : "false";
+    else if (a.kind == arg::STRING) v = json_string(a.value);
+    else v = a.value;
+    out += ind + "\"" + a.name + "\" : " + v + ",\n";
+  }
+  // replaces the trailing ",\n" of the last member by "\n", then closes the object (itself a member: trailing comma)
+  static void close(std::string& out, const std::string& ind) {
+    if (out.size() >= 2 && out.compare(out.size() - 2, 2, ",\n") == 0) out.erase(out.size() - 2, 1);
+    out += ind + "},\n";
   }
   arg root_;
 };

@@ -176,6 +176,22 @@ int main(int argc, char** argv) {
       for (const std::string& ln : model.model_compile_info()) w(ln);
     }
 
+    if (parser.boolean({"output", "save_cmdstan_config"})) {  // command.hpp:279-285 + write_config(structured_writer&)
+      std::unique_ptr<std::ostream> cf = create_stream(basename_suffix(output_file).first + "_config.json", sig_figs);
+      std::string js = "\n{\n  \"stan_major_version\" : \"2\",\n  \"stan_minor_version\" : \"36\",\n  \"stan_patch_version\" : \"0\",\n";
+      js += "  \"model_name\" : \"" + model.model_name() + "\",\n  \"start_datetime\" : \"" + std::string(date) + " UTC\",\n";
+      parser.echo_json(js, 1);
+      js += "  \"mpi_enabled\" : false,\n";
+      const std::vector<std::string> ci = model.model_compile_info();  // "stanc_version = ...", "stancflags = ..."
+      for (size_t i = 0; i < ci.size(); i++) {
+        const size_t eq = ci[i].find(" = ");
+        const std::string key = ci[i].substr(0, eq), val = eq == std::string::npos ? "" : ci[i].substr(eq + 3);
+        js += "  \"" + key + "\" : \"" + val + "\"" + (i + 1 < ci.size() ? ",\n" : "\n");
+      }
+      js += "}\n";
+      *cf << js;
+    }
+
     services::device_options opt;
     opt.unit_e = metric == "unit_e";  // command.hpp dispatches to hmc_nuts_unit_e[_adapt]; same call below with the identity metric
     opt.dense_e = metric == "dense_e";  // ... and to hmc_nuts_dense_e[_adapt] (command.hpp:620-660)

@@ -70,6 +70,8 @@ def _random_args(rng, dj):
         a.append(f"refresh={int(rng.choice([100, 7]))}")
     if rng.uniform() < 0.4:
         a.append(f"sig_figs={int(rng.choice([-1, 4, 12]))}")
+    if rng.uniform() < 0.3:
+        a.append(f"save_cmdstan_config={int(rng.integers(0, 2))}")
     return a
 
 
