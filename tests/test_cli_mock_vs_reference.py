@@ -107,3 +107,43 @@ def test_user_inits_and_metric_file_identical_to_reference(metric, adapt, tmp_pa
     a, b = _strip((mine_dir / "out.csv").read_text()), _strip((ref_dir / "out.csv").read_text())
     drop = lambda ls: [x for x in ls if not x.startswith("#     metric_file = ") and not x.startswith("# init = ")]
     assert drop(a) == drop(b)
+
+
+def test_per_chain_init_and_metric_files(tmp_path, mock_env):
+    """num_chains=2 with init=init.json / metric_file=met.json resolves to init_1.json, init_2.json, met_1.json, met_2.json
+    (get_vec_var_context, command_helper.hpp): both chains' files identical to the reference's."""
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    outs = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        d.mkdir()
+        for c, (th, im) in enumerate([(0.2, 0.5), (0.6, 1.5)], start=1):
+            (d / f"init_{c}.json").write_text(json.dumps({"theta": th}))
+            (d / f"met_{c}.json").write_text(json.dumps({"inv_metric": [im]}))
+        args = ["sample", "num_samples=8", "num_warmup=30", "algorithm=hmc", "metric_file=met.json", "num_chains=2", "data", f"file={dj}", "init=init.json",
+                "random", "seed=3", "output", "sig_figs=9", "file=o.csv"]
+        exe, env = ([CLI, "bernoulli"], mock_env) if who == "mine" else ([os.path.join(O.REF, "bernoulli")], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, who + r.stdout[-600:] + r.stderr[-600:]
+        outs[who] = [_strip((d / f"o_{c}.csv").read_text()) for c in (1, 2)]
+    assert outs["mine"] == outs["ref"]
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_std_normal_output_files_identical_to_reference(case, tmp_path, mock_env):
+    """a vector parameter (x.1, x.2, x.3): the 3-d standard normal is bit-exact in the oracle for diag_e / unit_e"""
+    rng = np.random.default_rng(1200 + case)
+    dj = tmp_path / "d.json"
+    dj.write_text(json.dumps({"D": 3}))
+    args = [a for a in _random_args(rng, str(dj)) if a != "metric=dense_e"]
+    if "random" not in args:
+        k = args.index("output")
+        args[k:k] = ["random", f"seed={int(rng.integers(0, 100000))}"]
+    mine_dir, ref_dir = tmp_path / "mine", tmp_path / "ref"
+    mine_dir.mkdir()
+    ref_dir.mkdir()
+    ref = subprocess.run([os.path.join(O.REF, "std_normal")] + args + ["file=out.csv"], cwd=ref_dir, capture_output=True, text=True)
+    mine = subprocess.run([CLI, "std_normal"] + args + ["file=out.csv"], cwd=mine_dir, capture_output=True, text=True, env=mock_env)
+    assert ref.returncode == 0 and mine.returncode == 0, " ".join(args) + mine.stdout[-500:] + mine.stderr[-500:] + ref.stderr[-500:]
+    assert _strip((mine_dir / "out.csv").read_text()) == _strip((ref_dir / "out.csv").read_text()), " ".join(args)
