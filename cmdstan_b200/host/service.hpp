@@ -227,26 +227,6 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   int64_t nu = 0, K = 0;
   b200nuts_num_params(eg.e[0], &nu, &K);
 
-  // window fallback notice (windowed_adaptation.hpp:42-67), once -- the reference prints it per chain
-  if (adapt_engaged && !opt.unit_e && num_warmup >= 20 && init_buffer + window + term_buffer > (unsigned)num_warmup) {
-    unsigned ib = (unsigned)(0.15 * num_warmup), tb = (unsigned)(0.1 * num_warmup);
-    std::stringstream m;
-    m << "WARNING: There aren't enough warmup iterations to fit the\n         three stages of adaptation as currently configured.\n"
-      << "         Reducing each adaptation stage to 15%/75%/10% of\n         the given number of warmup iterations:\n"
-      << "           init_buffer = " << ib << "\n           adapt_window = " << num_warmup - (ib + tb) << "\n           term_buffer = " << tb << "\n";
-    logger.info(m.str());
-  } else if (adapt_engaged && !opt.unit_e && num_warmup < 20) {
-    logger.info("WARNING: No variance estimation is\n         performed for num_warmup < 20\n");
-  }
-
-  // ---- header rows
-  std::vector<std::string> names = {"lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"};
-  model.constrained_param_names(names, true, true);
-  for (int c = 0; c < C; c++) {
-    if ((size_t)c < sample_writer.size()) sample_writer[c](names);
-    if ((size_t)c < diagnostic_writer.size()) diagnostic_writer[c](names);
-  }
-
   auto run_all = [&](int n_iter) -> int {
     std::vector<int> rcs(G, 0);
     std::vector<std::thread> th;
@@ -345,11 +325,35 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   const int64_t warm_rows = save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0;
   const int64_t samp_rows = (num_samples + num_thin - 1) / num_thin;
   int rc;
+  // ---- util::initialize + sampler set-up of every chain come first in the reference (hmc_nuts_diag_e_adapt.hpp:360-379): a
+  // failed initialisation ends the call before any notice, header row or iteration message
+  if ((rc = run_all(0))) return rc;
+  if ((rc = chain_errors())) return rc;
+
+  // window fallback notice (windowed_adaptation.hpp:42-67), once -- the reference prints it per chain
+  if (adapt_engaged && !opt.unit_e && num_warmup >= 20 && init_buffer + window + term_buffer > (unsigned)num_warmup) {
+    unsigned ib = (unsigned)(0.15 * num_warmup), tb = (unsigned)(0.1 * num_warmup);
+    std::stringstream m;
+    m << "WARNING: There aren't enough warmup iterations to fit the\n         three stages of adaptation as currently configured.\n"
+      << "         Reducing each adaptation stage to 15%/75%/10% of\n         the given number of warmup iterations:\n"
+      << "           init_buffer = " << ib << "\n           adapt_window = " << num_warmup - (ib + tb) << "\n           term_buffer = " << tb << "\n";
+    logger.info(m.str());
+  } else if (adapt_engaged && !opt.unit_e && num_warmup < 20) {
+    logger.info("WARNING: No variance estimation is\n         performed for num_warmup < 20\n");
+  }
+
+  // ---- header rows
+  std::vector<std::string> names = {"lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"};
+  model.constrained_param_names(names, true, true);
+  for (int c = 0; c < C; c++) {
+    if ((size_t)c < sample_writer.size()) sample_writer[c](names);
+    if ((size_t)c < diagnostic_writer.size()) diagnostic_writer[c](names);
+  }
+
   // ---- warm-up (generate_transitions with warmup = true)
   auto t0w = std::chrono::steady_clock::now();
   if ((rc = run_phase(num_warmup, 0, true))) return rc;
   double warm_delta_t = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0w).count() / 1000.0;
-  if (num_warmup == 0 && (rc = run_all(0))) return rc;  // initialisation happens inside the first run call
   if ((rc = chain_errors())) return rc;
   if ((rc = write_rows(0, warm_rows))) return rc;
   // ---- adaptation block (write_adapt_finish + write_sampler_state) and metric JSON

@@ -147,3 +147,24 @@ def test_std_normal_output_files_identical_to_reference(case, tmp_path, mock_env
     mine = subprocess.run([CLI, "std_normal"] + args + ["file=out.csv"], cwd=mine_dir, capture_output=True, text=True, env=mock_env)
     assert ref.returncode == 0 and mine.returncode == 0, " ".join(args) + mine.stdout[-500:] + mine.stderr[-500:] + ref.stderr[-500:]
     assert _strip((mine_dir / "out.csv").read_text()) == _strip((ref_dir / "out.csv").read_text()), " ".join(args)
+
+
+def test_failed_user_initialisation_like_reference(tmp_path, mock_env):
+    """theta = 1 has no finite unconstrained image: util::initialize fails before any notice, header row or iteration message
+    (hmc_nuts_diag_e_adapt.hpp:360-363) -- same exit code, same "Initialization failed." message, same (header-only) CSV file."""
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    ini = tmp_path / "init.json"
+    ini.write_text(json.dumps({"theta": 1.0}))
+    args = ["sample", "num_samples=8", "num_warmup=30", "data", f"file={dj}", f"init={ini}", "random", "seed=3", "output", "file=o.csv"]
+    out = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        d.mkdir()
+        exe, env = ([CLI, "bernoulli"], mock_env) if who == "mine" else ([os.path.join(O.REF, "bernoulli")], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        out[who] = (r.returncode, r.stdout + r.stderr, _strip((d / "o.csv").read_text()))
+    assert out["mine"][0] == out["ref"][0] == 1
+    assert "Initialization failed." in out["mine"][1] and "Initialization failed." in out["ref"][1]
+    assert "Iteration:" not in out["mine"][1] and "WARNING" not in out["mine"][1]
+    assert out["mine"][2] == out["ref"][2]
