@@ -168,3 +168,28 @@ def test_failed_user_initialisation_like_reference(tmp_path, mock_env):
     assert "Initialization failed." in out["mine"][1] and "Initialization failed." in out["ref"][1]
     assert "Iteration:" not in out["mine"][1] and "WARNING" not in out["mine"][1]
     assert out["mine"][2] == out["ref"][2]
+
+
+@pytest.mark.skipif(not O.have_ref("eight_schools_nc"), reason="oracle/_ref not built")
+def test_eight_schools_transformed_parameters_columns(tmp_path, mock_env):
+    """a model with transformed parameters (theta = mu + tau * theta_tilde written by write_array): same comment skeleton and
+    header row as the reference, and -- the oracle's closed-form gradient differs from reverse-mode AD in the last ulp, so the
+    funnel separates the two chains later -- the first 30 saved rows equal at 8 significant digits."""
+    dj = tmp_path / "es.json"
+    dj.write_text(json.dumps({"J": 8, "y": [28, 8, -3, 7, -1, 1, 18, 12], "sigma": [15, 10, 16, 11, 9, 11, 10, 18]}))
+    args = ["sample", "num_samples=10", "num_warmup=50", "save_warmup=1", "data", f"file={dj}", "random", "seed=3", "output", "sig_figs=8", "file=o.csv"]
+    out = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        d.mkdir()
+        exe, env = ([CLI, "eight_schools_nc"], mock_env) if who == "mine" else ([os.path.join(O.REF, "eight_schools_nc")], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, who + r.stdout[-600:] + r.stderr[-600:]
+        out[who] = _strip((d / "o.csv").read_text())
+    a, b = out["mine"], out["ref"]
+    assert len(a) == len(b)
+    body = lambda ls: [x for x in ls if not x.startswith("#")]
+    comments = lambda ls: [x for x in ls if x.startswith("#") and "Step size" not in x and not x[2:3].isdigit() and not x.startswith("# -")]
+    assert comments(a) == comments(b)
+    assert body(a)[0] == body(b)[0] and body(a)[0].endswith("theta_tilde.8,theta.1,theta.2,theta.3,theta.4,theta.5,theta.6,theta.7,theta.8")
+    assert body(a)[1:31] == body(b)[1:31]
