@@ -45,7 +45,7 @@ def _strip(text):
     return keep
 
 
-@pytest.mark.parametrize("case", range(30))
+@pytest.mark.parametrize("case", range(60))
 def test_output_files_identical_to_reference(case, tmp_path, mock_env):
     rng = np.random.default_rng(700 + case)
     dj = tmp_path / "b.json"
