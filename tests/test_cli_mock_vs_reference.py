@@ -193,3 +193,27 @@ def test_eight_schools_transformed_parameters_columns(tmp_path, mock_env):
     assert comments(a) == comments(b)
     assert body(a)[0] == body(b)[0] and body(a)[0].endswith("theta_tilde.8,theta.1,theta.2,theta.3,theta.4,theta.5,theta.6,theta.7,theta.8")
     assert body(a)[1:31] == body(b)[1:31]
+
+
+def test_chains_split_over_several_engines(tmp_path, mock_env):
+    """B200_DEVICES=0,1,2 splits the chains contiguously over three engines (one per GPU in production; chain c of engine g runs
+    stream id + first[g] + c): five chains with per-chain init and metric files give the reference's five files whatever the split."""
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    args = ["sample", "num_samples=12", "num_warmup=40", "save_warmup=1", "thin=2", "adapt", "save_metric=1", "algorithm=hmc", "metric_file=met.json", "num_chains=5",
+            "id=3", "data", f"file={dj}", "init=init.json", "random", "seed=8", "output", "sig_figs=10", "file=o.csv"]
+    outs = {}
+    for who, devs in (("ref", None), ("one", "0"), ("three", "0,1,2"), ("five", "0,1,2,3,4")):
+        d = tmp_path / who
+        d.mkdir()
+        for c in range(3, 8):
+            (d / f"init_{c}.json").write_text(json.dumps({"theta": 0.1 * (c - 1)}))
+            (d / f"met_{c}.json").write_text(json.dumps({"inv_metric": [0.3 * c]}))
+        if who == "ref":
+            r = subprocess.run([os.path.join(O.REF, "bernoulli")] + args, cwd=d, capture_output=True, text=True)
+        else:
+            r = subprocess.run([CLI, "bernoulli"] + args, cwd=d, capture_output=True, text=True, env=dict(mock_env, B200_DEVICES=devs))
+        assert r.returncode == 0, who + r.stdout[-600:] + r.stderr[-600:]
+        outs[who] = {f: _strip((d / f).read_text()) for f in sorted(os.listdir(d)) if f.startswith("o_") and f.endswith(".csv")}
+        assert sorted(outs[who]) == [f"o_{c}.csv" for c in range(3, 8)]
+    assert outs["one"] == outs["ref"] and outs["three"] == outs["ref"] and outs["five"] == outs["ref"]
