@@ -186,6 +186,14 @@ class argument_parser {
     return out;
   }
 
+  // `help-all`: the whole argument tree with types, defaults and valid values (the reference's argument_parser::help_printed
+  // prints the same tree with its own prose; names, nesting, defaults and ranges are the contract)
+  std::vector<std::string> help_all() const {
+    std::vector<std::string> out;
+    for (auto& k : root_.kids) help(*k, 0, out);
+    return out;
+  }
+
   // the same tree as members of a JSON object (argument_parser::print(structured_writer&), used by write_config for
   // `output save_cmdstan_config=1`, src/cmdstan/write_config.hpp:31-47): list arguments become {"value": v, v: {...}},
   // categories become objects, scalars JSON scalars.  Lines are appended to `out` at `depth` levels of two-space indentation,
@@ -248,6 +256,24 @@ class argument_parser {
     if (a.kind == arg::LIST)
       for (auto& k : a.kids)
         if (k->name == a.value && !k->kids.empty()) print(*k, depth + 1, out);
+  }
+  static void help(const arg& a, int depth, std::vector<std::string>& out) {
+    static const char* const kType[] = {"", "int", "unsigned int", "long long int", "double", "boolean", "string", "list element"};
+    const std::string ind(2 * depth, ' ');
+    if (a.kind == arg::CATEGORY) {
+      out.push_back(ind + a.name);
+    } else {
+      out.push_back(ind + a.name + "=<" + kType[a.kind] + ">");
+      if (a.kind == arg::LIST) {
+        std::string v;
+        for (auto& k : a.kids) v += (v.empty() ? "" : ", ") + k->name;
+        out.push_back(ind + "  Valid values: " + v);
+      } else if (!a.valid.empty()) {
+        out.push_back(ind + "  Valid values: " + a.valid);
+      }
+      out.push_back(ind + "  Defaults to " + a.def);
+    }
+    for (auto& k : a.kids) help(*k, depth + 1, out);
   }
   static std::string json_string(const std::string& v) {
     std::string r = "\"";

@@ -69,6 +69,23 @@ int main(int argc, char** argv) {
   for (int i = first; i < argc; i++) tokens.push_back(argv[i]);
   callbacks::stream_logger logger(std::cout, std::cout, std::cout, std::cerr, std::cerr);
   cmd::argument_parser parser;
+  if (tokens.empty() || tokens[0] == "help" || tokens[0] == "help-all") {  // argument_parser::parse_args help branches: exit 0
+    std::cout << "Usage: " << argv[0] << (first == 2 ? std::string(" ") + argv[1] : std::string(""))
+              << " <arg1> <subarg1_1> ... <subarg1_m> ... <arg_n> <subarg_n_1> ... <subarg_n_m>\n\n"
+              << "Inference method available in the B200 engine:\n"
+              << "  sample      Bayesian inference with Markov Chain Monte Carlo (algorithm=hmc engine=nuts metric=diag_e|unit_e|dense_e)\n\n"
+              << "Or see help information with\n  help        Prints help\n  help-all    Prints entire argument tree\n\n"
+              << "Additional configuration available by specifying\n  id, data, init, random, output, num_threads   (see help-all)\n";
+    if (!tokens.empty() && tokens[0] == "help-all") {
+      std::cout << "\n";
+      for (const std::string& ln : parser.help_all()) std::cout << ln << "\n";
+    }
+    if (tokens.empty()) {
+      std::cerr << "A method must be specified!\nFailed to parse arguments, terminating Stan" << std::endl;
+      return services::error_codes::USAGE;
+    }
+    return 0;
+  }
   try {
     parser.parse(tokens);
   } catch (const std::exception& e) {

@@ -126,3 +126,27 @@ def test_bad_data_refused_like_reference(kind, tmp_path):
     mine = _run([CLI, "bernoulli"], args, tmp_path)
     assert ref.returncode != 0 and mine.returncode != 0
     assert "no CUDA device" not in mine.stderr + mine.stdout   # refused for the data, not for the missing GPU
+
+
+def test_help_and_help_all_like_reference(tmp_path):
+    """`help` / `help-all` exit 0 in both programs; every argument of the B200 front end's tree appears in the reference's
+    help-all with the same name, in the same order (the reference's tree also holds the other methods)."""
+    import re
+    import cmdstan_b200
+    cmdstan_b200.load_library()
+    for h in ("help", "help-all"):
+        assert _run([os.path.join(O.REF, "bernoulli")], [h], tmp_path).returncode == 0
+        assert _run([CLI, "bernoulli"], [h], tmp_path).returncode == 0
+    # argument names in tree order (the reference prints its own prose for descriptions and for some defaults)
+    names = lambda out: [ln.strip().split("=<")[0] for ln in out.splitlines() if re.match(r"^\s*\S+=<.*>$", ln)]
+    ref = names(_run([os.path.join(O.REF, "bernoulli")], ["help-all"], tmp_path).stdout)
+    mine_out = _run([CLI, "bernoulli"], ["help-all"], tmp_path).stdout
+    mine = names(mine_out)
+    assert len(mine) >= 30
+    it = iter(ref)
+    missing = [n for n in mine if not any(n == r for r in it)]   # subsequence test
+    assert not missing, missing[:5]
+    for frag in ("num_samples=<int>", "Defaults to 1000", "delta=<double>", "Valid values: 0.1 <= delta <= 1", "Defaults to 0.8", "max_depth=<int>", "Defaults to 10",
+                 "Valid values: unit_e, diag_e, dense_e", "Defaults to diag_e"):
+        assert frag in mine_out
+    assert _run([os.path.join(O.REF, "bernoulli")], [], tmp_path).returncode != 0 and _run([CLI, "bernoulli"], [], tmp_path).returncode != 0
