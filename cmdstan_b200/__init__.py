@@ -32,14 +32,14 @@ class Config(C.Structure):
                 ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double), ("t0", C.c_double),
                 ("init_buffer", C.c_uint32), ("term_buffer", C.c_uint32), ("window", C.c_uint32), ("adapt_engaged", C.c_int32),
                 ("engine", C.c_int32), ("device", C.c_int32), ("store_draws", C.c_int32), ("row_shards", C.c_int32),
-                ("row_shard_rank", C.c_int32), ("metric", C.c_int32)]
+                ("row_shard_rank", C.c_int32), ("metric", C.c_int32), ("store_diagnostics", C.c_int32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b200nuts_last_error", "b200nuts_set_data_f64",
            "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
-           "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_rows_saved",
+           "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_fetch_diagnostics", "b200nuts_rows_saved",
            "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
            "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
            # include/b200nuts_model.h
@@ -82,6 +82,7 @@ def load_library(build=True):
     lib.b200nuts_log_prob_grad.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp]
     lib.b200nuts_run.argtypes = [vp, C.c_int]
     lib.b200nuts_fetch_draws.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp]
+    lib.b200nuts_fetch_diagnostics.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.b200nuts_rows_saved.argtypes = [vp]
     lib.b200nuts_rows_saved.restype = C.c_int64
     lib.b200nuts_get_adaptation.argtypes = [vp, vp, vp]
@@ -169,7 +170,7 @@ class Engine:
     def __init__(self, model, data, num_chains=1, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
                  num_samples=1000, num_thin=1, save_warmup=False, stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8,
                  gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50, window=25, adapt_engaged=True, engine="auto",
-                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None, metric="diag_e"):
+                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None, metric="diag_e", store_diagnostics=False):
         self.lib = load_library()
         cfg = Config()
         self.lib.b200nuts_default_config(C.byref(cfg))
@@ -182,6 +183,7 @@ class Engine:
         cfg.adapt_engaged, cfg.engine, cfg.device, cfg.store_draws = int(bool(adapt_engaged)), ENGINES[engine], int(device), int(bool(store_draws))
         cfg.row_shards, cfg.row_shard_rank = int(row_shards), int(row_shard_rank)
         cfg.metric = {"diag_e": 0, "unit_e": 1, "dense_e": 2}[metric]
+        cfg.store_diagnostics = int(bool(store_diagnostics))
         self.metric = metric
         self.cfg = cfg
         self.model = model
@@ -277,6 +279,15 @@ class Engine:
         if out is None:
             out = np.empty((nchains, nrows, 7 + k))
         self._chk(self.lib.b200nuts_fetch_draws(self.h, chain0, nchains, row0, nrows, int(constrained), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def fetch_diagnostics(self, chain0=0, nchains=None, row0=0, nrows=None):
+        """[nchains, nrows, 7 + 3 D]: sampler columns, unconstrained q, momentum p, gradient of the potential g of every saved
+        draw (the rows of CmdStan's `output diagnostic_file=`); needs store_diagnostics=True."""
+        nchains = self.num_chains - chain0 if nchains is None else nchains
+        nrows = self.rows_saved() - row0 if nrows is None else nrows
+        out = np.empty((nchains, nrows, 7 + 3 * self.D))
+        self._chk(self.lib.b200nuts_fetch_diagnostics(self.h, chain0, nchains, row0, nrows, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def summary(self, row0=0, nrows=None, constrained=True):

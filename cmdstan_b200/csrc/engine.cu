@@ -260,6 +260,7 @@ void b200nuts_default_config(b200nuts_config* c) {
   c->row_shards = 1;
   c->row_shard_rank = 0;
   c->metric = 0;
+  c->store_diagnostics = 0;
 }
 
 const char* b200nuts_last_error(const b200nuts_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
@@ -688,7 +689,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   // unit_e: no variance windows at all (adapt_unit_e_nuts::transition only learns the step size)
   s.dense = c.metric == 2;
   resolve_window(&s, (c.adapt_engaged && c.metric != 1) ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
-  s.ncol = 7 + e->D;
+  s.diag = c.store_diagnostics && c.store_draws ? 1 : 0;
+  s.ncol = 7 + e->D * (s.diag ? 3 : 1);
   s.rows_per_chain = c.store_draws ? (c.save_warmup ? (c.num_warmup + c.num_thin - 1) / c.num_thin : 0) + (c.num_samples + c.num_thin - 1) / c.num_thin : 0;
 
   const int C = e->C;
@@ -697,7 +699,7 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive);
   d = DeviceChains{};
   e->d_user_q0 = e->d_user_im = nullptr;
-  d.slab_stride = (size_t)num_vec_slots(c.max_depth, s.dense) * e->ld;
+  d.slab_stride = (size_t)num_vec_slots(c.max_depth, s.dense, s.diag) * e->ld;
   d.mat_stride = s.dense ? 3 * (size_t)e->D * e->D : 0;
   d.draws_stride = (size_t)s.rows_per_chain * s.ncol;
   CUDA_TRY(e, cudaMalloc(&d.cs, sizeof(ChainS) * C));
@@ -1052,6 +1054,23 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
     }
   }
   cudaFree(d_out);
+  return B200NUTS_OK;
+}
+
+int b200nuts_fetch_diagnostics(b200nuts_engine* e, int64_t chain0, int64_t nchains, int64_t row0, int64_t nrows, double* out) {
+  if (!e->chains_ready || !e->dc.draws || !e->scfg.diag) { e->err = "no diagnostics are stored (store_diagnostics=0, store_draws=0 or chains not initialised)"; return B200NUTS_USAGE; }
+  if (chain0 < 0 || nchains < 0 || chain0 + nchains > e->C || row0 < 0 || nrows < 0 || row0 + nrows > e->scfg.rows_per_chain) {
+    e->err = "fetch_diagnostics: range out of bounds";
+    return B200NUTS_USAGE;
+  }
+  if (nchains == 0 || nrows == 0) return B200NUTS_OK;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  // the stored rows are exactly the diagnostic rows: one strided device-to-host copy per chain
+  const size_t row_bytes = sizeof(double) * (size_t)e->scfg.ncol;
+  for (int64_t c = 0; c < nchains; c++)
+    CUDA_TRY(e, cudaMemcpyAsync(out + (size_t)c * nrows * e->scfg.ncol, e->dc.draws + (size_t)(chain0 + c) * e->dc.draws_stride + (size_t)row0 * e->scfg.ncol,
+                                row_bytes * nrows, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   return B200NUTS_OK;
 }
 

@@ -70,7 +70,10 @@ enum VecSlot {
   V_STACK      // + 5*level + {0: p_beg, 1: p_end, 2: rho, 3: proposal q, 4: proposal g}
 };
 // dense metric: 4 more scratch vectors after the tree stack (sharp momenta M^-1 p are recomputed where the reference stores them)
-B200_HD int num_vec_slots(int max_depth, int dense = 0) { return V_STACK + 5 * max_depth + (dense ? 4 : 0); }
+// diagnostics (cfg.diag): 1 + max_depth further vectors -- the momentum of the current sample and of each level's proposal
+B200_HD int num_vec_slots(int max_depth, int dense = 0, int diag = 0) {
+  return V_STACK + 5 * max_depth + (dense ? 4 : 0) + (diag ? 1 + max_depth : 0);
+}
 
 enum ChainState {
   ST_START = 0,
@@ -97,6 +100,8 @@ struct SamplerCfg {
   int D, ld, max_depth;
   int num_warmup, num_samples, num_thin, save_warmup;
   int adapt_engaged, user_inits;
+  int diag;              // 1: every saved row is [7 + 3 D]: the parameters are followed by the sample's momentum and by the gradient
+                         //    of the potential (what the reference sends to the diagnostic writer, mcmc_writer.hpp:156-176)
   int dense;             // 1: dense_e metric (per-chain D x D inverse metric, covariance windows); 0: diag_e / unit_e
   double stepsize, stepsize_jitter, delta, gamma, kappa, t0, init_radius;
   // resolved window schedule (windowed_adaptation::set_window_params)
@@ -139,6 +144,10 @@ struct ChainView {
 B200_DEV double* slot(const ChainView& c, const SamplerCfg& cfg, int k) { return c.v + (size_t)k * cfg.ld; }
 
 B200_DEV double* scratch(const ChainView& c, const SamplerCfg& cfg, int k) { return slot(c, cfg, V_STACK + 5 * cfg.max_depth + k); }
+// diagnostics slots: k = 0 momentum of the current sample, k = 1 + level momentum of that level's proposal
+B200_DEV double* diag_slot(const ChainView& c, const SamplerCfg& cfg, int k) {
+  return slot(c, cfg, V_STACK + 5 * cfg.max_depth + (cfg.dense ? 4 : 0) + k);
+}
 
 // ---- dense metric -----------------------------------------------------------------------------------------------------
 // out = M^-1 p  (dense_e_metric::dtau_dp, dense_e_metric.hpp:38).  Lane l owns rows l, l+32, ...; the matrix is column-major
@@ -324,6 +333,11 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
   if (take_right) {
     s->st_V[li] = s->st_V[ri];
     s->st_H[li] = s->st_H[ri];
+    if (cfg.diag) {
+      double* pl = diag_slot(c, cfg, 1 + li);
+      const double* pr = diag_slot(c, cfg, 1 + ri);
+      B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) pl[i] = pr[i];
+    }
   }
   s->sp = ri;
   bool persist = (a1 > 0 && a2 > 0);
@@ -568,6 +582,10 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             bq[i] = qi; bp[i] = pi; bg[i] = gi;
             pfb[i] = pi; pbf[i] = pi; rho[i] = pi;
           }
+          if (cfg.diag) {  // z_sample starts as the initial point with its fresh momentum
+            double* cp = diag_slot(c, cfg, 0);
+            B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) cp[i] = p[i];
+          }
         }
         s->curH = s->H0;  // energy of z_sample while it is still the initial point
         s->lsw = 0;
@@ -631,6 +649,10 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             E[2 * ld + i] = pi;
             E[3 * ld + i] = c.q[i];
             E[4 * ld + i] = c.g[i];
+          }
+          if (cfg.diag) {
+            double* pp = diag_slot(c, cfg, 1 + e);
+            B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) pp[i] = p[i];
           }
           s->st_lsw[e] = w;  // log_sum_exp(-inf, H0 - h)
           s->st_V[e] = (*c.zV);
@@ -733,6 +755,11 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         if (take) {
           s->curV = s->st_V[0];
           s->curH = s->st_H[0];
+          if (cfg.diag) {
+            double* cp = diag_slot(c, cfg, 0);
+            const double* pp = diag_slot(c, cfg, 1);
+            B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) cp[i] = pp[i];
+          }
         }
         a1 = warp_sum(a1); a2 = warp_sum(a2);
         b1 = warp_sum(b1); b2 = warp_sum(b2);
@@ -761,6 +788,14 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           }
           const double* cq = slot(c, cfg, V_CQ);
           B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) r[7 + i] = cq[i];
+          if (cfg.diag) {
+            const double* cp = diag_slot(c, cfg, 0);
+            const double* cg = slot(c, cfg, V_CG);
+            B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
+              r[7 + D + i] = cp[i];
+              r[7 + 2 * D + i] = cg[i];
+            }
+          }
           s->draws_row++;
         }
         s->iter++;

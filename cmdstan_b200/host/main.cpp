@@ -115,10 +115,6 @@ int main(int argc, char** argv) {
     std::cerr << "The number of warmup samples (num_warmup) must be greater than zero if adaptation is enabled." << std::endl;
     return services::error_codes::USAGE;
   }
-  if (!parser.str({"output", "diagnostic_file"}).empty()) {
-    std::cerr << "output diagnostic_file is not available in the B200 engine (momenta and gradients stay on the GPU)" << std::endl;
-    return services::error_codes::USAGE;
-  }
   if (parser.boolean({"method", "sample", "adapt", "save_metric"}) && !adapt_engaged) {
     std::cerr << "Saving the adapted metric (save_metric=1) can only be enabled when adaptation is engaged (adapt engaged=1)" << std::endl;
     return services::error_codes::USAGE;
@@ -173,7 +169,11 @@ int main(int argc, char** argv) {
 
     // writers
     std::vector<callbacks::unique_stream_writer> sample_writers;
-    std::vector<callbacks::writer> init_writers(num_chains), diagnostic_writers;
+    std::vector<callbacks::writer> init_writers(num_chains);
+    std::vector<callbacks::unique_stream_writer> diagnostic_writers;  // output diagnostic_file=: momenta and gradients of every saved draw
+    const std::string diagnostic_file = parser.str({"output", "diagnostic_file"});
+    if (!diagnostic_file.empty())
+      for (const std::string& f : make_filenames(diagnostic_file, "", ".csv", num_chains, id)) diagnostic_writers.emplace_back(create_stream(f, sig_figs), "# ");
     std::vector<services::json_metric_writer> metric_writers;
     for (const std::string& f : make_filenames(output_file, "", ".csv", num_chains, id)) sample_writers.emplace_back(create_stream(f, sig_figs), "# ");
     if (parser.boolean({"method", "sample", "adapt", "save_metric"}))
@@ -193,6 +193,13 @@ int main(int argc, char** argv) {
       for (const std::string& ln : model.model_compile_info()) w(ln);
     }
 
+    for (auto& w : diagnostic_writers) {  // command.hpp:288-291: write_stan + write_model + parser.print (no date, no compile info)
+      w("stan_version_major = 2");
+      w("stan_version_minor = 36");
+      w("stan_version_patch = 0");
+      w("model = " + model.model_name());
+      for (const std::string& ln : parser.echo()) w(ln);
+    }
     if (parser.boolean({"output", "save_cmdstan_config"})) {  // command.hpp:279-285 + write_config(structured_writer&)
       std::unique_ptr<std::ostream> cf = create_stream(basename_suffix(output_file).first + "_config.json", sig_figs);
       std::string js = "\n{\n  \"stan_major_version\" : \"2\",\n  \"stan_minor_version\" : \"36\",\n  \"stan_patch_version\" : \"0\",\n";

@@ -179,6 +179,11 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     return error_codes::CONFIG;
   }
 
+  // a diagnostic writer with a stream wants the momentum and gradient of every saved draw (mcmc_writer.hpp:156-176)
+  bool want_diag = false;
+  for (auto& w : diagnostic_writer)
+    if (w.stream()) want_diag = true;
+
   // ---- engines: chains split contiguously over the devices
   const int G = (int)std::max<size_t>(1, std::min<size_t>(opt.devices.size(), num_chains));
   engine_guard eg;
@@ -208,6 +213,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     cfg.window = window;
     cfg.adapt_engaged = adapt_engaged;
     cfg.metric = opt.dense_e ? 2 : (opt.unit_e ? 1 : 0);
+    cfg.store_diagnostics = want_diag ? 1 : 0;
     cfg.engine = opt.engine;
     cfg.device = opt.devices.empty() ? 0 : opt.devices[g];
     b200nuts_engine* e = nullptr;
@@ -345,10 +351,51 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   // ---- header rows
   std::vector<std::string> names = {"lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"};
   model.constrained_param_names(names, true, true);
+  // diagnostic header (base_hmc::get_sampler_diagnostic_names -> ps_point::get_param_names): the unconstrained parameter names,
+  // then p_<name>, then g_<name>
+  std::vector<std::string> diag_names(names.begin(), names.begin() + 7);
+  {
+    std::vector<std::string> un;
+    model.unconstrained_param_names(un, false, false);
+    for (const std::string& n : un) diag_names.push_back(n);
+    for (const std::string& n : un) diag_names.push_back("p_" + n);
+    for (const std::string& n : un) diag_names.push_back("g_" + n);
+  }
   for (int c = 0; c < C; c++) {
     if ((size_t)c < sample_writer.size()) sample_writer[c](names);
-    if ((size_t)c < diagnostic_writer.size()) diagnostic_writer[c](names);
+    if ((size_t)c < diagnostic_writer.size()) diagnostic_writer[c](diag_names);
   }
+  // rows [row0, row0 + nrows) of every chain -> its diagnostic writer (sampler columns, q, p, g)
+  auto write_diag_rows = [&](int64_t row0, int64_t nrows) -> int {
+    if (!want_diag || nrows <= 0) return 0;
+    const int64_t ncol = 7 + 3 * D;
+    std::vector<double> buf;
+    std::string text;
+    for (int g = 0; g < G; g++) {
+      const int Cg = first[g + 1] - first[g];
+      int64_t chunk = std::max<int64_t>(1, (int64_t)((1ull << 30) / (sizeof(double) * (size_t)ncol * (size_t)nrows)));
+      for (int64_t c0 = 0; c0 < Cg; c0 += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, Cg - c0);
+        buf.resize((size_t)m * nrows * ncol);
+        int rc = b200nuts_fetch_diagnostics(eg.e[g], c0, m, row0, nrows, buf.data());
+        if (rc) {
+          logger.error(b200nuts_last_error(eg.e[g]));
+          return rc;
+        }
+        for (int64_t c = 0; c < m; c++) {
+          const size_t chain = (size_t)(first[g] + c0 + c);
+          if (chain >= diagnostic_writer.size()) continue;
+          std::ostream* os = diagnostic_writer[chain].stream();
+          if (!os) continue;
+          text.clear();
+          const int prec = (int)os->precision();
+          for (int64_t r = 0; r < nrows; r++) internal::format_row(text, buf.data() + ((size_t)c * nrows + r) * ncol, ncol, prec);
+          os->write(text.data(), (std::streamsize)text.size());
+        }
+      }
+    }
+    return 0;
+  };
 
   // ---- warm-up (generate_transitions with warmup = true)
   auto t0w = std::chrono::steady_clock::now();
@@ -356,6 +403,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   double warm_delta_t = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0w).count() / 1000.0;
   if ((rc = chain_errors())) return rc;
   if ((rc = write_rows(0, warm_rows))) return rc;
+  if ((rc = write_diag_rows(0, warm_rows))) return rc;
   // ---- adaptation block (write_adapt_finish + write_sampler_state) and metric JSON
   {
     const int64_t MD = opt.dense_e ? D * D : D;
@@ -399,6 +447,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
   double sample_delta_t = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0s).count() / 1000.0;
   if ((rc = chain_errors())) return rc;
   if ((rc = write_rows(warm_rows, samp_rows))) return rc;
+  if ((rc = write_diag_rows(warm_rows, samp_rows))) return rc;
   // ---- timing footer (mcmc_writer::write_timing)
   auto timing = [&](auto& w) {
     const std::string title(" Elapsed Time: ");

@@ -86,6 +86,9 @@ typedef struct b200nuts_config {
                                2 dense_e: hmc_nuts_dense_e[_adapt] (stan/src/stan/services/sample/hmc_nuts_dense_e_adapt.hpp,
                                stan/mcmc/hmc/hamiltonians/dense_e_metric.hpp, stan/mcmc/covar_adaptation.hpp): a D x D
                                inverse metric per chain, covariance learned in the adaptation windows */
+  int32_t store_diagnostics; /* default 0; 1: every saved draw also keeps the sample's momentum and the gradient of the potential
+                               (what the reference sends to `output diagnostic_file=`: mcmc_writer::write_diagnostic_params,
+                               stan/src/stan/services/util/mcmc_writer.hpp:156-176), fetched with b200nuts_fetch_diagnostics */
 } b200nuts_config;
 
 typedef struct b200nuts_engine b200nuts_engine;
@@ -127,6 +130,9 @@ int b200nuts_run(b200nuts_engine* e, int n_iter);
    (constrained = 1, K = num_outputs) or the raw unconstrained q (constrained = 0, K = D) */
 int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, int64_t row0, int64_t nrows, int constrained,
                          double* out);
+/* rows of the diagnostic output (needs store_diagnostics = 1): out[nchains][nrows][7 + 3 D] = the seven sampler columns, the
+   unconstrained parameters q, the momentum p and the gradient of the potential g = -grad lp of each saved draw */
+int b200nuts_fetch_diagnostics(b200nuts_engine* e, int64_t chain0, int64_t nchains, int64_t row0, int64_t nrows, double* out);
 int64_t b200nuts_rows_saved(const b200nuts_engine* e); /* rows every chain has saved so far (min over chains) */
 
 /* On-device posterior summary of the saved rows [row0, row0+nrows) of all chains of this engine: the table the reference's

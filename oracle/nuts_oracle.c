@@ -916,7 +916,7 @@ static int learn_variance(sampler_t* s) { /* var_adaptation.hpp:17-46 */
  * Runs one chain exactly as services::sample::hmc_nuts_diag_e_adapt would (hmc_nuts_diag_e_adapt.hpp:58-112,
  * run_adaptive_sampler.hpp:47-103).  q0 != NULL: user-specified unconstrained inits (one try; the D uniforms of the unused
  * random context are still drawn when init_radius > 0).
- * draws: [(save_warmup? W:0 + S)/thin rows][7 + D] =
+ * draws: [(save_warmup? W:0 + S)/thin rows][7 + D] (7 + 3 D with c->diag: then q is followed by the sample's p and g) =
  *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, q (unconstrained).
  * adapt_out: [1 + D] = final step size, inverse metric ([1 + D*D], row-major, for dense_e).  inv_metric0 likewise [D] or
  * [D][D].  Returns 0 ok, 78 init failure, 70 stepsize failure.
@@ -987,7 +987,7 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   int adapt_flag = c->adapt_engaged;
   update_potential_gradient(&s, &s.z); /* z.V, z.g at q0 (init_stepsize / transition re-evaluate them anyway) */
   if (adapt_flag && init_stepsize(&s)) { rc = 70; goto done; } /* hmc_nuts_diag_e (no adapt) uses run_sampler: no init_stepsize */
-  int row = 0, ncol = 7 + D;
+  int row = 0, ncol = 7 + D * (c->diag ? 3 : 1);
   int total = c->num_warmup + c->num_samples;
   for (int it = 0; it < total; it++) {
     int warm = it < c->num_warmup;
@@ -1010,6 +1010,10 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
       double* r = draws + (size_t)row * ncol;
       r[0] = lp; r[1] = accept; r[2] = eps_used; r[3] = s.depth; r[4] = s.n_leapfrog; r[5] = s.divergent; r[6] = s.energy;
       memcpy(r + 7, s.z.q, D * sizeof(double));
+      if (c->diag) {
+        memcpy(r + 7 + D, s.z.p, D * sizeof(double));
+        memcpy(r + 7 + 2 * D, s.z.g, D * sizeof(double));
+      }
       row++;
     }
     if (it == c->num_warmup - 1 && adapt_flag) s.nom_epsilon = exp(s.x_bar); /* disengage_adaptation */

@@ -35,6 +35,9 @@ typedef struct {
   int dense_e; /* 1: adapt_dense_e_nuts / dense_e_nuts (S/mcmc/hmc/nuts/adapt_dense_e_nuts.hpp:20-50): dense inverse metric
                   (S/mcmc/hmc/hamiltonians/dense_e_metric.hpp:21-58, dense_e_point.hpp), covariance windows
                   (S/mcmc/covar_adaptation.hpp:17-45, M/prim/fun/welford_covar_estimator.hpp:10-50) */
+  int diag;    /* 1: rows carry the momentum and the potential's gradient of the sample after the parameters (7 + 3 D columns):
+                  what mcmc_writer::write_diagnostic_params sends to the diagnostic writer (services/util/mcmc_writer.hpp:156-176,
+                  base_hmc::get_sampler_diagnostics -> ps_point::get_params: q, p, g) */
 } oracle_config_t;
 
 double oracle_lp_grad(const model_t* m, const double* q, double* g);

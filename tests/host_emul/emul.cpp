@@ -15,7 +15,7 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
                               double stepsize, double jitter, int max_depth, double delta, double gamma, double kappa, double t0,
                               unsigned init_buffer, unsigned term_buffer, unsigned window, double init_radius, int adapt_engaged,
                               const double* q0, const double* inv_metric0, double* draws, double* adapt_out, long long* n_grad,
-                              int unit_e, int dense_e) {
+                              int unit_e, int dense_e, int diag) {
   ModelData m{};
   m.kind = kind; m.D = D; m.N = N; m.yr = yr; m.sigma = sigma; m.sum_y = sum_y;
   SamplerCfg cfg{};
@@ -26,10 +26,11 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
   cfg.delta = (delta > 0 && delta < 1) ? delta : 0.5; cfg.gamma = gamma > 0 ? gamma : 0.05;
   cfg.kappa = kappa > 0 ? kappa : 0.75; cfg.t0 = t0 > 0 ? t0 : 10; cfg.init_radius = init_radius;
   cfg.dense = dense_e;
+  cfg.diag = diag;
   resolve_window(&cfg, (adapt_engaged && !unit_e) ? num_warmup : 0, init_buffer, term_buffer, window);
-  cfg.ncol = 7 + D;
+  cfg.ncol = 7 + D * (diag ? 3 : 1);
   cfg.rows_per_chain = (save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0) + (num_samples + num_thin - 1) / num_thin;
-  std::vector<double> slab((size_t)num_vec_slots(max_depth, dense_e) * D, 0.0), q(D), g(D), mat(dense_e ? 3 * (size_t)D * D : 1, 0.0);
+  std::vector<double> slab((size_t)num_vec_slots(max_depth, dense_e, diag) * D, 0.0), q(D), g(D), mat(dense_e ? 3 * (size_t)D * D : 1, 0.0);
   ChainS s;
   std::memset(&s, 0, sizeof s);
   chain_init_scalars(&s, cfg);

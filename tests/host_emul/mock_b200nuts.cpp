@@ -123,7 +123,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   const int D = e->m.D, C = c.num_chains;
   const size_t md = c.metric == 2 ? (size_t)D * D : (size_t)D;
   e->rows_per_chain = (c.save_warmup ? (c.num_warmup + c.num_thin - 1) / c.num_thin : 0) + (c.num_samples + c.num_thin - 1) / c.num_thin;
-  e->draws.assign(C, std::vector<double>((size_t)e->rows_per_chain * (7 + D) + 1, 0.0));
+  const int ncol = 7 + D * (c.store_diagnostics ? 3 : 1);
+  e->draws.assign(C, std::vector<double>((size_t)e->rows_per_chain * ncol + 1, 0.0));
   e->adapt.assign(C, std::vector<double>(1 + md, 0.0));
   e->rc.assign(C, 0);
   e->ngrad.assign(C, 0);
@@ -136,6 +137,7 @@ int b200nuts_init_chains(b200nuts_engine* e) {
     oc.delta = c.delta; oc.gamma = c.gamma; oc.kappa = c.kappa; oc.t0 = c.t0;
     oc.init_buffer = c.init_buffer; oc.term_buffer = c.term_buffer; oc.window = c.window;
     oc.init_radius = c.init_radius; oc.adapt_engaged = c.adapt_engaged; oc.unit_e = c.metric == 1; oc.dense_e = c.metric == 2;
+    oc.diag = c.store_diagnostics;
     e->rc[k] = oracle_run_chain(&e->m, &oc, e->q0.empty() ? nullptr : e->q0.data() + (size_t)k * D,
                                 e->im.empty() ? nullptr : e->im.data() + (size_t)k * md, e->draws[k].data(), e->adapt[k].data(), nullptr,
                                 &e->ngrad[k]);
@@ -162,12 +164,19 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
   if (chain0 < 0 || chain0 + nchains > e->cfg.num_chains || row0 < 0 || row0 + nrows > e->rows_per_chain) { e->err = "fetch_draws: range out of bounds"; return B200NUTS_USAGE; }
   for (int64_t c = 0; c < nchains; c++)
     for (int64_t r = 0; r < nrows; r++) {
-      const double* src = e->draws[chain0 + c].data() + (size_t)(row0 + r) * (7 + D);
+      const double* src = e->draws[chain0 + c].data() + (size_t)(row0 + r) * (7 + D * (e->cfg.store_diagnostics ? 3 : 1));
       double* dst = out + ((size_t)c * nrows + r) * (7 + K);
       std::memcpy(dst, src, 7 * sizeof(double));
       if (constrained) oracle_write_array(&e->m, src + 7, dst + 7);
       else std::memcpy(dst + 7, src + 7, D * sizeof(double));
     }
+  return 0;
+}
+int b200nuts_fetch_diagnostics(b200nuts_engine* e, int64_t chain0, int64_t nchains, int64_t row0, int64_t nrows, double* out) {
+  if (!e->cfg.store_diagnostics) { e->err = "no diagnostics are stored"; return B200NUTS_USAGE; }
+  const int ncol = 7 + 3 * e->m.D;
+  for (int64_t c = 0; c < nchains; c++)
+    std::memcpy(out + (size_t)c * nrows * ncol, e->draws[chain0 + c].data() + (size_t)row0 * ncol, sizeof(double) * (size_t)nrows * ncol);
   return 0;
 }
 int64_t b200nuts_rows_saved(const b200nuts_engine* e) { return e->rows_per_chain; }

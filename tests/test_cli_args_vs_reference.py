@@ -72,6 +72,8 @@ def _random_args(rng, dj):
         a.append(f"sig_figs={int(rng.choice([-1, 4, 12]))}")
     if rng.uniform() < 0.3:
         a.append(f"save_cmdstan_config={int(rng.integers(0, 2))}")
+    if rng.uniform() < 0.3:
+        a.append("diagnostic_file=diag.csv")
     return a
 
 

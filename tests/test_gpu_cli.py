@@ -249,3 +249,26 @@ def test_cli_plugin_model(tmp_path):
     ini.write_text(json.dumps({"alpha": 0.0}))
     r = _cli("linreg", ["sample", "data", f"file={dj}", f"init={ini}"], tmp_path, env=env)
     assert r.returncode != 0 and "plug-in" in (r.stdout + r.stderr)
+
+
+@pytest.mark.skipif(not O.have_ref("bernoulli"), reason="oracle/_ref not built")
+def test_cli_diagnostic_file_vs_reference(tmp_path):
+    """`output diagnostic_file=d.csv`: header (stan version, model, configuration echo; no date), column names
+    (theta, p_theta, g_theta), rows (q, p, g of every saved draw) and timing footer as the unmodified reference writes them."""
+    dj = _bernoulli_json(tmp_path)
+    args = ["sample", "num_samples=30", "num_warmup=60", "save_warmup=1", "thin=2", "data", f"file={dj}", "random", "seed=12", "output", "sig_figs=12",
+            "diagnostic_file=d.csv"]
+    r = _cli("bernoulli", args + ["file=o.csv"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    (tmp_path / "ref").mkdir()
+    rr = subprocess.run([os.path.join(O.REF, "bernoulli")] + args + ["file=o.csv"], cwd=tmp_path / "ref", capture_output=True, text=True)
+    assert rr.returncode == 0, rr.stdout + rr.stderr
+    mine = _strip((tmp_path / "d.csv").read_text().splitlines())
+    ref = _strip((tmp_path / "ref" / "d.csv").read_text().splitlines())
+    assert len(mine) == len(ref)
+    assert [x for x in mine if x.startswith("#")] == [x for x in ref if x.startswith("#")]
+    bm, br = [x for x in mine if not x.startswith("#")], [x for x in ref if not x.startswith("#")]
+    assert bm[0] == br[0] == "lp__,accept_stat__,stepsize__,treedepth__,n_leapfrog__,divergent__,energy__,theta,p_theta,g_theta"
+    dm, dr = np.array([x.split(",") for x in bm[1:]], dtype=float), np.array([x.split(",") for x in br[1:]], dtype=float)
+    assert dm.shape == dr.shape == (45, 10)
+    assert np.array_equal(dm[:, 3:6], dr[:, 3:6]) and np.allclose(dm[:20], dr[:20], rtol=1e-9) and np.allclose(dm, dr, rtol=1e-4, atol=1e-6)

@@ -330,3 +330,36 @@ def test_irt_straggler_kernel_bit_identical(C, monkeypatch):
     m = O.Model("irt_2pl", data)
     r = O.run_chain(m, seed=77, chain_id=1, num_warmup=60, num_samples=25, save_warmup=1)
     assert np.array_equal(out[1][0][0, :6, 3:6], r["draws"][:6, 3:6]) and _rel(out[1][0][0, :6], r["draws"][:6], floor=1e-6) < 1e-8
+
+
+@pytest.mark.parametrize("name,engine", [("bernoulli", "auto"), ("eight_schools_nc", "auto"), ("eight_schools_nc", "lockstep"), ("std_normal", "lockstep")])
+def test_diagnostic_rows_vs_oracle(name, engine):
+    """store_diagnostics = 1 (what CmdStan's `output diagnostic_file=` carries: mcmc_writer::write_diagnostic_params): every saved
+    row is followed by the sample's momentum and the gradient of the potential.  Against the oracle's diagnostic rows (pinned to
+    the reference's diagnostic file byte for byte in tests/test_cli_mock_vs_reference.py); the ordinary draws are unchanged."""
+    data = cases.SMALL[name]
+    kw = dict(num_chains=3, random_seed=321, num_warmup=100, num_samples=40, save_warmup=True)
+    e = _engine(name, data, engine=engine, store_diagnostics=True, **kw)
+    e.init_chains()
+    e.run(140)
+    diag = e.fetch_diagnostics()
+    plain = e.fetch_draws(constrained=False)
+    e.close()
+    D = plain.shape[2] - 7
+    assert diag.shape == (3, 140, 7 + 3 * D) and np.array_equal(diag[:, :, :7 + D], plain)
+    e2 = _engine(name, data, engine=engine, **kw)   # same chains without diagnostics: identical draws
+    e2.init_chains()
+    e2.run(140)
+    assert np.array_equal(e2.fetch_draws(constrained=False), plain)
+    with pytest.raises(Exception):
+        e2.fetch_diagnostics()
+    e2.close()
+    m = O.Model(name, data)
+    K = 12 if name == "eight_schools_nc" else 40
+    for c in range(3):
+        r = O.run_chain(m, seed=321, chain_id=1 + c, num_warmup=100, num_samples=40, save_warmup=1, diag=1)
+        assert np.array_equal(diag[c, :K, 3:6], r["draws"][:K, 3:6])
+        assert _rel(diag[c, :K], r["draws"][:K], floor=1e-6) < 1e-8
+    # the gradient column is the gradient of the potential at the saved q
+    lp, g = m.lp_grad(diag[0, :, 7:7 + D])
+    assert _rel(diag[0, :, 7 + 2 * D:], -g, floor=1e-6) < 1e-9 and _rel(diag[0, :, 0], lp, floor=1e-6) < 1e-9

@@ -26,6 +26,9 @@ OPTS = [
     dict(seed=16, chain_id=2, num_warmup=200, num_samples=60, dense_e=1, save_warmup=1),           # hmc_nuts_dense_e_adapt
     dict(seed=17, chain_id=1, num_warmup=60, num_samples=30, dense_e=1, stepsize_jitter=0.2),      # fallback windows, jitter
     dict(seed=18, chain_id=5, num_warmup=10, num_samples=40, dense_e=1, adapt_engaged=0, stepsize=0.3),  # hmc_nuts_dense_e
+    dict(seed=19, chain_id=2, num_warmup=150, num_samples=60, save_warmup=1, num_thin=2, diag=1),  # diagnostic rows: q, p, g of every saved draw
+    dict(seed=20, chain_id=1, num_warmup=60, num_samples=40, save_warmup=1, diag=1, dense_e=1),
+    dict(seed=21, chain_id=3, num_warmup=0, num_samples=50, adapt_engaged=0, stepsize=0.4, max_depth=3, diag=1),
 ]
 
 
@@ -94,6 +97,8 @@ def _random_config(rng):
         kw["unit_e"] = 1
     elif metric == "dense":
         kw["dense_e"] = 1
+    if rng.uniform() < 0.3:
+        kw["diag"] = 1
     return kw
 
 
