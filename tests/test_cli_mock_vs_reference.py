@@ -217,3 +217,23 @@ def test_chains_split_over_several_engines(tmp_path, mock_env):
         outs[who] = {f: _strip((d / f).read_text()) for f in sorted(os.listdir(d)) if f.startswith("o_") and f.endswith(".csv")}
         assert sorted(outs[who]) == [f"o_{c}.csv" for c in range(3, 8)]
     assert outs["one"] == outs["ref"] and outs["three"] == outs["ref"] and outs["five"] == outs["ref"]
+
+
+@pytest.mark.parametrize("fname", ["out", "out.txt", "sub/out.csv", "out.a.csv"])
+@pytest.mark.parametrize("nch", [1, 2])
+def test_output_file_naming_like_reference(fname, nch, tmp_path, mock_env):
+    """file.hpp:92-212 (basename / suffix rules, _<chain id> tags, _metric.json, _config.json, diagnostic files): the same set of
+    files as the reference for names without suffix, with another suffix, in a sub-directory, with inner dots."""
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    args = ["sample", "num_samples=3", "num_warmup=20", f"num_chains={nch}", "adapt", "save_metric=1", "data", f"file={dj}", "random", "seed=3", "output",
+            f"file={fname}", "diagnostic_file=dg", "save_cmdstan_config=1"]
+    listing = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        (d / "sub").mkdir(parents=True)
+        exe, env = ([CLI, "bernoulli"], mock_env) if who == "mine" else ([os.path.join(O.REF, "bernoulli")], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, who + r.stdout[-500:] + r.stderr[-500:]
+        listing[who] = sorted(os.path.relpath(os.path.join(dp, f), d) for dp, _, fs in os.walk(d) for f in fs)
+    assert listing["mine"] == listing["ref"]
