@@ -326,9 +326,7 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
       L[4 * ld + i] = R[4 * ld + i];
     }
   }
-  a1 = warp_sum(a1); a2 = warp_sum(a2);
-  b1 = warp_sum(b1); b2 = warp_sum(b2);
-  c1 = warp_sum(c1); c2 = warp_sum(c2);
+  warp_sum6(a1, a2, b1, b2, c1, c2);
   s->st_lsw[li] = lsw_sub;
   if (take_right) {
     s->st_V[li] = s->st_V[ri];
@@ -761,9 +759,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) cp[i] = pp[i];
           }
         }
-        a1 = warp_sum(a1); a2 = warp_sum(a2);
-        b1 = warp_sum(b1); b2 = warp_sum(b2);
-        c1 = warp_sum(c1); c2 = warp_sum(c2);
+        warp_sum6(a1, a2, b1, b2, c1, c2);
         bool persist = (a1 > 0 && a2 > 0);
         persist &= (b1 > 0 && b2 > 0);
         persist &= (c1 > 0 && c2 > 0);

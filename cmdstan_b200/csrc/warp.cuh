@@ -22,6 +22,7 @@ inline int lane_id() { return 0; }
 inline double bcast0(double v) { return v; }
 inline int bcast0i(int v) { return v; }
 inline double warp_sum(double v) { return v; }
+inline void warp_sum6(double&, double&, double&, double&, double&, double&) {}
 inline void warp_sync() {}
 inline double dev_exp(double x) { return std::exp(x); }
 inline double dev_log(double x) { return std::log(x); }
@@ -43,6 +44,18 @@ B200_DEV_CALL double warp_sum(double v) {  // out of line: ~50 call sites in the
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
+}
+// six sums at once: the same xor butterfly per value (bit-identical to six warp_sum calls), but the 30 shuffles form 5
+// dependent rounds of 6 independent ones instead of 30 dependent steps -- the U-turn criteria of every tree merge need six dot
+// products, and the chain kernels are latency-bound.  Inlined (two call sites): reference parameters of an out-of-line
+// function would live in local memory
+B200_DEV void warp_sum6(double& a, double& b, double& c, double& d, double& e, double& f) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ta = __shfl_xor_sync(kFull, a, o), tb = __shfl_xor_sync(kFull, b, o), tc = __shfl_xor_sync(kFull, c, o);
+    const double td = __shfl_xor_sync(kFull, d, o), te = __shfl_xor_sync(kFull, e, o), tf = __shfl_xor_sync(kFull, f, o);
+    a += ta; b += tb; c += tc; d += td; e += te; f += tf;
+  }
 }
 B200_DEV void warp_sync() { __syncwarp(); }
 // one out-of-line copy of each double-precision transcendental: the chain kernels are instruction-cache bound
