@@ -237,3 +237,37 @@ def test_output_file_naming_like_reference(fname, nch, tmp_path, mock_env):
         assert r.returncode == 0, who + r.stdout[-500:] + r.stderr[-500:]
         listing[who] = sorted(os.path.relpath(os.path.join(dp, f), d) for dp, _, fs in os.walk(d) for f in fs)
     assert listing["mine"] == listing["ref"]
+
+
+EDGE = [
+    "sample num_samples=0 num_warmup=30 data file=DATA random seed=3 output",
+    "sample num_samples=5 num_warmup=0 adapt engaged=0 data file=DATA random seed=3 output",
+    "sample num_samples=3 num_warmup=25 thin=7 save_warmup=1 data file=DATA random seed=3 output",
+    "sample num_samples=0 num_warmup=0 adapt engaged=0 data file=DATA random seed=3 output",
+    "sample num_samples=10 num_warmup=19 data file=DATA random seed=3 output",                       # no variance estimation below 20
+    "sample num_samples=10 num_warmup=40 data file=DATA random seed=3 output",                       # 15 % / 75 % / 10 % fallback windows
+    "sample num_samples=10 num_warmup=30 algorithm=hmc engine=nuts max_depth=1 stepsize_jitter=1 data file=DATA init=0 random seed=3 output refresh=0",
+    "sample num_samples=4 num_warmup=150 adapt term_buffer=0 init_buffer=0 window=150 data file=DATA random seed=4294967295 output sig_figs=18",
+    "sample num_samples=4 num_warmup=30 adapt delta=0.1 data file=DATA random seed=0 id=0 output",
+]
+
+
+@pytest.mark.parametrize("line", EDGE, ids=[str(i) for i in range(len(EDGE))])
+def test_edge_case_command_lines_identical_to_reference(line, tmp_path, mock_env):
+    """degenerate sizes (no draws, no warm-up, thin beyond the draws), window fallbacks and their console warnings, depth 1,
+    full jitter, zero inits, the largest seed, id 0: output file AND console messages as the reference's."""
+    dj = tmp_path / "b.json"
+    dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
+    args = [a.replace("DATA", str(dj)) for a in line.split()] + ["file=o.csv"]
+    out = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        d.mkdir()
+        exe, env = ([CLI, "bernoulli"], mock_env) if who == "mine" else ([os.path.join(O.REF, "bernoulli")], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, who + r.stdout[-500:] + r.stderr[-500:]
+        console = [ln for ln in (r.stdout + r.stderr).splitlines()
+                   if ln.strip() and not any(t in ln for t in ("seconds", "Gradient evaluation", "leapfrog steps per", "Adjust your expectations", "file = "))]
+        out[who] = (_strip((d / "o.csv").read_text()), console)
+    assert out["mine"][0] == out["ref"][0]
+    assert out["mine"][1] == out["ref"][1]
