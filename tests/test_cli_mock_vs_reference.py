@@ -81,6 +81,10 @@ def test_output_files_identical_to_reference(case, tmp_path, mock_env):
     # progress messages on the console (the reference's chains are threads: their lines interleave, so compare as a multiset)
     it = lambda s: sorted(ln.strip() for ln in s.splitlines() if "Iteration:" in ln)
     assert it(mine.stdout) == it(ref.stdout), " ".join(args)
+    if nch == 1:   # one chain: the whole console text, in order
+        con = lambda r: [ln for ln in (r.stdout + r.stderr).splitlines()
+                         if ln.strip() and not any(t in ln for t in ("seconds", "Gradient evaluation", "leapfrog steps per", "Adjust your expectations", "file = ", "seed = "))]
+        assert con(mine) == con(ref), " ".join(args)
 
 
 @pytest.mark.parametrize("metric,adapt", [("diag_e", 1), ("diag_e", 0), ("dense_e", 1), ("dense_e", 0), ("unit_e", 0)])
