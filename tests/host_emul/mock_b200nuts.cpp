@@ -4,6 +4,7 @@
 // without a GPU and compared byte for byte with the UNMODIFIED reference (tests/test_cli_mock_vs_reference.py).  It is never
 // built into, linked with or loaded by the product; cmdstan_b200/libb200nuts.so has no CPU path.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -210,6 +211,27 @@ int b200nuts_find_model(const char* name) {
   for (int i = 0; i < 6; i++) if (!std::strcmp(k[i], name)) return i;
   return -1;
 }
-int b200nuts_output_name(b200nuts_engine*, int64_t, char*, int) { return B200NUTS_SOFTWARE; }
+int b200nuts_output_name(b200nuts_engine* e, int64_t k, char* buf, int buflen) {  // same names as the engine / host model objects
+  if (!e->ready) { int rc = finalize(e); if (rc) return rc; }
+  const long long N = e->m.N, K = e->m.K, i = k;
+  auto vec = [&](const char* n, long long j) { std::snprintf(buf, (size_t)buflen, "%s.%lld", n, j + 1); };
+  auto sc = [&](const char* n) { std::snprintf(buf, (size_t)buflen, "%s", n); };
+  switch (e->m.kind) {
+    case M_STD_NORMAL: vec("x", i); break;
+    case M_BERNOULLI: sc("theta"); break;
+    case M_EIGHT_SCHOOLS:
+      if (i == 0) sc("mu"); else if (i == 1) sc("tau"); else if (i < 2 + N) vec("theta_tilde", i - 2); else vec("theta", i - 2 - N);
+      break;
+    case M_LOGISTIC:
+    case M_POISSON:
+      if (i == 0) sc("alpha"); else vec("beta", i - 1);
+      break;
+    default:
+      if (i == 0) sc("sigma_theta"); else if (i < 1 + N) vec("theta", i - 1); else if (i == 1 + N) sc("sigma_a");
+      else if (i < 2 + N + K) vec("a", i - 2 - N); else if (i == 2 + N + K) sc("mu_b"); else if (i == 3 + N + K) sc("sigma_b");
+      else vec("b", i - 4 - N - K);
+  }
+  return 0;
+}
 
 }  // extern "C"
