@@ -253,6 +253,8 @@ EDGE = [
     "sample num_samples=10 num_warmup=30 algorithm=hmc engine=nuts max_depth=1 stepsize_jitter=1 data file=DATA init=0 random seed=3 output refresh=0",
     "sample num_samples=4 num_warmup=150 adapt term_buffer=0 init_buffer=0 window=150 data file=DATA random seed=4294967295 output sig_figs=18",
     "sample num_samples=4 num_warmup=30 adapt delta=0.1 data file=DATA random seed=0 id=0 output",
+    # the order and spelling cmdstanpy uses: top-level arguments first, then method=sample ...
+    "id=2 random seed=123 data file=DATA output refresh=10 sig_figs=6 method=sample num_samples=10 num_warmup=30 save_warmup=0 thin=1 algorithm=hmc engine=nuts max_depth=8 adapt engaged=1 delta=0.85",
 ]
 
 
@@ -262,7 +264,9 @@ def test_edge_case_command_lines_identical_to_reference(line, tmp_path, mock_env
     full jitter, zero inits, the largest seed, id 0: output file AND console messages as the reference's."""
     dj = tmp_path / "b.json"
     dj.write_text(json.dumps({"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}))
-    args = [a.replace("DATA", str(dj)) for a in line.split()] + ["file=o.csv"]
+    args = [a.replace("DATA", str(dj)) for a in line.split()]
+    k = args.index("output") + 1
+    args[k:k] = ["file=o.csv"]
     out = {}
     for who in ("mine", "ref"):
         d = tmp_path / who
