@@ -115,6 +115,7 @@ struct ChainS {
   unsigned long long rng[kRngWords];
   int state, err, iter, iter_end;
   int init_tries, iss_after, iss_dir, dir;
+  int init_partial, pad0_;  // init_partial: some initial values were left to the random context (up to 100 tries, like no inits)
   int depth, n_leapfrog, divergent, sp;
   unsigned leaf_count, n_leaves;
   unsigned win_counter, win_size, win_next;
@@ -142,6 +143,20 @@ struct ChainView {
 };
 
 B200_DEV double* slot(const ChainView& c, const SamplerCfg& cfg, int k) { return c.v + (size_t)k * cfg.ld; }
+
+// "not given" marker of user inits: a quiet NaN whose low payload bits carry the parameter's transform (see ST_INIT_DRAW)
+B200_HD int init_nan_code(double v) {
+  unsigned long long bits;
+  memcpy(&bits, &v, sizeof bits);
+  return (int)(bits & 3ull);
+}
+B200_HD double init_nan_with_code(int code) {
+  const unsigned long long bits = 0x7ff8000000000000ull | (unsigned long long)(code & 3);
+  double v;
+  memcpy(&v, &bits, sizeof v);
+  return v;
+}
+B200_DEV double init_logit(double th) { return dev_log(th / (1.0 - th)); }  // M/prim/fun/logit.hpp: log(u / (1 - u))
 
 B200_DEV double* scratch(const ChainView& c, const SamplerCfg& cfg, int k) { return slot(c, cfg, V_STACK + 5 * cfg.max_depth + k); }
 // diagnostics slots: k = 0 momentum of the current sample, k = 1 + level momentum of that level's proposal
@@ -465,9 +480,23 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       case ST_INIT_DRAW: {  // util::initialize (initialize.hpp:87-117)
         if (c.user_q0) {
           // initialize.hpp:93-101: the random_var_context is constructed (and draws its D uniforms) on every try, also when
-          // every value then comes from the user's context
+          // every value then comes from the user's context.  A NaN in the user's vector stands for "not given": the reference
+          // then keeps the random context's CONSTRAINED value and transform_inits maps it back, so the value is the round trip
+          // of the uniform draw through the parameter's transform (payload code: 0 none, 1 lower bound 0, 2 unit interval).
           if (cfg.init_radius != 0.0) warp_fill(s->rng, lane, c.q, D, 1, nullptr, cfg.init_radius);
-          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = c.user_q0[i];
+          double partial = 0.0;
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
+            const double user = c.user_q0[i];
+            if (user == user) {
+              c.q[i] = user;
+            } else {
+              const double u = cfg.init_radius != 0.0 ? c.q[i] : 0.0;
+              const int code = init_nan_code(user);
+              c.q[i] = code == 1 ? dev_log(dev_exp(u)) : (code == 2 ? init_logit(dev_inv_logit(u)) : u);
+              partial = 1.0;
+            }
+          }
+          s->init_partial = warp_sum(partial) > 0.0 ? 1 : 0;
         } else if (cfg.init_radius == 0.0) {
           B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;
         } else {
@@ -497,7 +526,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             s->state = ST_ITER_BEGIN;
           }
         } else {
-          const int max_tries = (c.user_q0 || cfg.init_radius == 0.0) ? 1 : 100;
+          const int max_tries = ((c.user_q0 && !s->init_partial) || cfg.init_radius == 0.0) ? 1 : 100;
           if (s->init_tries >= max_tries) {
             s->err = 78;  // error_codes::CONFIG -- "Initialization failed."
             s->state = ST_DONE;
@@ -830,6 +859,8 @@ B200_HD void chain_init_scalars(ChainS* s, const SamplerCfg& cfg) {
   s->iter = 0;
   s->iter_end = 0;
   s->init_tries = 0;
+  s->init_partial = 0;
+  s->pad0_ = 0;
   s->iss_after = 0;
   s->iss_dir = 0;
   s->dir = 0;

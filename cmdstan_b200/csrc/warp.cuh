@@ -9,6 +9,7 @@
 // shipped library.
 #pragma once
 #include <cstdint>
+#include <cstring>
 
 #ifdef B200_HOST_EMUL
 #include <cmath>

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/b200nuts.h"
 #include "../../include/b200nuts_model.h"
@@ -156,13 +157,21 @@ class device_model {
   }
 
   // constrained initial values -> unconstrained vector (model_base::transform_inits; lb_free = log,
-  // lub_free(0,1) = logit: stan/math/prim/constraint/lb_free.hpp, lub_free.hpp).  Every parameter must be present.
+  // lub_free(0,1) = logit: stan/math/prim/constraint/lb_free.hpp, lub_free.hpp).  Parameters that are absent are left to the engine.
   void transform_inits(const io::var_context& init, std::vector<double>& params_r) const {
     params_r.clear();
     if (is_plugin())  // the plug-in interface has no unconstraining transform: only random inits (init=<radius>)
       throw std::invalid_argument("user-specified initial values are not available for plug-in models (use init=<radius>)");
     for (auto& b : params_) {
-      if (!init.contains_r(b.name)) throw std::invalid_argument("variable does not exist; processing stage=parameter initialization; variable name=" + b.name + "; base type=double (partial inits are not supported by the B200 engine)");
+      if (!init.contains_r(b.name)) {
+        // partial inits (initialize.hpp:93-101: chained_var_context(init, random_context)): the engine draws this parameter like
+        // the reference's random context does; a quiet NaN whose payload carries the transform marks "not given" (csrc/nuts.cuh)
+        const unsigned long long bits = 0x7ff8000000000000ull | (unsigned long long)(b.constraint == LOWER0 ? 1 : (b.constraint == UNIT_INTERVAL ? 2 : 0));
+        double nan_code;
+        std::memcpy(&nan_code, &bits, sizeof nan_code);
+        for (int64_t i = 0; i < b.count(); i++) params_r.push_back(nan_code);
+        continue;
+      }
       const std::vector<double>& v = init.vals_r(b.name);
       if ((int64_t)v.size() != b.count()) throw std::invalid_argument("mismatch in number dimensions declared and found in context; processing stage=parameter initialization; variable name=" + b.name);
       for (double x : v) {

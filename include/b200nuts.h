@@ -111,7 +111,9 @@ int b200nuts_num_params(const b200nuts_engine* e, int64_t* num_unconstrained, in
 
 /* optional user inits q0[num_chains][D] (unconstrained scale) and inverse metric [num_chains][D] (dense_e:
    [num_chains][D][D], symmetric positive definite, else CONFIG "Inverse Euclidean metric not positive definite.");
-   NULL => reference behaviour (uniform(-R,R) draws from each chain's own stream; unit metric) */
+   NULL => reference behaviour (uniform(-R,R) draws from each chain's own stream; unit metric).  Partial inits: an element of
+   q0 that is a quiet NaN is "not given" and takes the value the reference's random context would give it (the low two payload
+   bits name the parameter's transform for the constrain/unconstrain round trip: 0 none, 1 lower bound 0, 2 unit interval) */
 int b200nuts_set_inits(b200nuts_engine* e, const double* q0);
 int b200nuts_set_inv_metric(b200nuts_engine* e, const double* inv_metric);
 

@@ -941,14 +941,30 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   oracle_rng_seed(&s.rng, c->seed, c->chain_id);
   /* ---- initialize ---- */
   int ok = 0;
-  int max_tries = (q0 || c->init_radius == 0.0) ? 1 : 100;
+  /* a NaN in q0 stands for "not given" (partial user inits): the reference keeps the random context's constrained value for such
+   * a parameter and transform_inits maps it back (initialize.hpp:93-101) -- the round trip of the uniform draw through the
+   * parameter's transform, coded in the NaN payload: 0 none, 1 lower bound 0, 2 unit interval */
+  int partial = 0;
+  if (q0)
+    for (int i = 0; i < D; i++) partial |= (q0[i] != q0[i]);
+  int max_tries = ((q0 && !partial) || c->init_radius == 0.0) ? 1 : 100;
   for (int t = 0; t < max_tries && !ok; t++) {
     if (q0) {
       /* initialize.hpp:93-101: the random_var_context is constructed -- and draws its D uniforms (random_var_context.hpp:43-66)
        * -- on every try, also when every value then comes from the user's context through the chained_var_context */
-      if (c->init_radius != 0.0)
-        for (int i = 0; i < D; i++) (void)oracle_uniform_real(&s.rng, -c->init_radius, c->init_radius);
-      memcpy(s.z.q, q0, D * sizeof(double));
+      for (int i = 0; i < D; i++) {
+        double u = c->init_radius != 0.0 ? oracle_uniform_real(&s.rng, -c->init_radius, c->init_radius) : 0.0;
+        if (q0[i] == q0[i]) {
+          s.z.q[i] = q0[i];
+        } else {
+          uint64_t bits;
+          memcpy(&bits, &q0[i], sizeof bits);
+          int code = (int)(bits & 3u);
+          if (code == 1) s.z.q[i] = log(exp(u));
+          else if (code == 2) { double th = inv_logit(u); s.z.q[i] = log(th / (1.0 - th)); }
+          else s.z.q[i] = u;
+        }
+      }
     }
     else if (c->init_radius == 0.0) memset(s.z.q, 0, D * sizeof(double));
     else for (int i = 0; i < D; i++) s.z.q[i] = oracle_uniform_real(&s.rng, -c->init_radius, c->init_radius);

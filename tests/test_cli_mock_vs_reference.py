@@ -279,3 +279,26 @@ def test_edge_case_command_lines_identical_to_reference(line, tmp_path, mock_env
         out[who] = (_strip((d / "o.csv").read_text()), console)
     assert out["mine"][0] == out["ref"][0]
     assert out["mine"][1] == out["ref"][1]
+
+
+@pytest.mark.skipif(not O.have_ref("eight_schools_nc"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("init", [{"mu": 1.5}, {"tau": 0.7}, {"theta_tilde": [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]}, {"mu": -2, "tau": 3}],
+                         ids=["mu", "tau", "theta_tilde", "mu+tau"])
+def test_partial_user_inits_like_reference(init, tmp_path, mock_env):
+    """partial inits (initialize.hpp:93-101, chained_var_context): the parameters the user leaves out take the random context's
+    values -- drawn for ALL parameters in declaration order, constrained, and mapped back by transform_inits.  Same first rows
+    as the reference at 8 significant digits (the funnel separates closed-form and AD gradients later)."""
+    dj = tmp_path / "es.json"
+    dj.write_text(json.dumps({"J": 8, "y": [28, 8, -3, 7, -1, 1, 18, 12], "sigma": [15, 10, 16, 11, 9, 11, 10, 18]}))
+    ini = tmp_path / "i.json"
+    ini.write_text(json.dumps(init))
+    args = ["sample", "num_samples=5", "num_warmup=30", "save_warmup=1", "data", f"file={dj}", f"init={ini}", "random", "seed=3", "output", "sig_figs=8", "file=o.csv"]
+    body = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        d.mkdir()
+        exe, env = ([CLI, "eight_schools_nc"], mock_env) if who == "mine" else ([os.path.join(O.REF, "eight_schools_nc")], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, who + r.stdout[-500:] + r.stderr[-500:]
+        body[who] = [x for x in (d / "o.csv").read_text().splitlines() if x and not x.startswith("#")]
+    assert body["mine"][:12] == body["ref"][:12]

@@ -74,6 +74,29 @@ def test_user_dense_metric():
     assert E.run_chain(kind, D, data, inv_metric=bad, seed=1, num_warmup=20, num_samples=5, dense_e=1)["rc"] == 78
 
 
+def _nan_code(code):
+    return np.frombuffer(np.uint64(0x7ff8000000000000 | code).tobytes(), dtype=np.float64)[0]
+
+
+def test_partial_user_inits():
+    """NaN-coded "not given" entries of the user's initial vector (partial inits): the device and the oracle draw the random
+    context for every parameter, keep the user's values, and round-trip the others through their transform (code 1: lower
+    bound 0, code 2: unit interval); with a partial vector initialisation may retry like a random one."""
+    name, kind, D, data = MODELS[2]   # eight schools: mu free, tau lower-bounded, theta_tilde free
+    q0 = np.array([0.3, _nan_code(1)] + [_nan_code(0)] * 4 + [0.1, -0.2, 0.3, _nan_code(0)])
+    for kw in (dict(seed=3, chain_id=1, num_warmup=60, num_samples=20, save_warmup=1), dict(seed=4, chain_id=2, num_warmup=30, num_samples=10, init_radius=0.0),
+               dict(seed=5, chain_id=1, num_warmup=40, num_samples=10, init_radius=0.5, dense_e=1)):
+        a = O.run_chain(O.Model(name, data), q0=q0, **kw)
+        b = E.run_chain(kind, D, data, q0=q0, **kw)
+        assert a["rc"] == b["rc"] == 0
+        assert np.array_equal(a["draws"], b["draws"]) and a["stepsize"] == b["stepsize"]
+    name, kind, D, data = MODELS[0]   # bernoulli: theta in (0, 1)
+    q0 = np.array([_nan_code(2)])
+    a = O.run_chain(O.Model(name, data), q0=q0, seed=9, num_warmup=30, num_samples=10)
+    b = E.run_chain(kind, D, data, q0=q0, seed=9, num_warmup=30, num_samples=10)
+    assert a["rc"] == b["rc"] == 0 and np.array_equal(a["draws"], b["draws"])
+
+
 def test_init_failure_code():
     """eight schools with sigma so small that every U(-2,2) init overflows is not constructible here; instead check the
     documented failure path with an impossible user init: lp = -inf => error_codes::CONFIG (78)."""
