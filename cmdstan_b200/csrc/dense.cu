@@ -1,4 +1,5 @@
-// The chain kernels with the dense-metric code paths compiled in (nuts.cuh B200_WITH_DENSE = 1): hmc_nuts_dense_e[_adapt].
+// The chain kernels with the dense-metric code paths AND the diagnostics bookkeeping compiled in (nuts.cuh B200_WITH_DENSE = 1):
+// hmc_nuts_dense_e[_adapt] and any run with store_diagnostics.
 // Same source as engine.cu's kernels (chains.cuh / nuts.cuh); kept in their own translation unit so that the diag_e / unit_e
 // kernels -- the path the benchmarks run -- do not carry the dense branches.  Built with --fmad=false like engine.cu.
 #define B200_WITH_DENSE 1

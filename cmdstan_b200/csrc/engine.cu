@@ -813,14 +813,14 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       int wpb = per_sm < kFusedMaxWarps ? (per_sm < 1 ? 1 : per_sm) : kFusedMaxWarps;
       while ((size_t)wpb * chain_bytes > 56 * 1024 && wpb > 1) wpb--;
       const size_t smem = (size_t)wpb * chain_bytes;
-      if (e->scfg.dense) {
+      if (e->scfg.dense || e->scfg.diag) {
         CUDA_TRY(e, launch_fused_dense(e->scfg, e->md, e->dc, C, true, wpb, chain_words, smem, e->stream));
       } else {
         auto k = fused_chain_kernel<true, 0>;
         CUDA_TRY(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<(C + wpb - 1) / wpb, 32 * wpb, smem, e->stream>>>(e->scfg, e->md, e->dc, C, wpb, chain_words);
       }
-    } else if (e->scfg.dense) {
+    } else if (e->scfg.dense || e->scfg.diag) {
       CUDA_TRY(e, launch_fused_dense(e->scfg, e->md, e->dc, C, false, kChainsPerBlock, 0, 0, e->stream));
     } else {
       fused_chain_kernel<false, 0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C, kChainsPerBlock, 0);
@@ -844,7 +844,7 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       const bool check = (step % kCheck) == 0;
       int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
       if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
-      if (e->scfg.dense) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
+      if (e->scfg.dense || e->scfg.diag) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else advance_kernel<0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;
@@ -861,7 +861,7 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
         ev_used = 0;
         if (*e->h_nactive == 0) break;
         b.hint_active = *e->h_nactive;
-        if (e->irt_tail == 2 && e->md.kind == MODEL_IRT2PL && !e->scfg.dense && *e->h_nactive <= 2 * e->sm_count) {
+        if (e->irt_tail == 2 && e->md.kind == MODEL_IRT2PL && !e->scfg.dense && !e->scfg.diag && *e->h_nactive <= 2 * e->sm_count) {
           // only stragglers are left: one CTA per remaining chain runs it to the end of this call on the device (irt_tail.cu)
           cudaEvent_t a = next_event(), bb = next_event();
           cudaEventRecord(a, e->stream);

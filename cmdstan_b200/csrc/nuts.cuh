@@ -42,6 +42,17 @@
 #define B200_PRAGMA_(x) _Pragma(#x)
 #define B200_PRAGMA(x) B200_PRAGMA_(x)
 #define B200_VEC_LOOP B200_PRAGMA(unroll B200_VEC_UNROLL)
+// the six U-turn dot products of a merge: one interleaved butterfly (5 dependent shuffle rounds) in the latency-bound long-vector
+// build; six calls of the one shared out-of-line warp_sum in the instruction-cache-bound default build (r01l / r01m: the
+// inlined form cost the c2 fused kernel ~4 %).  Same bits either way.
+#if B200_VEC_UNROLL > 1
+#define B200_SUM6(a, b, c, d, e, f) warp_sum6(a, b, c, d, e, f)
+#else
+#define B200_SUM6(a, b, c, d, e, f) \
+  do {                              \
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d); e = warp_sum(e); f = warp_sum(f); \
+  } while (0)
+#endif
 
 // The dense-metric code paths are compiled only where B200_WITH_DENSE is 1 (dense.cu, the host emulation): the fused chain
 // kernels of the small models are instruction-cache bound, and carrying the dense branches cost c2 15 % (profiles r01i).
@@ -49,6 +60,9 @@
 #define B200_WITH_DENSE 1
 #endif
 #define B200_DENSE(cfg) (B200_WITH_DENSE && (cfg).dense)
+// the diagnostics bookkeeping (momentum of every proposal) is compiled with the dense paths: runs with store_diagnostics use
+// the kernels of dense.cu, the default kernels stay small (r01l: carrying these branches cost the c2 fused kernel 7 %)
+#define B200_DIAG(cfg) (B200_WITH_DENSE && (cfg).diag)
 
 namespace b200 {
 
@@ -341,12 +355,12 @@ B200_DEV_CALL bool merge_top(const ChainView& c, const SamplerCfg& cfg, int lane
       L[4 * ld + i] = R[4 * ld + i];
     }
   }
-  warp_sum6(a1, a2, b1, b2, c1, c2);
+  B200_SUM6(a1, a2, b1, b2, c1, c2);
   s->st_lsw[li] = lsw_sub;
   if (take_right) {
     s->st_V[li] = s->st_V[ri];
     s->st_H[li] = s->st_H[ri];
-    if (cfg.diag) {
+    if (B200_DIAG(cfg)) {
       double* pl = diag_slot(c, cfg, 1 + li);
       const double* pr = diag_slot(c, cfg, 1 + ri);
       B200_VEC_LOOP for (int i = lane; i < cfg.D; i += kWarp) pl[i] = pr[i];
@@ -609,7 +623,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             bq[i] = qi; bp[i] = pi; bg[i] = gi;
             pfb[i] = pi; pbf[i] = pi; rho[i] = pi;
           }
-          if (cfg.diag) {  // z_sample starts as the initial point with its fresh momentum
+          if (B200_DIAG(cfg)) {  // z_sample starts as the initial point with its fresh momentum
             double* cp = diag_slot(c, cfg, 0);
             B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) cp[i] = p[i];
           }
@@ -677,7 +691,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             E[3 * ld + i] = c.q[i];
             E[4 * ld + i] = c.g[i];
           }
-          if (cfg.diag) {
+          if (B200_DIAG(cfg)) {
             double* pp = diag_slot(c, cfg, 1 + e);
             B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) pp[i] = p[i];
           }
@@ -782,13 +796,13 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         if (take) {
           s->curV = s->st_V[0];
           s->curH = s->st_H[0];
-          if (cfg.diag) {
+          if (B200_DIAG(cfg)) {
             double* cp = diag_slot(c, cfg, 0);
             const double* pp = diag_slot(c, cfg, 1);
             B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) cp[i] = pp[i];
           }
         }
-        warp_sum6(a1, a2, b1, b2, c1, c2);
+        B200_SUM6(a1, a2, b1, b2, c1, c2);
         bool persist = (a1 > 0 && a2 > 0);
         persist &= (b1 > 0 && b2 > 0);
         persist &= (c1 > 0 && c2 > 0);
@@ -813,7 +827,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           }
           const double* cq = slot(c, cfg, V_CQ);
           B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) r[7 + i] = cq[i];
-          if (cfg.diag) {
+          if (B200_DIAG(cfg)) {
             const double* cp = diag_slot(c, cfg, 0);
             const double* cg = slot(c, cfg, V_CG);
             B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
