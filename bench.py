@@ -370,7 +370,12 @@ def main():
             ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
             tr = ncu_traffic(model) if args.scale == 1.0 else None
+            try:   # the bound of this kernel is the scalar FP64 pipe: its own measured FMA rate beside the DGEMM rate
+                fma_peak = B.measure_fp64_fma_peak(local_rank)
+            except Exception:
+                fma_peak = None
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
+                    "fp64_fma_peak": fma_peak, "frac_of_fma_peak": (ach / fma_peak) if ach and fma_peak else None,
                     "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,
                     "note": "bound is FP64 ALU + transcendental throughput; normalised by the measured DGEMM rate"}
         else:

@@ -41,7 +41,7 @@ EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b2
            "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
            "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_fetch_diagnostics", "b200nuts_rows_saved",
            "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
-           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
+           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_measure_fp64_fma_peak", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
            # include/b200nuts_model.h
            "b200nuts_register_model", "b200nuts_load_model_library", "b200nuts_find_model", "b200nuts_output_name"]
 
@@ -93,6 +93,7 @@ def load_library(build=True):
     lib.b200nuts_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.b200nuts_summary.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp]
     lib.b200nuts_summarize_draws.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_char_p, C.c_int]
+    lib.b200nuts_measure_fp64_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.b200nuts_register_model.argtypes = [vp]
     lib.b200nuts_load_model_library.argtypes = [C.c_char_p]
     lib.b200nuts_find_model.argtypes = [C.c_char_p]
@@ -110,6 +111,16 @@ def load_model_library(path):
     if rc < 0:
         raise B200NutsError(-rc, lib.b200nuts_last_error(None).decode())
     return rc
+
+
+def measure_fp64_fma_peak(device=0):
+    """Measured FP64 FMA rate of the device in TFLOP/s (roofline denominator of the scalar-FP64-bound kernels)."""
+    lib = load_library()
+    v = C.c_double()
+    rc = lib.b200nuts_measure_fp64_fma_peak(int(device), C.byref(v))
+    if rc:
+        raise B200NutsError(rc, lib.b200nuts_last_error(None).decode())
+    return v.value
 
 
 def find_model(name):

@@ -1124,6 +1124,51 @@ int b200nuts_summary(b200nuts_engine* e, int64_t row0, int64_t nrows, int constr
   return summary_run(a, out, &e->err);
 }
 
+// ---- FP64 FMA peak (roofline denominator of the scalar-FP64-bound kernels)
+}  // extern "C"
+namespace {
+__global__ void __launch_bounds__(256) fma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {  // 8 independent dependency chains per thread
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace
+extern "C" {
+int b200nuts_measure_fp64_fma_peak(int device, double* tflops) {
+  int ndev = 0, sms = 0;
+  if (!tflops || cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "measure_fp64_fma_peak: no such CUDA device";
+    return B200NUTS_SOFTWARE;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+  double* d_out = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&d_out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) { g_create_error = "measure_fp64_fma_peak: cudaMalloc failed"; return B200NUTS_SOFTWARE; }
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {  // first repetition warms up
+    cudaEventRecord(e0);
+    fma_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms > 0) best = std::max(best, 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12);
+  }
+  const cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  if (err != cudaSuccess || best <= 0.0) { g_create_error = std::string("measure_fp64_fma_peak: ") + cudaGetErrorString(err); return B200NUTS_SOFTWARE; }
+  *tflops = best;
+  return B200NUTS_OK;
+}
+
 // ---- plug-in registry (include/b200nuts_model.h) -----------------------------------------------------------------------
 int b200nuts_register_model(const b200nuts_model_vtable* vt) {
   if (!vt || vt->abi != B200NUTS_MODEL_ABI || !vt->name || !vt->create || !vt->log_prob_grad) {

@@ -159,6 +159,10 @@ int b200nuts_get_chain_status(b200nuts_engine* e, int32_t* err, int32_t* iter, i
    kernel family (gradient stage) measured with CUDA events on the launching stream */
 int b200nuts_get_timing(b200nuts_engine* e, double* run_seconds, int64_t* kernel_launches, double* grad_kernel_seconds);
 
+/* Measured FP64 FMA rate of `device` in TFLOP/s (a register-resident chain of independent DFMAs on every SM): the roofline
+   denominator of the kernels bound by the scalar FP64 pipe (IRT), SURVEY.md section 8d "must be measured on the box". */
+int b200nuts_measure_fp64_fma_peak(int device, double* tflops);
+
 /* Row-sharded GLMs: called on the engine's stream position after the partial gradient kernel of every leapfrog with a
    DEVICE buffer of `count` doubles that must be summed element-wise across all shards, identically on every shard
    (e.g. ncclAllReduce on `cuda_stream`).  Must be set when row_shards > 1. */
