@@ -363,3 +363,10 @@ def test_diagnostic_rows_vs_oracle(name, engine):
     # the gradient column is the gradient of the potential at the saved q
     lp, g = m.lp_grad(diag[0, :, 7:7 + D])
     assert _rel(diag[0, :, 7 + 2 * D:], -g, floor=1e-6) < 1e-9 and _rel(diag[0, :, 0], lp, floor=1e-6) < 1e-9
+
+
+def test_fp64_fma_peak_is_measurable():
+    """b200nuts_measure_fp64_fma_peak: a plausible FP64 FMA rate for a data-centre GPU (B200 nominal ~37 TFLOP/s)"""
+    import cmdstan_b200 as B
+    v = B.measure_fp64_fma_peak(0)
+    assert 5.0 < v < 90.0, v
