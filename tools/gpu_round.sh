@@ -20,8 +20,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:glm_
    python bench.py --num-warmup 30 --steps 4 --warmup 3 --no-cpu > $O/${TAG}_ncu_full_stdout.log 2>&1
 ( time timeout 300 python bench.py --workload c2 --steps 200 ) > $O/${TAG}_bench_c2.log 2>&1
 ( time timeout 300 python bench.py --workload c1 --steps 1000 ) > $O/${TAG}_bench_c1.log 2>&1
-( time timeout 600 python bench.py --workload c4 --steps 50 --num-warmup 300 --no-cpu ) > $O/${TAG}_bench_c4.log 2>&1
+( time B200_BENCH_VERBOSE=1 timeout 420 python bench.py --workload c4 --no-cpu ) > $O/${TAG}_bench_c4.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:irt_grad -s 40 -c 1 -o $O/${TAG}_irt \
    python bench.py --workload c4 --chains 2048 --num-warmup 20 --steps 4 --warmup 3 --no-cpu > $O/${TAG}_ncu_irt_stdout.log 2>&1
-( time timeout 600 python bench.py --workload c5 --steps 30 --num-warmup 150 --no-cpu ) > $O/${TAG}_bench_c5.log 2>&1
+( time timeout 420 python bench.py --workload c5 --no-cpu ) > $O/${TAG}_bench_c5.log 2>&1
 ls -la $O
