@@ -65,8 +65,12 @@ class argument_parser {
     // method
     arg* method = root_.add(mk(arg::LIST, "method", "sample"));
     arg* sample = method->add(mk(arg::CATEGORY, "sample", ""));
-    for (const char* other : {"optimize", "variational", "diagnose", "generate_quantities", "pathfinder", "log_prob", "laplace"})
-      method->add(mk(arg::CATEGORY, other, ""));
+    for (const char* other : {"optimize", "variational", "diagnose", "generate_quantities", "pathfinder"}) method->add(mk(arg::CATEGORY, other, ""));
+    arg* lpm = method->add(mk(arg::CATEGORY, "log_prob", ""));  // arguments/arg_log_prob.hpp
+    lpm->add(mk(arg::STRING, "unconstrained_params", ""));
+    lpm->add(mk(arg::STRING, "constrained_params", ""));
+    lpm->add(mk(arg::BOOL, "jacobian", "true"));
+    method->add(mk(arg::CATEGORY, "laplace", ""));
     sample->add(mk(arg::INT, "num_samples", "1000", "0 <= num_samples", [](const arg& a) { return a.integer() >= 0; }));
     sample->add(mk(arg::INT, "num_warmup", "1000", "0 <= num_warmup", [](const arg& a) { return a.integer() >= 0; }));
     sample->add(mk(arg::BOOL, "save_warmup", "false"));

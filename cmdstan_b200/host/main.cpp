@@ -50,6 +50,87 @@ std::string model_from_argv0(const std::string& a0) {
   return slash == std::string::npos ? a0 : a0.substr(slash + 1);
 }
 
+// method=log_prob (src/cmdstan/command_helper.hpp:520-600 services_log_prob_grad): log density and its gradient at sets of
+// parameter values read from JSON -- `unconstrained_params` {"params_r": [..] or [[..], ..]} or `constrained_params` (one set of
+// named values, mapped through transform_inits) -- evaluated on the device (b200nuts_log_prob_grad), written as "lp__, g_<name>.."
+int run_log_prob(b200::cmd::argument_parser& parser, const std::string& model_name) {
+  using namespace b200;
+  const std::string upath = parser.str({"method", "log_prob", "unconstrained_params"});
+  const std::string cpath = parser.str({"method", "log_prob", "constrained_params"});
+  const bool jacobian = parser.boolean({"method", "log_prob", "jacobian"});
+  const int sig_figs = (int)parser.integer({"output", "sig_figs"});
+  if (upath.empty() == cpath.empty()) {
+    std::cerr << (upath.empty() ? "No input parameter files provided, call to log_prob done." : "Cannot specify both input files of both constrained and unconstrained parameter values.") << std::endl;
+    return services::error_codes::USAGE;
+  }
+  long long seed_arg = parser.integer({"random", "seed"});
+  if (seed_arg < 0) {
+    const unsigned int s = (unsigned int)(std::time(nullptr) % 4294967296ULL);
+    parser.find({"random", "seed"})->value = parser.find({"random", "seed"})->def = std::to_string(s);
+  }
+  for (const std::string& ln : parser.echo()) std::cout << ln << std::endl;
+  std::cout << std::endl;
+  b200nuts_engine* e = nullptr;
+  try {
+    io::var_context data = io::read_json_file(parser.str({"data", "file"}));
+    model::device_model& model = model::new_model(model_name, data, 0, &std::cout);
+    const int64_t D = model.num_params_r();
+    std::vector<double> q;
+    if (!upath.empty()) {
+      io::var_context u = io::read_json_file(upath);
+      const std::vector<double>& v = u.vals_r("params_r");
+      const std::vector<int64_t>& dims = u.dims_r("params_r");
+      if (dims.size() <= 1) {
+        if ((int64_t)v.size() != D) throw std::invalid_argument("Incorrect number of unconstrained parameters provided! Model has " + std::to_string(D) + " parameters but " + std::to_string(v.size()) + " were found.");
+        q = v;
+      } else {
+        const int64_t n = dims[0], d = dims[1];
+        if (d != D) throw std::invalid_argument("Incorrect number of unconstrained parameters provided! Model has " + std::to_string(D) + " parameters but " + std::to_string(d) + " were found.");
+        // the reference's JSON reader flattens the matrix column-major and get_uparams_r re-reads it row-major
+        // (command_helper.hpp:548-556): element (i, j) of set i is the flat element i*D + j of that column-major buffer
+        q.resize((size_t)n * D);
+        for (int64_t k = 0; k < n * D; k++) q[(size_t)k] = v[(size_t)((k % n) * D + k / n)];
+      }
+    } else {
+      io::var_context c = io::read_json_file(cpath);
+      model.transform_inits(c, q);
+    }
+    const int64_t n = (int64_t)q.size() / D;
+    b200nuts_config cfg;
+    b200nuts_default_config(&cfg);
+    cfg.model = model.model_id();
+    int rc = b200nuts_create(&cfg, &e);
+    if (rc) throw std::runtime_error(b200nuts_last_error(nullptr));
+    std::vector<double> lp((size_t)n), g((size_t)n * D);
+    if ((rc = model.upload(e)) || (rc = b200nuts_log_prob_grad(e, q.data(), n, jacobian ? 1 : 0, lp.data(), g.data()))) throw std::runtime_error(b200nuts_last_error(e));
+    std::unique_ptr<std::ostream> out = create_stream(parser.str({"output", "file"}), sig_figs);
+    char date[64];
+    std::time_t now = std::time(nullptr);
+    std::strftime(date, sizeof date, "%Y-%m-%d %H:%M:%S", std::gmtime(&now));
+    *out << "# stan_version_major = 2\n# stan_version_minor = 36\n# stan_version_patch = 0\n# model = " << model.model_name() << "\n# start_datetime = " << date << " UTC\n";
+    for (const std::string& ln : parser.echo()) *out << "# " << ln << "\n";
+    for (const std::string& ln : model.model_compile_info()) *out << "# " << ln << "\n";
+    std::vector<std::string> names;
+    model.unconstrained_param_names(names, false, false);
+    *out << "lp__";
+    for (const std::string& nm : names) *out << ",g_" << nm;
+    *out << "\n";
+    for (int64_t i = 0; i < n; i++) {
+      *out << lp[(size_t)i];
+      for (int64_t k = 0; k < D; k++) *out << "," << g[(size_t)(i * D + k)];
+      *out << "\n";
+    }
+    b200nuts_destroy(e);
+    return 0;
+  } catch (const std::domain_error& ex) {
+    std::cerr << ex.what() << std::endl;
+  } catch (const std::exception& ex) {
+    std::cerr << ex.what() << std::endl;
+  }
+  if (e) b200nuts_destroy(e);
+  return 1;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -92,6 +173,7 @@ int main(int argc, char** argv) {
     std::cerr << e.what() << std::endl << "Failed to parse arguments, terminating Stan" << std::endl;
     return services::error_codes::USAGE;
   }
+  if (parser.str({"method"}) == "log_prob") return run_log_prob(parser, model_name);
   if (parser.str({"method"}) != "sample") {
     std::cerr << "method=" << parser.str({"method"}) << " is not available in the B200 engine (only `sample` with algorithm=hmc engine=nuts metric=diag_e|unit_e|dense_e)" << std::endl;
     return services::error_codes::USAGE;

@@ -302,3 +302,50 @@ def test_partial_user_inits_like_reference(init, tmp_path, mock_env):
         assert r.returncode == 0, who + r.stdout[-500:] + r.stderr[-500:]
         body[who] = [x for x in (d / "o.csv").read_text().splitlines() if x and not x.startswith("#")]
     assert body["mine"][:12] == body["ref"][:12]
+
+
+def _read_lp_csv(path):
+    lines = [x for x in open(path).read().splitlines() if x and not x.startswith("#")]
+    return lines[0], np.array([r.split(",") for r in lines[1:]], dtype=float)
+
+
+@pytest.mark.skipif(not O.have_ref("eight_schools_nc"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("model,kind", [("bernoulli", "u2d"), ("bernoulli", "u1d"), ("bernoulli", "constrained"), ("eight_schools_nc", "u2d"),
+                                        ("eight_schools_nc", "constrained")])
+def test_log_prob_method_like_reference(model, kind, tmp_path, mock_env):
+    """`method=log_prob` (command_helper.hpp:520-600): same configuration echo, header, column names (lp__, g_<name>) and values as
+    the reference, for unconstrained sets given as a vector or a matrix (with the reference's column-major / row-major re-reading
+    of the matrix) and for one set of constrained values."""
+    if model == "bernoulli":
+        data, D = {"N": 10, "y": [0, 1, 0, 0, 0, 0, 0, 0, 0, 1]}, 1
+        cons = {"theta": 0.3}
+    else:
+        data, D = {"J": 8, "y": [28, 8, -3, 7, -1, 1, 18, 12], "sigma": [15, 10, 16, 11, 9, 11, 10, 18]}, 10
+        cons = {"mu": 1.5, "tau": 2.5, "theta_tilde": [0.1, -0.2, 0.3, -0.4, 0.5, -0.6, 0.7, -0.8]}
+    dj = tmp_path / "d.json"
+    dj.write_text(json.dumps(data))
+    pj = tmp_path / "p.json"
+    rng = np.random.default_rng(5)
+    if kind == "u2d":
+        pj.write_text(json.dumps({"params_r": rng.uniform(-2, 2, size=(4, D)).tolist()}))
+        arg = f"unconstrained_params={pj}"
+    elif kind == "u1d":
+        pj.write_text(json.dumps({"params_r": rng.uniform(-2, 2, size=D).tolist()}))
+        arg = f"unconstrained_params={pj}"
+    else:
+        pj.write_text(json.dumps(cons))
+        arg = f"constrained_params={pj}"
+    args = ["log_prob", arg, "data", f"file={dj}", "output", "file=lp.csv", "sig_figs=14"]
+    res = {}
+    for who in ("mine", "ref"):
+        d = tmp_path / who
+        d.mkdir()
+        exe, env = ([CLI, model], mock_env) if who == "mine" else ([os.path.join(O.REF, model)], None)
+        r = subprocess.run(exe + args, cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, who + r.stdout[-500:] + r.stderr[-500:]
+        hdr, vals = _read_lp_csv(d / "lp.csv")
+        comments = [x for x in (d / "lp.csv").read_text().splitlines() if x.startswith("#") and not any(t in x for t in ("start_datetime", "stanc", "seed =", "file = "))]
+        res[who] = (hdr, vals, comments)
+    assert res["mine"][0] == res["ref"][0] and res["mine"][2] == res["ref"][2]
+    assert res["mine"][1].shape == res["ref"][1].shape
+    np.testing.assert_allclose(res["mine"][1], res["ref"][1], rtol=1e-11, atol=1e-12)

@@ -272,3 +272,25 @@ def test_cli_diagnostic_file_vs_reference(tmp_path):
     dm, dr = np.array([x.split(",") for x in bm[1:]], dtype=float), np.array([x.split(",") for x in br[1:]], dtype=float)
     assert dm.shape == dr.shape == (45, 10)
     assert np.array_equal(dm[:, 3:6], dr[:, 3:6]) and np.allclose(dm[:20], dr[:20], rtol=1e-9) and np.allclose(dm, dr, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.skipif(not O.have_ref("eight_schools_nc"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("jacobian", [1, 0])
+def test_cli_log_prob_method_vs_reference(jacobian, tmp_path):
+    """`method=log_prob` on the device against the reference's (reverse-mode AD of the real stan::math densities), with and
+    without the Jacobian terms: gate 1 (1e-10) through the command line."""
+    dj = tmp_path / "es.json"
+    dj.write_text(json.dumps({"J": 8, "y": [28, 8, -3, 7, -1, 1, 18, 12], "sigma": [15, 10, 16, 11, 9, 11, 10, 18]}))
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps({"params_r": np.random.default_rng(3).uniform(-2, 2, size=(6, 10)).tolist()}))
+    args = ["log_prob", f"unconstrained_params={pj}", f"jacobian={jacobian}", "data", f"file={dj}", "output", "sig_figs=16"]
+    r = _cli("eight_schools_nc", args + ["file=mine.csv"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rr = subprocess.run([os.path.join(O.REF, "eight_schools_nc")] + args + ["file=ref.csv"], cwd=tmp_path, capture_output=True, text=True)
+    assert rr.returncode == 0, rr.stdout + rr.stderr
+    rd = lambda f: [x for x in (tmp_path / f).read_text().splitlines() if x and not x.startswith("#")]
+    a, b = rd("mine.csv"), rd("ref.csv")
+    assert a[0] == b[0] == "lp__," + ",".join(["g_mu", "g_tau"] + [f"g_theta_tilde.{i}" for i in range(1, 9)])
+    va, vb = np.array([x.split(",") for x in a[1:]], dtype=float), np.array([x.split(",") for x in b[1:]], dtype=float)
+    assert va.shape == vb.shape == (6, 11)
+    assert np.max(np.abs(va - vb) / np.maximum(1e-9, np.abs(vb))) < 1e-10
