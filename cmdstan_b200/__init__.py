@@ -14,12 +14,14 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "hmc_nuts_dense_e_adapt", "hmc_nuts_dense_e", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id", "load_model_library", "find_model"]
+__all__ = ["Engine", "hmc_nuts_diag_e_adapt", "hmc_nuts_diag_e", "hmc_nuts_unit_e_adapt", "hmc_nuts_unit_e", "hmc_nuts_dense_e_adapt", "hmc_nuts_dense_e", "hmc_static_diag_e_adapt", "hmc_static_diag_e", "hmc_static_unit_e_adapt",
+           "hmc_static_unit_e", "hmc_static_dense_e_adapt", "hmc_static_dense_e", "STATIC_SAMPLER_COLUMNS", "param_names", "B200NutsError", "MODELS", "load_library", "SAMPLER_COLUMNS", "SUMMARY_COLUMNS", "summarize_draws", "nccl_unique_id", "load_model_library", "find_model"]
 
 MODELS = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
 ENGINES = {"auto": 0, "fused": 1, "lockstep": 2}
 SUMMARY_COLUMNS = ["Mean", "MCSE", "StdDev", "MAD", "5%", "50%", "95%", "ESS_bulk", "ESS_tail", "R_hat"]
 SAMPLER_COLUMNS = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
+STATIC_SAMPLER_COLUMNS = ["lp__", "accept_stat__", "stepsize__", "int_time__", "energy__"]   # base_static_hmc::get_sampler_param_names
 
 # stan::services::error_codes (stan/src/stan/services/error_codes.hpp)
 OK, USAGE, DATAERR, NOINPUT, SOFTWARE, CONFIG = 0, 64, 65, 66, 70, 78
@@ -32,7 +34,7 @@ class Config(C.Structure):
                 ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double), ("t0", C.c_double),
                 ("init_buffer", C.c_uint32), ("term_buffer", C.c_uint32), ("window", C.c_uint32), ("adapt_engaged", C.c_int32),
                 ("engine", C.c_int32), ("device", C.c_int32), ("store_draws", C.c_int32), ("row_shards", C.c_int32),
-                ("row_shard_rank", C.c_int32), ("metric", C.c_int32), ("store_diagnostics", C.c_int32)]
+                ("row_shard_rank", C.c_int32), ("metric", C.c_int32), ("store_diagnostics", C.c_int32), ("static_hmc", C.c_int32), ("int_time", C.c_double)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
@@ -181,7 +183,7 @@ class Engine:
     def __init__(self, model, data, num_chains=1, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
                  num_samples=1000, num_thin=1, save_warmup=False, stepsize=1.0, stepsize_jitter=0.0, max_depth=10, delta=0.8,
                  gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50, window=25, adapt_engaged=True, engine="auto",
-                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None, metric="diag_e", store_diagnostics=False):
+                 device=0, store_draws=True, row_shards=1, row_shard_rank=0, allreduce=None, metric="diag_e", store_diagnostics=False, static_hmc=False, int_time=2 * np.pi):
         self.lib = load_library()
         cfg = Config()
         self.lib.b200nuts_default_config(C.byref(cfg))
@@ -195,6 +197,7 @@ class Engine:
         cfg.row_shards, cfg.row_shard_rank = int(row_shards), int(row_shard_rank)
         cfg.metric = {"diag_e": 0, "unit_e": 1, "dense_e": 2}[metric]
         cfg.store_diagnostics = int(bool(store_diagnostics))
+        cfg.static_hmc, cfg.int_time = int(bool(static_hmc)), float(int_time)
         self.metric = metric
         self.cfg = cfg
         self.model = model
@@ -357,14 +360,15 @@ def param_names(model, data):
 
 def _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
                  num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa, t0, init_buffer, term_buffer,
-                 window, logger, device, engine, adapt_engaged, metric):
+                 window, logger, device, engine, adapt_engaged, metric, int_time=None):
     log = logger or (lambda msg: None)
     try:
         e = Engine(model, data, num_chains=num_chains, random_seed=random_seed, init_chain_id=init_chain_id,
                    init_radius=init_radius, num_warmup=num_warmup, num_samples=num_samples, num_thin=num_thin,
                    save_warmup=save_warmup, stepsize=stepsize, stepsize_jitter=stepsize_jitter, max_depth=max_depth, delta=delta,
                    gamma=gamma, kappa=kappa, t0=t0, init_buffer=init_buffer, term_buffer=term_buffer, window=window,
-                   adapt_engaged=adapt_engaged, engine=engine, device=device, metric=metric)
+                   adapt_engaged=adapt_engaged, engine=engine, device=device, metric=metric, static_hmc=int_time is not None,
+                   int_time=int_time if int_time is not None else 2 * np.pi)
     except B200NutsError as ex:
         log(str(ex))
         return ex.code, None
@@ -386,6 +390,9 @@ def _run_service(model, data, num_chains, init, init_inv_metric, random_seed, in
         eps, im = e.adaptation()
         draws = e.fetch_draws()
         names = SAMPLER_COLUMNS + e.output_names()
+        if int_time is not None:   # static HMC: the engine's rows carry L, 1, 0 where NUTS has treedepth, n_leapfrog, divergent
+            draws = np.concatenate([draws[:, :, :3], np.full(draws.shape[:2] + (1,), float(int_time)), draws[:, :, 6:]], axis=2)
+            names = STATIC_SAMPLER_COLUMNS + e.output_names()
         return OK, dict(draws=draws, columns=names, stepsize=eps, inv_metric=im, timing=dict(warmup=warm_s, sampling=samp_s), n_grad=ng)
     except B200NutsError as ex:
         log(str(ex))
@@ -460,3 +467,22 @@ def hmc_nuts_dense_e(model, data, num_chains=1, init=None, init_inv_metric=None,
     return _run_service(model, data, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples,
                         num_thin, save_warmup, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75, 50, 25, logger, device,
                         engine, False, "dense_e")
+
+
+def _static_service(metric, adapt):
+    def service(model, data, num_chains=1, init=None, init_inv_metric=None, random_seed=0, init_chain_id=1, init_radius=2.0, num_warmup=1000,
+                num_samples=1000, num_thin=1, save_warmup=False, refresh=100, stepsize=1.0, stepsize_jitter=0.0, int_time=2 * np.pi, delta=0.8,
+                gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50, window=25, logger=None, device=0, engine="auto"):
+        return _run_service(model, data, num_chains, init, None if metric == "unit_e" else init_inv_metric, random_seed, init_chain_id, init_radius,
+                            num_warmup, num_samples, num_thin, save_warmup, stepsize, stepsize_jitter, 10, delta, gamma, kappa, t0, init_buffer,
+                            term_buffer, window, logger, device, engine, adapt, metric, int_time=float(int_time))
+    service.__name__ = "hmc_static_%s%s" % (metric, "_adapt" if adapt else "")
+    service.__doc__ = ("stan::services::sample::%s (stan/src/stan/services/sample/%s.hpp): static HMC with integration time `int_time` "
+                       "(stan/mcmc/hmc/static/base_static_hmc.hpp:41-70), %s metric, %s.  Result columns: STATIC_SAMPLER_COLUMNS + the model's."
+                       % (service.__name__, service.__name__, metric, "step size (and metric) adapted in windows" if adapt else "no adaptation"))
+    return service
+
+
+hmc_static_diag_e_adapt, hmc_static_diag_e = _static_service("diag_e", True), _static_service("diag_e", False)
+hmc_static_unit_e_adapt, hmc_static_unit_e = _static_service("unit_e", True), _static_service("unit_e", False)
+hmc_static_dense_e_adapt, hmc_static_dense_e = _static_service("dense_e", True), _static_service("dense_e", False)

@@ -261,6 +261,8 @@ void b200nuts_default_config(b200nuts_config* c) {
   c->row_shard_rank = 0;
   c->metric = 0;
   c->store_diagnostics = 0;
+  c->static_hmc = 0;
+  c->int_time = 6.28318530717958647692;
 }
 
 const char* b200nuts_last_error(const b200nuts_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
@@ -284,6 +286,8 @@ int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
   if (cfg->stepsize_jitter < 0 || cfg->stepsize_jitter > 1) { g_create_error = "stepsize_jitter must be in [0, 1]"; return B200NUTS_USAGE; }
   if (cfg->init_radius < 0) { g_create_error = "init radius must be >= 0"; return B200NUTS_USAGE; }
   if (cfg->metric < 0 || cfg->metric > 2) { g_create_error = "metric must be 0 (diag_e), 1 (unit_e) or 2 (dense_e)"; return B200NUTS_USAGE; }
+  if (cfg->static_hmc && !(cfg->int_time > 0)) { g_create_error = "int_time must be > 0"; return B200NUTS_USAGE; }
+  if (cfg->static_hmc && cfg->store_diagnostics) { g_create_error = "store_diagnostics is available for the NUTS engine only"; return B200NUTS_CONFIG; }
   if (cfg->row_shards < 1 || cfg->row_shard_rank < 0 || cfg->row_shard_rank >= cfg->row_shards) { g_create_error = "bad row shard configuration"; return B200NUTS_USAGE; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -690,6 +694,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   s.dense = c.metric == 2;
   resolve_window(&s, (c.adapt_engaged && c.metric != 1) ? (unsigned)c.num_warmup : 0u, c.init_buffer, c.term_buffer, c.window);
   s.diag = c.store_diagnostics && c.store_draws ? 1 : 0;
+  s.static_hmc = c.static_hmc ? 1 : 0;
+  s.int_time = c.int_time;
   s.ncol = 7 + e->D * (s.diag ? 3 : 1);
   s.rows_per_chain = c.store_draws ? (c.save_warmup ? (c.num_warmup + c.num_thin - 1) / c.num_thin : 0) + (c.num_samples + c.num_thin - 1) / c.num_thin : 0;
 
@@ -813,14 +819,14 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       int wpb = per_sm < kFusedMaxWarps ? (per_sm < 1 ? 1 : per_sm) : kFusedMaxWarps;
       while ((size_t)wpb * chain_bytes > 56 * 1024 && wpb > 1) wpb--;
       const size_t smem = (size_t)wpb * chain_bytes;
-      if (e->scfg.dense || e->scfg.diag) {
+      if (e->scfg.dense || e->scfg.diag || e->scfg.static_hmc) {
         CUDA_TRY(e, launch_fused_dense(e->scfg, e->md, e->dc, C, true, wpb, chain_words, smem, e->stream));
       } else {
         auto k = fused_chain_kernel<true, 0>;
         CUDA_TRY(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<(C + wpb - 1) / wpb, 32 * wpb, smem, e->stream>>>(e->scfg, e->md, e->dc, C, wpb, chain_words);
       }
-    } else if (e->scfg.dense || e->scfg.diag) {
+    } else if (e->scfg.dense || e->scfg.diag || e->scfg.static_hmc) {
       CUDA_TRY(e, launch_fused_dense(e->scfg, e->md, e->dc, C, false, kChainsPerBlock, 0, 0, e->stream));
     } else {
       fused_chain_kernel<false, 0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->md, e->dc, C, kChainsPerBlock, 0);
@@ -844,7 +850,7 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       const bool check = (step % kCheck) == 0;
       int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
       if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
-      if (e->scfg.dense || e->scfg.diag) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
+      if (e->scfg.dense || e->scfg.diag || e->scfg.static_hmc) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else advance_kernel<0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;
@@ -861,7 +867,7 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
         ev_used = 0;
         if (*e->h_nactive == 0) break;
         b.hint_active = *e->h_nactive;
-        if (e->irt_tail == 2 && e->md.kind == MODEL_IRT2PL && !e->scfg.dense && !e->scfg.diag && *e->h_nactive <= 2 * e->sm_count) {
+        if (e->irt_tail == 2 && e->md.kind == MODEL_IRT2PL && !e->scfg.dense && !e->scfg.diag && !e->scfg.static_hmc && *e->h_nactive <= 2 * e->sm_count) {
           // only stragglers are left: one CTA per remaining chain runs it to the end of this call on the device (irt_tail.cu)
           cudaEvent_t a = next_event(), bb = next_event();
           cudaEventRecord(a, e->stream);

@@ -63,6 +63,8 @@
 // the diagnostics bookkeeping (momentum of every proposal) is compiled with the dense paths: runs with store_diagnostics use
 // the kernels of dense.cu, the default kernels stay small (r01l: carrying these branches cost the c2 fused kernel 7 %)
 #define B200_DIAG(cfg) (B200_WITH_DENSE && (cfg).diag)
+// static HMC (S/mcmc/hmc/static/base_static_hmc.hpp) likewise lives only in the full-featured kernels of dense.cu
+#define B200_STATIC(cfg) (B200_WITH_DENSE && (cfg).static_hmc)
 
 namespace b200 {
 
@@ -102,6 +104,9 @@ enum ChainState {
   ST_DOUBLING_BEGIN,
   ST_LEAF_BEGIN,
   ST_LEAF,            // waits
+  ST_STATIC_STEP_BEGIN,  // static HMC: one of the L leapfrogs of a transition
+  ST_STATIC_STEP,        // waits
+  ST_STATIC_END,
   ST_TRANS_END,
   ST_ITER_NEXT,
   ST_DONE             // chain stopped with an error code
@@ -114,6 +119,9 @@ struct SamplerCfg {
   int D, ld, max_depth;
   int num_warmup, num_samples, num_thin, save_warmup;
   int adapt_engaged, user_inits;
+  int static_hmc;        // 1: static HMC (base_static_hmc.hpp:41-70): L = max(1, (int)(int_time / nominal stepsize)) leapfrogs and a
+                         //    Metropolis test per transition; rows: lp__, accept_stat__, stepsize__, L, 1, 0, energy__, q
+  double int_time;
   int diag;              // 1: every saved row is [7 + 3 D]: the parameters are followed by the sample's momentum and by the gradient
                          //    of the potential (what the reference sends to the diagnostic writer, mcmc_writer.hpp:156-176)
   int dense;             // 1: dense_e metric (per-chain D x D inverse metric, covariance windows); 0: diag_e / unit_e
@@ -129,7 +137,8 @@ struct ChainS {
   unsigned long long rng[kRngWords];
   int state, err, iter, iter_end;
   int init_tries, iss_after, iss_dir, dir;
-  int init_partial, pad0_;  // init_partial: some initial values were left to the random context (up to 100 tries, like no inits)
+  int init_partial, st_L;   // init_partial: some initial values were left to the random context (up to 100 tries, like no inits)
+  int st_i, pad1_;          // static HMC: L_ (st_L) and the leapfrogs done in this transition (st_i)
   int depth, n_leapfrog, divergent, sp;
   unsigned leaf_count, n_leaves;
   unsigned win_counter, win_size, win_next;
@@ -597,6 +606,10 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_ISS_END: {  // z restored to z_init (the current sample is untouched); adapt_diag_e_nuts.hpp:35-40
         if (s->iss_after == 1) {
+          if (B200_STATIC(cfg)) {  // ... and after the init_stepsize that follows a metric update
+            const int L = (int)(cfg.int_time / s->eps_nom);
+            s->st_L = L < 1 ? 1 : L;
+          }
           s->mu = dev_log(10 * s->eps_nom);
           s->sa_counter = 0;
           s->s_bar = 0;
@@ -612,6 +625,11 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         s->eps = s->eps_nom;  // sample_stepsize, base_hmc.hpp:195-200
         if (cfg.stepsize_jitter != 0.0) s->eps *= 1.0 + cfg.stepsize_jitter * (2.0 * warp_uniform01(s->rng, lane) - 1.0);
         s->H0 = refresh_from_current(c, cfg, lane);
+        if (B200_STATIC(cfg)) {  // base_static_hmc::transition: z_init is the current sample (kept in V_CQ / V_CG / curV)
+          s->st_i = 0;
+          s->state = ST_STATIC_STEP_BEGIN;
+          break;
+        }
         {
           const double* p = slot(c, cfg, V_P);
           double* fq = slot(c, cfg, V_FQ); double* fp = slot(c, cfg, V_FP); double* fg = slot(c, cfg, V_FG);
@@ -809,6 +827,47 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         s->state = persist ? ST_DOUBLING_BEGIN : ST_TRANS_END;
         break;
       }
+      case ST_STATIC_STEP_BEGIN: {
+        if (s->st_i >= s->st_L) {
+          s->state = ST_STATIC_END;
+          break;
+        }
+        leapfrog_begin(c, cfg, s->eps, lane);
+        s->state = ST_STATIC_STEP;
+        return ADV_NEED_GRAD;
+      }
+      case ST_STATIC_STEP: {
+        double hraw;
+        s->lsw = leapfrog_end(c, cfg, s->eps, lane, &hraw);  // H of the working point (NaN -> +inf); raw value for energy__
+        s->curH = hraw;
+        s->n_grad++;
+        s->st_i++;
+        s->state = ST_STATIC_STEP_BEGIN;
+        break;
+      }
+      case ST_STATIC_END: {  // base_static_hmc.hpp:56-69
+        const double h = s->lsw;
+        double accept_prob = dev_exp(s->H0 - h);
+        bool reject = false;
+        if (accept_prob < 1) reject = warp_uniform01(s->rng, lane) > accept_prob;
+        if (reject) {
+          s->curH = s->H0;  // H(z_init) with the momentum drawn for this transition
+        } else {
+          double* cq = slot(c, cfg, V_CQ);
+          double* cg = slot(c, cfg, V_CG);
+          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
+            cq[i] = c.q[i];
+            cg[i] = c.g[i];
+          }
+          s->curV = (*c.zV);
+        }
+        s->sum_metro = accept_prob > 1 ? 1 : accept_prob;
+        s->n_leapfrog = 1;      // accept_stat = sum_metro / n_leapfrog in ST_TRANS_END
+        s->depth = s->st_L;     // row column 3: L (the writer prints int_time__ instead)
+        s->divergent = 0;
+        s->state = ST_TRANS_END;
+        break;
+      }
       case ST_TRANS_END: {  // base_nuts.hpp:194-203, generate_transitions.hpp:70-75, adapt_diag_e_nuts.hpp:28-41
         const double accept_stat = s->sum_metro / (double)s->n_leapfrog;
         const bool warm = s->iter < cfg.num_warmup;
@@ -840,6 +899,10 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         s->iter++;
         if (cfg.adapt_engaged && warm) {
           learn_stepsize(s, cfg, accept_stat);
+          if (B200_STATIC(cfg)) {  // adapt_*_static_hmc::transition: update_L_() after every step-size update
+            const int L = (int)(cfg.int_time / s->eps_nom);
+            s->st_L = L < 1 ? 1 : L;
+          }
           const int upd = learn_variance(c, cfg, lane);
           if (upd < 0) {
             s->err = 70;  // "Numerical overflow in metric adaptation."
@@ -874,7 +937,12 @@ B200_HD void chain_init_scalars(ChainS* s, const SamplerCfg& cfg) {
   s->iter_end = 0;
   s->init_tries = 0;
   s->init_partial = 0;
-  s->pad0_ = 0;
+  s->st_i = 0;
+  s->pad1_ = 0;
+  {  // base_static_hmc::set_nominal_stepsize_and_T(stepsize, int_time): L from the stepsize ARGUMENT
+    int L = cfg.static_hmc ? (int)(cfg.int_time / (cfg.stepsize > 0 ? cfg.stepsize : 0.1)) : 0;
+    s->st_L = L < 1 ? 1 : L;
+  }
   s->iss_after = 0;
   s->iss_dir = 0;
   s->dir = 0;

@@ -30,7 +30,8 @@ struct arg {
   arg* parent = nullptr;
   double rval = 0.0;  // REAL: the parsed value at full precision (`value` holds the 6-digit echo)
 
-  bool is_default() const { return value == def; }
+  double def_rval = 0.0;  // REAL: the default at full precision (int_time defaults to 2 pi, echoed as 6.28319)
+  bool is_default() const { return kind == REAL ? rval == def_rval : value == def; }
   arg* child(const std::string& n) {
     for (auto& k : kids)
       if (k->name == n) return k.get();
@@ -52,7 +53,7 @@ inline std::unique_ptr<arg> mk(arg::kind_t k, const std::string& name, const std
   a->kind = k;
   a->name = name;
   a->value = a->def = def;
-  a->rval = std::strtod(def.c_str(), nullptr);
+  a->rval = a->def_rval = std::strtod(def.c_str(), nullptr);
   a->valid = valid;
   a->ok = ok;
   return a;
@@ -90,7 +91,8 @@ class argument_parser {
     algo->add(mk(arg::CATEGORY, "fixed_param", ""));
     arg* engine = hmc->add(mk(arg::LIST, "engine", "nuts"));
     arg* stat = engine->add(mk(arg::CATEGORY, "static", ""));
-    stat->add(mk(arg::REAL, "int_time", "6.28319", "0 < int_time", [](const arg& a) { return a.real() > 0; }));
+    arg* int_time = stat->add(mk(arg::REAL, "int_time", "6.28319", "0 < int_time", [](const arg& a) { return a.real() > 0; }));
+    int_time->rval = int_time->def_rval = 6.28318530717958647692;  // arguments/arg_int_time.hpp: 2 pi
     arg* nuts = engine->add(mk(arg::CATEGORY, "nuts", ""));
     nuts->add(mk(arg::INT, "max_depth", "10", "0 < max_depth", [](const arg& a) { return a.integer() > 0; }));
     arg* metric = hmc->add(mk(arg::LIST, "metric", "diag_e"));

@@ -179,9 +179,10 @@ int main(int argc, char** argv) {
     return services::error_codes::USAGE;
   }
   const std::string metric = parser.str({"method", "sample", "algorithm", "hmc", "metric"});
-  if (parser.str({"method", "sample", "algorithm"}) != "hmc" || parser.str({"method", "sample", "algorithm", "hmc", "engine"}) != "nuts" ||
+  const std::string hmc_engine = parser.str({"method", "sample", "algorithm", "hmc", "engine"});
+  if (parser.str({"method", "sample", "algorithm"}) != "hmc" || (hmc_engine != "nuts" && hmc_engine != "static") ||
       (metric != "diag_e" && metric != "unit_e" && metric != "dense_e")) {
-    std::cerr << "only algorithm=hmc engine=nuts metric=diag_e|unit_e|dense_e is available in the B200 engine" << std::endl;
+    std::cerr << "only algorithm=hmc engine=nuts|static metric=diag_e|unit_e|dense_e is available in the B200 engine" << std::endl;
     return services::error_codes::USAGE;
   }
   const unsigned num_chains = (unsigned)parser.integer({"method", "sample", "num_chains"});
@@ -301,6 +302,12 @@ int main(int argc, char** argv) {
     services::device_options opt;
     opt.unit_e = metric == "unit_e";  // command.hpp dispatches to hmc_nuts_unit_e[_adapt]; same call below with the identity metric
     opt.dense_e = metric == "dense_e";  // ... and to hmc_nuts_dense_e[_adapt] (command.hpp:620-660)
+    opt.static_hmc = hmc_engine == "static";  // ... and to the six hmc_static_* services
+    opt.int_time = parser.real({"method", "sample", "algorithm", "hmc", "engine", "static", "int_time"});
+    if (opt.static_hmc && !diagnostic_writers.empty()) {
+      std::cerr << "output diagnostic_file is available with engine=nuts only in the B200 engine" << std::endl;
+      return services::error_codes::USAGE;
+    }
     if (const char* dv = std::getenv("B200_DEVICES")) {
       opt.devices.clear();
       std::stringstream ss(dv);

@@ -53,6 +53,8 @@ struct device_options {
   int format_threads = 8;          // host threads used to format CSV rows (per-chain files are independent)
   bool unit_e = false;             // identity metric (the hmc_nuts_unit_e* services below set it)
   bool dense_e = false;            // dense metric (the hmc_nuts_dense_e* services below set it)
+  bool static_hmc = false;         // static HMC instead of NUTS (the hmc_static_* services: base_static_hmc.hpp:41-70)
+  double int_time = 6.28318530717958647692;
 };
 
 // metric_writer interface: one JSON record per chain (callbacks::structured_writer's use in write_sampler_state_struct)
@@ -214,6 +216,8 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
     cfg.adapt_engaged = adapt_engaged;
     cfg.metric = opt.dense_e ? 2 : (opt.unit_e ? 1 : 0);
     cfg.store_diagnostics = want_diag ? 1 : 0;
+    cfg.static_hmc = opt.static_hmc ? 1 : 0;
+    cfg.int_time = opt.int_time;
     cfg.engine = opt.engine;
     cfg.device = opt.devices.empty() ? 0 : opt.devices[g];
     b200nuts_engine* e = nullptr;
@@ -301,7 +305,18 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
               if (!os) continue;
               text.clear();
               const int prec = (int)os->precision();
-              for (int64_t r = 0; r < nrows; r++) internal::format_row(text, buf.data() + ((size_t)c * nrows + r) * ncol, ncol, prec);
+              for (int64_t r = 0; r < nrows; r++) {
+                double* row = buf.data() + ((size_t)c * nrows + r) * ncol;
+                if (opt.static_hmc) {  // engine row: lp, accept, stepsize, L, 1, 0, energy, values -> lp, accept, stepsize, int_time, energy, values
+                  row[4] = row[2];
+                  row[3] = row[1];
+                  row[2] = row[0];
+                  row[5] = opt.int_time;
+                  internal::format_row(text, row + 2, ncol - 2, prec);
+                } else {
+                  internal::format_row(text, row, ncol, prec);
+                }
+              }
               os->write(text.data(), (std::streamsize)text.size());
             }
           });
@@ -350,6 +365,7 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
 
   // ---- header rows
   std::vector<std::string> names = {"lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"};
+  if (opt.static_hmc) names = {"lp__", "accept_stat__", "stepsize__", "int_time__", "energy__"};  // base_static_hmc::get_sampler_param_names
   model.constrained_param_names(names, true, true);
   // diagnostic header (base_hmc::get_sampler_diagnostic_names -> ps_point::get_param_names): the unconstrained parameter names,
   // then p_<name>, then g_<name>
@@ -532,6 +548,34 @@ int hmc_nuts_dense_e(Model& model, size_t num_chains, const std::vector<InitCont
                                 num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth, 0.8, 0.05, 0.75, 10.0, 75u, 50u, 25u,
                                 interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, false);
 }
+
+// ---- static HMC (services/sample/hmc_static_{diag,unit,dense}_e[_adapt].hpp; base_static_hmc.hpp:41-70): same engine, L =
+// max(1, int(int_time / stepsize)) leapfrogs and a Metropolis test per transition; columns lp__, accept_stat__, stepsize__,
+// int_time__, energy__.  Parameter lists as in the reference (int_time where the NUTS services have max_depth).
+#define B200_STATIC_SERVICE(NAME, DENSE, UNIT, ADAPT)                                                                                        \
+  template <class Model, typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter, typename DiagnosticWriter> \
+  int NAME(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init, const std::vector<InitInvContextPtr>& init_inv_metric,   \
+           unsigned int random_seed, unsigned int init_chain_id, double init_radius, int num_warmup, int num_samples, int num_thin,         \
+           bool save_warmup, int refresh, double stepsize, double stepsize_jitter, double int_time, double delta, double gamma,             \
+           double kappa, double t0, unsigned int init_buffer, unsigned int term_buffer, unsigned int window,                                \
+           callbacks::interrupt& interrupt, callbacks::logger& logger, std::vector<InitWriter>& init_writer,                                \
+           std::vector<SampleWriter>& sample_writer, std::vector<DiagnosticWriter>& diagnostic_writer, device_options opt = device_options()) { \
+    opt.static_hmc = true;                                                                                                                   \
+    opt.int_time = int_time;                                                                                                                 \
+    opt.dense_e = DENSE;                                                                                                                     \
+    opt.unit_e = UNIT;                                                                                                                       \
+    std::vector<json_metric_writer> none;                                                                                                    \
+    return hmc_nuts_diag_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples, \
+                                 num_thin, save_warmup, refresh, stepsize, stepsize_jitter, 10, delta, gamma, kappa, t0, init_buffer,        \
+                                 term_buffer, window, interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, ADAPT);   \
+  }
+B200_STATIC_SERVICE(hmc_static_diag_e_adapt, false, false, true)
+B200_STATIC_SERVICE(hmc_static_diag_e, false, false, false)
+B200_STATIC_SERVICE(hmc_static_unit_e_adapt, false, true, true)
+B200_STATIC_SERVICE(hmc_static_unit_e, false, true, false)
+B200_STATIC_SERVICE(hmc_static_dense_e_adapt, true, false, true)
+B200_STATIC_SERVICE(hmc_static_dense_e, true, false, false)
+#undef B200_STATIC_SERVICE
 
 // stan::services::sample::hmc_nuts_unit_e_adapt (services/sample/hmc_nuts_unit_e_adapt.hpp): identity metric, step size adapted
 template <class Model, typename InitContextPtr, typename InitWriter, typename SampleWriter, typename DiagnosticWriter,

@@ -89,6 +89,12 @@ typedef struct b200nuts_config {
   int32_t store_diagnostics; /* default 0; 1: every saved draw also keeps the sample's momentum and the gradient of the potential
                                (what the reference sends to `output diagnostic_file=`: mcmc_writer::write_diagnostic_params,
                                stan/src/stan/services/util/mcmc_writer.hpp:156-176), fetched with b200nuts_fetch_diagnostics */
+  int32_t static_hmc;       /* default 0; 1: static HMC instead of NUTS -- services hmc_static_{diag,unit,dense}_e[_adapt]
+                               (stan/src/stan/services/sample/hmc_static_*.hpp, stan/mcmc/hmc/static/base_static_hmc.hpp): every
+                               transition runs L = max(1, (int)(int_time / stepsize)) leapfrogs and a Metropolis test.  Saved rows
+                               keep seven leading columns: lp__, accept_stat__, stepsize__, L, 1, 0, energy__ (CmdStan's writer
+                               prints stepsize__, int_time__, energy__) */
+  double int_time;          /* default 2 pi (arguments/arg_static.hpp) */
 } b200nuts_config;
 
 typedef struct b200nuts_engine b200nuts_engine;

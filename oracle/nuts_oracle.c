@@ -816,6 +816,35 @@ static double transition(sampler_t* s, double* lp_out) {
   return accept_prob;
 }
 
+/* base_static_hmc::transition, S/mcmc/hmc/static/base_static_hmc.hpp:41-70 */
+static double transition_static(sampler_t* s, int L, double* lp_out) {
+  int D = s->D;
+  s->epsilon = s->nom_epsilon;
+  if (s->epsilon_jitter) s->epsilon *= 1.0 + s->epsilon_jitter * (2.0 * oracle_uniform01(&s->rng) - 1.0);
+  sample_p(s, &s->z);
+  update_potential_gradient(s, &s->z);
+  point_t z_init = pt_alloc(D);
+  pt_copy(&z_init, &s->z);
+  double H0 = hamiltonian(s, &s->z);
+  for (int i = 0; i < L; i++) evolve(s, &s->z, s->epsilon);
+  double h = hamiltonian(s, &s->z);
+  if (isnan(h)) h = INFINITY;
+  double accept_prob = exp(H0 - h);
+  if (accept_prob < 1 && oracle_uniform01(&s->rng) > accept_prob) pt_copy(&s->z, &z_init);
+  accept_prob = accept_prob > 1 ? 1 : accept_prob;
+  s->energy = hamiltonian(s, &s->z);
+  s->depth = L;
+  s->n_leapfrog = 1;
+  s->divergent = 0;
+  *lp_out = -s->z.V;
+  pt_free(&z_init);
+  return accept_prob;
+}
+static int static_L(double T, double nom_eps) { /* base_static_hmc::update_L_ */
+  int L = (int)(T / nom_eps);
+  return L < 1 ? 1 : L;
+}
+
 static void sa_restart(sampler_t* s) { s->sa_counter = 0; s->s_bar = 0; s->x_bar = 0; }
 static void learn_stepsize(sampler_t* s, double adapt_stat) { /* stepsize_adaptation.hpp:55-71 */
   ++s->sa_counter;
@@ -1004,18 +1033,23 @@ int oracle_run_chain(const model_t* model, const oracle_config_t* c, const doubl
   update_potential_gradient(&s, &s.z); /* z.V, z.g at q0 (init_stepsize / transition re-evaluate them anyway) */
   if (adapt_flag && init_stepsize(&s)) { rc = 70; goto done; } /* hmc_nuts_diag_e (no adapt) uses run_sampler: no init_stepsize */
   int row = 0, ncol = 7 + D * (c->diag ? 3 : 1);
+  /* static HMC: set_nominal_stepsize_and_T(stepsize, int_time) fixes L from the stepsize ARGUMENT; init_stepsize above changed
+   * nom_epsilon without touching L (base_hmc::init_stepsize writes nom_epsilon_ directly) */
+  int L = c->static_hmc ? static_L(c->int_time, c->stepsize > 0 ? c->stepsize : 0.1) : 0;
   int total = c->num_warmup + c->num_samples;
   for (int it = 0; it < total; it++) {
     int warm = it < c->num_warmup;
     double lp;
-    double accept = transition(&s, &lp);
+    double accept = c->static_hmc ? transition_static(&s, L, &lp) : transition(&s, &lp);
     double eps_used = s.epsilon;
     if (adapt_flag && warm) {
       learn_stepsize(&s, accept);
+      if (c->static_hmc) L = static_L(c->int_time, s.nom_epsilon); /* adapt_*_static_hmc::transition: update_L_() */
       int upd = learn_variance(&s);
       if (upd < 0) { rc = 70; goto done; }
       if (upd) {
         if (init_stepsize(&s)) { rc = 70; goto done; }
+        if (c->static_hmc) L = static_L(c->int_time, s.nom_epsilon);
         s.mu = log(10 * s.nom_epsilon);
         sa_restart(&s);
       }

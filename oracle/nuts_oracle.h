@@ -38,6 +38,11 @@ typedef struct {
   int diag;    /* 1: rows carry the momentum and the potential's gradient of the sample after the parameters (7 + 3 D columns):
                   what mcmc_writer::write_diagnostic_params sends to the diagnostic writer (services/util/mcmc_writer.hpp:156-176,
                   base_hmc::get_sampler_diagnostics -> ps_point::get_params: q, p, g) */
+  int static_hmc;  /* 1: static HMC (S/mcmc/hmc/static/base_static_hmc.hpp:41-70, adapt_diag_e_static_hmc.hpp:27-50 and its unit_e /
+                      dense_e siblings): L = max(1, (int)(int_time / nominal stepsize)) leapfrogs, Metropolis accept.  Rows keep seven
+                      leading columns: lp__, accept_stat__, stepsize__, L, 1, 0, energy__ (the writer prints stepsize__, int_time__,
+                      energy__) */
+  double int_time;
 } oracle_config_t;
 
 double oracle_lp_grad(const model_t* m, const double* q, double* g);

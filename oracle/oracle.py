@@ -28,7 +28,7 @@ class ConfigT(C.Structure):
                 ("num_thin", C.c_int), ("save_warmup", C.c_int), ("stepsize", C.c_double), ("stepsize_jitter", C.c_double),
                 ("max_depth", C.c_int), ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double),
                 ("t0", C.c_double), ("init_buffer", C.c_uint), ("term_buffer", C.c_uint), ("window", C.c_uint),
-                ("init_radius", C.c_double), ("adapt_engaged", C.c_int), ("unit_e", C.c_int), ("dense_e", C.c_int), ("diag", C.c_int)]
+                ("init_radius", C.c_double), ("adapt_engaged", C.c_int), ("unit_e", C.c_int), ("dense_e", C.c_int), ("diag", C.c_int), ("static_hmc", C.c_int), ("int_time", C.c_double)]
 
 
 _lib = None
@@ -118,7 +118,7 @@ class Model:
 
 DEFAULTS = dict(seed=0, chain_id=1, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=0, stepsize=1.0,
                 stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75,
-                term_buffer=50, window=25, init_radius=2.0, adapt_engaged=1, unit_e=0, dense_e=0, diag=0)
+                term_buffer=50, window=25, init_radius=2.0, adapt_engaged=1, unit_e=0, dense_e=0, diag=0, static_hmc=0, int_time=2 * np.pi)
 
 
 def run_chain(model, q0=None, inv_metric=None, **kw):

@@ -25,7 +25,7 @@ def lib():
 
 def run_chain(kind, D, data, seed=0, chain_id=1, num_warmup=1000, num_samples=1000, num_thin=1, save_warmup=0, stepsize=1.0,
               stepsize_jitter=0.0, max_depth=10, delta=0.8, gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50,
-              window=25, init_radius=2.0, adapt_engaged=1, q0=None, inv_metric=None, unit_e=0, dense_e=0, diag=0):
+              window=25, init_radius=2.0, adapt_engaged=1, q0=None, inv_metric=None, unit_e=0, dense_e=0, diag=0, static_hmc=0, int_time=2 * np.pi):
     yr = np.ascontiguousarray(data.get("y", [0.0]), dtype=np.float64)
     sg = np.ascontiguousarray(data.get("sigma", [1.0]), dtype=np.float64)
     N = len(yr) if kind in (1, 2) else 0
@@ -44,6 +44,6 @@ def run_chain(kind, D, data, seed=0, chain_id=1, num_warmup=1000, num_samples=10
                               C.c_uint(init_buffer), C.c_uint(term_buffer), C.c_uint(window), C.c_double(init_radius),
                               C.c_int(adapt_engaged), None if q0a is None else q0a.ctypes.data_as(C.c_void_p),
                               None if ima is None else ima.ctypes.data_as(C.c_void_p), draws.ctypes.data_as(C.c_void_p),
-                              adapt.ctypes.data_as(C.c_void_p), C.byref(ng), C.c_int(unit_e), C.c_int(dense_e), C.c_int(diag))
+                              adapt.ctypes.data_as(C.c_void_p), C.byref(ng), C.c_int(unit_e), C.c_int(dense_e), C.c_int(diag), C.c_int(static_hmc), C.c_double(int_time))
     im = adapt[1:].copy().reshape(D, D) if dense_e else adapt[1:].copy()
     return dict(draws=draws, stepsize=adapt[0], inv_metric=im, n_grad=ng.value, rc=rc)

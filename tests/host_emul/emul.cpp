@@ -15,7 +15,7 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
                               double stepsize, double jitter, int max_depth, double delta, double gamma, double kappa, double t0,
                               unsigned init_buffer, unsigned term_buffer, unsigned window, double init_radius, int adapt_engaged,
                               const double* q0, const double* inv_metric0, double* draws, double* adapt_out, long long* n_grad,
-                              int unit_e, int dense_e, int diag) {
+                              int unit_e, int dense_e, int diag, int static_hmc, double int_time) {
   ModelData m{};
   m.kind = kind; m.D = D; m.N = N; m.yr = yr; m.sigma = sigma; m.sum_y = sum_y;
   SamplerCfg cfg{};
@@ -27,6 +27,8 @@ extern "C" int emul_run_chain(int kind, int D, int N, const double* yr, const do
   cfg.kappa = kappa > 0 ? kappa : 0.75; cfg.t0 = t0 > 0 ? t0 : 10; cfg.init_radius = init_radius;
   cfg.dense = dense_e;
   cfg.diag = diag;
+  cfg.static_hmc = static_hmc;
+  cfg.int_time = int_time;
   resolve_window(&cfg, (adapt_engaged && !unit_e) ? num_warmup : 0, init_buffer, term_buffer, window);
   cfg.ncol = 7 + D * (diag ? 3 : 1);
   cfg.rows_per_chain = (save_warmup ? (num_warmup + num_thin - 1) / num_thin : 0) + (num_samples + num_thin - 1) / num_thin;

@@ -62,6 +62,7 @@ void b200nuts_default_config(b200nuts_config* c) {
   c->num_chains = 1; c->init_chain_id = 1; c->init_radius = 2.0; c->num_warmup = 1000; c->num_samples = 1000; c->num_thin = 1;
   c->stepsize = 1.0; c->max_depth = 10; c->delta = 0.8; c->gamma = 0.05; c->kappa = 0.75; c->t0 = 10.0;
   c->init_buffer = 75; c->term_buffer = 50; c->window = 25; c->adapt_engaged = 1; c->store_draws = 1; c->row_shards = 1;
+  c->int_time = 6.28318530717958647692;
 }
 const char* b200nuts_last_error(const b200nuts_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
 int b200nuts_create(const b200nuts_config* cfg, b200nuts_engine** out) {
@@ -139,6 +140,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
     oc.init_buffer = c.init_buffer; oc.term_buffer = c.term_buffer; oc.window = c.window;
     oc.init_radius = c.init_radius; oc.adapt_engaged = c.adapt_engaged; oc.unit_e = c.metric == 1; oc.dense_e = c.metric == 2;
     oc.diag = c.store_diagnostics;
+    oc.static_hmc = c.static_hmc;
+    oc.int_time = c.int_time;
     e->rc[k] = oracle_run_chain(&e->m, &oc, e->q0.empty() ? nullptr : e->q0.data() + (size_t)k * D,
                                 e->im.empty() ? nullptr : e->im.data() + (size_t)k * md, e->draws[k].data(), e->adapt[k].data(), nullptr,
                                 &e->ngrad[k]);

@@ -50,8 +50,11 @@ def _random_args(rng, dj):
                 a.append(f"{name}={rng.choice(vals)}")
     if rng.uniform() < 0.7:
         a.append("algorithm=hmc")
-        if rng.uniform() < 0.6:
+        u = rng.uniform()
+        if u < 0.5:
             a += ["engine=nuts", f"max_depth={int(rng.integers(1, 12))}"]
+        elif u < 0.7:
+            a += ["engine=static", f"int_time={rng.choice([0.4, 2.5, 6.28319])}"]
         if rng.uniform() < 0.5:
             a.append(f"metric={rng.choice(['diag_e', 'unit_e', 'dense_e'])}")
         if rng.uniform() < 0.4:
@@ -72,7 +75,7 @@ def _random_args(rng, dj):
         a.append(f"sig_figs={int(rng.choice([-1, 4, 12]))}")
     if rng.uniform() < 0.3:
         a.append(f"save_cmdstan_config={int(rng.integers(0, 2))}")
-    if rng.uniform() < 0.3:
+    if rng.uniform() < 0.3 and "engine=static" not in a:   # the B200 engine keeps momenta for the NUTS engine only
         a.append("diagnostic_file=diag.csv")
     return a
 

@@ -370,3 +370,21 @@ def test_fp64_fma_peak_is_measurable():
     import cmdstan_b200 as B
     v = B.measure_fp64_fma_peak(0)
     assert 5.0 < v < 90.0, v
+
+
+@pytest.mark.parametrize("name,engine,okw", [("bernoulli", "auto", {}), ("eight_schools_nc", "auto", dict(dense_e=1)), ("eight_schools_nc", "lockstep", {}),
+                                              ("std_normal", "lockstep", dict(unit_e=1))])
+def test_static_hmc_matched_stream_vs_oracle(name, engine, okw):
+    """static HMC on the device (hmc_static_*: base_static_hmc.hpp:41-70) against the oracle's (pinned to the reference's
+    engine=static output digit for digit in tests/test_oracle.py): accept/reject pattern, step sizes and draws of the first
+    transitions; rows carry lp__, accept_stat__, stepsize__, L, 1, 0, energy__."""
+    data = cases.SMALL[name]
+    metric = "dense_e" if okw.get("dense_e") else ("unit_e" if okw.get("unit_e") else "diag_e")
+    d, eps, im = _run(name, data, C=3, engine=engine, metric=metric, static_hmc=True, int_time=1.5, stepsize_jitter=0.2)
+    m = O.Model(name, data)
+    K = 12 if name == "eight_schools_nc" else 40
+    for c in range(3):
+        r = O.run_chain(m, seed=1234, chain_id=1 + c, num_warmup=150, num_samples=100, save_warmup=1, static_hmc=1, int_time=1.5, stepsize_jitter=0.2, **okw)
+        assert np.array_equal(d[c, :K, 3:6], r["draws"][:K, 3:6])          # L, 1, 0
+        assert _rel(d[c, :K], r["draws"][:K], floor=1e-6) < 1e-8
+        assert (d[c, :, 4] == 1).all() and (d[c, :, 5] == 0).all() and (d[c, :, 3] >= 1).all()

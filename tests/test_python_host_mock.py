@@ -94,3 +94,17 @@ def test_error_codes_surface(B):
     assert rc == B.USAGE and res is None
     rc, res = B.hmc_nuts_diag_e_adapt("bernoulli", cases.BERNOULLI, init=np.array([[np.inf]]), num_warmup=20, num_samples=5)
     assert rc == B.CONFIG and res is None   # Initialization failed.
+
+
+def test_static_hmc_services(B):
+    """hmc_static_{diag,unit,dense}_e[_adapt] mirrors over the mock: columns lp__, accept_stat__, stepsize__, int_time__, energy__
+    and draws equal to the oracle's static HMC (which is pinned to the reference's engine=static output)."""
+    name, data = "eight_schools_nc", cases.EIGHT_SCHOOLS
+    m = O.Model(name, data)
+    for fn, okw in ((B.hmc_static_diag_e_adapt, {}), (B.hmc_static_unit_e_adapt, dict(unit_e=1)), (B.hmc_static_dense_e, dict(dense_e=1, adapt_engaged=0)),
+                    (B.hmc_static_diag_e, dict(adapt_engaged=0))):
+        rc, res = fn(name, data, num_chains=2, random_seed=3, num_warmup=60, num_samples=20, save_warmup=True, int_time=1.7, stepsize=0.3)
+        assert rc == 0 and res["columns"][:5] == B.STATIC_SAMPLER_COLUMNS and res["columns"][5] == "mu"
+        r = O.run_chain(m, seed=3, chain_id=2, num_warmup=60, num_samples=20, save_warmup=1, static_hmc=1, int_time=1.7, stepsize=0.3, **okw)
+        want = np.concatenate([r["draws"][:, :3], np.full((80, 1), 1.7), r["draws"][:, 6:7], m.write_array(r["draws"][:, 7:])], axis=1)
+        assert np.array_equal(res["draws"][1], want)

@@ -29,6 +29,10 @@ OPTS = [
     dict(seed=19, chain_id=2, num_warmup=150, num_samples=60, save_warmup=1, num_thin=2, diag=1),  # diagnostic rows: q, p, g of every saved draw
     dict(seed=20, chain_id=1, num_warmup=60, num_samples=40, save_warmup=1, diag=1, dense_e=1),
     dict(seed=21, chain_id=3, num_warmup=0, num_samples=50, adapt_engaged=0, stepsize=0.4, max_depth=3, diag=1),
+    dict(seed=22, chain_id=1, num_warmup=150, num_samples=60, save_warmup=1, static_hmc=1, int_time=3.5, stepsize_jitter=0.2),   # hmc_static_diag_e_adapt
+    dict(seed=23, chain_id=2, num_warmup=20, num_samples=60, static_hmc=1, int_time=1.5, adapt_engaged=0, stepsize=0.3),          # hmc_static_diag_e
+    dict(seed=24, chain_id=1, num_warmup=150, num_samples=30, static_hmc=1, int_time=2.0, dense_e=1, save_warmup=1),              # hmc_static_dense_e_adapt
+    dict(seed=25, chain_id=4, num_warmup=100, num_samples=30, static_hmc=1, int_time=0.05, unit_e=1, num_thin=2),                  # L = 1; hmc_static_unit_e_adapt
 ]
 
 
@@ -122,6 +126,9 @@ def _random_config(rng):
         kw["dense_e"] = 1
     if rng.uniform() < 0.3:
         kw["diag"] = 1
+    elif rng.uniform() < 0.3:
+        kw["static_hmc"] = 1
+        kw["int_time"] = float(rng.choice([0.3, 2.0, 6.28]))
     return kw
 
 
