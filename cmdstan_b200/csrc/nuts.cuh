@@ -483,6 +483,30 @@ B200_DEV_CALL int learn_variance(const ChainView& c, const SamplerCfg& cfg, int 
   return 0;
 }
 
+// util::initialize with a user context (initialize.hpp:93-101), out of line: it runs once per chain and would only bloat the
+// state machine.  The random_var_context is constructed (and draws its D uniforms) on every try, also when every value then
+// comes from the user's context.  A NaN in the user's vector stands for "not given": the reference then keeps the random
+// context's CONSTRAINED value and transform_inits maps it back, so the value is the round trip of the uniform draw through the
+// parameter's transform (payload code: 0 none, 1 lower bound 0, 2 unit interval).
+B200_DEV_CALL void init_from_user(const ChainView& c, const SamplerCfg& cfg, int lane) {
+  ChainS* s = c.s;
+  const int D = cfg.D;
+  if (cfg.init_radius != 0.0) warp_fill(s->rng, lane, c.q, D, 1, nullptr, cfg.init_radius);
+  double partial = 0.0;
+  B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
+    const double user = c.user_q0[i];
+    if (user == user) {
+      c.q[i] = user;
+    } else {
+      const double u = cfg.init_radius != 0.0 ? c.q[i] : 0.0;
+      const int code = init_nan_code(user);
+      c.q[i] = code == 1 ? dev_log(dev_exp(u)) : (code == 2 ? init_logit(dev_inv_logit(u)) : u);
+      partial = 1.0;
+    }
+  }
+  s->init_partial = warp_sum(partial) > 0.0 ? 1 : 0;
+}
+
 // Resume the chain: consumes the gradient stage's result for z.q when the chain was waiting for one, then runs
 // until the next gradient is wanted (ADV_NEED_GRAD) or the chain has nothing left to do (ADV_IDLE).
 B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
@@ -502,24 +526,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
       }
       case ST_INIT_DRAW: {  // util::initialize (initialize.hpp:87-117)
         if (c.user_q0) {
-          // initialize.hpp:93-101: the random_var_context is constructed (and draws its D uniforms) on every try, also when
-          // every value then comes from the user's context.  A NaN in the user's vector stands for "not given": the reference
-          // then keeps the random context's CONSTRAINED value and transform_inits maps it back, so the value is the round trip
-          // of the uniform draw through the parameter's transform (payload code: 0 none, 1 lower bound 0, 2 unit interval).
-          if (cfg.init_radius != 0.0) warp_fill(s->rng, lane, c.q, D, 1, nullptr, cfg.init_radius);
-          double partial = 0.0;
-          B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) {
-            const double user = c.user_q0[i];
-            if (user == user) {
-              c.q[i] = user;
-            } else {
-              const double u = cfg.init_radius != 0.0 ? c.q[i] : 0.0;
-              const int code = init_nan_code(user);
-              c.q[i] = code == 1 ? dev_log(dev_exp(u)) : (code == 2 ? init_logit(dev_inv_logit(u)) : u);
-              partial = 1.0;
-            }
-          }
-          s->init_partial = warp_sum(partial) > 0.0 ? 1 : 0;
+          init_from_user(c, cfg, lane);
         } else if (cfg.init_radius == 0.0) {
           B200_VEC_LOOP for (int i = lane; i < D; i += kWarp) c.q[i] = 0.0;
         } else {
@@ -827,6 +834,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         s->state = persist ? ST_DOUBLING_BEGIN : ST_TRANS_END;
         break;
       }
+#if B200_WITH_DENSE  // static HMC lives only in the full-featured kernels (dense.cu)
       case ST_STATIC_STEP_BEGIN: {
         if (s->st_i >= s->st_L) {
           s->state = ST_STATIC_END;
@@ -868,6 +876,7 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
         s->state = ST_TRANS_END;
         break;
       }
+#endif
       case ST_TRANS_END: {  // base_nuts.hpp:194-203, generate_transitions.hpp:70-75, adapt_diag_e_nuts.hpp:28-41
         const double accept_stat = s->sum_metro / (double)s->n_leapfrog;
         const bool warm = s->iter < cfg.num_warmup;
