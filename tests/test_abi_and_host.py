@@ -95,3 +95,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("# oracle", "").lower() or f == "analyze.py" and "oracle" not in txt.lower(), f
+
+
+def test_default_chain_kernels_stay_small():
+    """The fused chain kernels of the small models are instruction-cache bound: carrying the dense-metric branches cost c2 15 %, the
+    diagnostics bookkeeping 7 % (profiles r01i, r01l).  Optional features are compiled only into csrc/dense.cu's kernels; this
+    guards the text size of the default ones (83.8 KB in the build that measured 1.04e7 ESS/s on c2)."""
+    import shutil
+    import subprocess
+    import cmdstan_b200 as B
+    from cmdstan_b200 import _build
+    B.load_library()
+    obj = os.path.join(_build.CSRC, "engine.o")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(obj) or not os.path.exists(tool):
+        pytest.skip("engine.o / cuobjdump not available")
+    out = subprocess.run([tool, "-elf", obj], capture_output=True, text=True).stdout
+    sizes = {}
+    for ln in out.splitlines():
+        p = ln.split()
+        if len(p) >= 4 and p[-1].startswith(".text._ZN4b200") and ("fused_chain_kernel" in p[-1] or "advance_kernel" in p[-1]):
+            sizes[p[-1]] = int(p[2], 16)
+    fused = [v for k, v in sizes.items() if "fused_chain_kernelILb1ELi0" in k]
+    assert fused and fused[0] <= 90 * 1024, sizes
