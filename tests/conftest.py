@@ -14,11 +14,24 @@ def pytest_configure(config):
 
 
 def _have_gpu():
+    if os.environ.get("B200_TESTS_ASSUME_GPU"):   # test development only: run the CLI-level "gpu" tests over the CPU mock of the ABI
+        return True
     try:
         import torch
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+if os.environ.get("B200_TESTS_ASSUME_GPU"):   # test development only: the Python host loads the CPU mock of the ABI as well
+    try:
+        from cmdstan_b200 import _build as _b
+        _mock = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul", "mock", "libb200nuts.so")
+        if os.path.exists(_mock):
+            _b.LIB = _mock
+            _b.needs_build = lambda: False
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
