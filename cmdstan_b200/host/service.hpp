@@ -570,11 +570,29 @@ int hmc_nuts_dense_e(Model& model, size_t num_chains, const std::vector<InitCont
                                  term_buffer, window, interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, ADAPT);   \
   }
 B200_STATIC_SERVICE(hmc_static_diag_e_adapt, false, false, true)
-B200_STATIC_SERVICE(hmc_static_diag_e, false, false, false)
 B200_STATIC_SERVICE(hmc_static_unit_e_adapt, false, true, true)
-B200_STATIC_SERVICE(hmc_static_unit_e, false, true, false)
 B200_STATIC_SERVICE(hmc_static_dense_e_adapt, true, false, true)
-B200_STATIC_SERVICE(hmc_static_dense_e, true, false, false)
+// the non-adaptive services take no adaptation parameters (services/sample/hmc_static_diag_e.hpp:62-70)
+#define B200_STATIC_SERVICE_FIXED(NAME, DENSE, UNIT)                                                                                         \
+  template <class Model, typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter, typename DiagnosticWriter> \
+  int NAME(Model& model, size_t num_chains, const std::vector<InitContextPtr>& init, const std::vector<InitInvContextPtr>& init_inv_metric,   \
+           unsigned int random_seed, unsigned int init_chain_id, double init_radius, int num_warmup, int num_samples, int num_thin,         \
+           bool save_warmup, int refresh, double stepsize, double stepsize_jitter, double int_time, callbacks::interrupt& interrupt,         \
+           callbacks::logger& logger, std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,                       \
+           std::vector<DiagnosticWriter>& diagnostic_writer, device_options opt = device_options()) {                                       \
+    opt.static_hmc = true;                                                                                                                   \
+    opt.int_time = int_time;                                                                                                                 \
+    opt.dense_e = DENSE;                                                                                                                     \
+    opt.unit_e = UNIT;                                                                                                                       \
+    std::vector<json_metric_writer> none;                                                                                                    \
+    return hmc_nuts_diag_e_adapt(model, num_chains, init, init_inv_metric, random_seed, init_chain_id, init_radius, num_warmup, num_samples, \
+                                 num_thin, save_warmup, refresh, stepsize, stepsize_jitter, 10, 0.8, 0.05, 0.75, 10.0, 75u, 50u, 25u,        \
+                                 interrupt, logger, init_writer, sample_writer, diagnostic_writer, none, opt, false);                        \
+  }
+B200_STATIC_SERVICE_FIXED(hmc_static_diag_e, false, false)
+B200_STATIC_SERVICE_FIXED(hmc_static_unit_e, false, true)
+B200_STATIC_SERVICE_FIXED(hmc_static_dense_e, true, false)
+#undef B200_STATIC_SERVICE_FIXED
 #undef B200_STATIC_SERVICE
 
 // stan::services::sample::hmc_nuts_unit_e_adapt (services/sample/hmc_nuts_unit_e_adapt.hpp): identity metric, step size adapted

@@ -118,3 +118,13 @@ def test_default_chain_kernels_stay_small():
             sizes[p[-1]] = int(p[2], 16)
     fused = [v for k, v in sizes.items() if "fused_chain_kernelILb1ELi0" in k]
     assert fused and fused[0] <= 90 * 1024, sizes
+
+
+def test_all_service_mirrors_compile():
+    """The front end reaches the twelve service mirrors through two of them; the other ten are templates nobody instantiates.
+    tests/host_emul/service_instantiation.cpp calls each with the front end's writer types and the reference's argument
+    order (services/sample/hmc_{nuts,static}_{diag,unit,dense}_e[_adapt].hpp) -- a syntax-only compile keeps them honest."""
+    import subprocess
+    src = os.path.join(HERE, "host_emul", "service_instantiation.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
