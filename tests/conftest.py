@@ -34,7 +34,21 @@ if os.environ.get("B200_TESTS_ASSUME_GPU"):   # test development only: the Pytho
         pass
 
 
+# GPU tests written after the last hardware session of the round (profiles/README.md, "validated on hardware"): they run
+# last, so that a `-x` run reports the hardware-validated suite before it reaches them.  Empty this list once they have run.
+NOT_YET_RUN_ON_HARDWARE = (
+    "test_static_hmc_matched_stream_vs_oracle",
+    "test_fp64_fma_peak_is_measurable",
+    "test_cli_log_prob_method_vs_reference",
+    "test_cli_diagnostic_file_vs_reference",
+    "test_diagnostic_rows_vs_oracle",   # its content ran on hardware as tools/gpu_quickcheck.py (profiles/r01l_quickcheck.txt), the test itself did not
+)
+
+
 def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if it.name.split("[")[0] in NOT_YET_RUN_ON_HARDWARE]
+    if late:
+        items[:] = [it for it in items if it not in late] + late
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
