@@ -246,7 +246,7 @@ def main():
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries are missing (built from /root/reference by oracle/build_ref.sh)"}))
             return
-        line = {"impl": "reference", "metric": "min_bulk_ESS_per_sec", "value": r["value"], "unit": "ESS/s", "n_gpus": 0, "steps": K, "warmup": W,
+        line = {"impl": "reference", "metric": "min_bulk_ESS_per_sec", "value": r["value"], "unit": "ESS/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * r["sampling_s"] / max(1, r["draws"] // max(1, (4 if args.workload == "c1" else cores))),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_common,
                 "grad_evals_per_sec": r["grad_evals_per_s"],
