@@ -33,11 +33,19 @@ namespace {
 constexpr int TR = 64, TC = 64, NT = 256;
 constexpr int DS_LD = TC + 4;
 
+#ifdef B200_SIMT_EMUL  // CPU test-suite only (tests/host_emul/simt): the kernels of this file run on host threads
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) { simt::dmma(d0, d1, a, b); }
+#define B200_DYN_SMEM(name) double* name = reinterpret_cast<double*>(simt::dyn_smem())
+#define B200_LAUNCH(kernel, grid, block, smem_bytes, stream, arg) simt::launch(grid, block, smem_bytes, [&] { kernel(arg); })
+#else
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
+#define B200_DYN_SMEM(name) extern __shared__ __align__(128) double name[]
+#define B200_LAUNCH(kernel, grid, block, smem_bytes, stream, arg) kernel<<<grid, block, smem_bytes, stream>>>(arg)
+#endif
 
 __host__ __device__ inline int xs_ld_for(int Dk) { return Dk + 4; }  // Dk % 8 == 0  =>  ld % 8 == 4
 
@@ -54,6 +62,16 @@ struct GlmTcArgs {
 };
 
 // ---- TMA (1-D bulk copy) + mbarrier plumbing ------------------------------------------------------------------------
+#ifdef B200_SIMT_EMUL
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { simt::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { simt::mbar_expect_tx_arrive(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) { simt::mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  simt::tma_load_1d(smem_dst, gsrc, bytes, bar);
+}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void fence_mbarrier_init() {}
+#else
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -80,6 +98,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
 
 // phase A of one warp: acc[4 row blocks][NB column blocks] += X tile rows . q columns   (NB = column blocks in use)
 template <int NB>
@@ -120,7 +140,7 @@ __device__ __forceinline__ void phase_b(double (&gacc)[MB][2][2], const double* 
 // MB: 8-row blocks of G per warp half (Dk <= 16*MB)
 template <int LINK, int MB>
 __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
-  extern __shared__ __align__(128) double smem[];
+  B200_DYN_SMEM(smem);
   const int Dk = a.Dk;
   const int xs_ld = xs_ld_for(Dk);
   double* Bs = smem;                               // [TC][xs_ld]     chain-major copy of the q rows of the chain tile
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   // columns [ldq, Dk) of the B tile are never written by the bulk copies: zero them once
   for (int e = tid; e < TC * (Dk - a.ldq); e += NT) {
@@ -357,7 +377,7 @@ __device__ __forceinline__ bool warp_arrive_is_last(int* cnt, int lane) {
 
 template <int LINK, int MB>
 __global__ void __launch_bounds__(NT3, 1) glm_dmma3_kernel(const GlmTcArgs a) {
-  extern __shared__ __align__(128) double smem[];
+  B200_DYN_SMEM(smem);
   const int Dk = a.Dk;
   const int xs_ld = xs_ld_for(Dk);
   double* Bs = smem;                                // [TC][xs_ld]
@@ -388,7 +408,7 @@ __global__ void __launch_bounds__(NT3, 1) glm_dmma3_kernel(const GlmTcArgs a) {
     mbar_init(&fullX[1], 1);
     mbar_init(fullB, 1);
     doneX[0] = doneX[1] = doneB[0] = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   for (int e = tid; e < TC * (Dk - a.ldq); e += NT3) {  // columns [ldq, Dk) of the q tile are never written by the bulk copies
     const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
@@ -563,7 +583,7 @@ __global__ void __launch_bounds__(NT3, 1) glm_dmma3_kernel(const GlmTcArgs a) {
 // =====================================================================================================================
 template <int LINK, int MB, int NST>
 __global__ void __launch_bounds__(NT3, 1) glm_dmma4_kernel(const GlmTcArgs a) {
-  extern __shared__ __align__(128) double smem[];
+  B200_DYN_SMEM(smem);
   const int Dk = a.Dk;
   const int xs_ld = xs_ld_for(Dk);
   double* Bs = smem;                                  // [TC][xs_ld]
@@ -595,7 +615,7 @@ __global__ void __launch_bounds__(NT3, 1) glm_dmma4_kernel(const GlmTcArgs a) {
     }
     mbar_init(fullB, 1);
     doneB[0] = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   for (int e = tid; e < TC * (Dk - a.ldq); e += NT3) {
     const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
@@ -803,11 +823,11 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
     if (nst == 3) {                                                                                \
       auto k = glm_dmma4_kernel<LINK, MB, 3>;                                                      \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);            \
-      k<<<ws.P, NT3, smem4, stream>>>(a);                                                          \
+      B200_LAUNCH(k, ws.P, NT3, smem4, stream, a);                                                          \
     } else {                                                                                       \
       auto k = glm_dmma4_kernel<LINK, MB, 2>;                                                      \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);            \
-      k<<<ws.P, NT3, smem4, stream>>>(a);                                                          \
+      B200_LAUNCH(k, ws.P, NT3, smem4, stream, a);                                                          \
     }                                                                                              \
   }
     if (a.Dk <= 16) {
@@ -828,7 +848,7 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
   {                                                                                           \
     auto k = glm_dmma3_kernel<LINK, MB>;                                                      \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);         \
-    k<<<ws.P, NT3, smem3, stream>>>(a);                                                       \
+    B200_LAUNCH(k, ws.P, NT3, smem3, stream, a);                                                       \
   }
     if (a.Dk <= 16) {
       if (logistic) LAUNCH3(0, 2) else LAUNCH3(1, 2)
@@ -847,7 +867,7 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
   {                                                                                          \
     auto k = glm_dmma_kernel<LINK, MB>;                                                      \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-    k<<<ws.P, NT, smem, stream>>>(a);                                                        \
+    B200_LAUNCH(k, ws.P, NT, smem, stream, a);                                                         \
   }
   if (a.Dk <= 16) {
     if (logistic) LAUNCH(0, 1) else LAUNCH(1, 1)

@@ -1,0 +1,274 @@
+// TEST-ONLY stand-in for <cuda_runtime.h>: runs __global__ kernels of cmdstan_b200/csrc on HOST THREADS so that the CPU
+// test-suite can execute the data-heavy gradient kernels (DMMA fragments, TMA + mbarrier pipelines, warp shuffles, the
+// last-arriver refill protocol) without a GPU, and so that ThreadSanitizer can look for shared-memory races in them.
+//
+// Model: one std::thread per CUDA thread; the CTAs of a grid run one after another (so `__shared__` can be `static`).
+//   __syncthreads / __syncwarp   -> mutex + condition-variable barriers (block / warp)
+//   __shfl_sync, __shfl_xor_sync -> post to a per-warp slot, barrier, read the source lane's slot (two slots alternate, one
+//                                   barrier per collective)
+//   mma.sync.m8n8k4.f64          -> the PTX ISA fragment layout: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+//                                   d0,d1 = D[lane>>2][2 (lane&3) + {0,1}];  D = A B + C as an FMA chain over k
+//   mbarrier                     -> pending-arrival count + transaction-byte count + phase bit per barrier object
+//   cp.async.bulk (1-D TMA)      -> memcpy by the issuing thread, then complete_tx on the barrier
+// Every blocking wait has a time-out that aborts with a message: a protocol deadlock fails the test instead of hanging it.
+// The kernel sources opt in with B200_SIMT_EMUL (a handful of #ifdefs around inline PTX and <<<>>>).  Never shipped.
+#pragma once
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __restrict__
+#define __align__(n) alignas(n)
+#define __shared__ static
+
+using std::isfinite;
+using std::isnan;
+
+typedef void* cudaStream_t;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F>
+inline int cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+namespace simt {
+
+struct Dim3 { unsigned x = 1, y = 1, z = 1; };
+
+[[noreturn]] inline void die(const char* what) {
+  std::fprintf(stderr, "simt: %s\n", what);
+  std::fflush(stderr);
+  std::_Exit(86);
+}
+
+constexpr int kWaitSeconds = 120;
+
+struct Barrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, count = 0;
+  unsigned gen = 0;
+  void wait(const char* what) {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned g = gen;
+    if (++count == n) {
+      count = 0;
+      gen++;
+      cv.notify_all();
+    } else if (!cv.wait_for(lk, std::chrono::seconds(kWaitSeconds), [&] { return gen != g; })) {
+      die(what);
+    }
+  }
+};
+
+struct Warp {
+  Barrier bar;
+  uint64_t slot[2][32][2];
+};
+
+struct MBar {
+  std::mutex m;
+  std::condition_variable cv;
+  int init_count = 0, pending = 0;
+  long long tx = 0;
+  unsigned phase = 0;
+  void maybe_complete() {
+    if (pending == 0 && tx == 0) {
+      phase ^= 1u;
+      pending = init_count;
+      cv.notify_all();
+    }
+  }
+};
+
+struct Block {
+  Barrier bar;
+  std::vector<std::unique_ptr<Warp>> warps;
+  std::vector<unsigned char> dyn;
+  std::mutex mbar_m;
+  std::map<const void*, std::unique_ptr<MBar>> mbars;
+  MBar& mbar(const void* p, bool create) {
+    std::lock_guard<std::mutex> lk(mbar_m);
+    auto it = mbars.find(p);
+    if (it == mbars.end()) {
+      if (!create) die("mbarrier used before mbarrier.init");
+      it = mbars.emplace(p, std::make_unique<MBar>()).first;
+    }
+    return *it->second;
+  }
+};
+
+struct ThreadCtx {
+  Block* blk = nullptr;
+  Warp* warp = nullptr;
+  int lane = 0;
+  unsigned op = 0;
+};
+inline thread_local ThreadCtx tc;
+
+inline void* dyn_smem() { return tc.blk->dyn.data() + ((128 - (reinterpret_cast<uintptr_t>(tc.blk->dyn.data()) & 127)) & 127); }
+
+}  // namespace simt
+
+inline thread_local simt::Dim3 threadIdx, blockIdx;
+inline simt::Dim3 blockDim, gridDim;
+
+namespace simt {
+
+// run `body` as grid x block CUDA threads (1-D), one CTA at a time
+inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, const std::function<void()>& body) {
+  if (block % 32) die("block size must be a multiple of 32");
+  blockDim.x = block;
+  gridDim.x = grid;
+  for (unsigned b = 0; b < grid; b++) {
+    Block blk;
+    blk.bar.n = (int)block;
+    blk.dyn.assign(dyn_bytes + 256, 0xCD);  // poisoned: reading never-written shared memory shows up as garbage
+    for (unsigned w = 0; w < block / 32; w++) {
+      blk.warps.emplace_back(new Warp());
+      blk.warps.back()->bar.n = 32;
+    }
+    std::vector<std::thread> ts;
+    ts.reserve(block);
+    for (unsigned t = 0; t < block; t++)
+      ts.emplace_back([&, t] {
+        threadIdx.x = t;
+        blockIdx.x = b;
+        tc.blk = &blk;
+        tc.warp = blk.warps[t / 32].get();
+        tc.lane = (int)(t % 32);
+        tc.op = 0;
+        body();
+      });
+    for (auto& th : ts) th.join();
+  }
+}
+
+template <class T>
+inline uint64_t bits(T v) {
+  static_assert(sizeof(T) <= 8, "");
+  uint64_t b = 0;
+  std::memcpy(&b, &v, sizeof(T));
+  return b;
+}
+template <class T>
+inline T unbits(uint64_t b) {
+  T v;
+  std::memcpy(&v, &b, sizeof(T));
+  return v;
+}
+
+// every lane posts (w0, w1); returns the slot array of the warp for this collective
+inline const uint64_t (*exchange(uint64_t w0, uint64_t w1))[2] {
+  Warp* w = tc.warp;
+  const unsigned s = tc.op++ & 1u;
+  w->slot[s][tc.lane][0] = w0;
+  w->slot[s][tc.lane][1] = w1;
+  w->bar.wait("warp collective: not all 32 lanes arrived (divergent collective or deadlock)");
+  return w->slot[s];
+}
+
+}  // namespace simt
+
+inline void __syncthreads() { simt::tc.blk->bar.wait("__syncthreads: not all threads arrived"); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::tc.warp->bar.wait("__syncwarp: not all lanes arrived"); }
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+#ifdef SIMT_MUTANT_EARLY_REFILL  // deliberately broken build (tests of the tests): the second arriver of eight is told it is the last
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST) + 6; }
+#else
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+#endif
+
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) {
+  auto s = simt::exchange(simt::bits(v), 0);
+  return simt::unbits<T>(s[src & 31][0]);
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int mask) {
+  auto s = simt::exchange(simt::bits(v), 0);
+  return simt::unbits<T>(s[(simt::tc.lane ^ mask) & 31][0]);
+}
+template <class T>
+inline T __ldcg(const T* p) { return *p; }
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+
+inline int __double2loint(double x) { return (int)(uint32_t)(simt::bits(x) & 0xffffffffu); }
+inline int __double2hiint(double x) { return (int)(uint32_t)(simt::bits(x) >> 32); }
+inline double __hiloint2double(int hi, int lo) { return simt::unbits<double>(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo); }
+
+namespace simt {
+
+// mma.sync.aligned.m8n8k4.row.col.f64
+inline void dmma(double& d0, double& d1, double a, double b) {
+  auto s = exchange(bits(a), bits(b));
+  const int lane = tc.lane, i = lane >> 2, j0 = 2 * (lane & 3);
+  double r[2] = {d0, d1};
+  for (int jj = 0; jj < 2; jj++) {
+    const int j = j0 + jj;
+    for (int k = 0; k < 4; k++) r[jj] = std::fma(unbits<double>(s[i * 4 + k][0]), unbits<double>(s[j * 4 + k][1]), r[jj]);
+  }
+  d0 = r[0];
+  d1 = r[1];
+}
+
+inline void mbar_init(const void* bar, unsigned count) {
+  MBar& m = tc.blk->mbar(bar, true);
+  std::lock_guard<std::mutex> lk(m.m);
+  m.init_count = m.pending = (int)count;
+  m.tx = 0;
+  m.phase = 0;
+}
+inline void mbar_expect_tx_arrive(const void* bar, unsigned bytes) {
+  MBar& m = tc.blk->mbar(bar, false);
+  std::lock_guard<std::mutex> lk(m.m);
+  if (m.pending <= 0) die("mbarrier: more arrivals than the barrier was initialised for");
+  m.tx += bytes;
+  m.pending--;
+  m.maybe_complete();
+}
+inline void mbar_complete_tx(const void* bar, unsigned bytes) {
+  MBar& m = tc.blk->mbar(bar, false);
+  std::lock_guard<std::mutex> lk(m.m);
+  m.tx -= bytes;
+  m.maybe_complete();
+}
+inline void mbar_wait(const void* bar, unsigned parity) {
+#ifdef SIMT_MUTANT_SKIP_MBAR_WAIT  // deliberately broken build (tests of the tests): consumers do not wait for the bulk copies
+  (void)bar;
+  (void)parity;
+  return;
+#endif
+  MBar& m = tc.blk->mbar(bar, false);
+  std::unique_lock<std::mutex> lk(m.m);
+  if (!m.cv.wait_for(lk, std::chrono::seconds(kWaitSeconds), [&] { return (m.phase & 1u) != (parity & 1u); }))
+    die("mbarrier.try_wait never succeeded (deadlock in the pipeline protocol)");
+}
+inline void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, const void* bar) {
+  if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(smem_dst) & 15u) || (reinterpret_cast<uintptr_t>(gsrc) & 15u))
+    die("cp.async.bulk: size and both addresses must be multiples of 16 bytes");
+  std::memcpy(smem_dst, gsrc, bytes);
+  mbar_complete_tx(bar, bytes);
+}
+
+}  // namespace simt

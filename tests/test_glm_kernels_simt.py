@@ -1,0 +1,168 @@
+"""CPU suite: the FP64 tensor-core GLM gradient kernels (cmdstan_b200/csrc/glm_dmma.cu) executed on host threads by the SIMT
+stand-in under tests/host_emul/simt (DMMA fragment layouts of the PTX ISA, TMA bulk copies + mbarriers, warp shuffles, the
+last-arriver refill protocol), through the product's own launcher.
+
+ * v2 (block-synchronous, the default) and v3 (warp-asynchronous) have run on hardware (profiles/README.md): here they are
+   the controls that show the rig reproduces the device semantics;
+ * v4 (three X stages, register-shuffle derivative exchange) has NOT run on hardware yet: this is its functional validation;
+ * the same sources built with -fsanitize=thread look for shared-memory races in the pipelines, and two deliberately broken
+   builds (consumers that do not wait for the bulk copies; a refill issued before the last reader is done) show the race
+   detector and the protocol checks have teeth.
+
+Reference values: numpy restatement of bernoulli_logit_glm_lpmf.hpp:121-142 / poisson_log_glm_lpmf.hpp:117-132 (the sums the
+oracle's GLM log-density takes); tolerance 1e-12 relative (gate of the GPU parity tests: 1e-10)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMUL = os.path.join(HERE, "host_emul")
+SRC = os.path.join(EMUL, "glm_simt.cpp")
+DEPS = [SRC, os.path.join(EMUL, "simt", "cuda_runtime.h")] + [os.path.join(ROOT, "cmdstan_b200", "csrc", f) for f in ("glm_dmma.cu", "fastmath.cuh", "kernels.h", "models.cuh", "warp.cuh")]
+CXX = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-Wno-tsan", "-I", os.path.join(EMUL, "simt")]
+
+
+def _stale(out):
+    return not os.path.exists(out) or max(os.path.getmtime(d) for d in DEPS) > os.path.getmtime(out)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    so = os.path.join(EMUL, "libglm_simt.so")
+    if _stale(so):
+        subprocess.check_call(CXX + ["-fPIC", "-shared", SRC, "-o", so])
+    L = C.CDLL(so)
+    L.glm_simt_run.argtypes = [C.c_int] * 9 + [C.c_void_p] * 6
+    L.glm_simt_smem_bytes.restype = C.c_size_t
+    return L
+
+
+def _problem(logistic, N, D, Cn, seed):
+    rng = np.random.default_rng(seed)
+    Dk, ldq = (D + 7) // 8 * 8, (D + 1) // 2 * 2
+    X = np.zeros((N, Dk))
+    X[:, 0] = 1.0
+    X[:, 1:D] = rng.normal(size=(N, D - 1))
+    Q = np.zeros((Cn, ldq))
+    Q[:, :D] = 0.3 * rng.normal(size=(Cn, D))
+    y = (rng.random(N) < 0.5).astype(np.int32) if logistic else rng.poisson(2.0, size=N).astype(np.int32)
+    return X, y, Q, Dk, ldq
+
+
+def _run(lib, variant, logistic, X, y, Q, D, lst, n_list, P):
+    N, Dk = X.shape
+    Cn, ldq = Q.shape
+    Gp = np.full((P, Cn, Dk), np.nan)
+    LPp = np.full((P, Cn), np.nan)
+    rc = lib.glm_simt_run(variant, int(logistic), N, D, Dk, ldq, Cn, n_list, P, X.ctypes.data, y.ctypes.data, Q.ctypes.data,
+                          lst.ctypes.data if lst is not None else None, Gp.ctypes.data, LPp.ctypes.data)
+    assert rc == 1
+    return Gp, LPp
+
+
+def _reference(logistic, X, y, Q, D, idx):
+    eta = X[:, :D] @ Q[idx, :D].T
+    if logistic:
+        s = 2.0 * y - 1.0
+        t = s[:, None] * eta
+        lp = -np.logaddexp(0.0, -t)
+        d = s[:, None] / (1.0 + np.exp(t))
+    else:
+        lp = y[:, None] * eta - np.exp(eta)
+        d = y[:, None] - np.exp(eta)
+    return lp.sum(0), (X.T @ d).T
+
+
+# (logistic, N, D, chains, requesting, P, list?)  -- Dk 16/32/64/104/112 select the MB template and 3 vs 2 X stages (v4);
+# ragged last row tile, underfilled chain tiles (1, 7, 65 requesting chains), n_it < stages, several chain tiles x row tiles
+SHAPES = [
+    (1, 300, 13, 70, 70, 2, False),
+    (1, 64, 9, 8, 1, 1, True),
+    (0, 257, 30, 40, 7, 3, True),
+    (1, 500, 51, 90, 65, 2, True),
+    (0, 330, 60, 64, 64, 5, False),
+    (1, 640, 101, 140, 130, 2, True),
+    (0, 450, 110, 70, 70, 3, False),
+    (1, 129, 101, 200, 33, 3, True),
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "-".join(str(v) for v in s))
+def test_partials_against_numpy(lib, variant, shape):
+    logistic, N, D, Cn, n_list, P, use_list = shape
+    X, y, Q, Dk, _ = _problem(logistic, N, D, Cn, seed=N + D)
+    assert lib.glm_simt_smem_bytes(variant, Dk) <= 232448   # the dynamic shared memory a CTA may opt in to on sm_100
+    lst = np.random.default_rng(1).permutation(Cn)[:n_list].astype(np.int32) if use_list else None
+    Gp, LPp = _run(lib, variant, logistic, X, y, Q, D, lst, n_list, P)
+    idx = lst if lst is not None else np.arange(n_list)
+    lp_ref, g_ref = _reference(logistic, X, y, Q, D, idx)
+    assert np.all(np.isnan(Gp[:, n_list:])) and np.all(np.isnan(LPp[:, n_list:]))   # slots past the list are never written
+    assert np.all(np.isfinite(Gp[:, :n_list])) and np.all(np.isfinite(LPp[:, :n_list]))
+    LP, G = LPp[:, :n_list].sum(0), Gp[:, :n_list].sum(0)
+    assert np.max(np.abs(LP - lp_ref) / np.abs(lp_ref)) < 1e-12
+    assert np.max(np.abs(G - g_ref)) / np.max(np.abs(g_ref)) < 1e-12
+    assert np.all(G[:, D:] == 0.0)   # padded design columns carry no gradient
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], SHAPES[5], SHAPES[6]], ids=lambda s: "-".join(str(v) for v in s))
+def test_v4_has_the_summation_order_of_v3(lib, shape):
+    """glm_dmma.cu, v4 header: "Summation order per chain is that of v3" -- the partials agree bit for bit"""
+    logistic, N, D, Cn, n_list, P, use_list = shape
+    X, y, Q, _, _ = _problem(logistic, N, D, Cn, seed=5)
+    lst = np.arange(n_list, dtype=np.int32)[::-1].copy() if use_list else None
+    a = _run(lib, 2, logistic, X, y, Q, D, lst, n_list, P)
+    b = _run(lib, 3, logistic, X, y, Q, D, lst, n_list, P)
+    assert np.array_equal(a[0][:, :n_list], b[0][:, :n_list]) and np.array_equal(a[1][:, :n_list], b[1][:, :n_list])
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_a_chain_does_not_depend_on_its_batch(lib, variant):
+    """kernels.h: results for a chain depend only on that chain's q -- whichever other chains request a gradient in the same
+    launch and whichever slot of the chain tile it lands in (hmc_nuts_diag_e_adapt_parallel_match_test.cpp:73-153)"""
+    logistic, N, D, Cn, P = 1, 400, 21, 100, 3
+    X, y, Q, _, _ = _problem(logistic, N, D, Cn, seed=11)
+    full = np.arange(Cn, dtype=np.int32)
+    Gf, Lf = _run(lib, variant, logistic, X, y, Q, D, full, Cn, P)
+    sub = np.array([93, 5, 64, 17, 70, 2, 99, 31, 8, 50, 63], dtype=np.int32)
+    Gs, Ls = _run(lib, variant, logistic, X, y, Q, D, sub, len(sub), P)
+    assert np.array_equal(Gs[:, :len(sub)], Gf[:, sub]) and np.array_equal(Ls[:, :len(sub)], Lf[:, sub])
+
+
+# ---- ThreadSanitizer ---------------------------------------------------------------------------------------------------
+def _tsan_exe(name, defines=()):
+    exe = os.path.join(EMUL, name + ".exe")
+    if _stale(exe):
+        r = subprocess.run(CXX + ["-fsanitize=thread", "-DGLM_SIMT_MAIN"] + ["-D" + d for d in defines] + [SRC, "-o", exe], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("no ThreadSanitizer tool chain: " + r.stderr[-300:])
+    return exe
+
+
+def _tsan_run(exe, args):
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66 halt_on_error=0")
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, env=env, timeout=900)
+    if "FATAL: ThreadSanitizer" in r.stderr and "data race" not in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run here: " + r.stderr[-300:])
+    return r
+
+
+# variant logistic N D chains requesting P
+TSAN_CASES = [(1, 1, 700, 51, 200, 77, 3), (2, 1, 640, 101, 140, 130, 2), (3, 1, 640, 101, 140, 130, 2), (3, 0, 900, 110, 70, 70, 3), (3, 1, 200, 13, 70, 70, 3)]
+
+
+@pytest.mark.parametrize("case", TSAN_CASES, ids=lambda c: "-".join(str(v) for v in c))
+def test_no_shared_memory_race(case):
+    r = _tsan_run(_tsan_exe("glm_simt_tsan"), case)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr and "simt:" not in r.stderr, r.stderr[-3000:]
+    assert r.stdout.startswith("lp checksum")
+
+
+@pytest.mark.parametrize("mutant", ["SIMT_MUTANT_SKIP_MBAR_WAIT", "SIMT_MUTANT_EARLY_REFILL"])
+def test_the_race_detector_sees_a_broken_pipeline(mutant):
+    r = _tsan_run(_tsan_exe("glm_simt_tsan_" + mutant.lower(), [mutant]), (3, 1, 320, 13, 70, 70, 1))
+    assert r.returncode != 0 and ("data race" in r.stderr or "simt:" in r.stderr)
