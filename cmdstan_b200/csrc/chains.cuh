@@ -43,6 +43,27 @@ __device__ __forceinline__ void warp_copy_words(void* dst, const void* src, int 
 static_assert(sizeof(ChainS) % 8 == 0, "ChainS is copied as 8-byte words");
 constexpr int kChainWords = (int)(sizeof(ChainS) / 8);
 
+#ifdef B200_SIMT_EMUL  // CPU test-suite only (tests/host_emul/simt): the chain kernels run on host threads
+#define B200_DYN_SMEM_WORDS(name) unsigned long long* name = reinterpret_cast<unsigned long long*>(simt::dyn_smem())
+// The device's lanes read and write the chain's warp-uniform scalar block (ChainS) in lockstep; the rig's lanes are free-running
+// threads, so there each lane works on a private replica (all replicas evolve identically; the random stream is only ever
+// touched by lane 0, whose replica is the one stored back)
+#define B200_SCALARS_BEGIN(v)       \
+  ChainS* const simt_home = (v).s;  \
+  ChainS simt_replica = *simt_home; \
+  __syncwarp();                     \
+  (v).s = &simt_replica
+#define B200_SCALARS_END(v, lane)                \
+  __syncwarp();                                  \
+  if ((lane) == 0) *simt_home = simt_replica;    \
+  (v).s = simt_home;                             \
+  __syncwarp()
+#else
+#define B200_DYN_SMEM_WORDS(name) extern __shared__ __align__(16) unsigned long long name[]
+#define B200_SCALARS_BEGIN(v)
+#define B200_SCALARS_END(v, lane)
+#endif
+
 // ---- lock-step engine: advance every chain to its next gradient request
 // and collect the requesting chains: active[c] flag + compacted index list (order irrelevant: a chain's gradient
 // depends on its own q only).  The chain's scalar block is staged in shared memory for the launch (one coalesced
@@ -60,7 +81,9 @@ __global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCf
   warp_copy_words(&sh[w], gs, kChainWords, lane);
   __syncwarp();
   v.s = &sh[w];
+  B200_SCALARS_BEGIN(v);
   const int r = advance(v, cfg, lane);
+  B200_SCALARS_END(v, lane);
   __syncwarp();
   warp_copy_words(gs, &sh[w], kChainWords, lane);
   if (lane == 0) {
@@ -78,7 +101,7 @@ __global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCf
 constexpr int kFusedMaxWarps = 7;  // 4 blocks x 7 warps = 28 resident chains per SM (4096 chains = one wave on 148 SMs)
 template <bool SMEM, int TAG>
 __global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(SamplerCfg cfg, ModelData md, DeviceChains d, int C, int warps_per_block, int chain_smem_words) {
-  extern __shared__ __align__(16) unsigned long long fused_smem[];
+  B200_DYN_SMEM_WORDS(fused_smem);
   const int w = threadIdx.x >> 5;
   const int c = blockIdx.x * warps_per_block + w;
   if (c >= C) return;
@@ -101,6 +124,7 @@ __global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(Sam
     if (lane == 0) *v.zV = *g.zV;
     __syncwarp();
   }
+  B200_SCALARS_BEGIN(v);
   while (advance(v, cfg, lane) == ADV_NEED_GRAD) {
     __syncwarp();
     const double lp = lp_grad_small(md, v.q, v.g, lane);
@@ -108,6 +132,7 @@ __global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(Sam
     *v.zV = -lp;
     __syncwarp();
   }
+  B200_SCALARS_END(v, lane);
   if (SMEM) {
     __syncwarp();
     warp_copy_words(g.s, v.s, kChainWords, lane);

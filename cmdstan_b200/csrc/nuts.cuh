@@ -793,11 +793,11 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
             if (fwd) {
               rho_bck = rho[i];
               rho_fwd = S[2 * ld + i];
-              pfb[i] = S[i];
+              if (!dense) pfb[i] = S[i];  // dense: stored above, and other lanes may still be reading it in dense_sharp
             } else {
               rho_fwd = rho[i];
               rho_bck = S[2 * ld + i];
-              pbf[i] = S[i];
+              if (!dense) pbf[i] = S[i];
             }
             const double v_pfb = pfb[i], v_pbf = pbf[i], v_pff = pff[i], v_pbb = pbb[i];
             const double sh_pff = dense ? s0[i] : m * v_pff, sh_pbb = dense ? s1[i] : m * v_pbb, sh_pfb = dense ? s2[i] : m * v_pfb,

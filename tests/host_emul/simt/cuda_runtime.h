@@ -17,6 +17,8 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <dlfcn.h>
+#include <execinfo.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -35,13 +37,14 @@
 #define __noinline__
 #define __launch_bounds__(...)
 #define __restrict__
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 
 using std::isfinite;
 using std::isnan;
 
 typedef void* cudaStream_t;
+typedef int cudaError_t;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F>
 inline int cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
@@ -59,29 +62,55 @@ struct Dim3 { unsigned x = 1, y = 1, z = 1; };
   std::_Exit(86);
 }
 
-constexpr int kWaitSeconds = 120;
+inline int wait_seconds() {  // SIMT_WAIT_SECONDS: shorter when hunting a deadlock
+  static const int v = std::getenv("SIMT_WAIT_SECONDS") ? std::atoi(std::getenv("SIMT_WAIT_SECONDS")) : 120;
+  return v;
+}
 
+// sense-reversing barrier on two atomics; waiters spin with sched_yield (hundreds of oversubscribed threads: a futex round trip
+// per collective would dominate the run time).  Acquire/release on `gen` orders everything before the barrier in any thread
+// before everything after it in every thread, which is also what ThreadSanitizer sees.
 struct Barrier {
-  std::mutex m;
-  std::condition_variable cv;
-  int n = 0, count = 0;
-  unsigned gen = 0;
-  void wait(const char* what) {
-    std::unique_lock<std::mutex> lk(m);
-    const unsigned g = gen;
-    if (++count == n) {
-      count = 0;
-      gen++;
-      cv.notify_all();
-    } else if (!cv.wait_for(lk, std::chrono::seconds(kWaitSeconds), [&] { return gen != g; })) {
-      die(what);
+  std::atomic<int> count{0};
+  std::atomic<unsigned> gen{0};
+  int n = 0;
+  // returns false on time-out
+  bool arrive_and_wait() {
+    const unsigned g = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      count.store(0, std::memory_order_relaxed);
+      gen.store(g + 1, std::memory_order_release);
+      return true;
     }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0; gen.load(std::memory_order_acquire) == g; spins++) {
+      std::this_thread::yield();
+      if ((spins & 0xfff) == 0xfff && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(wait_seconds())) return false;
+    }
+    return true;
+  }
+  void wait(const char* what) {
+    if (!arrive_and_wait()) die(what);
   }
 };
 
 struct Warp {
   Barrier bar;
   uint64_t slot[2][32][2];
+  // post-mortem of a collective that not every lane reached: where each lane last entered one, and whether it has left the kernel
+  void* where[32][8] = {};
+  int depth[32] = {};
+  int state[32] = {};  // 0 running, 1 inside a collective, 2 exited
+  void report() {
+    for (int l = 0; l < 32; l++) {
+      std::fprintf(stderr, "simt:   lane %2d %s", l, state[l] == 2 ? "exited " : (state[l] == 1 ? "waiting" : "running"));
+      for (int k = 1; k < depth[l]; k++) {
+        Dl_info info;
+        if (dladdr(where[l][k], &info) && info.dli_fbase) std::fprintf(stderr, " +0x%zx", (size_t)((char*)where[l][k] - (char*)info.dli_fbase));
+      }
+      std::fprintf(stderr, "\n");
+    }
+  }
 };
 
 struct MBar {
@@ -124,6 +153,9 @@ struct ThreadCtx {
 };
 inline thread_local ThreadCtx tc;
 
+// warp barrier with the post-mortem bookkeeping (addresses are offsets into the test library: addr2line -e <lib> <offsets>)
+inline void warp_wait(const char* what);
+
 inline void* dyn_smem() { return tc.blk->dyn.data() + ((128 - (reinterpret_cast<uintptr_t>(tc.blk->dyn.data()) & 127)) & 127); }
 
 }  // namespace simt
@@ -132,6 +164,55 @@ inline thread_local simt::Dim3 threadIdx, blockIdx;
 inline simt::Dim3 blockDim, gridDim;
 
 namespace simt {
+
+// host threads that play the CUDA threads of a CTA; kept alive between launches (the lock-step engine launches thousands)
+struct Pool {
+  std::mutex m;
+  std::condition_variable cv_start, cv_done;
+  std::vector<std::thread> workers;
+  unsigned epoch = 0, n_active = 0, remaining = 0;
+  const std::function<void(unsigned)>* job = nullptr;
+  bool stop = false;
+  void worker(unsigned i) {
+    unsigned seen = 0;
+    std::unique_lock<std::mutex> lk(m);
+    for (;;) {
+      cv_start.wait(lk, [&] { return stop || epoch != seen; });
+      if (stop) return;
+      seen = epoch;
+      if (i >= n_active) continue;
+      const std::function<void(unsigned)>* j = job;
+      lk.unlock();
+      (*j)(i);
+      lk.lock();
+      if (--remaining == 0) cv_done.notify_one();
+    }
+  }
+  void run(unsigned n, const std::function<void(unsigned)>& f) {
+    std::unique_lock<std::mutex> lk(m);
+    while (workers.size() < n) {
+      const unsigned i = (unsigned)workers.size();
+      workers.emplace_back([this, i] { worker(i); });
+    }
+    job = &f;
+    n_active = remaining = n;
+    epoch++;
+    cv_start.notify_all();
+    cv_done.wait(lk, [&] { return remaining == 0; });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv_start.notify_all();
+    for (auto& t : workers) t.join();
+  }
+};
+inline Pool& pool() {
+  static Pool p;
+  return p;
+}
 
 // run `body` as grid x block CUDA threads (1-D), one CTA at a time
 inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, const std::function<void()>& body) {
@@ -146,20 +227,29 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, const std::f
       blk.warps.emplace_back(new Warp());
       blk.warps.back()->bar.n = 32;
     }
-    std::vector<std::thread> ts;
-    ts.reserve(block);
-    for (unsigned t = 0; t < block; t++)
-      ts.emplace_back([&, t] {
-        threadIdx.x = t;
-        blockIdx.x = b;
-        tc.blk = &blk;
-        tc.warp = blk.warps[t / 32].get();
-        tc.lane = (int)(t % 32);
-        tc.op = 0;
-        body();
-      });
-    for (auto& th : ts) th.join();
+    pool().run(block, [&](unsigned t) {
+      threadIdx.x = t;
+      blockIdx.x = b;
+      tc.blk = &blk;
+      tc.warp = blk.warps[t / 32].get();
+      tc.lane = (int)(t % 32);
+      tc.op = 0;
+      body();
+      tc.warp->state[tc.lane] = 2;
+    });
   }
+}
+
+inline void warp_wait(const char* what) {
+  Warp* w = tc.warp;
+  const int l = tc.lane;
+  w->depth[l] = backtrace(w->where[l], 8);
+  w->state[l] = 1;
+  if (!w->bar.arrive_and_wait()) {
+    w->report();
+    die(what);
+  }
+  w->state[l] = 0;
 }
 
 template <class T>
@@ -182,14 +272,14 @@ inline const uint64_t (*exchange(uint64_t w0, uint64_t w1))[2] {
   const unsigned s = tc.op++ & 1u;
   w->slot[s][tc.lane][0] = w0;
   w->slot[s][tc.lane][1] = w1;
-  w->bar.wait("warp collective: not all 32 lanes arrived (divergent collective or deadlock)");
+  warp_wait("warp collective: not all 32 lanes arrived (divergent collective, or lanes that left the kernel early)");
   return w->slot[s];
 }
 
 }  // namespace simt
 
 inline void __syncthreads() { simt::tc.blk->bar.wait("__syncthreads: not all threads arrived"); }
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::tc.warp->bar.wait("__syncwarp: not all lanes arrived"); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_wait("__syncwarp: not all lanes arrived"); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 #ifdef SIMT_MUTANT_EARLY_REFILL  // deliberately broken build (tests of the tests): the second arriver of eight is told it is the last
@@ -261,7 +351,7 @@ inline void mbar_wait(const void* bar, unsigned parity) {
 #endif
   MBar& m = tc.blk->mbar(bar, false);
   std::unique_lock<std::mutex> lk(m.m);
-  if (!m.cv.wait_for(lk, std::chrono::seconds(kWaitSeconds), [&] { return (m.phase & 1u) != (parity & 1u); }))
+  if (!m.cv.wait_for(lk, std::chrono::seconds(wait_seconds()), [&] { return (m.phase & 1u) != (parity & 1u); }))
     die("mbarrier.try_wait never succeeded (deadlock in the pipeline protocol)");
 }
 inline void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, const void* bar) {
