@@ -49,10 +49,12 @@ int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream)
   const char* var = getenv("B200NUTS_IRT_VARIANT");
   int occ = var ? atoi(var) : 1;
   if (var && var[0] == 'a') occ = (b.hint_active < 0 ? b.C : b.hint_active) >= 296 ? 2 : 1;
-#define IRT_LAUNCH(IPL)                                                                                                                     \
-  {                                                                                                                                         \
-    if (occ == 2) irt_grad_kernel<IPL, 2><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld); \
-    else irt_grad_kernel<IPL, 1><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);          \
+#define IRT_LAUNCH(IPL)                                                                                                          \
+  {                                                                                                                              \
+    auto k1 = irt_grad_kernel<IPL, 1>;                                                                                           \
+    auto k2 = irt_grad_kernel<IPL, 2>;                                                                                           \
+    if (occ == 2) IRT_KERNEL_LAUNCH(k2, b.C, stream, m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);     \
+    else IRT_KERNEL_LAUNCH(k1, b.C, stream, m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);              \
   }
   if (ipl <= 2) IRT_LAUNCH(2)
   else if (ipl <= 4) IRT_LAUNCH(4)

@@ -6,6 +6,12 @@
 #include "fastmath.cuh"
 #include "kernels.h"
 
+#ifdef B200_SIMT_EMUL  // CPU test-suite only (tests/host_emul/simt): the kernels run on host threads
+#define IRT_KERNEL_LAUNCH(kernel, grid, stream, ...) simt::launch(grid, IRT_NT, 0, [&] { kernel(__VA_ARGS__); })
+#else
+#define IRT_KERNEL_LAUNCH(kernel, grid, stream, ...) kernel<<<grid, IRT_NT, 0, stream>>>(__VA_ARGS__)
+#endif
+
 namespace b200 {
 
 constexpr int IRT_NT = 256;

@@ -46,6 +46,11 @@ __global__ void __launch_bounds__(IRT_NT, 1) irt_tail_kernel(SamplerCfg cfg, Dev
   if (warp == 0) warp_copy_words(&sh, gs, kChainWords, lane);
   __syncthreads();
   v.s = &sh;
+#ifdef B200_SIMT_EMUL  // the rig's lanes are free-running: warp 0's lanes each work on a replica of the scalar block (chains.cuh)
+  ChainS simt_replica = sh;
+  __syncthreads();
+  if (warp == 0) v.s = &simt_replica;
+#endif
   for (;;) {
     // the chain is waiting for the gradient at z.q (written by advance, possibly earlier in this very kernel: coherent loads)
     irt_chain_body<IPL, 1, true>(y, I, J, cfg.D, v.q, v.g, v.zV);
@@ -60,6 +65,10 @@ __global__ void __launch_bounds__(IRT_NT, 1) irt_tail_kernel(SamplerCfg cfg, Dev
     __syncthreads();
     if (!s_more) break;
   }
+#ifdef B200_SIMT_EMUL
+  if (threadIdx.x == 0) sh = simt_replica;
+  __syncthreads();
+#endif
   if (warp == 0) warp_copy_words(gs, &sh, kChainWords, lane);
 }
 
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(IRT_NT, 1) irt_tail_kernel(SamplerCfg cfg, Dev
 
 int launch_irt_grad_nf(const ModelData& m, const GradBatch& b, cudaStream_t stream) {
   const int ipl = (m.K + IRT_G - 1) / IRT_G;
-  IRT_NF_DISPATCH(ipl, (irt_grad_kernel_nf<IPL><<<b.C, IRT_NT, 0, stream>>>(m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld)))
+  IRT_NF_DISPATCH(ipl, IRT_KERNEL_LAUNCH(irt_grad_kernel_nf<IPL>, b.C, stream, m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld))
   return 1;
 }
 
@@ -81,7 +90,7 @@ int launch_irt_grad_nf(const ModelData& m, const GradBatch& b, cudaStream_t stre
 void launch_irt_tail(const SamplerCfg& cfg, const DeviceChains& d, const ModelData& m, const int* list, const int* n_list, int n_max,
                      cudaStream_t stream) {
   const int ipl = (m.K + IRT_G - 1) / IRT_G;
-  IRT_NF_DISPATCH(ipl, (irt_tail_kernel<IPL><<<n_max, IRT_NT, 0, stream>>>(cfg, d, m.y8, m.N, m.K, list, n_list)))
+  IRT_NF_DISPATCH(ipl, IRT_KERNEL_LAUNCH(irt_tail_kernel<IPL>, n_max, stream, cfg, d, m.y8, m.N, m.K, list, n_list))
 }
 
 }  // namespace b200
