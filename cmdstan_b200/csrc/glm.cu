@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(NT, 1)
 glm_partial_kernel(const double* __restrict__ X, int ldx, const int* __restrict__ y, int N, int Dp, const double* __restrict__ Q,
                    int ldq, int D, const int* __restrict__ active, int C, long long n_row_tiles, int P, int cap,
                    double* __restrict__ Gp, double* __restrict__ LPp) {
-  extern __shared__ double smem[];
+  B200_DYN_SMEM(smem);
   const int xs_ld = Dp + 1;
   double* Bs = smem;                        // [Dp][TC]
   double* Xs = Bs + (size_t)Dp * TC;        // [TR][Dp+1]
@@ -275,11 +275,11 @@ static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspa
     if (Dp <= 112) {
       auto k = glm_partial_kernel<LINK, 7>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, NT, smem, stream>>>(m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, T, P, ws.C, ws.Gp, ws.LPp);
+      B200_LAUNCH(k, grid, NT, smem, stream, m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, T, P, ws.C, ws.Gp, ws.LPp);
     } else {
       auto k = glm_partial_kernel<LINK, 11>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, NT, smem, stream>>>(m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, T, P, ws.C, ws.Gp, ws.LPp);
+      B200_LAUNCH(k, grid, NT, smem, stream, m.X, m.ldx, m.yi, m.N, Dp, b.Q, b.ld, m.D, b.active, C, T, P, ws.C, ws.Gp, ws.LPp);
     }
     launches++;
   }
@@ -287,10 +287,10 @@ static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspa
   const int* list = tc ? b.list : nullptr;
   const int* n_list = tc ? b.n_list : nullptr;
   const long long tot = (long long)C * (1 + Dp);
-  glm_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ws.Gp, ws.LPp, P, ws.C, Dp, list, n_list, C, b.active, ws.R);
+  B200_LAUNCH(glm_reduce_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, ws.Gp, ws.LPp, P, ws.C, Dp, list, n_list, C, b.active, ws.R);
   launches++;
   if (ar) ar(ws.R, (long long)ws.C * (1 + Dp), (void*)stream, ar_user);
-  glm_finish_kernel<LINK><<<(C * 32 + 127) / 128, 128, 0, stream>>>(ws.R, Dp, b.Q, b.ld, m.D, b.active, C, b.G, b.zV);
+  B200_LAUNCH(glm_finish_kernel<LINK>, (C * 32 + 127) / 128, 128, 0, stream, ws.R, Dp, b.Q, b.ld, m.D, b.active, C, b.G, b.zV);
   launches++;
   return launches;
 }

@@ -35,16 +35,12 @@ constexpr int DS_LD = TC + 4;
 
 #ifdef B200_SIMT_EMUL  // CPU test-suite only (tests/host_emul/simt): the kernels of this file run on host threads
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) { simt::dmma(d0, d1, a, b); }
-#define B200_DYN_SMEM(name) double* name = reinterpret_cast<double*>(simt::dyn_smem())
-#define B200_LAUNCH(kernel, grid, block, smem_bytes, stream, arg) simt::launch(grid, block, smem_bytes, [&] { kernel(arg); })
 #else
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
-#define B200_DYN_SMEM(name) extern __shared__ __align__(128) double name[]
-#define B200_LAUNCH(kernel, grid, block, smem_bytes, stream, arg) kernel<<<grid, block, smem_bytes, stream>>>(arg)
 #endif
 
 __host__ __device__ inline int xs_ld_for(int Dk) { return Dk + 4; }  // Dk % 8 == 0  =>  ld % 8 == 4

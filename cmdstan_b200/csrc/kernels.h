@@ -12,6 +12,16 @@
 
 #include "models.cuh"
 
+// Kernel launches and dynamic shared memory of the gradient kernels go through these two macros so that the CPU test-suite can
+// run the same kernels on host threads (tests/host_emul/simt); in the product they are the plain CUDA constructs.
+#ifdef B200_SIMT_EMUL
+#define B200_DYN_SMEM(name) double* name = reinterpret_cast<double*>(simt::dyn_smem())
+#define B200_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) simt::launch(grid, block, smem_bytes, [&] { kernel(__VA_ARGS__); })
+#else
+#define B200_DYN_SMEM(name) extern __shared__ __align__(128) double name[]
+#define B200_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) kernel<<<grid, block, smem_bytes, stream>>>(__VA_ARGS__)
+#endif
+
 namespace b200 {
 
 typedef int (*allreduce_fn)(void* device_buf, int64_t count, void* cuda_stream, void* user);

@@ -49,6 +49,10 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F>
 inline int cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
@@ -130,6 +134,7 @@ struct MBar {
 
 struct Block {
   Barrier bar;
+  std::atomic<int> votes[3] = {};  // __syncthreads_or: three rotating accumulators
   std::vector<std::unique_ptr<Warp>> warps;
   std::vector<unsigned char> dyn;
   std::mutex mbar_m;
@@ -149,7 +154,7 @@ struct ThreadCtx {
   Block* blk = nullptr;
   Warp* warp = nullptr;
   int lane = 0;
-  unsigned op = 0;
+  unsigned op = 0, bop = 0;
 };
 inline thread_local ThreadCtx tc;
 
@@ -215,11 +220,12 @@ inline Pool& pool() {
 }
 
 // run `body` as grid x block CUDA threads (1-D), one CTA at a time
-inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, const std::function<void()>& body) {
+inline void launch(dim3 grid, unsigned block, size_t dyn_bytes, const std::function<void()>& body) {
   if (block % 32) die("block size must be a multiple of 32");
   blockDim.x = block;
-  gridDim.x = grid;
-  for (unsigned b = 0; b < grid; b++) {
+  gridDim.x = grid.x;
+  gridDim.y = grid.y;
+  for (unsigned b = 0; b < grid.x * grid.y; b++) {
     Block blk;
     blk.bar.n = (int)block;
     blk.dyn.assign(dyn_bytes + 256, 0xCD);  // poisoned: reading never-written shared memory shows up as garbage
@@ -229,11 +235,13 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, const std::f
     }
     pool().run(block, [&](unsigned t) {
       threadIdx.x = t;
-      blockIdx.x = b;
+      blockIdx.x = b % grid.x;
+      blockIdx.y = b / grid.x;
       tc.blk = &blk;
       tc.warp = blk.warps[t / 32].get();
       tc.lane = (int)(t % 32);
       tc.op = 0;
+      tc.bop = 0;
       body();
       tc.warp->state[tc.lane] = 2;
     });
@@ -279,6 +287,16 @@ inline const uint64_t (*exchange(uint64_t w0, uint64_t w1))[2] {
 }  // namespace simt
 
 inline void __syncthreads() { simt::tc.blk->bar.wait("__syncthreads: not all threads arrived"); }
+inline int __syncthreads_or(int pred) {
+  simt::Block* b = simt::tc.blk;
+  const unsigned n = simt::tc.bop++;
+  // call n accumulates in slot n % 3 and clears slot (n + 1) % 3, which was last read in call n - 2: every thread finished that
+  // call before it arrived at the barrier of call n - 1, which this thread has passed
+  b->votes[(n + 1) % 3].store(0, std::memory_order_relaxed);
+  if (pred) b->votes[n % 3].store(1, std::memory_order_relaxed);
+  b->bar.wait("__syncthreads_or: not all threads arrived");
+  return b->votes[n % 3].load(std::memory_order_relaxed);
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_wait("__syncwarp: not all lanes arrived"); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

@@ -22,7 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 EMUL = os.path.join(HERE, "host_emul")
 SRC = os.path.join(EMUL, "glm_simt.cpp")
-DEPS = [SRC, os.path.join(EMUL, "simt", "cuda_runtime.h")] + [os.path.join(ROOT, "cmdstan_b200", "csrc", f) for f in ("glm_dmma.cu", "fastmath.cuh", "kernels.h", "models.cuh", "warp.cuh")]
+SRC2 = os.path.join(EMUL, "glm_simt_stage.cpp")
+DEPS = [SRC, SRC2, os.path.join(EMUL, "simt", "cuda_runtime.h")] + [os.path.join(ROOT, "cmdstan_b200", "csrc", f) for f in ("glm_dmma.cu", "glm.cu", "fastmath.cuh", "kernels.h", "models.cuh", "warp.cuh")]
 CXX = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-Wno-tsan", "-I", os.path.join(EMUL, "simt")]
 
 
@@ -34,9 +35,10 @@ def _stale(out):
 def lib():
     so = os.path.join(EMUL, "libglm_simt.so")
     if _stale(so):
-        subprocess.check_call(CXX + ["-fPIC", "-shared", SRC, "-o", so])
+        subprocess.check_call(CXX + ["-fPIC", "-shared", SRC, SRC2, "-o", so])
     L = C.CDLL(so)
     L.glm_simt_run.argtypes = [C.c_int] * 9 + [C.c_void_p] * 6
+    L.glm_simt_grad.argtypes = [C.c_int] * 7 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2
     L.glm_simt_smem_bytes.restype = C.c_size_t
     return L
 
@@ -133,11 +135,43 @@ def test_a_chain_does_not_depend_on_its_batch(lib, variant):
     assert np.array_equal(Gs[:, :len(sub)], Gf[:, sub]) and np.array_equal(Ls[:, :len(sub)], Lf[:, sub])
 
 
+# ---- the whole gradient stage (partial kernel of each variant, reduction over row groups, priors and signs) vs the oracle -------
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("name,N,K", [("logistic", 300, 12), ("poisson_glm", 257, 30), ("logistic", 200, 100)])
+def test_gradient_stage_against_the_oracle(lib, variant, name, N, K):
+    """launch_glm_grad (kernels.h): zV = -lp, G = -grad lp with lp = log_prob_propto_jacobian of the oracle's GLM
+    (bernoulli_logit_glm / poisson_log_glm + normal priors), for requesting chains only; 1e-12 (GPU gate: 1e-10)"""
+    from oracle import oracle as O
+    import cases
+    data = cases.logistic_data(N, K, seed=3) if name == "logistic" else cases.poisson_data(N, K, seed=3)
+    D, Cn = K + 1, 70
+    ldq = (D + 3) & ~3
+    Dk = (D + 7) & ~7
+    X = np.zeros((N, Dk))
+    X[:, 0] = 1.0
+    X[:, 1:D] = data["X"]
+    y = np.ascontiguousarray(data["y"], dtype=np.int32)
+    Q = np.zeros((Cn, ldq))
+    Q[:, :D] = 0.2 * np.random.default_rng(K).normal(size=(Cn, D))
+    req = np.array(sorted(np.random.default_rng(2).permutation(Cn)[:41]), dtype=np.int32)
+    active = np.zeros(Cn, dtype=np.int32)
+    active[req] = 1
+    G, zV = np.full((Cn, ldq), np.nan), np.full(Cn, np.nan)
+    n = lib.glm_simt_grad(variant, int(name == "logistic"), N, D, ldq, Cn, 5, X.ctypes.data, y.ctypes.data, Q.ctypes.data, active.ctypes.data,
+                          req.ctypes.data, len(req), G.ctypes.data, zV.ctypes.data)
+    assert n == 3
+    lp, g = O.Model(name, data).lp_grad(Q[req][:, :D])
+    assert np.max(np.abs(zV[req] + lp) / np.abs(lp)) < 1e-12
+    assert np.max(np.abs(G[req][:, :D] + g)) / np.max(np.abs(g)) < 1e-12
+    idle = np.setdiff1d(np.arange(Cn), req)
+    assert np.all(np.isnan(zV[idle])) and np.all(np.isnan(G[idle]))   # chains that did not ask are not touched
+
+
 # ---- ThreadSanitizer ---------------------------------------------------------------------------------------------------
 def _tsan_exe(name, defines=()):
     exe = os.path.join(EMUL, name + ".exe")
     if _stale(exe):
-        r = subprocess.run(CXX + ["-fsanitize=thread", "-DGLM_SIMT_MAIN"] + ["-D" + d for d in defines] + [SRC, "-o", exe], capture_output=True, text=True)
+        r = subprocess.run(CXX + ["-fsanitize=thread", "-DGLM_SIMT_MAIN"] + ["-D" + d for d in defines] + [SRC, SRC2, "-o", exe], capture_output=True, text=True)
         if r.returncode != 0:
             pytest.skip("no ThreadSanitizer tool chain: " + r.stderr[-300:])
     return exe
