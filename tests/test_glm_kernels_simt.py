@@ -167,6 +167,39 @@ def test_gradient_stage_against_the_oracle(lib, variant, name, N, K):
     assert np.all(np.isnan(zV[idle])) and np.all(np.isnan(G[idle]))   # chains that did not ask are not touched
 
 
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_gradient_stage_edge_values(lib, variant):
+    """the +-20 cut-offs of bernoulli_logit_glm (linear predictors of +-60), and poisson_log_glm with exp(eta) overflowing:
+    the reference throws a domain error there (non-finite sum of the derivative) => rejected proposal, V = +inf"""
+    from oracle import oracle as O
+    import cases
+    N, K, Cn = 130, 6, 9
+    D = K + 1
+    ldq, Dk = (D + 3) & ~3, (D + 7) & ~7
+    for name in ("logistic", "poisson_glm"):
+        data = cases.logistic_data(N, K, seed=4) if name == "logistic" else cases.poisson_data(N, K, seed=4)
+        data = dict(data, X=data["X"] * (10.0 if name == "logistic" else 1.0))
+        X = np.zeros((N, Dk))
+        X[:, 0] = 1.0
+        X[:, 1:D] = data["X"]
+        y = np.ascontiguousarray(data["y"], dtype=np.int32)
+        Q = np.zeros((Cn, ldq))
+        Q[:, :D] = np.random.default_rng(1).normal(size=(Cn, D)) * np.linspace(0.1, 4.0, Cn)[:, None]
+        if name == "poisson_glm":
+            Q[Cn - 1, 0] = 800.0    # exp overflows for every row
+            Q[Cn - 2, 0] = 600.0    # finite exp, huge derivative
+        G, zV = np.full((Cn, ldq), np.nan), np.full(Cn, np.nan)
+        lib.glm_simt_grad(variant, int(name == "logistic"), N, D, ldq, Cn, 3, X.ctypes.data, y.ctypes.data, Q.ctypes.data, None, None, 0, G.ctypes.data, zV.ctypes.data)
+        lp, g = O.Model(name, data).lp_grad(Q[:, :D])
+        if name == "logistic":
+            assert np.abs(X[:, :D] @ Q[:, :D].T).max() > 60.0
+        ok = np.isfinite(lp)
+        assert ok.sum() >= Cn - 1
+        assert np.array_equal(np.isposinf(zV), ~ok)         # V = +inf exactly where the oracle's lp is -inf
+        assert np.max(np.abs(zV[ok] + lp[ok]) / np.abs(lp[ok])) < 1e-12
+        assert np.max(np.abs(G[ok][:, :D] + g[ok]) / np.max(np.abs(g[ok]), axis=1, keepdims=True)) < 1e-12
+
+
 # ---- ThreadSanitizer ---------------------------------------------------------------------------------------------------
 def _tsan_exe(name, defines=()):
     exe = os.path.join(EMUL, name + ".exe")
