@@ -50,6 +50,12 @@ def pytest_collection_modifyitems(config, items):
     if late:
         items[:] = [it for it in items if it not in late] + late
     if _have_gpu():
+        # a kernel that never returns must not hold the box until the caller's limit: every GPU test gets a wall-clock limit
+        # (pytest-timeout, thread method: the process is ended, which also releases the CUDA context)
+        if config.pluginmanager.hasplugin("timeout"):
+            for it in items:
+                if "gpu" in it.keywords and not it.get_closest_marker("timeout"):
+                    it.add_marker(pytest.mark.timeout(900, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
