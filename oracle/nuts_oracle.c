@@ -455,6 +455,9 @@ double oracle_lp_grad(const model_t* m, const double* q, double* g) {
     case M_LOGISTIC: return lp_grad_logistic(m, q, g);
     case M_IRT2PL: return lp_grad_irt(m, q, g);
     case M_POISSON: return lp_grad_poisson(m, q, g);
+    case M_MOCK_FLAT:
+      for (int i = 0; i < m->D; i++) g[i] = 0.0;
+      return 0.0;
   }
   return NAN;
 }
@@ -733,11 +736,17 @@ static int build_tree(sampler_t* s, int depth, point_t* z_propose, double* p_sha
 }
 
 /* base_nuts.hpp:78-204.  q_in/out = s->z.q ; returns accept_stat, sets lp */
+static double transition_from_momentum(sampler_t* s, double* lp_out);
 static double transition(sampler_t* s, double* lp_out) {
-  int D = s->D;
   s->epsilon = s->nom_epsilon; /* base_hmc.hpp:195-200 */
   if (s->epsilon_jitter) s->epsilon *= 1.0 + s->epsilon_jitter * (2.0 * oracle_uniform01(&s->rng) - 1.0);
   sample_p(s, &s->z);
+  return transition_from_momentum(s, lp_out);
+}
+/* base_nuts.hpp:88-204: everything after `this->hamiltonian_.sample_p(this->z_, this->rand_int_)` (separate so that the
+   reference's mock-Hamiltonian KATs, whose sample_p is a no-op, can enter here with a given momentum) */
+static double transition_from_momentum(sampler_t* s, double* lp_out) {
+  int D = s->D;
   update_potential_gradient(s, &s->z);
   point_t z_fwd = pt_alloc(D), z_bck = pt_alloc(D), z_sample = pt_alloc(D), z_propose = pt_alloc(D);
   pt_copy(&z_fwd, &s->z);
@@ -1139,4 +1148,75 @@ void oracle_evolve_kat(const model_t* model, const double* q, const double* p, c
   out[3 * D] = s.z.V;
   pt_free(&s.z);
   free(s.inv_metric);
+}
+
+/* ---- ST/unit/mcmc/hmc/nuts/base_nuts_test.cpp restated.  The reference runs these on mock classes (mock_hmc.hpp): log_prob == 0,
+   sample_p a no-op, evolve: q += eps p, H == 0 everywhere, U-turn criterion overridden to `true`.  With the flat model, a unit
+   metric and a fixed momentum the real classes behave identically where the tests look: the leapfrog leaves p unchanged and moves q
+   by eps p, H is the same at every point, and rho . p_sharp > 0 always.  Where the mock's p_sharp (= q) differs from the real one
+   (= p) the expectation is not restated. */
+static void kat_sampler(sampler_t* s, const model_t* model, uint32_t seed, uint32_t chain, const double* q0, const double* p0, double eps,
+                        int max_depth) {
+  memset(s, 0, sizeof *s);
+  s->model = model;
+  s->D = model->D;
+  s->z = pt_alloc(model->D);
+  s->inv_metric = (double*)malloc(model->D * sizeof(double));
+  for (int i = 0; i < model->D; i++) {
+    s->inv_metric[i] = 1.0;
+    s->z.q[i] = q0[i];
+    s->z.p[i] = p0[i];
+  }
+  s->nom_epsilon = s->epsilon = eps;
+  s->max_depth = max_depth;
+  s->max_deltaH = 1000;
+  oracle_rng_seed(&s->rng, seed, chain);
+}
+/* TEST(McmcNutsBaseNuts, transition), base_nuts_test.cpp:335-372: a transition that starts from a GIVEN momentum.
+   out: accept_stat, lp, depth, n_leapfrog, divergent, q[D] */
+void oracle_nuts_transition_kat(const model_t* model, uint32_t seed, uint32_t chain, const double* q0, const double* p0, double eps,
+                                int max_depth, double* out) {
+  sampler_t s;
+  kat_sampler(&s, model, seed, chain, q0, p0, eps, max_depth);
+  double lp = 0;
+  out[0] = transition_from_momentum(&s, &lp);
+  out[1] = lp;
+  out[2] = s.depth;
+  out[3] = s.n_leapfrog;
+  out[4] = s.divergent;
+  memcpy(out + 5, s.z.q, s.D * sizeof(double));
+  pt_free(&s.z);
+  free(s.inv_metric);
+}
+/* TEST(McmcNutsBaseNuts, build_tree_test), base_nuts_test.cpp:139-195, and TEST(McmcUnitENuts, build_tree_test),
+   unit_e_nuts_test.cpp:10-95: build_tree(depth, ..., H0, sign, ...) from (q0, p0) with rho = p0; H0 is taken as given
+   (h0_relative == 0) or as an offset from H(q0, p0).
+   out: valid, n_leapfrog, log_sum_weight, sum_metro_prob, then rho, p_begin, p_sharp_begin, p_end, p_sharp_end, z.q, z.p (D each) */
+void oracle_nuts_build_tree_kat(const model_t* model, uint32_t seed, uint32_t chain, const double* q0, const double* p0, double eps, int depth,
+                                double sign, double H0, int h0_relative, double* out) {
+  sampler_t s;
+  kat_sampler(&s, model, seed, chain, q0, p0, eps, 10);
+  update_potential_gradient(&s, &s.z);
+  const int D = s.D;
+  point_t z_propose = pt_alloc(D);
+  double* buf = (double*)calloc(5 * (size_t)D, sizeof(double));
+  double *p_sharp_begin = buf, *p_sharp_end = buf + D, *rho = buf + 2 * D, *p_begin = buf + 3 * D, *p_end = buf + 4 * D;
+  for (int i = 0; i < D; i++) rho[i] = s.z.p[i];
+  double lsw = -INFINITY, sum_metro = 0;
+  int n_leapfrog = 0;
+  if (h0_relative) H0 += hamiltonian(&s, &s.z);
+  out[0] = build_tree(&s, depth, &z_propose, p_sharp_begin, p_sharp_end, rho, p_begin, p_end, H0, sign, &n_leapfrog, &lsw, &sum_metro);
+  out[1] = n_leapfrog;
+  out[2] = lsw;
+  out[3] = sum_metro;
+  const double* vecs[7] = {rho, p_begin, p_sharp_begin, p_end, p_sharp_end, s.z.q, s.z.p};
+  for (int k = 0; k < 7; k++) memcpy(out + 4 + (size_t)k * D, vecs[k], D * sizeof(double));
+  pt_free(&z_propose);
+  pt_free(&s.z);
+  free(buf);
+  free(s.inv_metric);
+}
+/* TEST(McmcNutsDerivedNuts, compute_criterion_{unit,diag,dense}_e), ST/unit/mcmc/hmc/nuts/derived_nuts_test.cpp:14-132 */
+int oracle_criterion_kat(const double* p_sharp_minus, const double* p_sharp_plus, const double* rho, int n) {
+  return criterion(p_sharp_minus, p_sharp_plus, rho, n);
 }

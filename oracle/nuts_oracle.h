@@ -7,7 +7,8 @@
 extern "C" {
 #endif
 
-enum { M_STD_NORMAL = 0, M_BERNOULLI = 1, M_EIGHT_SCHOOLS = 2, M_LOGISTIC = 3, M_IRT2PL = 4, M_POISSON = 5 };
+enum { M_STD_NORMAL = 0, M_BERNOULLI = 1, M_EIGHT_SCHOOLS = 2, M_LOGISTIC = 3, M_IRT2PL = 4, M_POISSON = 5,
+       M_MOCK_FLAT = 6 /* log_prob == 0: the mock_model of ST/unit/mcmc/hmc/mock_hmc.hpp:13-35, KATs only */ };
 
 typedef struct {
   int kind;
@@ -50,6 +51,14 @@ int oracle_num_outputs(const model_t* m);
 void oracle_write_array(const model_t* m, const double* q, double* out);
 int oracle_run_chain(const model_t* model, const oracle_config_t* c, const double* q0, const double* inv_metric0, double* draws,
                      double* adapt_out, double* q_init_out, long* grad_evals_out);
+
+/* the reference's sampler unit tests restated: base_nuts_test.cpp:139-195, 335-372; unit_e_nuts_test.cpp:10-95 */
+void oracle_nuts_transition_kat(const model_t* model, uint32_t seed, uint32_t chain, const double* q0, const double* p0, double eps,
+                                int max_depth, double* out);
+void oracle_nuts_build_tree_kat(const model_t* model, uint32_t seed, uint32_t chain, const double* q0, const double* p0, double eps, int depth,
+                                double sign, double H0, int h0_relative, double* out);
+
+int oracle_criterion_kat(const double* p_sharp_minus, const double* p_sharp_plus, const double* rho, int n);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
 
 M_STD_NORMAL, M_BERNOULLI, M_EIGHT_SCHOOLS, M_LOGISTIC, M_IRT2PL, M_POISSON = range(6)
-KIND_BY_NAME = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5}
+KIND_BY_NAME = {"std_normal": 0, "bernoulli": 1, "eight_schools_nc": 2, "logistic": 3, "irt_2pl": 4, "poisson_glm": 5,
+                "mock_flat": 6}   # mock_flat: log_prob == 0, the mock_model of the reference's sampler unit tests (KATs only)
 
 
 class ModelT(C.Structure):
@@ -76,7 +77,7 @@ class Model:
             self._keep.append(a)
             return a
 
-        if name == "std_normal":
+        if name in ("std_normal", "mock_flat"):
             m.D = int(data.get("D", 3))
         elif name == "bernoulli":
             y = arr(data["y"], np.int32)
