@@ -1220,3 +1220,26 @@ void oracle_nuts_build_tree_kat(const model_t* model, uint32_t seed, uint32_t ch
 int oracle_criterion_kat(const double* p_sharp_minus, const double* p_sharp_plus, const double* rho, int n) {
   return criterion(p_sharp_minus, p_sharp_plus, rho, n);
 }
+/* TEST(McmcCovarAdaptation, learn_covariance), ST/unit/mcmc/covar_adaptation_test.cpp:5-31: n_learn samples q fed to the dense
+   (covariance) window logic; covar_out [D][D] */
+int oracle_learn_covariance_kat(int D, const double* q, int n_learn, unsigned num_warmup, unsigned init_buffer, unsigned term_buffer,
+                                unsigned window, double* covar_out) {
+  sampler_t s;
+  memset(&s, 0, sizeof s);
+  s.D = D;
+  s.dense = 1;
+  s.z = pt_alloc(D);
+  memcpy(s.z.q, q, D * sizeof(double));
+  s.inv_metric = (double*)calloc((size_t)D * D, sizeof(double));
+  s.chol = (double*)calloc((size_t)D * D, sizeof(double));
+  s.tmpv = (double*)calloc(D, sizeof(double));
+  s.wf_m = (double*)calloc(D, sizeof(double));
+  s.wf_m2 = (double*)calloc((size_t)D * D, sizeof(double));
+  s.adapt_window_counter = 0; s.adapt_window_size = 0; s.adapt_next_window = 0u - 1u;
+  set_window_params(&s, num_warmup, init_buffer, term_buffer, window);
+  int updates = 0;
+  for (int i = 0; i < n_learn; i++) updates += learn_variance(&s) != 0;
+  memcpy(covar_out, s.inv_metric, (size_t)D * D * sizeof(double));
+  pt_free(&s.z); free(s.inv_metric); free(s.chol); free(s.tmpv); free(s.wf_m); free(s.wf_m2);
+  return updates;
+}

@@ -58,6 +58,8 @@ void oracle_nuts_transition_kat(const model_t* model, uint32_t seed, uint32_t ch
 void oracle_nuts_build_tree_kat(const model_t* model, uint32_t seed, uint32_t chain, const double* q0, const double* p0, double eps, int depth,
                                 double sign, double H0, int h0_relative, double* out);
 
+int oracle_learn_covariance_kat(int D, const double* q, int n_learn, unsigned num_warmup, unsigned init_buffer, unsigned term_buffer,
+                                unsigned window, double* covar_out);
 int oracle_criterion_kat(const double* p_sharp_minus, const double* p_sharp_plus, const double* rho, int n);
 
 #ifdef __cplusplus
