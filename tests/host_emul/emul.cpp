@@ -93,6 +93,27 @@ extern "C" int emul_learn_variance_kat(int D, const double* q, int n_learn, unsi
   return updates;
 }
 
+// covar_adaptation_test.cpp restated on the device code (dense windows: Welford covariance in the chain's matrix block)
+extern "C" int emul_learn_covariance_kat(int D, const double* q, int n_learn, unsigned num_warmup, unsigned init_buffer,
+                                         unsigned term_buffer, unsigned window, double* covar_out) {
+  SamplerCfg cfg{};
+  cfg.D = D; cfg.ld = D; cfg.dense = 1;
+  resolve_window(&cfg, num_warmup, init_buffer, term_buffer, window);
+  std::vector<double> slab((size_t)num_vec_slots(1, 1, 0) * D, 0.0), qq(D), g(D), mat(3 * (size_t)D * D, 0.0);
+  ChainS s;
+  std::memset(&s, 0, sizeof s);
+  s.win_size = cfg.w_size0; s.win_next = cfg.w_next0;
+  double zV = 0;
+  ChainView c{&s, qq.data(), g.data(), &zV, slab.data(), nullptr, nullptr};
+  c.mat = mat.data();
+  for (int i = 0; i < D; i++) slab[(size_t)V_CQ * D + i] = q[i];
+  int updates = 0;
+  for (int i = 0; i < n_learn; i++) updates += learn_variance(c, cfg, 0) > 0;
+  for (int i = 0; i < D; i++)
+    for (int j = 0; j < D; j++) covar_out[(size_t)i * D + j] = mat[(size_t)j * D + i];
+  return updates;
+}
+
 // expl_leapfrog::evolve through the DEVICE code path (leapfrog_begin, model gradient, leapfrog_end) for the std-normal model:
 // same KATs as the oracle's oracle_evolve_kat.  out = q[D], p[D], g[D], V, H
 extern "C" void emul_evolve_kat(int D, const double* q, const double* p, const double* inv_metric, double eps, double* out) {
