@@ -45,6 +45,8 @@ extern "C" size_t glm_simt_smem_bytes(int variant, int Dk) {
 }
 
 #ifdef GLM_SIMT_MAIN
+extern "C" int glm_simt_grad(int variant, int logistic, int N, int D, int ldq, int C, int sm_count, const double* X, const int* y, const double* Q,
+                             const int* active, const int* list, int n_list, double* G, double* zV);  // glm_simt_stage.cpp
 // stand-alone form for ThreadSanitizer (g++ -fsanitize=thread -DGLM_SIMT_MAIN): synthetic data, one launch, a checksum
 #include <random>
 int main(int argc, char** argv) {
@@ -67,6 +69,14 @@ int main(int argc, char** argv) {
   for (int c = 0; c < C; c++)
     for (int k = 0; k < D; k++) Q[(size_t)c * ldq + k] = 0.3 * nd(gen);
   for (int s = 0; s < n_list; s++) list[s] = (int)((s * 7919LL) % C);
+  if (variant == 0) {  // the register-tiled DFMA kernel + reduction + finishing kernel of glm.cu (every chain requests)
+    std::vector<double> G((size_t)C * ldq, 0.0), zV(C, 0.0);
+    glm_simt_grad(0, logistic, N, D, ldq, C, P, X.data(), y.data(), Q.data(), nullptr, nullptr, 0, G.data(), zV.data());
+    double sum = 0;
+    for (int c = 0; c < C; c++) sum -= zV[c];
+    std::printf("lp checksum %.17g\n", sum);
+    return 0;
+  }
   glm_simt_run(variant, logistic, N, D, Dk, ldq, C, n_list, P, X.data(), y.data(), Q.data(), list.data(), Gp.data(), LPp.data());
   double sum = 0;
   for (int p = 0; p < P; p++)

@@ -222,7 +222,7 @@ def _tsan_run(exe, args):
 
 
 # variant logistic N D chains requesting P
-TSAN_CASES = [(1, 1, 700, 51, 200, 77, 3), (2, 1, 640, 101, 140, 130, 2), (3, 1, 640, 101, 140, 130, 2), (3, 0, 900, 110, 70, 70, 3), (3, 1, 200, 13, 70, 70, 3)]
+TSAN_CASES = [(0, 1, 300, 51, 70, 70, 3), (1, 1, 700, 51, 200, 77, 3), (2, 1, 640, 101, 140, 130, 2), (3, 1, 640, 101, 140, 130, 2), (3, 0, 900, 110, 70, 70, 3), (3, 1, 200, 13, 70, 70, 3)]
 
 
 @pytest.mark.parametrize("case", TSAN_CASES, ids=lambda c: "-".join(str(v) for v in c))
