@@ -128,3 +128,17 @@ def test_all_service_mirrors_compile():
     src = os.path.join(HERE, "host_emul", "service_instantiation.cpp")
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_product_build_has_no_test_rig_code():
+    """B200_SIMT_EMUL / B200_HOST_EMUL / B200_FASTMATH_HOST exist for the CPU test rigs only: the build recipe never defines them
+    and nothing of the rigs' namespace ends up in the shipped library"""
+    import subprocess
+    from cmdstan_b200 import _build
+    recipe = open(_build.__file__).read()
+    for macro in ("B200_SIMT_EMUL", "B200_HOST_EMUL", "B200_FASTMATH_HOST"):
+        assert macro not in recipe
+    if not os.path.exists(_build.LIB):
+        pytest.skip("library not built")
+    syms = subprocess.run(["nm", "-C", _build.LIB], capture_output=True, text=True).stdout
+    assert "simt::" not in syms and "emul_" not in syms and "oracle_" not in syms
