@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
   double* Ds = Xs0 + (size_t)2 * TR * xs_ld;       // [TR][DS_LD]
   double* ys0 = Ds + (size_t)TR * DS_LD;           // [2][TR]  2y-1 / y as double
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ys0 + 2 * TR);  // fullX[0], fullX[1], fullB
+  double* exptab = ys0 + 2 * TR + 4;                // [32]  2^(j/32) (fastmath.cuh)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int p = blockIdx.x;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
     mbar_init(&bars[2], 1);
     fence_mbarrier_init();
   }
+  exp_table_load(exptab, tid);
   // columns [ldq, Dk) of the B tile are never written by the bulk copies: zero them once
   for (int e = tid; e < TC * (Dk - a.ldq); e += NT) {
     const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
@@ -222,7 +224,9 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
   if (tid < TR) load_y(0, 0);
 
   double gacc[MB][2][2];
-  double lpacc[2][2];
+  double lpacc[2][2];       // poisson: running sums of the log-likelihood terms
+  LogitAcc lacc[2][2];      // logistic: the same in product form (fastmath.cuh)
+  int n_pad = 0;            // logistic: rows past the end of the row group (X == 0 => eta == 0) this lane evaluated
   int ct = 0, rt = 0;
   for (long long it = 0; it < n_it; it++) {
     const int buf = (int)(it & 1);
@@ -232,6 +236,14 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
 #pragma unroll
         for (int n = 0; n < 2; n++) gacc[m][n][0] = gacc[m][n][1] = 0.0;
       lpacc[0][0] = lpacc[0][1] = lpacc[1][0] = lpacc[1][1] = 0.0;
+      if (LINK == 0) {
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+          logit_acc_init(lacc[n][0]);
+          logit_acc_init(lacc[n][1]);
+        }
+        n_pad = 0;
+      }
       mbar_wait(&bars[2], (unsigned)(ct & 1));
     }
     mbar_wait(&bars[buf], (unsigned)((it >> 1) & 1));
@@ -270,15 +282,29 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
       const int r = a_rb + mi * 8 + gid;
       const bool valid = row0 + r < row_end;
       const double yd = ys[r];
+      if (LINK == 0) n_pad += valid ? 0 : 1;
 #pragma unroll
       for (int ni = 0; ni < 2; ni++) {
         if (ni >= nb) continue;
-        double lv[2], dv[2];
+        double dv[2];
+        if (LINK == 0) {
 #pragma unroll
-        for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
+          for (int j = 0; j < 2; j++) dv[j] = logit_term(lacc[ni][j], acc[mi][ni][j], yd, exptab);
+        } else {
+          double lv[2];
 #pragma unroll
-        for (int j = 0; j < 2; j++) lpacc[ni][j] += valid ? lv[j] : 0.0;
+          for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
+#pragma unroll
+          for (int j = 0; j < 2; j++) lpacc[ni][j] += valid ? lv[j] : 0.0;
+        }
         *reinterpret_cast<double2*>(&Ds[r * DS_LD + a_cb + ni * 8 + 2 * tig]) = make_double2(dv[0], dv[1]);
+      }
+    }
+    if (LINK == 0) {  // four more factors in (1, 2] per accumulator: keep the running products' exponents in the integers
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        logit_acc_fold(lacc[ni][0]);
+        logit_acc_fold(lacc[ni][1]);
       }
     }
     __syncthreads();
@@ -310,7 +336,7 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
       for (int ni = 0; ni < 2; ni++)
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          double v = lpacc[ni][j];
+          double v = LINK == 0 ? (ni < nb ? logit_acc_value(lacc[ni][j], n_pad) : 0.0) : lpacc[ni][j];
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -789,7 +815,7 @@ size_t glm_tc3_smem_bytes(int Dk) {
 int glm_tc_max_dk() { return 112; }
 
 size_t glm_tc_smem_bytes(int Dk) {
-  return ((size_t)TC * xs_ld_for(Dk) + (size_t)2 * TR * xs_ld_for(Dk) + (size_t)TR * DS_LD + 2 * TR + 4) * sizeof(double);
+  return ((size_t)TC * xs_ld_for(Dk) + (size_t)2 * TR * xs_ld_for(Dk) + (size_t)TR * DS_LD + 2 * TR + 4 + 32) * sizeof(double);
 }
 
 int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, cudaStream_t stream) {

@@ -47,14 +47,16 @@ __device__ __forceinline__ void irt_chain_body(const signed char* __restrict__ y
   const double st = exp(u_st), sa = exp(u_sa), sb = exp(u_sb);
 
   __shared__ double s_a[OCC == 2 ? IRT_G * IRT_MAX_IPL : 1], s_b[OCC == 2 ? IRT_G * IRT_MAX_IPL : 1];
+  __shared__ double s_exptab[32];
   double a[OCC == 2 ? 1 : IPL], b[OCC == 2 ? 1 : IPL], ga[IPL], gb[IPL];
+  exp_table_load(s_exptab, tid);
   if (OCC == 2) {
     if (tid < IRT_G * IRT_MAX_IPL) {
       s_a[tid] = tid < J ? exp(IRT_LDQ(u_a + tid)) : 0.0;   // a = 0 for padding items: no gradient contribution by construction
       s_b[tid] = tid < J ? IRT_LDQ(bq + tid) : 0.0;
     }
-    __syncthreads();
   }
+  __syncthreads();
 #pragma unroll
   for (int t = 0; t < IPL; t++) {
     const int j = sub + IRT_G * t;
@@ -65,7 +67,11 @@ __device__ __forceinline__ void irt_chain_body(const signed char* __restrict__ y
     ga[t] = 0.0;
     gb[t] = 0.0;
   }
-  double lp = 0.0, s2 = 0.0;
+  // log-likelihood of this thread's responses in product form (fastmath.cuh): one multiplication per response, one log at the end
+  LogitAcc lacc;
+  logit_acc_init(lacc);
+  double s2 = 0.0;
+  int since_fold = 0;
   for (int i0 = 0; i0 < I; i0 += NGRP) {  // warp-uniform trip count: the shuffles below need every lane
     const int i = i0 + grp;
     const bool person = i < I;
@@ -76,18 +82,21 @@ __device__ __forceinline__ void irt_chain_body(const signed char* __restrict__ y
 #pragma unroll
     for (int t = 0; t < IPL; t++) {
       const int j = sub + IRT_G * t;
-      const bool valid = j < J;
-      const double sgn = valid ? 2.0 * yrow[j] - 1.0 : 1.0;
+      const int yv = j < J ? yrow[j] : 0;
+      const double sgn = __hiloint2double((int)(0xbff00000u ^ ((unsigned)yv << 31)), 0);   // 2y - 1
       const double at = OCC == 2 ? s_a[j] : a[t], bt = OCC == 2 ? s_b[j] : b[t];
       const double diff = th - bt;
-      double lpi, d;
-      link_eval<0>(at * diff, sgn, lpi, d);
-      lp += valid ? lpi : 0.0;
+      const double d = logit_term(lacc, at * diff, sgn, s_exptab);   // padding items: at == 0 => eta == 0 (see logit_acc_value)
       const double da = d * at;
       gth += da;
       gb[t] -= da;
       ga[t] += d * diff;
     }
+    }
+    since_fold += IPL;
+    if (since_fold > 800) {  // the running product gains at most one binade per response
+      logit_acc_fold(lacc);
+      since_fold = 0;
     }
     gth += __shfl_xor_sync(0xffffffffu, gth, 1);
     gth += __shfl_xor_sync(0xffffffffu, gth, 2);
@@ -111,6 +120,15 @@ __device__ __forceinline__ void irt_chain_body(const signed char* __restrict__ y
       s_gb[warp][sub + IRT_G * t] = vb;
     }
   }
+  logit_acc_fold(lacc);
+  int n_pad = 0;   // padding item slots (j >= J) this thread evaluated: one per slot and person
+  {
+    int my_persons = 0;
+    for (int i0 = 0; i0 < I; i0 += NGRP) my_persons += (i0 + grp < I) ? 1 : 0;
+#pragma unroll
+    for (int t = 0; t < IPL; t++) n_pad += (sub + IRT_G * t >= J) ? my_persons : 0;
+  }
+  double lp = logit_acc_value(lacc, n_pad);
   lp = warp_sum(lp);
   s2 = warp_sum(s2);
   if (lane == 0) {

@@ -24,3 +24,39 @@ extern "C" void fastmath_link(int link, const double* eta, const double* yd, int
 extern "C" void fastmath_exp(const double* x, int n, double* out) {
   for (int i = 0; i < n; i++) out[i] = b200::fast_exp(x[i]);
 }
+
+// ---- round 2: table-driven exp and the product form of the logistic log-likelihood
+extern "C" void fastmath_exp_t(const double* x, int n, double* out) {
+  for (int i = 0; i < n; i++) out[i] = b200::fast_exp_t(x[i], b200::kExp2Tab32);
+}
+extern "C" void fastmath_rcp3(const double* x, int n, double* out) {
+  for (int i = 0; i < n; i++) out[i] = b200::fast_rcp3(x[i]);
+}
+// every observation through its own accumulator: the per-term value and derivative
+extern "C" void fastmath_logit_terms(const double* eta, const double* yd, int n, double* lp, double* d) {
+  for (int i = 0; i < n; i++) {
+    b200::LogitAcc a;
+    b200::logit_acc_init(a);
+    d[i] = b200::logit_term(a, eta[i], yd[i], b200::kExp2Tab32);
+    b200::logit_acc_fold(a);
+    lp[i] = b200::logit_acc_value(a);
+  }
+}
+// all observations through ONE accumulator, folded every `fold_every` terms; `n_pad` padding observations (eta == 0) are mixed in
+// and taken out again by logit_acc_value
+extern "C" double fastmath_logit_sum(const double* eta, const double* yd, int n, int fold_every, int n_pad, double* d) {
+  b200::LogitAcc a;
+  b200::logit_acc_init(a);
+  int pads = 0;
+  for (int i = 0; i < n; i++) {
+    d[i] = b200::logit_term(a, eta[i], yd[i], b200::kExp2Tab32);
+    if (pads < n_pad && i % 3 == 0) {
+      b200::logit_term(a, (i & 1) ? 0.0 : -0.0, (i & 2) ? 1.0 : -1.0, b200::kExp2Tab32);
+      pads++;
+    }
+    if ((i + 1) % fold_every == 0) b200::logit_acc_fold(a);
+  }
+  for (; pads < n_pad; pads++) b200::logit_term(a, 0.0, 1.0, b200::kExp2Tab32);
+  b200::logit_acc_fold(a);
+  return b200::logit_acc_value(a, n_pad);
+}
