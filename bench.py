@@ -139,7 +139,7 @@ def algorithmic_work(w, data, model, D):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def run_reference(wname, w, data, cores, warm_state=None, budget_s=60.0, scale_note=""):
+def run_reference(wname, w, data, cores, warm_state=None, budget_s=60.0, scale_note="", max_draws=400):
     """Bounded sample of the workload through oracle/_ref/<model> (CmdStan 2.36 `sample`), chains in parallel.
     Small models run the full adaptive path (long enough for the 1 ms timer); the GLMs are warm-started from an
     adapted state (stepsize, inverse metric, positions) with adapt engaged=0 so that only the sampling phase is timed."""
@@ -180,7 +180,7 @@ def run_reference(wname, w, data, cores, warm_state=None, budget_s=60.0, scale_n
         probe = time.time() - t0
         res_p, _, _ = O.ref_sample(model, data, num_chains=chains, seed=4321, num_warmup=0, num_samples=1, sig_figs=8, num_threads=cores, tmpdir=td,
                                    adapt_engaged=False, stepsize=eps, metric_file=os.path.join(td, "metric.json"), init=os.path.join(td, "init.json"))
-        ns = int(max(8, min(400, budget_s / max(probe / 3.0, 1e-3) * 0.8)))
+        ns = int(max(8, min(max_draws, budget_s / max(probe / 3.0, 1e-3) * 0.8)))
         res, wall, _ = O.ref_sample(model, data, num_chains=chains, seed=4321, num_warmup=0, num_samples=ns, sig_figs=8, num_threads=cores, tmpdir=td,
                                     adapt_engaged=False, stepsize=eps, metric_file=os.path.join(td, "metric.json"), init=os.path.join(td, "init.json"))
         sample = f"{chains} chains x {ns} sampling transitions warm-started from the adapted state (adapt engaged=0, stepsize={eps:.4g}), num_threads={cores}{scale_note}"
@@ -191,7 +191,237 @@ def run_reference(wname, w, data, cores, warm_state=None, budget_s=60.0, scale_n
     mess, _ = A.min_bulk_ess(torch.tensor(draws))
     nleap = float(draws[:, :, 4].sum())
     return dict(value=mess / samp_s, unit="min_bulk_ESS/s", cores=cores, kind="reference", sample=sample, sampling_s=samp_s, wall_s=wall,
-                grad_evals_per_s=nleap / samp_s, min_bulk_ess=mess, draws=int(draws.shape[0] * draws.shape[1]))
+                grad_evals_per_s=nleap / samp_s, min_bulk_ess=mess, draws=int(draws.shape[0] * draws.shape[1]), draws_per_chain=int(draws.shape[1]))
+
+
+ESS_WINDOW = 200   # draws per chain the ESS-per-draw factor of `value` is estimated over (the K timed ones are its last K)
+
+
+def common_config(wname, w, num_warmup, K, world, scale_note, chains_total, ess_window):
+    """`config` of the JSON line: the SAME dict for the GPU arm and the reference arm (the driver compares them)."""
+    model = w["model"]
+    mode = "none" if world == 1 else ("rows + ncclAllReduce per leapfrog" if model == "poisson_glm" else "chains")
+    return {"workload": wname + ": " + w["desc"] + scale_note, "num_warmup": num_warmup, "timed_transitions": K,
+            "chains": chains_total, "ess_window_draws": ess_window,
+            "inputs": "synthetic data of the named shape (SURVEY 8d seeds); c3/c5 data sets exceed L2 (80 MB / 4 GB), chain state resident in HBM",
+            "sharding": mode,
+            "gradient_count": "grad evals = sum of n_leapfrog__ (both arms); the reference's extra gradient at the start of every "
+                              "transition is not executed by the GPU engine (cached) and not counted for either arm"}
+
+
+class LineGuard:
+    """The one JSON line must be printed whatever the optional legs (extra workloads, CPU baseline) do: after `limit_s` the
+    guard prints the line as it stands and ends the process."""
+
+    def __init__(self, limit_s):
+        self.line, self.done, self.lock = None, False, threading.Lock()
+        self.timer = threading.Timer(limit_s, self._expire)
+        self.timer.daemon = True
+
+    def arm(self, line):
+        self.line = line
+        self.timer.start()
+
+    def _expire(self):
+        with self.lock:
+            if self.done or self.line is None:
+                return
+            self.done = True
+            self.line.setdefault("notes", []).append("optional legs cut off by the time guard")
+            print(json.dumps(self.line), flush=True)
+        os._exit(0)
+
+    def finish(self):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            self.timer.cancel()
+            print(json.dumps(self.line), flush=True)
+
+
+def run_gpu_workload(wname, K, W, num_warmup, chains_per_gpu, scale, rank, world, local_rank, note, ess_window, primary=True,
+                     strong_chains=False, dump_warm=""):
+    """One workload on this process' GPU (all ranks call it together).  Returns (result dict on rank 0 else None, engine-side
+    leftovers for the CPU leg).  K transitions are timed; the ESS-per-draw factor comes from the last `ess_window` draws."""
+    import torch
+    import torch.distributed as dist
+    import cmdstan_b200 as B
+    from cmdstan_b200 import sharding as S
+    w = WORKLOADS[wname]
+    model = w["model"]
+    dev = torch.device("cuda", local_rank)
+    data = make_data(w, scale)
+    row_mode = model == "poisson_glm" and world > 1   # c5: rows data-sharded, one NCCL all-reduce per leapfrog (SURVEY 8e mode 2)
+    C = chains_per_gpu
+    ess_window = max(K, ess_window)
+    Wx = max(W, ess_window - K)                         # untimed sampling transitions before the timed K
+    num_samples = Wx + K
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_setup = time.time()
+    if row_mode:
+        e = S.row_sharded_engine(model, data, rank, world, transport=os.environ.get("B200_BENCH_TRANSPORT", "nccl"), device=local_rank,
+                                 num_chains=C, random_seed=20241017, init_chain_id=1, num_warmup=num_warmup, num_samples=num_samples)
+    else:   # chains shard: rank r runs stream ids 1 + r*C ... (no data-path collective)
+        e = B.Engine(model, data, num_chains=C, random_seed=20241017, init_chain_id=1 + rank * C, num_warmup=num_warmup,
+                     num_samples=num_samples, device=local_rank)
+    e.init_chains()
+    note(f"{wname}: engine ready, data uploaded")
+    if os.environ.get("B200_BENCH_VERBOSE") and num_warmup > 20:   # adaptation in pieces, to see where the time goes
+        done, adapt_s = 0, 0.0
+        while done < num_warmup:
+            n = min(max(10, num_warmup // 10), num_warmup - done)
+            e.run(n)
+            s_, l_, g_ = e.timing()
+            adapt_s, done = adapt_s + s_, done + n
+            note(f"{wname}: warm-up {done}/{num_warmup}: last {n} transitions {s_:.2f} s device, {l_} launches, gradient stage {g_:.2f} s")
+    else:
+        e.run(num_warmup)
+        adapt_s, _, _ = e.timing()
+    e.run(Wx)
+    _, _, ng1 = e.chain_status()
+    setup_wall = time.time() - t_setup
+    # ---- timed region: K transitions of every chain
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t0 = time.time()
+    e.run(K)
+    torch.cuda.synchronize()
+    run_wall = time.time() - t0
+    barrier()
+    clk = clocks.stop()
+    run_s, launches, grad_s = e.timing()
+    note(f"{wname}: timed region: {run_s:.3f} s device, {launches} launches, gradient stage {grad_s:.3f} s")
+    err, it, ng2 = e.chain_status()
+    assert (err == 0).all(), f"chains stopped with errors: {np.unique(err)}"
+    # ---- D2H of the timed draws through the C ABI (part of e2e)
+    t0 = time.time()
+    draws = e.fetch_draws(row0=Wx, nrows=K, constrained=True)
+    fetch_s = time.time() - t0
+    # ---- H2D leg of e2e: a fresh engine uploads the same host data set
+    t0 = time.time()
+    e2 = B.Engine(model, S.shard_rows(data, rank, world) if row_mode else data, num_chains=1, device=local_rank)
+    torch.cuda.synchronize()
+    h2d_s = time.time() - t0
+    e2.close()
+    eps, im = e.adaptation()
+    ar_us, ar_bytes = (e.measure_allreduce(200) if row_mode else (None, None))
+
+    # stansummary's table computed on the device from the HBM-resident draws (b200nuts_summary, pinned to the reference's
+    # stansummary goldens by tests/test_gpu_summary.py): bulk ESS and R-hat of lp__ and every model column over the ESS window,
+    # pooled over this rank's chains
+    r0 = Wx + K - ess_window
+    tab = e.summary(row0=r0, nrows=ess_window, constrained=True)
+    cols = [0] + list(range(7, tab.shape[0]))
+    ess_cols = torch.tensor([v if v == v else float("inf") for v in tab[cols, B.SUMMARY_COLUMNS.index("ESS_bulk")]], dtype=torch.float64, device=dev)
+    rhat_max = torch.tensor([float(np.nanmax(tab[cols, B.SUMMARY_COLUMNS.index("R_hat")]))], dtype=torch.float64, device=dev)
+    if ess_window != K:   # the K timed draws alone (round 1's definition), reported beside
+        tabK = e.summary(row0=Wx, nrows=K, constrained=True)
+        essK = torch.tensor([v if v == v else float("inf") for v in tabK[cols, B.SUMMARY_COLUMNS.index("ESS_bulk")]], dtype=torch.float64, device=dev)
+    else:
+        essK = ess_cols.clone()
+    ess_impl = "b200nuts_summary (CUDA; pinned to the stansummary goldens and to cmdstan_b200.analyze on hardware by tests/test_gpu_summary.py)"
+    if primary and tab.shape[0] <= 400:
+        # the headline uses ONE ESS implementation for both arms: cmdstan_b200.analyze (torch restatement of the reference's
+        # split_rank_normalized_ess, pinned to stansummary), the same function run_reference applies to the reference's draws;
+        # the device summary's value is kept beside it as a cross-check
+        from cmdstan_b200 import analyze as A
+        win = torch.tensor(e.fetch_draws(row0=r0, nrows=ess_window, constrained=True))
+        _, per = A.min_bulk_ess(win, device=dev)
+        dev_min = float(ess_cols.min())
+        ess_cols = torch.tensor([v if v == v else float("inf") for v in per], dtype=torch.float64, device=dev)
+        ess_impl = f"cmdstan_b200.analyze.min_bulk_ess (both arms); device summary of the same window gives {dev_min:.6g} on rank 0"
+        del win
+    note(f"{wname}: summary done")
+    nleap = torch.tensor([float(draws[:, :, 4].sum()), float((ng2 - ng1).sum())], dtype=torch.float64, device=dev)
+    times = torch.tensor([run_s, run_wall + fetch_s + h2d_s, grad_s, adapt_s, float(ar_us or 0.0)], dtype=torch.float64, device=dev)
+    div = torch.tensor([float(draws[:, :, 5].sum()), float(draws[:, :, 3].mean()), float(np.max(ng2 - ng1))], dtype=torch.float64, device=dev)
+    if world > 1:
+        if not row_mode:   # row mode: every rank holds the same chains -- nothing to add up
+            dist.all_reduce(ess_cols, op=dist.ReduceOp.SUM)   # ESS of independent chain sets adds
+            dist.all_reduce(essK, op=dist.ReduceOp.SUM)
+            dist.all_reduce(nleap, op=dist.ReduceOp.SUM)
+            dist.all_reduce(div[:2], op=dist.ReduceOp.SUM)
+        dist.all_reduce(rhat_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    min_ess_w, min_ess_K = float(ess_cols.min()), float(essK.min())
+    run_s, e2e_s, grad_s, adapt_s, ar_us = [float(v) for v in times]
+    n_chains_job = C * (1 if row_mode else world)
+    ess_per_draw = min_ess_w / (n_chains_job * ess_window)
+    ess_timed = ess_per_draw * n_chains_job * K            # ESS of the K timed transitions at the window's ESS-per-draw rate
+    out = None
+    leftovers = dict(engine=e, data=data, eps=eps, im=im, Wx=Wx, K=K, C=C)
+    if rank == 0:
+        pk, pk_src = peaks()
+        work = algorithmic_work(w, data, model, e.D)
+        n_grad_launch = max(1, int(div[2]))   # lock-step: one gradient-stage launch per leapfrog of the slowest chain
+        n_chain_grads = float(nleap[1])       # chain-gradients executed in the timed region (all ranks)
+        roof = None
+        if work["kind"] == "tensor":
+            # dominant kernel: fused GLM gradient; bound: FP64 tensor pipe; peak measured live with a DGEMM.  achieved = algorithmic
+            # flops of the chain-gradients actually served (requesting chains are compacted) / time in the gradient stage
+            fl = work["flops"] * n_chain_grads / world   # per rank: chains/world (chain mode) or rows/world (row mode)
+            ach = fl / grad_s / 1e12 if grad_s > 0 else None
+            peak = measure_fp64_peak(dev)
+            tr = ncu_traffic(model) if scale == 1.0 and world == 1 else None
+            bytes_rank = work["bytes_per_batch"] / (world if row_mode else 1)
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
+                    "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "algorithmic_bytes_per_launch": bytes_rank,
+                    "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
+                    "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "avg_chains_per_launch": n_chain_grads / (1 if row_mode else world) / n_grad_launch,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                    "hbm_gbs_achieved": bytes_rank / (grad_s / n_grad_launch) / 1e9 if grad_s > 0 else None, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src}
+            if row_mode:
+                roof["allreduce_us_per_leapfrog"] = ar_us
+                roof["allreduce_payload_bytes"] = ar_bytes
+                roof["allreduce_frac_of_gradient_stage"] = (ar_us * 1e-6 * n_grad_launch / grad_s) if grad_s > 0 else None
+        elif work["kind"] == "fp64":
+            fl = work["flops"] * n_chain_grads / world
+            ach = fl / grad_s / 1e12 if grad_s > 0 else None
+            peak = measure_fp64_peak(dev)
+            tr = ncu_traffic(model) if scale == 1.0 else None
+            try:   # the bound of this kernel is the scalar FP64 pipe: its own measured FMA rate beside the DGEMM rate
+                fma_peak = B.measure_fp64_fma_peak(local_rank)
+            except Exception:
+                fma_peak = None
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
+                    "fp64_fma_peak": fma_peak, "frac_of_fma_peak": (ach / fma_peak) if ach and fma_peak else None,
+                    "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,
+                    "note": "bound is FP64 ALU + transcendental throughput; flops at SURVEY 8d's 25 per response; normalised by the measured DGEMM rate"}
+        else:
+            # fused chain kernel: latency/occupancy-bound by construction (tens of flops per gradient); report HBM traffic rate
+            byt = float(nleap[1]) * (work["bytes_per_chain"] + 8 * e.D * 8.0)
+            ach = byt / run_s / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk.get("hbm_gbs"), "unit": "GB/s", "frac": ach / pk.get("hbm_gbs"), "traffic": None,
+                    "kernel": "fused_chain_kernel", "note": "latency-bound by construction (SURVEY.md 8d): state stays in L1/L2; fraction is small on purpose", "peak_source": pk_src}
+        out = {
+            "value": ess_timed / run_s, "unit": "ESS/s", "ms_per_step": 1e3 * run_s / K,
+            "scaling": "strong" if (row_mode or strong_chains) else "weak",
+            "grad_evals_per_sec": float(nleap[0]) / run_s, "grad_evals_executed_per_sec": float(nleap[1]) / run_s,
+            "min_bulk_ess_window": min_ess_w, "ess_per_draw": ess_per_draw, "ess_window_draws": ess_window, "ess_implementation": ess_impl,
+            "value_from_timed_draws_only": min_ess_K / run_s, "rhat_max": float(rhat_max[0]),
+            "chains": n_chains_job, "chains_per_gpu": C, "timed_draws": int(n_chains_job * K),
+            "divergences": float(div[0]), "mean_treedepth": float(div[1]) / (1 if row_mode else world),
+            "adaptation_s": adapt_s, "setup_wall_s": setup_wall, "median_stepsize": float(np.median(eps)),
+            "lockstep_launches_per_transition": n_grad_launch / K,
+            # SURVEY 8d: also per (warm-up + sampling) second -- the ESS rate scaled to the reference's 1000 sampling transitions,
+            # over the device time of the adaptation actually run plus 1000 transitions at the timed rate
+            "ess_per_sec_incl_warmup_1000_draws": (ess_per_draw * n_chains_job * 1000.0) / (adapt_s + run_s * 1000.0 / K) if K > 0 else None,
+            "e2e": {"value": ess_timed / e2e_s, "unit": "ESS/s", "h2d_bytes_per_step": data_bytes(data) / (world if row_mode else 1) / K,
+                    "d2h_bytes_per_step": int(draws.nbytes / K), "h2d_s": h2d_s, "run_wall_s": run_wall, "d2h_s": fetch_s},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": clk,
+        }
+        if dump_warm:
+            nk = min(C, 64)
+            np.savez(dump_warm, q=e.fetch_draws(chain0=0, nchains=nk, row0=Wx + K - 1, nrows=1, constrained=False)[:, 0, 7:],
+                     inv_metric=im[:nk], stepsize=eps[:nk])
+    return out, leftovers
 
 
 def main():
@@ -206,6 +436,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale the data rows (testing only; invalidates the number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
+    ap.add_argument("--ess-window", type=int, default=-1, help="draws per chain the ESS-per-draw factor is estimated over (default 200 for c1-c3, the timed K otherwise)")
+    ap.add_argument("--extras", default=os.environ.get("B200_BENCH_EXTRAS", "auto"),
+                    help="additional workloads measured after the headline and attached to the line as `multi_gpu_configs` (north_star's two "
+                         "multi-GPU configurations): 'auto' = c4 (8192 chains split over the GPUs) and c5 (rows split over the GPUs, NCCL "
+                         "all-reduce per leapfrog) when the headline workload is c3; 'none'; or a comma list")
     ap.add_argument("--dump-warm", default="", help="write the adapted state (q, inv_metric, stepsize of up to 64 chains) to this .npz: "
                     "the warm-start fixture of the reference arm (tests/golden/warm_<workload>.npz)")
     args = ap.parse_args()
@@ -227,8 +462,10 @@ def main():
     cores = os.cpu_count() or 1
     K, W = max(args.steps, 4), max(args.warmup, 3)
     scale_note = "" if args.scale == 1.0 else f" [rows scaled x{args.scale}]"
-    cfg_common = {"workload": args.workload + ": " + w["desc"] + scale_note, "num_warmup": args.num_warmup, "timed_transitions": K,
-                  "inputs": "data set larger than L2 for c3/c5; chain state resident in HBM", "sharding": ("rows + ncclAllReduce per leapfrog" if model == "poisson_glm" else "chains") if world > 1 else "none"}
+    ess_window = args.ess_window if args.ess_window > 0 else (max(K, ESS_WINDOW) if args.workload in ("c1", "c2", "c3") else K)
+    C = args.chains or w["chains"]
+    chains_total = C if model == "poisson_glm" else C * world
+    cfg_common = common_config(args.workload, w, args.num_warmup, K, world, scale_note, chains_total, ess_window)
 
     if args.impl == "reference":
         if rank != 0:
@@ -242,14 +479,15 @@ def main():
         elif model not in ("bernoulli", "eight_schools_nc"):
             print(json.dumps({"impl": "reference", "unavailable": f"no warm-start fixture tests/golden/warm_{args.workload}.npz for this workload"}))
             return
-        r = run_reference(args.workload, w, data, cores, warm, budget_s=max(20.0, 12.0 * K / 10), scale_note=scale_note)
+        # bounded sample: enough CPU time for about ESS_WINDOW transitions per chain at c3 (0.2 s each on one core)
+        r = run_reference(args.workload, w, data, cores, warm, budget_s=max(60.0, 12.0 * K / 10), scale_note=scale_note, max_draws=max(ess_window, 8))
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries are missing (built from /root/reference by oracle/build_ref.sh)"}))
             return
         line = {"impl": "reference", "metric": "min_bulk_ESS_per_sec", "value": r["value"], "unit": "ESS/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * r["sampling_s"] / max(1, r["draws"] // max(1, (4 if args.workload == "c1" else cores))),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_common,
-                "grad_evals_per_sec": r["grad_evals_per_s"],
+                "grad_evals_per_sec": r["grad_evals_per_s"], "min_bulk_ess": r["min_bulk_ess"], "draws_per_chain": r["draws_per_chain"],
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "ESS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -257,163 +495,67 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import cmdstan_b200 as B
-    from cmdstan_b200 import analyze as A
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    data = make_data(w, args.scale)
-    C = args.chains or w["chains"]
-    num_samples = W + K
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- set-up (untimed): upload, initialise, run the reference's windowed adaptation
-    t_setup = time.time()
-    from cmdstan_b200 import sharding as S
-    row_mode = model == "poisson_glm" and world > 1   # c5: rows data-sharded, one NCCL all-reduce per leapfrog (SURVEY 8e mode 2)
-    if row_mode:
-        e = S.row_sharded_engine(model, data, rank, world, transport=os.environ.get("B200_BENCH_TRANSPORT", "nccl"), device=local_rank,
-                                 num_chains=C, random_seed=20241017, init_chain_id=1, num_warmup=args.num_warmup, num_samples=num_samples)
-    else:   # chains shard (weak scaling): rank r runs stream ids 1 + r*C ... (no data-path collective)
-        e = B.Engine(model, data, num_chains=C, random_seed=20241017, init_chain_id=1 + rank * C, num_warmup=args.num_warmup,
-                     num_samples=num_samples, device=local_rank)
-    e.init_chains()
-    note("engine ready, data uploaded")
-    if os.environ.get("B200_BENCH_VERBOSE") and args.num_warmup > 20:   # adaptation in pieces, to see where the time goes
-        done, adapt_s, adapt_launches, adapt_grad_s = 0, 0.0, 0, 0.0
-        while done < args.num_warmup:
-            n = min(max(10, args.num_warmup // 10), args.num_warmup - done)
-            e.run(n)
-            s_, l_, g_ = e.timing()
-            adapt_s, adapt_launches, adapt_grad_s, done = adapt_s + s_, adapt_launches + l_, adapt_grad_s + g_, done + n
-            note(f"warm-up {done}/{args.num_warmup}: last {n} transitions {s_:.2f} s device, {l_} launches, gradient stage {g_:.2f} s")
-    else:
-        e.run(args.num_warmup)
-        adapt_s, adapt_launches, adapt_grad_s = e.timing()
-    _, _, ng0 = e.chain_status()
-    e.run(W)
-    _, _, ng1 = e.chain_status()
-    setup_wall = time.time() - t_setup
-    # ---- timed region: K transitions of every chain
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    t0 = time.time()
-    e.run(K)
-    torch.cuda.synchronize()
-    run_wall = time.time() - t0
-    barrier()
-    clk = clocks.stop()
-    run_s, launches, grad_s = e.timing()
-    note(f"timed region: {run_s:.3f} s device, {launches} launches, gradient stage {grad_s:.3f} s")
-    err, it, ng2 = e.chain_status()
-    assert (err == 0).all(), f"chains stopped with errors: {np.unique(err)}"
-    # ---- D2H of the timed draws through the C ABI (part of e2e)
-    t0 = time.time()
-    draws = e.fetch_draws(row0=W, nrows=K, constrained=True)
-    fetch_s = time.time() - t0
-    # ---- H2D leg of e2e: a fresh engine uploads the same host data set
-    t0 = time.time()
-    e2 = B.Engine(model, S.shard_rows(data, rank, world) if row_mode else data, num_chains=1, device=local_rank)
-    torch.cuda.synchronize()
-    h2d_s = time.time() - t0
-    e2.close()
-    eps, im = e.adaptation()
-
-    # bulk ESS of lp__ and every model column of the timed draws, pooled over this rank's chains: stansummary's table computed
-    # on the device from the HBM-resident draws (b200nuts_summary; the torch restatement in cmdstan_b200/analyze.py gives the
-    # same numbers but loops over columns in Python -- minutes at c4's 1211 columns x 8192 chains)
-    tab = e.summary(row0=W, nrows=K, constrained=True)
-    ess_cols = tab[[0] + list(range(7, tab.shape[0])), B.SUMMARY_COLUMNS.index("ESS_bulk")]
-    ess_cols = torch.tensor([v if v == v else float("inf") for v in ess_cols], dtype=torch.float64, device=dev)
-    note("summary done")
-    nleap = torch.tensor([float(draws[:, :, 4].sum()), float((ng2 - ng1).sum())], dtype=torch.float64, device=dev)
-    times = torch.tensor([run_s, run_wall + fetch_s + h2d_s, grad_s, adapt_s], dtype=torch.float64, device=dev)
-    div = torch.tensor([float(draws[:, :, 5].sum()), float(draws[:, :, 3].mean())], dtype=torch.float64, device=dev)
-    if world > 1:
-        if not row_mode:   # row mode: every rank holds the same chains -- nothing to add up
-            dist.all_reduce(ess_cols, op=dist.ReduceOp.SUM)   # ESS of independent chain sets adds
-            dist.all_reduce(nleap, op=dist.ReduceOp.SUM)
-            dist.all_reduce(div, op=dist.ReduceOp.SUM)
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    min_ess = float(ess_cols.min())
-    run_s, e2e_s, grad_s, adapt_s = [float(v) for v in times]
-
+    res, left = run_gpu_workload(args.workload, K, W, args.num_warmup, C, args.scale, rank, world, local_rank, note, ess_window,
+                                 primary=True, dump_warm=args.dump_warm)
+    guard = LineGuard(float(os.environ.get("B200_BENCH_GUARD_S", "660")) - (time.time() - t_start))
+    line = None
     if rank == 0:
-        pk, pk_src = peaks()
-        work = algorithmic_work(w, data, model, e.D)
-        n_grad_launch = max(1, int(np.max(ng2 - ng1)))  # lock-step: one gradient-stage launch per leapfrog of the slowest chain
-        roof = None
-        n_chain_grads = float(nleap[1])  # chain-gradients actually executed in the timed region (all ranks)
-        if work["kind"] == "tensor":
-            # dominant kernel: fused GLM gradient.  bound: FP64 tensor pipe; peak measured live below with a DGEMM.
-            # achieved = algorithmic flops of the chain-gradients actually served (requesting chains are compacted, so a
-            # launch serves fewer than C chains once trees of different depth interleave) / time in the gradient stage
-            fl = work["flops"] * n_chain_grads / world   # per rank: chains/world (chain mode) or rows/world (row mode)
-            ach = fl / grad_s / 1e12 if grad_s > 0 else None
-            peak = measure_fp64_peak(dev)
-            tr = ncu_traffic(model) if args.scale == 1.0 and world == 1 else None
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
-                    "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "algorithmic_bytes_per_launch": work["bytes_per_batch"],
-                    "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
-                    "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "avg_chains_per_launch": n_chain_grads / world / n_grad_launch,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                    "hbm_gbs_achieved": work["bytes_per_batch"] / (grad_s / n_grad_launch) / 1e9 if grad_s > 0 else None, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src}
-        elif work["kind"] == "fp64":
-            fl = work["flops"] * n_chain_grads / world
-            ach = fl / grad_s / 1e12 if grad_s > 0 else None
-            peak = measure_fp64_peak(dev)
-            tr = ncu_traffic(model) if args.scale == 1.0 else None
-            try:   # the bound of this kernel is the scalar FP64 pipe: its own measured FMA rate beside the DGEMM rate
-                fma_peak = B.measure_fp64_fma_peak(local_rank)
-            except Exception:
-                fma_peak = None
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
-                    "fp64_fma_peak": fma_peak, "frac_of_fma_peak": (ach / fma_peak) if ach and fma_peak else None,
-                    "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "kernel": "irt_grad_kernel", "launches": n_grad_launch, "avg_launch_ms": 1e3 * grad_s / n_grad_launch,
-                    "note": "bound is FP64 ALU + transcendental throughput; normalised by the measured DGEMM rate"}
-        else:
-            # fused chain kernel: latency/occupancy-bound by construction (tens of flops per gradient); report HBM traffic rate
-            byt = float(nleap[1]) * (work["bytes_per_chain"] + 8 * e.D * 8.0)
-            ach = byt / run_s / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": pk.get("hbm_gbs"), "unit": "GB/s", "frac": ach / pk.get("hbm_gbs"), "traffic": None,
-                    "kernel": "fused_chain_kernel", "note": "latency-bound by construction (SURVEY.md 8d): state stays in L1/L2; fraction is small on purpose", "peak_source": pk_src}
-        line = {
-            "metric": "min_bulk_ESS_per_sec", "value": min_ess / run_s, "unit": "ESS/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * run_s / K, "higher_is_better": True, "scaling": "strong" if row_mode else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(cfg_common, chains_per_gpu=C, l2="data set (80 MB) + chain state exceed L2 reuse between steps" if model == "logistic" else "n/a"),
-            "grad_evals_per_sec": float(nleap[0]) / run_s, "grad_evals_executed_per_sec": float(nleap[1]) / run_s,
-            "min_bulk_ess": min_ess, "timed_draws": int(C * K * (1 if row_mode else world)), "divergences": float(div[0]), "mean_treedepth": float(div[1]) / (1 if row_mode else world),
-            "adaptation_s": adapt_s, "setup_wall_s": setup_wall, "median_stepsize": float(np.median(eps)),
-            # also per (warm-up + sampling) second -- the timed ESS scaled to the reference's 1000 sampling transitions,
-            # over the device time of the adaptation actually run plus 1000 transitions at the timed rate
-            "ess_per_sec_incl_warmup_1000_draws": (min_ess * 1000.0 / K) / (adapt_s + run_s * 1000.0 / K) if K > 0 else None,
-            "e2e": {"value": min_ess / e2e_s, "unit": "ESS/s", "h2d_bytes_per_step": data_bytes(data) / K, "d2h_bytes_per_step": int(draws.nbytes / K),
-                    "h2d_s": h2d_s, "run_wall_s": run_wall, "d2h_s": fetch_s},
-            "gpu_launches": int(launches), "roofline": roof, "clocks": clk,
-        }
-        if args.dump_warm:
-            nk = min(C, 64)
-            np.savez(args.dump_warm, q=e.fetch_draws(chain0=0, nchains=nk, row0=W + K - 1, nrows=1, constrained=False)[:, 0, 7:],
-                     inv_metric=im[:nk], stepsize=eps[:nk])
-        if not args.no_cpu and world >= 1:
-            try:
-                warm = dict(q=e.fetch_draws(chain0=0, nchains=min(C, cores), row0=W + K - 1, nrows=1, constrained=False)[:, 0, 7:],
-                            inv_metric=im[:min(C, cores)], stepsize=eps)
-                cb = run_reference(args.workload, w, data, cores, warm, budget_s=args.cpu_budget, scale_note=scale_note)
-                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else {"value": None, "unit": "ESS/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
-                if cb:
-                    line["cpu_baseline"]["grad_evals_per_sec"] = cb["grad_evals_per_s"]
-            except Exception as ex:  # the CPU leg must never take the GPU number down with it
-                line["cpu_baseline"] = {"value": None, "unit": "ESS/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"[:300]}
-        print(json.dumps(line))
+        line = {"metric": "min_bulk_ESS_per_sec", "value": res["value"], "unit": "ESS/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cfg_common}
+        line.update({k: v for k, v in res.items() if k not in ("value", "unit", "ms_per_step", "scaling")})
+        line["notes"] = ["value = (min bulk-ESS per draw over the last ess_window_draws draws of every chain, incl. the timed ones) x timed draws / "
+                         "device time of the timed transitions; value_from_timed_draws_only is round 1's definition (ESS of the K timed draws alone, "
+                         "optimistic for short K)"]
+        guard.arm(line)
+    e = left["engine"]
+    # ---- CPU baseline (rank 0, N = 1 only: the reference arm of the driver covers the other N)
+    if rank == 0 and not args.no_cpu and world == 1:
+        try:
+            eps, im, Wx = left["eps"], left["im"], left["Wx"]
+            warm = dict(q=e.fetch_draws(chain0=0, nchains=min(C, cores), row0=Wx + K - 1, nrows=1, constrained=False)[:, 0, 7:],
+                        inv_metric=im[:min(C, cores)], stepsize=eps)
+            e.close()
+            cb = run_reference(args.workload, w, left["data"], cores, warm, budget_s=args.cpu_budget, scale_note=scale_note, max_draws=max(ess_window, 8))
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else {"value": None, "unit": "ESS/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
+            if cb:
+                line["cpu_baseline"]["grad_evals_per_sec"] = cb["grad_evals_per_s"]
+        except Exception as ex:  # the CPU leg must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "ESS/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"[:300]}
     e.close()
+    left.clear()
+    # ---- north_star's two multi-GPU configurations, measured in the same run and attached to the line
+    extras = args.extras
+    if extras == "auto":
+        extras = "c4,c5" if (args.workload == "c3" and args.scale == 1.0 and not args.chains) else "none"
+    if extras != "none":
+        attached = {}
+        for xw in extras.split(","):
+            if time.time() - t_start > float(os.environ.get("B200_BENCH_EXTRA_START_LIMIT_S", "420")):
+                attached[xw] = {"skipped": "time budget of the bench run"}
+                continue
+            try:
+                ww = WORKLOADS[xw]
+                # c4: 8192 chains split over the GPUs (strong scaling, no collective); c5: all chains on every GPU, rows split
+                xc = ww["chains"] if ww["model"] == "poisson_glm" else max(1, ww["chains"] // world)
+                xr, xl = run_gpu_workload(xw, ww.get("steps", 30), 3, ww.get("num_warmup", 150), xc, 1.0, rank, world, local_rank, note,
+                                          ww.get("steps", 30), primary=False, strong_chains=True)
+                xl["engine"].close()
+                xl.clear()
+                if rank == 0:
+                    xr["config"] = common_config(xw, ww, ww.get("num_warmup", 150), ww.get("steps", 30), world, "", xr["chains"], xr["ess_window_draws"])
+                    attached[xw] = xr
+            except Exception as ex:
+                attached[xw] = {"failed": f"{type(ex).__name__}: {ex}"[:300]}
+        if rank == 0:
+            line["multi_gpu_configs"] = attached
+    if rank == 0:
+        guard.finish()
     if world > 1:
         dist.destroy_process_group()
 

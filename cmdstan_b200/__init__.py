@@ -43,7 +43,7 @@ EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b2
            "b200nuts_set_data_i32", "b200nuts_set_data_i8", "b200nuts_num_params", "b200nuts_set_inits", "b200nuts_set_inv_metric",
            "b200nuts_init_chains", "b200nuts_log_prob_grad", "b200nuts_run", "b200nuts_fetch_draws", "b200nuts_fetch_diagnostics", "b200nuts_rows_saved",
            "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
-           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_measure_fp64_fma_peak", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
+           "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_measure_allreduce", "b200nuts_measure_fp64_fma_peak", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
            # include/b200nuts_model.h
            "b200nuts_register_model", "b200nuts_load_model_library", "b200nuts_find_model", "b200nuts_output_name"]
 
@@ -93,6 +93,7 @@ def load_library(build=True):
     lib.b200nuts_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     lib.b200nuts_nccl_get_unique_id.argtypes = [vp]
     lib.b200nuts_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.b200nuts_measure_allreduce.argtypes = [vp, C.c_int, C.POINTER(C.c_double), i64p]
     lib.b200nuts_summary.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp]
     lib.b200nuts_summarize_draws.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_char_p, C.c_int]
     lib.b200nuts_measure_fp64_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -246,6 +247,13 @@ class Engine:
         _point_at_bundled_nccl()
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._chk(self.lib.b200nuts_nccl_init(self.h, buf, int(nranks), int(rank)))
+
+    def measure_allreduce(self, iters=200):
+        """row-sharded engines: (average microseconds, payload bytes) of the per-leapfrog all-reduce, `iters` of them back to
+        back on the engine's stream (collective: call on every rank)."""
+        us, nb = C.c_double(), C.c_int64()
+        self._chk(self.lib.b200nuts_measure_allreduce(self.h, int(iters), C.byref(us), C.byref(nb)))
+        return us.value, nb.value
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

@@ -219,6 +219,7 @@ struct b200nuts_engine {
   int* h_nactive = nullptr;  // pinned
   void* d_glm_ws = nullptr;
   GlmWorkspace glm_ws;
+  int glm_ws_N = -1, glm_ws_D = -1;  // data shape the workspace was sized for
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> grad_events;
@@ -338,6 +339,14 @@ static int64_t prod(const int64_t* dims, int nd) {
   return p;
 }
 
+// A data variable was (re)set: the model dimensions may change, so everything sized from them is stale -- the chains (buffers,
+// SamplerCfg D / ld) must be re-initialised (b200nuts_init_chains) and the GLM workspace is rebuilt for the new shapes.
+static void data_changed(b200nuts_engine* e) {
+  e->data_ready = false;
+  e->chains_ready = false;
+  e->glm_ws_N = e->glm_ws_D = -1;
+}
+
 // plug-in models: keep the variable as given; the model's create() validates and uploads it
 static int plugin_set_data(b200nuts_engine* e, const char* name, int dtype, const void* host, const int64_t* dims, int nd) {
   static const size_t kSize[3] = {8, 4, 1};
@@ -349,9 +358,9 @@ static int plugin_set_data(b200nuts_engine* e, const char* name, int dtype, cons
   const size_t bytes = (size_t)prod(dims, nd) * kSize[dtype];
   v.bytes.assign((const unsigned char*)host, (const unsigned char*)host + bytes);
   for (auto& o : e->plug_data)
-    if (o.name == v.name) { o = std::move(v); e->data_ready = false; return B200NUTS_OK; }
+    if (o.name == v.name) { o = std::move(v); data_changed(e); return B200NUTS_OK; }
   e->plug_data.push_back(std::move(v));
-  e->data_ready = false;
+  data_changed(e);
   return B200NUTS_OK;
 }
 
@@ -373,7 +382,7 @@ int b200nuts_set_data_f64(b200nuts_engine* e, const char* name, const double* ho
     e->err = "unknown f64 data variable '" + n + "' for this model";
     return B200NUTS_DATAERR;
   }
-  e->data_ready = false;
+  data_changed(e);
   return B200NUTS_OK;
 }
 
@@ -396,7 +405,7 @@ int b200nuts_set_data_i32(b200nuts_engine* e, const char* name, const int32_t* h
     e->err = "unknown i32 data variable '" + n + "' for this model";
     return B200NUTS_DATAERR;
   }
-  e->data_ready = false;
+  data_changed(e);
   return B200NUTS_OK;
 }
 
@@ -410,7 +419,7 @@ int b200nuts_set_data_i8(b200nuts_engine* e, const char* name, const int8_t* hos
     e->h_y8.assign(host, host + cnt);
     e->y8_rows = dims[0];
     e->y8_cols = dims[1];
-    e->data_ready = false;
+    data_changed(e);
     return B200NUTS_OK;
   }
   e->err = "unknown i8 data variable '" + n + "' for this model";
@@ -648,6 +657,27 @@ int b200nuts_nccl_init(b200nuts_engine* e, const void* id128, int nranks, int ra
   return B200NUTS_OK;
 }
 
+int b200nuts_measure_allreduce(b200nuts_engine* e, int iters, double* usec, int64_t* payload_bytes) {
+  if (!e->ar || e->cfg.row_shards <= 1) { e->err = "measure_allreduce: the engine is not row-sharded (no all-reduce hook installed)"; return B200NUTS_USAGE; }
+  if (!e->d_glm_ws) { e->err = "measure_allreduce: b200nuts_init_chains must be called first"; return B200NUTS_USAGE; }
+  if (iters < 1) iters = 1;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  const long long count = (long long)e->glm_ws.C * (1 + e->glm_ws.Dp);
+  CUDA_TRY(e, cudaMemsetAsync(e->glm_ws.R, 0, sizeof(double) * (size_t)count, e->stream));
+  for (int w = 0; w < 3; w++)
+    if (e->ar(e->glm_ws.R, count, (void*)e->stream, e->ar_user)) { e->err = "measure_allreduce: the all-reduce hook failed"; return B200NUTS_SOFTWARE; }
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  for (int i = 0; i < iters; i++)
+    if (e->ar(e->glm_ws.R, count, (void*)e->stream, e->ar_user)) { e->err = "measure_allreduce: the all-reduce hook failed"; return B200NUTS_SOFTWARE; }
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  if (usec) *usec = 1e3 * ms / iters;
+  if (payload_bytes) *payload_bytes = (int64_t)count * 8;
+  return B200NUTS_OK;
+}
+
 int b200nuts_set_allreduce(b200nuts_engine* e, b200nuts_allreduce_fn fn, void* user) {
   e->ar = fn;
   e->ar_user = user;
@@ -656,12 +686,16 @@ int b200nuts_set_allreduce(b200nuts_engine* e, b200nuts_allreduce_fn fn, void* u
 
 static int ensure_glm_ws(b200nuts_engine* e, int C) {
   if (!(e->md.kind == MODEL_LOGISTIC || e->md.kind == MODEL_POISSON)) return B200NUTS_OK;
-  if (e->d_glm_ws && e->glm_ws.C >= C) return B200NUTS_OK;
+  if (e->d_glm_ws && e->glm_ws.C >= C && e->glm_ws_N == e->md.N && e->glm_ws_D == e->md.D) return B200NUTS_OK;
   free_dev(e->d_glm_ws);
   e->d_glm_ws = nullptr;
   size_t bytes = glm_workspace_bytes(e->md.N, e->md.D, C, e->sm_count, &e->glm_ws);
   CUDA_TRY(e, cudaMalloc(&e->d_glm_ws, bytes));
   glm_workspace_bind(&e->glm_ws, e->d_glm_ws);
+  e->glm_ws_N = e->md.N;  // P is a function of N, Dp of D: a workspace is only reusable for the shapes it was sized for
+  e->glm_ws_D = e->md.D;
+  // the all-reduce payload of a row-sharded run covers the rows of every chain, requesting or not: never uninitialised memory
+  CUDA_TRY(e, cudaMemsetAsync(e->glm_ws.R, 0, sizeof(double) * (size_t)e->glm_ws.C * (1 + e->glm_ws.Dp), e->stream));
   const char* v = getenv("B200NUTS_GLM_VARIANT");
   e->glm_ws.variant = v ? atoi(v) : 1;
   return B200NUTS_OK;
@@ -883,8 +917,15 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       }
       cudaEvent_t a = next_event(), bb = next_event();
       cudaEventRecord(a, e->stream);
-      launches += launch_gradient(e, b);
+      const int nl = launch_gradient(e, b);
       cudaEventRecord(bb, e->stream);
+      if (nl < 0) {  // the exchange step of a row-sharded run failed: stop here, the chains' state is no longer meaningful
+        cudaStreamSynchronize(e->stream);
+        e->chains_ready = false;
+        e->err = "all-reduce of the (log density, gradient) partials failed with code " + std::to_string(-nl) + "; the run was stopped";
+        return B200NUTS_SOFTWARE;
+      }
+      launches += nl;
     }
   }
   CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
@@ -925,7 +966,12 @@ int b200nuts_log_prob_grad(b200nuts_engine* e, const double* q, int64_t n, int j
     for (int i = 0; i < m; i++) std::memcpy(hq.data() + (size_t)i * ld, q + (size_t)(off + i) * D, sizeof(double) * D);
     cudaMemcpyAsync(dQ, hq.data(), sizeof(double) * m * ld, cudaMemcpyHostToDevice, e->stream);
     GradBatch b{dQ, dG, dV, nullptr, m, ld};
-    launch_gradient(e, b, jacobian);
+    if (launch_gradient(e, b, jacobian) < 0) {
+      cudaStreamSynchronize(e->stream);
+      cudaFree(dQ); cudaFree(dG); cudaFree(dV);
+      e->err = "log_prob_grad: the all-reduce of the row-shard partials failed";
+      return B200NUTS_SOFTWARE;
+    }
     if (!jacobian && !e->plug) remove_jacobian_kernel<<<(m + 127) / 128, 128, 0, e->stream>>>(e->md.kind, D, e->md.N, e->md.K, dQ, dG, dV, m, ld);
     cudaMemcpyAsync(hg.data(), dG, sizeof(double) * m * ld, cudaMemcpyDeviceToHost, e->stream);
     cudaMemcpyAsync(hv.data(), dV, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream);

@@ -289,7 +289,11 @@ static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspa
   const long long tot = (long long)C * (1 + Dp);
   B200_LAUNCH(glm_reduce_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, ws.Gp, ws.LPp, P, ws.C, Dp, list, n_list, C, b.active, ws.R);
   launches++;
-  if (ar) ar(ws.R, (long long)ws.C * (1 + Dp), (void*)stream, ar_user);
+  if (ar) {  // row sharding: the exchange step of the leapfrog.  A failed collective must stop the run: the finishing kernel
+             // would read un-reduced partials and the ranks' control flow would separate
+    const int rc = ar(ws.R, (long long)ws.C * (1 + Dp), (void*)stream, ar_user);
+    if (rc != 0) return -(rc > 0 ? rc : 1);
+  }
   B200_LAUNCH(glm_finish_kernel<LINK>, (C * 32 + 127) / 128, 128, 0, stream, ws.R, Dp, b.Q, b.ld, m.D, b.active, C, b.G, b.zV);
   launches++;
   return launches;

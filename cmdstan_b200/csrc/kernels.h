@@ -48,7 +48,7 @@ struct GlmWorkspace {
 size_t glm_workspace_bytes(int N, int D, int C, int sm_count, GlmWorkspace* ws);  // fills P, C, Dp (= D padded to 8); returns total bytes
 void glm_workspace_bind(GlmWorkspace* ws, void* base);
 int glm_max_dim();
-// returns the number of kernels launched
+// returns the number of kernels launched, or -(code) when the all-reduce callback of a row-sharded run reported failure `code`
 int launch_glm_grad(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, allreduce_fn ar, void* ar_user,
                     bool add_prior, cudaStream_t stream);
 

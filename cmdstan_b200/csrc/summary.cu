@@ -397,7 +397,7 @@ int summary_run(const SummaryArgs& a, double* host_out, std::string* err) {
   const long long n_full = C * n, n_split = M * h;
   if (n < 2) { *err = "summary: at least 2 draws per chain are needed"; return 64; }
   if (n > kMaxChainLen) { *err = "summary: more than 24000 draws per chain are not supported"; return 78; }
-  if (n_full >= (1ll << 32)) { *err = "summary: more than 2^32 draws per column are not supported"; return 78; }
+  if (n_full > 2147483647ll) { *err = "summary: more than 2^31 - 1 draws per column are not supported"; return 78; }  // cub's item counts are int
   const int ncols = 7 + (a.constrained ? a.K_out : a.D);
   const bool odd = (n & 1) != 0;
   cudaStream_t st = a.stream;

@@ -360,7 +360,8 @@ int hmc_nuts_diag_e_adapt(Model& model, size_t num_chains, const std::vector<Ini
       << "           init_buffer = " << ib << "\n           adapt_window = " << num_warmup - (ib + tb) << "\n           term_buffer = " << tb << "\n";
     logger.info(m.str());
   } else if (adapt_engaged && !opt.unit_e && num_warmup < 20) {
-    logger.info("WARNING: No variance estimation is\n         performed for num_warmup < 20\n");
+    // windowed_adaptation's constructor names the estimator: "variance" (var_adaptation.hpp), "covariance" (covar_adaptation.hpp)
+    logger.info(std::string("WARNING: No ") + (opt.dense_e ? "covariance" : "variance") + " estimation is\n         performed for num_warmup < 20\n");
   }
 
   // ---- header rows

@@ -181,6 +181,11 @@ int b200nuts_set_allreduce(b200nuts_engine* e, b200nuts_allreduce_fn fn, void* u
    device; this installs the all-reduce hook above with ncclAllReduce on the engine's stream. */
 int b200nuts_nccl_get_unique_id(void* id128);
 int b200nuts_nccl_init(b200nuts_engine* e, const void* id128, int nranks, int rank);
+/* Cost of the exchange step of a row-sharded engine: enqueues `iters` all-reduces of exactly the per-leapfrog payload
+   ((1 + D padded to 8) x chains doubles) back to back on the engine's stream through the installed hook and returns their
+   average duration in microseconds, timed with CUDA events (collective: every shard must call it with the same `iters`).
+   The payload buffer is zeroed first and is scratch between gradient stages, so chains are unaffected. */
+int b200nuts_measure_allreduce(b200nuts_engine* e, int iters, double* usec_per_allreduce, int64_t* payload_bytes);
 
 #ifdef __cplusplus
 }

@@ -259,6 +259,7 @@ EDGE = [
     "sample num_samples=3 num_warmup=25 thin=7 save_warmup=1 data file=DATA random seed=3 output",
     "sample num_samples=0 num_warmup=0 adapt engaged=0 data file=DATA random seed=3 output",
     "sample num_samples=10 num_warmup=19 data file=DATA random seed=3 output",                       # no variance estimation below 20
+    "sample num_samples=10 num_warmup=19 algorithm=hmc metric=dense_e data file=DATA random seed=3 output",   # ... "No covariance estimation" for dense_e
     "sample num_samples=10 num_warmup=40 data file=DATA random seed=3 output",                       # 15 % / 75 % / 10 % fallback windows
     "sample num_samples=10 num_warmup=30 algorithm=hmc engine=nuts max_depth=1 stepsize_jitter=1 data file=DATA init=0 random seed=3 output refresh=0",
     "sample num_samples=4 num_warmup=150 adapt term_buffer=0 init_buffer=0 window=150 data file=DATA random seed=4294967295 output sig_figs=18",
