@@ -145,11 +145,10 @@ __global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(Sam
 
 // advance_big.cu: the same kernel built with B200_VEC_UNROLL = 8 (bit-identical results)
 void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
-// irt_tail.cu (experimental straggler path of the IRT model)
-struct GradBatch;
-int launch_irt_grad_nf(const ModelData& m, const GradBatch& b, cudaStream_t stream);
-void launch_irt_tail(const SamplerCfg& cfg, const DeviceChains& d, const ModelData& m, const int* list, const int* n_list, int n_max,
-                     cudaStream_t stream);
+// irt.cu: latency form for the stragglers of an IRT run (one cluster of 8 CTAs, or one CTA, per remaining chain)
+bool irt_solo_supported(const ModelData& m);
+cudaError_t launch_irt_solo(const SamplerCfg& cfg, const DeviceChains& d, const ModelData& m, const int* list, const int* n_list, int n_max,
+                            int cluster_size, cudaStream_t stream);
 // dense.cu: the kernels built with B200_WITH_DENSE = 1 (metric = dense_e)
 void launch_advance_dense(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
 cudaError_t launch_fused_dense(const SamplerCfg& cfg, const ModelData& md, const DeviceChains& d, int C, bool smem_state, int warps_per_block,

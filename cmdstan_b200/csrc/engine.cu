@@ -226,8 +226,10 @@ struct b200nuts_engine {
   allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
   void* nccl_comm = nullptr;  // ncclComm_t owned by the engine (b200nuts_nccl_init)
-  int irt_tail = 0;           // EXPERIMENTAL (B200NUTS_IRT_TAIL): 0 off; 1 "nf": irt_tail.cu's gradient kernel; 2: + straggler kernel
-  double last_run_s = 0, last_grad_s = 0;
+  int irt_solo = 48;          // IRT: at most this many requesting chains => the latency kernel finishes them (B200NUTS_IRT_SOLO; 0 = never)
+  int irt_solo_cluster = 8;   // CTAs per chain of the latency kernel: 8 (cluster) or 1 (B200NUTS_IRT_SOLO_CLUSTER, or set after a failed cluster launch)
+  double last_run_s = 0, last_grad_s = 0, last_solo_s = 0;
+  int last_solo_chains = 0;
   long long last_launches = 0;
 };
 
@@ -802,10 +804,8 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   }
   rc = ensure_glm_ws(e, C);
   if (rc) return rc;
-  {
-    const char* t = getenv("B200NUTS_IRT_TAIL");
-    e->irt_tail = !t || !t[0] || t[0] == '0' ? 0 : (t[0] == 'n' ? 1 : 2);
-  }
+  if (const char* t = getenv("B200NUTS_IRT_SOLO")) e->irt_solo = atoi(t);
+  if (const char* t = getenv("B200NUTS_IRT_SOLO_CLUSTER")) e->irt_solo_cluster = atoi(t) == 1 ? 1 : 8;
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   CUDA_TRY(e, cudaGetLastError());
   e->chains_ready = true;
@@ -823,7 +823,6 @@ static int launch_gradient(b200nuts_engine* e, const GradBatch& b, int jacobian 
     case MODEL_POISSON:
       return launch_glm_grad(e->md, b, e->glm_ws, e->cfg.row_shards > 1 ? e->ar : nullptr, e->ar_user, true, e->stream);
     case MODEL_IRT2PL:
-      if (e->irt_tail) return launch_irt_grad_nf(e->md, b, e->stream);
       return launch_irt_grad(e->md, b, e->stream);
     default:
       grad_small_kernel<<<(b.C + 3) / 4, 128, 0, e->stream>>>(e->md, b.Q, b.G, b.zV, b.active, b.C, b.ld);
@@ -839,6 +838,8 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
   const int total = e->cfg.num_warmup + e->cfg.num_samples;
   long long launches = 0;
   double grad_ms = 0;
+  e->last_solo_s = 0;
+  e->last_solo_chains = 0;
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   set_iter_end_kernel<<<(C + 255) / 256, 256, 0, e->stream>>>(e->dc.cs, C, n_iter, total);
   launches++;
@@ -901,17 +902,26 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
         ev_used = 0;
         if (*e->h_nactive == 0) break;
         b.hint_active = *e->h_nactive;
-        if (e->irt_tail == 2 && e->md.kind == MODEL_IRT2PL && !e->scfg.dense && !e->scfg.diag && !e->scfg.static_hmc && *e->h_nactive <= 2 * e->sm_count) {
-          // only stragglers are left: one CTA per remaining chain runs it to the end of this call on the device (irt_tail.cu)
+        if (e->irt_solo > 0 && e->md.kind == MODEL_IRT2PL && !e->plug && !e->scfg.dense && !e->scfg.diag && !e->scfg.static_hmc &&
+            *e->h_nactive <= e->irt_solo && irt_solo_supported(e->md)) {
+          // only stragglers are left: each gets a cluster of eight SMs that runs it to the end of this call on the device (irt.cu)
           cudaEvent_t a = next_event(), bb = next_event();
           cudaEventRecord(a, e->stream);
-          launch_irt_tail(e->scfg, e->dc, e->md, e->d_list, counter, *e->h_nactive, e->stream);
+          cudaError_t le = launch_irt_solo(e->scfg, e->dc, e->md, e->d_list, counter, *e->h_nactive, e->irt_solo_cluster, e->stream);
+          if (le != cudaSuccess && e->irt_solo_cluster != 1) {  // no cluster launch on this device / configuration: one CTA per chain
+            cudaGetLastError();
+            e->irt_solo_cluster = 1;
+            le = launch_irt_solo(e->scfg, e->dc, e->md, e->d_list, counter, *e->h_nactive, 1, e->stream);
+          }
+          if (le != cudaSuccess) { e->err = std::string("launch of the IRT latency kernel: ") + cudaGetErrorString(le); return B200NUTS_SOFTWARE; }
           cudaEventRecord(bb, e->stream);
           launches++;
           CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-          float tail_ms = 0;
-          cudaEventElapsedTime(&tail_ms, a, bb);
-          grad_ms += tail_ms;  // gradient + the stragglers' own advance work
+          float solo_ms = 0;
+          cudaEventElapsedTime(&solo_ms, a, bb);
+          grad_ms += solo_ms;  // gradient + the stragglers' own advance work
+          e->last_solo_s = solo_ms * 1e-3;
+          e->last_solo_chains = *e->h_nactive;
           break;
         }
       }

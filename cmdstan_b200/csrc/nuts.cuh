@@ -104,6 +104,7 @@ enum ChainState {
   ST_DOUBLING_BEGIN,
   ST_LEAF_BEGIN,
   ST_LEAF,            // waits
+  ST_SUBTREE_END,     // the subtree of this doubling is complete (or was abandoned): extend the trajectory, next doubling or end
   ST_STATIC_STEP_BEGIN,  // static HMC: one of the L leapfrogs of a transition
   ST_STATIC_STEP,        // waits
   ST_STATIC_END,
@@ -138,7 +139,7 @@ struct ChainS {
   int state, err, iter, iter_end;
   int init_tries, iss_after, iss_dir, dir;
   int init_partial, st_L;   // init_partial: some initial values were left to the random context (up to 100 tries, like no inits)
-  int st_i, pad1_;          // static HMC: L_ (st_L) and the leapfrogs done in this transition (st_i)
+  int st_i, sub_valid;      // static HMC: L_ (st_L) and the leapfrogs done in this transition (st_i); sub_valid: ST_SUBTREE_END's input
   int depth, n_leapfrog, divergent, sp;
   unsigned leaf_count, n_leaves;
   unsigned win_counter, win_size, win_next;
@@ -737,7 +738,12 @@ B200_DEV int advance(const ChainView& c, const SamplerCfg& cfg, int lane) {
           s->state = ST_LEAF_BEGIN;
           break;
         }
-        // ---- subtree finished (or aborted): base_nuts.hpp:142,154 then :156-192
+        s->sub_valid = valid ? 1 : 0;
+        s->state = ST_SUBTREE_END;
+        break;
+      }
+      case ST_SUBTREE_END: {  // subtree finished (or aborted): base_nuts.hpp:142,154 then :156-192
+        const bool valid = s->sub_valid != 0;
         const bool fwd = s->dir == 1;
         {
           const double* p = slot(c, cfg, V_P);
@@ -947,7 +953,7 @@ B200_HD void chain_init_scalars(ChainS* s, const SamplerCfg& cfg) {
   s->init_tries = 0;
   s->init_partial = 0;
   s->st_i = 0;
-  s->pad1_ = 0;
+  s->sub_valid = 0;
   {  // base_static_hmc::set_nominal_stepsize_and_T(stepsize, int_time): L from the stepsize ARGUMENT
     int L = cfg.static_hmc ? (int)(cfg.int_time / (cfg.stepsize > 0 ? cfg.stepsize : 0.1)) : 0;
     s->st_L = L < 1 ? 1 : L;

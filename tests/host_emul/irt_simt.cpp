@@ -1,19 +1,19 @@
-// TEST-ONLY: the IRT 2PL gradient kernels (cmdstan_b200/csrc/irt.cu: one- and two-CTA-per-SM forms; irt_tail.cu: the
-// contraction-free form and the EXPERIMENTAL straggler kernel that loops gradient + advance inside one CTA) executed on host
-// threads by the SIMT stand-in under tests/host_emul/simt, through the product's launchers.  The gradient kernels run on
-// hardware every round (controls); the straggler kernel has not yet -- tests/test_irt_kernels_simt.py is its functional
-// validation: chains finished by it must equal chains finished by the lock-step engine bit for bit.
+// TEST-ONLY: the IRT 2PL kernels (cmdstan_b200/csrc/irt.cu: the throughput gradient kernel in its one- and two-CTA-per-SM forms,
+// and the latency kernel irt_solo_kernel in its one-CTA-per-chain form -- the cluster form needs distributed shared memory, which
+// the rig does not model; both forms share the block arithmetic, the CTA-cooperative advance step and the hand-over logic)
+// executed on host threads by the SIMT stand-in under tests/host_emul/simt, through the product's launchers.
+// tests/test_irt_kernels_simt.py: chains finished by the latency kernel must equal chains finished by the lock-step engine bit
+// for bit.
 #define B200_SIMT_EMUL 1
 #define B200_FASTMATH_HOST 1
 #include <cuda_runtime.h>  // tests/host_emul/simt/cuda_runtime.h
 
-#include "../../cmdstan_b200/csrc/irt_tail.cu"
 #include "../../cmdstan_b200/csrc/irt.cu"
 #include "../../cmdstan_b200/csrc/host_seed.h"
 
 using namespace b200;
 
-// form 1 / 2: irt.cu with one / two CTAs per SM; 3: irt_tail.cu's irt_grad_kernel_nf.  Q, G: [C][ld]; zV: [C].
+// form 1 / 2: irt_grad_kernel with one / two CTAs per SM.  Q, G: [C][ld]; zV: [C].
 extern "C" int irt_simt_grad(int form, int I, int J, int C, int ld, const signed char* y, const double* Q, const int* active, const int* list, int n_list,
                              double* G, double* zV) {
   ModelData m{};
@@ -23,14 +23,13 @@ extern "C" int irt_simt_grad(int form, int I, int J, int C, int ld, const signed
   b.Q = Q; b.G = G; b.zV = zV; b.active = active; b.C = C; b.ld = ld;
   int nl = n_list;
   if (list) { b.list = list; b.n_list = &nl; }
-  if (form == 3) return launch_irt_grad_nf(m, b, nullptr);
   setenv("B200NUTS_IRT_VARIANT", form == 2 ? "2" : "1", 1);
   return launch_irt_grad(m, b, nullptr);
 }
 
-// C chains of the IRT model through the lock-step engine (advance kernel + irt_grad_kernel_nf per leapfrog); after
-// `tail_after` lock-steps (< 0: never) the chains still requesting a gradient are handed to irt_tail_kernel, which runs each of
-// them to the end in one launch.  draws: [C][rows][7 + D].  Returns the number of launches.
+// C chains of the IRT model through the lock-step engine (advance kernel + irt_grad_kernel per leapfrog); after
+// `tail_after` lock-steps (< 0: never) the chains still requesting a gradient are handed to irt_solo_kernel (one CTA per chain),
+// which runs each of them to the end in one launch.  draws: [C][rows][7 + D].  Returns the number of launches.
 extern "C" long long irt_simt_run(int C, int I, int J, const signed char* y, unsigned seed, int num_warmup, int num_samples, int max_depth,
                                   long long tail_after, double* draws, long long* n_grad, int* err) {
   ModelData m{};
@@ -68,11 +67,11 @@ extern "C" long long irt_simt_run(int C, int I, int J, const signed char* y, uns
     if (n_active == 0) break;
     b.n_list = &n_active;
     if (tail_after >= 0 && step >= tail_after) {
-      launch_irt_tail(cfg, d, m, list.data(), &n_active, n_active, nullptr);
+      launch_irt_solo(cfg, d, m, list.data(), &n_active, n_active, 1, nullptr);
       launches++;
       continue;  // one more advance launch finds every chain idle
     }
-    launches += launch_irt_grad_nf(m, b, nullptr);
+    launches += launch_irt_grad(m, b, nullptr);
   }
   for (int c = 0; c < C; c++) {
     n_grad[c] = cs[c].n_grad;

@@ -305,28 +305,34 @@ def test_irt_kernel_forms_bit_identical(monkeypatch):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
-@pytest.mark.skipif(not os.environ.get("B200_TEST_EXPERIMENTAL"), reason="experimental: set B200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("C", [5, 400])
-def test_irt_straggler_kernel_bit_identical(C, monkeypatch):
-    """B200NUTS_IRT_TAIL=1 (irt_tail.cu: once at most 2 chains per SM still request gradients, one CTA per chain runs it to the
-    end of the call on the device) against the same gradient kernel driven step by step from the host (=nf): identical draws,
-    step sizes, metrics and gradient counts.  C = 5: the whole run happens in the straggler kernel; C = 400: it takes over
-    when the faster chains have finished."""
-    data = cases.irt_data(60, 12)
+@pytest.mark.parametrize("C,shape", [(5, (60, 12)), (400, (60, 12)), (20, (1000, 100))], ids=["5chains", "400chains", "c4size"])
+def test_irt_latency_kernel_bit_identical(C, shape, monkeypatch):
+    """The stragglers of an IRT run are finished by the latency kernel (irt.cu, irt_solo_kernel: one cluster of eight CTAs per
+    remaining chain runs it to the end of the call on the device; in the reference a chain never waits for another,
+    hmc_nuts_diag_e_adapt.hpp:387-401) once at most B200NUTS_IRT_SOLO chains still request gradients.  Against the same chains
+    driven step by step from the host (B200NUTS_IRT_SOLO=0): identical draws, step sizes, metrics and gradient counts, for the
+    cluster form and for the one-CTA-per-chain form.  5 / 20 chains: the whole run happens in the latency kernel; 400: it takes
+    over when the faster chains have finished.  (1000, 100) is c4's shape: D = 1204, 125 persons per block."""
+    data = cases.irt_data(*shape)
+    nw, ns = (60, 25) if shape[0] < 500 else (12, 6)
     out = []
-    for mode in ("nf", "1"):
-        monkeypatch.setenv("B200NUTS_IRT_TAIL", mode)
-        e = _engine("irt_2pl", data, num_chains=C, random_seed=77, num_warmup=60, num_samples=25, save_warmup=True)
+    for solo, cl in (("0", "8"), ("48", "8"), ("48", "1")):
+        monkeypatch.setenv("B200NUTS_IRT_SOLO", solo)
+        monkeypatch.setenv("B200NUTS_IRT_SOLO_CLUSTER", cl)
+        e = _engine("irt_2pl", data, num_chains=C, random_seed=77, num_warmup=nw, num_samples=ns, save_warmup=True)
         e.init_chains()
-        for n in (40, 45):   # two calls: the straggler kernel must leave every chain resumable
+        for n in (nw * 2 // 3, nw + ns - nw * 2 // 3):   # two calls: the latency kernel must leave every chain resumable
             e.run(n)
         err, it, ng = e.chain_status()
-        assert (err == 0).all() and (it == 85).all()
+        assert (err == 0).all() and (it == nw + ns).all()
         out.append((e.fetch_draws(constrained=False), e.adaptation(), ng))
         e.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
-    assert np.array_equal(out[0][2], out[1][2])
+    for k in (1, 2):
+        assert np.array_equal(out[0][0], out[k][0]), k
+        assert np.array_equal(out[0][1][0], out[k][1][0]) and np.array_equal(out[0][1][1], out[k][1][1]), k
+        assert np.array_equal(out[0][2], out[k][2]), k
+    if shape[0] > 500:
+        return
     m = O.Model("irt_2pl", data)
     r = O.run_chain(m, seed=77, chain_id=1, num_warmup=60, num_samples=25, save_warmup=1)
     assert np.array_equal(out[1][0][0, :6, 3:6], r["draws"][:6, 3:6]) and _rel(out[1][0][0, :6], r["draws"][:6], floor=1e-6) < 1e-8

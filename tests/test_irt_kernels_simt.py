@@ -1,13 +1,13 @@
-"""CPU suite: the IRT 2PL gradient kernels (cmdstan_b200/csrc/irt.cu, irt_tail.cu) executed on host threads by the SIMT
-stand-in under tests/host_emul/simt, through the product's launchers.
+"""CPU suite: the IRT 2PL kernels (cmdstan_b200/csrc/irt.cu) executed on host threads by the SIMT stand-in under
+tests/host_emul/simt, through the product's launchers.
 
- * the cross-chain gradient kernel in its three builds (one CTA per SM, two CTAs per SM, contraction-free) against the oracle's
-   log-density and gradient (tolerance 1e-12; gate of the GPU parity tests: 1e-10), with request lists / active flags, for the
-   items-per-lane templates 2, 4, 13; the three builds perform the same operations in the same order (equal bit for bit when
-   the compiler contracts nothing, which is how the rig is built);
- * the EXPERIMENTAL straggler kernel (irt_tail.cu: one CTA per remaining chain loops gradient + advance until the chain is
-   idle; not yet run on hardware): chains handed to it after any number of lock-steps must finish with the draws of the
-   lock-step engine bit for bit; ThreadSanitizer sees no race between the advancing warp and the gradient's eight warps."""
+ * the throughput gradient kernel in its two builds (one CTA per SM, two CTAs per SM) against the oracle's log-density and
+   gradient (tolerance 1e-12; gate of the GPU parity tests: 1e-10), with request lists / active flags, for the items-per-lane
+   templates 2, 4, 13; the two builds perform the same operations in the same order (equal bit for bit);
+ * the latency kernel (irt_solo_kernel, here in its one-CTA-per-chain form; the eight-CTA cluster form shares everything but the
+   distributed-shared-memory gather and is covered on hardware): the person-block arithmetic, the CTA-cooperative leaf step
+   (solo_leaf.cuh) and the generic advance() fallback: chains handed to it after any number of lock-steps must finish with the
+   draws of the lock-step engine bit for bit; ThreadSanitizer sees no race between its phases."""
 # A one-off randomised run of the gradient checks (917 shapes: 1..129 persons, 1..128 items -- every items-per-lane template --,
 # 1..4 chains, parameter scales 0.3 / 1 / 3) found no mismatch with the oracle and no difference between the three builds.
 import ctypes as C
@@ -26,7 +26,7 @@ ROOT = os.path.dirname(HERE)
 EMUL = os.path.join(HERE, "host_emul")
 SRC = os.path.join(EMUL, "irt_simt.cpp")
 DEPS = [SRC, os.path.join(EMUL, "simt", "cuda_runtime.h")] + [os.path.join(ROOT, "cmdstan_b200", "csrc", f) for f in
-                                                               ("irt.cu", "irt_tail.cu", "irt_body.cuh", "chains.cuh", "nuts.cuh", "rng.cuh", "fastmath.cuh", "warp.cuh", "models.cuh")]
+                                                               ("irt.cu", "solo_leaf.cuh", "irt_body.cuh", "chains.cuh", "nuts.cuh", "rng.cuh", "fastmath.cuh", "warp.cuh", "models.cuh")]
 CXX = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-ffp-contract=off", "-Wno-tsan", "-Wno-unknown-pragmas", "-I", os.path.join(EMUL, "simt")]
 vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -64,7 +64,7 @@ def _grad(lib, form, I, J, Cn, active=None, lst=None):
 def test_gradient_kernel_builds_against_the_oracle(lib, shape):
     I, J = shape
     out = []
-    for form in (1, 2, 3):
+    for form in (1, 2):
         G, zV, g_ref, v_ref = _grad(lib, form, I, J, 3)
         assert np.max(np.abs(G - g_ref)) / np.max(np.abs(g_ref)) < 1e-12 and np.max(np.abs(zV - v_ref) / np.abs(v_ref)) < 1e-12
         out.append((G, zV))
@@ -72,7 +72,7 @@ def test_gradient_kernel_builds_against_the_oracle(lib, shape):
         assert np.array_equal(G, out[0][0]) and np.array_equal(zV, out[0][1])
 
 
-@pytest.mark.parametrize("form", [1, 2, 3])
+@pytest.mark.parametrize("form", [1, 2])
 def test_request_list_and_active_flags(lib, form):
     I, J, Cn = 23, 9, 6
     full = _grad(lib, form, I, J, Cn)
@@ -98,15 +98,16 @@ def _run(lib, Cn, I, J, nw, ns, max_depth, tail_after, seed=3):
     return draws, ng, err, launches
 
 
-def test_straggler_kernel_finishes_chains_like_the_lock_step_engine(lib):
-    Cn, I, J = 2, 20, 6   # D = 36: two elements per lane in the advancing warp
-    base = _run(lib, Cn, I, J, 8, 4, 4, -1)
-    assert np.all(base[2] == 0) and np.all(base[1] > 50) and np.all(np.isfinite(base[0]))
-    assert len(np.unique(base[0][:, :, 7])) > 8 * Cn      # the chains moved
+@pytest.mark.parametrize("shape", [(2, 20, 6, 8, 4), (1, 290, 5, 6, 3)], ids=["D36", "D304"])
+def test_latency_kernel_finishes_chains_like_the_lock_step_engine(lib, shape):
+    Cn, I, J, nw, ns = shape   # D = 36: a fraction of the CTA's threads hold an element; D = 304: some threads hold two
+    base = _run(lib, Cn, I, J, nw, ns, 4, -1)
+    assert np.all(base[2] == 0) and np.all(base[1] > 8) and np.all(np.isfinite(base[0]))
+    assert len(np.unique(base[0][:, :, 7])) >= 3      # the chains moved
     for tail_after in (0, 7):
-        t = _run(lib, Cn, I, J, 8, 4, 4, tail_after)
+        t = _run(lib, Cn, I, J, nw, ns, 4, tail_after)
         assert np.array_equal(t[0], base[0]) and np.array_equal(t[1], base[1]) and np.all(t[2] == 0)
-        assert t[3] == 2 * tail_after + 3   # tail_after x (advance + gradient), advance, straggler kernel, the advance that finds every chain idle
+        assert t[3] == 2 * tail_after + 3   # tail_after x (advance + gradient), advance, latency kernel, the advance that finds every chain idle
 
 
 def test_straggler_kernel_has_no_race():
