@@ -45,7 +45,7 @@ EXPORTS = ["b200nuts_default_config", "b200nuts_create", "b200nuts_destroy", "b2
            "b200nuts_get_adaptation", "b200nuts_get_chain_status", "b200nuts_get_timing", "b200nuts_set_allreduce",
            "b200nuts_nccl_get_unique_id", "b200nuts_nccl_init", "b200nuts_measure_allreduce", "b200nuts_measure_fp64_fma_peak", "b200nuts_summary", "b200nuts_summary_num_stats", "b200nuts_summarize_draws",
            # include/b200nuts_model.h
-           "b200nuts_register_model", "b200nuts_load_model_library", "b200nuts_find_model", "b200nuts_output_name"]
+           "b200nuts_register_model", "b200nuts_load_model_library", "b200nuts_find_model", "b200nuts_output_name", "b200nuts_transform_inits"]
 
 _lib = None
 
@@ -101,6 +101,7 @@ def load_library(build=True):
     lib.b200nuts_load_model_library.argtypes = [C.c_char_p]
     lib.b200nuts_find_model.argtypes = [C.c_char_p]
     lib.b200nuts_output_name.argtypes = [vp, C.c_int64, C.c_char_p, C.c_int]
+    lib.b200nuts_transform_inits.argtypes = [vp, vp, C.c_int64, vp]
     _lib = lib
     return lib
 
@@ -270,6 +271,14 @@ class Engine:
     def set_inits(self, q0):
         a = None if q0 is None else _np(q0, np.float64).reshape(self.num_chains, self.D)
         self._chk(self.lib.b200nuts_set_inits(self.h, None if a is None else a.ctypes.data_as(C.c_void_p)))
+
+    def transform_inits(self, x):
+        """model_base::transform_inits: initial values on the constrained scale, x [n, K] in write_array's column order (NaN = not
+        given) -> unconstrained q [n, D] for set_inits (built-in models and plug-in models with vtable.transform_inits)."""
+        x = _np(x, np.float64).reshape(-1, self.K)
+        q = np.empty((x.shape[0], self.D))
+        self._chk(self.lib.b200nuts_transform_inits(self.h, x.ctypes.data_as(C.c_void_p), x.shape[0], q.ctypes.data_as(C.c_void_p)))
+        return q
 
     def set_inv_metric(self, im):
         shape = (self.num_chains, self.D, self.D) if self.metric == "dense_e" else (self.num_chains, self.D)

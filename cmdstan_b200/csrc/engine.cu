@@ -1233,7 +1233,7 @@ int b200nuts_measure_fp64_fma_peak(int device, double* tflops) {
 
 // ---- plug-in registry (include/b200nuts_model.h) -----------------------------------------------------------------------
 int b200nuts_register_model(const b200nuts_model_vtable* vt) {
-  if (!vt || vt->abi != B200NUTS_MODEL_ABI || !vt->name || !vt->create || !vt->log_prob_grad) {
+  if (!vt || vt->abi < 1 || vt->abi > B200NUTS_MODEL_ABI || !vt->name || !vt->create || !vt->log_prob_grad) {
     g_create_error = "register_model: bad vtable (abi, name, create and log_prob_grad are required)";
     return -B200NUTS_USAGE;
   }
@@ -1307,6 +1307,56 @@ int b200nuts_output_name(b200nuts_engine* e, int64_t k, char* buf, int buflen) {
       break;
     default: vec("v", i);
   }
+  return B200NUTS_OK;
+}
+
+int b200nuts_transform_inits(b200nuts_engine* e, const double* x, int64_t n, double* q) {
+  int rc = finalize_data(e);
+  if (rc) return rc;
+  const int64_t D = e->D, K = e->K_out;
+  if (e->plug) {
+    if (e->plug->abi < 2 || !e->plug->transform_inits) {
+      e->err = std::string(e->plug->name) + ": the model has no transform_inits (user-specified initial values are not available; use init=<radius>)";
+      return B200NUTS_USAGE;
+    }
+    char msg[512] = {0};
+    for (int64_t c = 0; c < n; c++) {
+      rc = e->plug->transform_inits(e->plug_model, x + c * K, q + c * D, msg, (int)sizeof msg);
+      if (rc) {
+        e->err = msg[0] ? msg : "transform_inits failed";
+        return B200NUTS_CONFIG;
+      }
+    }
+    return B200NUTS_OK;
+  }
+  // built-in models: the parameters are the first D output columns, element-wise transforms (M/prim/constraint/lb_free.hpp, lub_free.hpp)
+  const int I = e->md.N, J = e->md.K;
+  auto kind_of = [&](int64_t i) -> int {  // 0 identity, 1 lower bound 0, 2 unit interval
+    switch (e->md.kind) {
+      case MODEL_BERNOULLI: return 2;
+      case MODEL_EIGHT_SCHOOLS: return i == 1 ? 1 : 0;
+      case MODEL_IRT2PL: return (i == 0 || i == 1 + I || (i >= 2 + I && i < 2 + I + J) || i == 3 + I + J) ? 1 : 0;
+      default: return 0;
+    }
+  };
+  for (int64_t c = 0; c < n; c++)
+    for (int64_t i = 0; i < D; i++) {
+      const double v = x[c * K + i];
+      const int kd = kind_of(i);
+      double u;
+      if (v != v) {
+        u = b200nuts_init_not_given(kd);
+      } else if (kd == 1) {
+        if (!(v >= 0)) { e->err = "lb_free: Bounded variable is " + std::to_string(v) + ", but must be greater than or equal to 0"; return B200NUTS_CONFIG; }
+        u = std::log(v);
+      } else if (kd == 2) {
+        if (!(v >= 0 && v <= 1)) { e->err = "lub_free: Bounded variable is " + std::to_string(v) + ", but must be in the interval [0, 1]"; return B200NUTS_CONFIG; }
+        u = std::log(v / (1 - v));
+      } else {
+        u = v;
+      }
+      q[c * D + i] = u;
+    }
   return B200NUTS_OK;
 }
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <sstream>
 #include <stdexcept>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -160,8 +161,10 @@ class device_model {
   // lub_free(0,1) = logit: stan/math/prim/constraint/lb_free.hpp, lub_free.hpp).  Parameters that are absent are left to the engine.
   void transform_inits(const io::var_context& init, std::vector<double>& params_r) const {
     params_r.clear();
-    if (is_plugin())  // the plug-in interface has no unconstraining transform: only random inits (init=<radius>)
-      throw std::invalid_argument("user-specified initial values are not available for plug-in models (use init=<radius>)");
+    if (is_plugin()) {  // the model's own transform_inits (include/b200nuts_model.h), through the C ABI
+      plugin_transform_inits(init, params_r);
+      return;
+    }
     for (auto& b : params_) {
       if (!init.contains_r(b.name)) {
         // partial inits (initialize.hpp:93-101: chained_var_context(init, random_context)): the engine draws this parameter like
@@ -276,6 +279,35 @@ class device_model {
     num_params_r_ = D;
     return true;
   }
+  // constrained values of the init context, laid out like the plug-in's output columns (NaN = not given), then
+  // b200nuts_transform_inits.  The context's variables are matched to the columns by base name ("beta" -> "beta.1", ...).
+  void plugin_transform_inits(const io::var_context& init, std::vector<double>& params_r) const {
+    const size_t K = plugin_outputs_.size();
+    std::vector<double> x(K, std::numeric_limits<double>::quiet_NaN());
+    size_t k = 0;
+    while (k < K) {
+      const std::string b = plugin_outputs_[k].substr(0, plugin_outputs_[k].find('.'));
+      size_t cnt = 0;
+      while (k + cnt < K && plugin_outputs_[k + cnt].substr(0, plugin_outputs_[k + cnt].find('.')) == b) cnt++;
+      if (init.contains_r(b)) {
+        const std::vector<double>& v = init.vals_r(b);
+        if (v.size() != cnt) throw std::invalid_argument("mismatch in number dimensions declared and found in context; processing stage=parameter initialization; variable name=" + b);
+        std::copy(v.begin(), v.end(), x.begin() + k);
+      }
+      k += cnt;
+    }
+    if (!plugin_engine_) {
+      b200nuts_config cfg;
+      b200nuts_default_config(&cfg);
+      cfg.model = id_;
+      if (b200nuts_create(&cfg, &plugin_engine_)) throw std::runtime_error(b200nuts_last_error(nullptr));
+      if (upload_all(plugin_engine_, plugin_data_)) throw std::invalid_argument(b200nuts_last_error(plugin_engine_));
+    }
+    params_r.assign((size_t)num_params_r_, 0.0);
+    const int rc = b200nuts_transform_inits(plugin_engine_, x.data(), 1, params_r.data());
+    if (rc == B200NUTS_CONFIG) throw std::domain_error(b200nuts_last_error(plugin_engine_));
+    if (rc) throw std::invalid_argument(b200nuts_last_error(plugin_engine_));
+  }
   static void expand(const block_t& b, std::vector<std::string>& names) {
     if (b.size < 0) names.push_back(b.name);
     else
@@ -295,6 +327,14 @@ class device_model {
   std::vector<int8_t> y8_;
   io::var_context plugin_data_;
   std::vector<std::string> plugin_outputs_;
+  mutable b200nuts_engine* plugin_engine_ = nullptr;  // holds the plug-in's model object for transform_inits (created on first use)
+
+ public:
+  ~device_model() {
+    if (plugin_engine_) b200nuts_destroy(plugin_engine_);
+  }
+  device_model(const device_model&) = delete;
+  device_model& operator=(const device_model&) = delete;
 };
 
 // the reference's link-time hook, with the model selected by name instead of by linking a stanc-generated class

@@ -157,8 +157,25 @@ int linreg_output_name(void* model, int64_t k, char* buf, int buflen) {
   else std::snprintf(buf, (size_t)buflen, "sigma");
   return B200NUTS_OK;
 }
+// transform_inits (model_base.hpp:348): outputs are (alpha, beta[K], sigma); sigma has a lower bound 0 (lb_free = log)
+int linreg_transform_inits(void* model, const double* x, double* q, char* err, int errlen) {
+  auto* m = (LinReg*)model;
+  const int K = m->K;
+  for (int i = 0; i <= K; i++) q[i] = x[i] == x[i] ? x[i] : b200nuts_init_not_given(0);
+  const double sigma = x[K + 1];
+  if (sigma != sigma) {
+    q[K + 1] = b200nuts_init_not_given(1);
+  } else if (!(sigma >= 0)) {
+    std::snprintf(err, (size_t)errlen, "lb_free: Bounded variable is %g, but must be greater than or equal to 0", sigma);
+    return B200NUTS_CONFIG;
+  } else {
+    q[K + 1] = std::log(sigma);
+  }
+  return 0;
+}
+
 const b200nuts_model_vtable kLinReg = {B200NUTS_MODEL_ABI, "linreg", linreg_create, linreg_destroy, linreg_log_prob_grad, linreg_write_array,
-                                       linreg_output_name};
+                                       linreg_output_name, linreg_transform_inits};
 
 // ---------------------------------------------------------------------------------------------------------------------
 // eight_schools_plugin: the built-in density behind the plug-in interface (bit-for-bit check of the mechanism)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200NUTS_MODEL_ABI 1
+#define B200NUTS_MODEL_ABI 2 /* 2: transform_inits added at the end of the vtable; vtables with abi == 1 are still accepted */
 #define B200NUTS_MODEL_PLUGIN_BASE 100
 
 enum b200nuts_dtype { B200NUTS_F64 = 0, B200NUTS_I32 = 1, B200NUTS_I8 = 2 };
@@ -72,7 +72,27 @@ typedef struct b200nuts_model_vtable {
 
   /* constrained_param_names(): name of output column k ("beta.3"); NULL: "v<k+1>" */
   int (*output_name)(void* model, int64_t k, char* buf, int buflen);
+
+  /* (abi >= 2; may be NULL) transform_inits (stan/src/stan/model/model_base.hpp:348, :596): the user's initial values on the
+     CONSTRAINED scale -> the unconstrained vector, for ONE chain, on the HOST (it runs once per chain at set-up, like the
+     reference's serial loop hmc_nuts_diag_e_adapt.hpp:360-362).
+       x [num_outputs]: write_array's column order (the parameters are its first columns; transformed parameters and generated
+                        quantities that follow are ignored).  NaN = the user gave no value for this element.
+       q [num_params_r] out.  For an element the user did not give write b200nuts_init_not_given(code), code = 0 unbounded, 1 lower
+                        bound 0, 2 unit interval: the engine then draws it on the unconstrained scale exactly like the reference's
+                        random_var_context (initialize.hpp:93-101).  Models with other transforms report "not given" for the
+                        whole vector when anything is missing (the engine then uses random inits).
+     Returns 0, or 78 (CONFIG) with a message in err when a value violates its constraint (lb_free / lub_free throw there).
+     NULL: init=<file> is refused for this model, only init=<radius> works. */
+  int (*transform_inits)(void* model, const double* x, double* q, char* err, int errlen);
 } b200nuts_model_vtable;
+
+/* the "not given" marker of transform_inits: a quiet NaN whose low payload bits carry the parameter's transform */
+static inline double b200nuts_init_not_given(int code) {
+  union { uint64_t u; double d; } v;
+  v.u = 0x7ff8000000000000ull | (uint64_t)(code & 3);
+  return v.d;
+}
 
 typedef const b200nuts_model_vtable* (*b200nuts_model_entry_fn)(int index);
 
@@ -87,6 +107,10 @@ int b200nuts_find_model(const char* name);
 /* constrained_param_names of output column k of an engine's model (built-in or plug-in); valid after the data is set */
 struct b200nuts_engine;
 int b200nuts_output_name(struct b200nuts_engine* e, int64_t k, char* buf, int buflen);
+/* model_base::transform_inits for n chains: x HOST [n][num_outputs] (NaN = not given) -> q HOST [n][num_params_r], ready for
+   b200nuts_set_inits.  Built-in models apply their own transforms; plug-in models need vtable.transform_inits (else 64 USAGE).
+   A value outside its constraint gives 78 (CONFIG) with the reference's message. */
+int b200nuts_transform_inits(struct b200nuts_engine* e, const double* x, int64_t n, double* q);
 
 #ifdef __cplusplus
 }

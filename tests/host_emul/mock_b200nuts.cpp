@@ -209,6 +209,7 @@ int b200nuts_nccl_get_unique_id(void*) { return B200NUTS_SOFTWARE; }
 int b200nuts_measure_fp64_fma_peak(int, double*) { return B200NUTS_SOFTWARE; }
 int b200nuts_nccl_init(b200nuts_engine*, const void*, int, int) { return B200NUTS_SOFTWARE; }
 int b200nuts_measure_allreduce(b200nuts_engine*, int, double*, int64_t*) { return B200NUTS_SOFTWARE; }
+int b200nuts_transform_inits(b200nuts_engine*, const double*, int64_t, double*) { return B200NUTS_SOFTWARE; }
 int b200nuts_register_model(const b200nuts_model_vtable*) { return -B200NUTS_SOFTWARE; }
 int b200nuts_load_model_library(const char*) { g_err = "mock: no plug-ins"; return -B200NUTS_SOFTWARE; }
 int b200nuts_find_model(const char* name) {

@@ -108,3 +108,58 @@ def test_plugin_data_errors(B):
     with pytest.raises(B.B200NutsError) as ei:
         B.Engine("eight_schools_plugin", cases.EIGHT_SCHOOLS, engine="fused")
     assert ei.value.code == B.CONFIG
+
+
+def test_plugin_transform_inits(B):
+    """vtable.transform_inits (model_base::transform_inits, model_base.hpp:348): user inits on the constrained scale for a plug-in
+    model.  The linear regression's sigma has a lower bound: lb_free = log.  A run initialised through it starts where a run
+    initialised with the hand-computed unconstrained vector starts (identical draws); elements the user did not give are drawn
+    by the engine like the reference's random context; a negative sigma is refused with lb_free's message; a model without the
+    callback refuses user inits."""
+    data, truth = _linreg_data()
+    K = 5
+    kw = dict(num_chains=3, random_seed=9, num_warmup=40, num_samples=10, save_warmup=True)
+    e = B.Engine("linreg", data, **kw)
+    x = np.tile(truth, (3, 1)) + 0.1 * np.arange(3)[:, None]
+    q = e.transform_inits(x)
+    assert np.array_equal(q[:, :K + 1], x[:, :K + 1]) and np.array_equal(q[:, K + 1], np.log(x[:, K + 1]))
+    e.set_inits(q)
+    e.init_chains()
+    e.run(50)
+    d_user = e.fetch_draws(constrained=False)
+    e.close()
+    e = B.Engine("linreg", data, **kw)
+    e.set_inits(np.concatenate([x[:, :K + 1], np.log(x[:, K + 1:])], axis=1))
+    e.init_chains()
+    e.run(50)
+    assert np.array_equal(e.fetch_draws(constrained=False), d_user)
+    # partial inits: sigma not given -> marked, the engine draws log sigma ~ U(-2, 2) and keeps the given values
+    xp = x.copy()
+    xp[:, K + 1] = np.nan
+    qp = e.transform_inits(xp)
+    assert np.isnan(qp[:, K + 1]).all() and np.array_equal(qp[:, :K + 1], x[:, :K + 1])
+    e.close()
+    e = B.Engine("linreg", data, num_warmup=0, num_samples=1, adapt_engaged=False, num_chains=3, random_seed=9, stepsize=1e-9)
+    e.set_inits(qp)
+    e.init_chains()
+    e.run(1)
+    d0 = e.fetch_draws(constrained=False)[:, 0, 7:]   # a step of 1e-9: the first draw is the initial point
+    assert np.allclose(d0[:, :K + 1], x[:, :K + 1], atol=1e-6) and (np.abs(d0[:, K + 1]) <= 2.0).all() and len(set(d0[:, K + 1])) == 3
+    xb = x.copy()
+    xb[1, K + 1] = -0.3
+    with pytest.raises(B.B200NutsError) as ei:
+        e.transform_inits(xb)
+    assert ei.value.code == B.CONFIG and "lb_free" in str(ei.value)
+    e.close()
+    s = B.Engine("eight_schools_plugin", cases.EIGHT_SCHOOLS)
+    with pytest.raises(B.B200NutsError) as ei:
+        s.transform_inits(np.zeros((1, s.K)))
+    assert ei.value.code == B.USAGE and "transform_inits" in str(ei.value)
+    s.close()
+    # built-in models answer the same call with their own transforms
+    b = B.Engine("eight_schools_nc", cases.EIGHT_SCHOOLS)
+    xs = np.full((1, b.K), np.nan)
+    xs[0, :2] = [1.5, 2.0]
+    qs = b.transform_inits(xs)
+    assert qs[0, 0] == 1.5 and qs[0, 1] == np.log(2.0) and np.isnan(qs[0, 2:]).all()
+    b.close()
