@@ -922,6 +922,9 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
           grad_ms += solo_ms;  // gradient + the stragglers' own advance work
           e->last_solo_s = solo_ms * 1e-3;
           e->last_solo_chains = *e->h_nactive;
+          if (getenv("B200NUTS_VERBOSE"))
+            std::fprintf(stderr, "[b200nuts] latency kernel: %d chains handed over after %lld lock-steps, %.3f s (cluster of %d)\n", *e->h_nactive, step,
+                         e->last_solo_s, e->irt_solo_cluster);
           break;
         }
       }

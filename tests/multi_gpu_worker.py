@@ -38,12 +38,15 @@ def main():
     dist.init_process_group("cpu:gloo,cuda:nccl")
     kw = dict(random_seed=4242, num_warmup=40, num_samples=20, save_warmup=True)
     # ---- rows: poisson GLM, every rank all chains, one all-reduce per leapfrog
-    data = cases.poisson_data(4000, 6)
+    data = cases.poisson_data(4003, 6)   # not a multiple of the world size: shards differ by one row
     res = {}
     for transport in ("nccl", "torch"):
         e = S.row_sharded_engine("poisson_glm", data, rank, world, transport=transport, device=lr, num_chains=5, init_chain_id=1, **kw)
         q = np.random.default_rng(1).uniform(-1, 1, size=(7, e.D))
         lp, g = e.log_prob_grad(q)
+        if transport == "nccl":   # the exchange step's own cost is measurable (bench.py reports it per leapfrog)
+            us, nbytes = e.measure_allreduce(50)
+            assert nbytes == 5 * (1 + 8) * 8 and 0.5 < us < 5000.0, (us, nbytes)
         d, eps = run(e, 60)
         res[transport] = (lp, g, d, eps)
         allr = gather((lp, g, d, eps), rank, world)
@@ -58,14 +61,19 @@ def main():
         lp, g, d, eps = res["nccl"]
         assert np.allclose(lp, lp1, rtol=1e-12) and np.allclose(g, g1, rtol=1e-10, atol=1e-9)
         assert np.array_equal(d[:, :6, 3:6], d1[:, :6, 3:6]) and np.allclose(d[:, :6], d1[:, :6], rtol=1e-8, atol=1e-10)
-    # ---- chains: eight schools, 6 chains over the ranks == one engine with 6 chains, bit for bit
-    e = S.chain_sharded_engine("eight_schools_nc", cases.EIGHT_SCHOOLS, rank, world, num_chains=6, init_chain_id=3, device=lr, **kw)
-    d, eps = run(e, 60)
-    parts = gather((d, eps), rank, world)
+    # ---- chains: 24 chains over the ranks == one engine with 24 chains, bit for bit (eight schools: fused engine; IRT: lock-step
+    # engine + latency kernel, the mode of north_star's config c4)
+    ok = True
+    for model, mdata in (("eight_schools_nc", cases.EIGHT_SCHOOLS), ("irt_2pl", cases.irt_data(40, 9))):
+        e = S.chain_sharded_engine(model, mdata, rank, world, num_chains=24, init_chain_id=3, device=lr, **kw)
+        d, eps = run(e, 60)
+        parts = gather((d, eps), rank, world)
+        if rank == 0:
+            e = B.Engine(model, mdata, num_chains=24, init_chain_id=3, device=lr, **kw)
+            d1, eps1 = run(e, 60)
+            ok = ok and np.array_equal(np.concatenate([p[0] for p in parts]), d1) and np.array_equal(np.concatenate([p[1] for p in parts]), eps1)
     if rank == 0:
-        e = B.Engine("eight_schools_nc", cases.EIGHT_SCHOOLS, num_chains=6, init_chain_id=3, device=lr, **kw)
-        d1, eps1 = run(e, 60)
-        assert np.array_equal(np.concatenate([p[0] for p in parts]), d1) and np.array_equal(np.concatenate([p[1] for p in parts]), eps1)
+        assert ok
         print("MULTI_GPU_OK world=%d" % world)
     dist.barrier()
     dist.destroy_process_group()
