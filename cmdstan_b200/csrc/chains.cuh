@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(32 * kFusedMaxWarps, 4) fused_chain_kernel(Sam
   }
 }
 
+// advance_cta.cu: one CTA per chain for very long parameter vectors (bit-identical results)
+constexpr int kAdvanceCtaD = 512;
+constexpr int kAdvanceCtaMaxLd = 4608;  // 6 * ld doubles of shared memory must fit (216 KB)
+cudaError_t launch_advance_cta(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
 // advance_big.cu: the same kernel built with B200_VEC_UNROLL = 8 (bit-identical results)
 void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
 // irt.cu: latency form for the stragglers of an IRT run (one cluster of 8 CTAs, or one CTA, per remaining chain)

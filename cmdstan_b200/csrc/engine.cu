@@ -226,6 +226,7 @@ struct b200nuts_engine {
   allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
   void* nccl_comm = nullptr;  // ncclComm_t owned by the engine (b200nuts_nccl_init)
+  int advance_cta = 1;        // long parameter vectors: one CTA per chain in the advance step (B200NUTS_ADVANCE_CTA=0: one warp per chain)
   int irt_solo = 48;          // IRT: at most this many requesting chains => the latency kernel finishes them (B200NUTS_IRT_SOLO; 0 = never)
   int irt_solo_cluster = 8;   // CTAs per chain of the latency kernel: 8 (cluster) or 1 (B200NUTS_IRT_SOLO_CLUSTER, or set after a failed cluster launch)
   double last_run_s = 0, last_grad_s = 0, last_solo_s = 0;
@@ -804,6 +805,7 @@ int b200nuts_init_chains(b200nuts_engine* e) {
   }
   rc = ensure_glm_ws(e, C);
   if (rc) return rc;
+  if (const char* t = getenv("B200NUTS_ADVANCE_CTA")) e->advance_cta = atoi(t) != 0;
   if (const char* t = getenv("B200NUTS_IRT_SOLO")) e->irt_solo = atoi(t);
   if (const char* t = getenv("B200NUTS_IRT_SOLO_CLUSTER")) e->irt_solo_cluster = atoi(t) == 1 ? 1 : 8;
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -886,6 +888,7 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
       if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
       if (e->scfg.dense || e->scfg.diag || e->scfg.static_hmc) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
+      else if (e->advance_cta && e->D >= kAdvanceCtaD && e->ld <= kAdvanceCtaMaxLd) CUDA_TRY(e, launch_advance_cta(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream));
       else if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else advance_kernel<0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;

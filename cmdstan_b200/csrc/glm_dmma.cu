@@ -362,6 +362,284 @@ __global__ void __launch_bounds__(NT, 1) glm_dmma_kernel(const GlmTcArgs a) {
 
 
 // =====================================================================================================================
+// v5 (round 2): v2's register blocking (each warp: 32 rows x 16 chains in phase A, MB design-column blocks x 16 chains in phase
+// B -- 6 fragment loads per 8 DMMAs; v3 / v4's 8 x 1 blocking needs 9 and measured 20 % slower on hardware, r01d / r02a), but
+// the CTA is TWO GROUPS of four warps that run out of phase.  The r02d capture of v2 shows both tensor phases bound by the DMMA
+// pipe (62 % of the time), and the rest spent where all eight warps leave the pipe idle together: the link (13 %), the
+// block-wide barriers (11 %), tile set-up.  Here group g owns chain columns [32 g, 32 g + 32) of the chain tile: the two
+// groups share the X / q tiles in shared memory but nothing else, synchronise internally with named barriers of 128 threads,
+// and group 1 starts half a tile late -- so while one group evaluates the link or waits at its barrier, the other one's DMMAs
+// keep the pipe busy (each SM sub-partition holds one warp of each group).  Shared buffers are recycled by the last of the
+// eight warps to release them (v3's protocol: hardware-validated in r01d / r02a, race-checked on the CPU rig).
+// Summation order per chain is v2's: results are bit-identical to v2.
+// =====================================================================================================================
+#ifdef B200_SIMT_EMUL
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) { simt::named_bar_sync(id, nthreads); }
+__device__ __forceinline__ void group_bar_arrive(int id, int nthreads) { simt::named_bar_arrive(id, nthreads); }
+#else
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void group_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#endif
+
+// one arrival per warp on a shared counter; returns true (to the whole warp) in the warp that arrived last of the CTA's eight,
+// after resetting the counter.  Orders the warp's earlier shared-memory reads before the refill the last arriver issues.
+__device__ __forceinline__ bool warp_arrive_is_last8(int* cnt, int lane) {
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(cnt, 1) == NT / 32 - 1;
+    if (last) {
+      *cnt = 0;
+      __threadfence_block();
+    }
+  }
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+template <int LINK, int MB>
+__global__ void __launch_bounds__(NT, 1) glm_dmma5_kernel(const GlmTcArgs a) {
+  B200_DYN_SMEM(smem);
+  const int Dk = a.Dk;
+  const int xs_ld = xs_ld_for(Dk);
+  double* Bs = smem;                               // [TC][xs_ld]     chain-major copy of the q rows of the chain tile
+  double* Xs0 = Bs + (size_t)TC * xs_ld;           // [2][TR][xs_ld]  double-buffered X tile
+  double* Ds = Xs0 + (size_t)2 * TR * xs_ld;       // [TR][DS_LD]     columns [32 g, 32 g + 32): group g's derivative tile
+  double* ys0 = Ds + (size_t)TR * DS_LD;           // [2][TR]  2y-1 / y as double
+  double* lpred = ys0 + 2 * TR;                    // [2][TC]  log-likelihood partials of the two row halves
+  double* exptab = lpred + 2 * TC;                 // [32]     2^(j/32) (fastmath.cuh)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(exptab + 32);  // fullX[0], fullX[1], fullB
+  int* doneX = reinterpret_cast<int*>(bars + 3);   // [2] warps done with X buffer b
+  int* doneB = doneX + 2;                          // warps done with the q tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int grp = warp >> 2, gw = warp & 3;        // group, warp inside the group
+  const int gtid = tid & 127;                      // thread inside the group
+  const int p = blockIdx.x;
+  const int n_list = a.n_list ? *a.n_list : a.n_fixed;
+  const int n_ct = (n_list + TC - 1) / TC;
+
+  // fixed row group of this CTA
+  const long long t_begin = (long long)p * a.n_row_tiles / a.P, t_end = (long long)(p + 1) * a.n_row_tiles / a.P;
+  const long long row_begin = t_begin * TR;
+  long long row_end = t_end * TR;
+  if (row_end > a.N) row_end = a.N;
+  const int n_rt = (int)(t_end - t_begin);
+  const long long n_it = (long long)n_ct * n_rt;
+  if (n_it == 0) return;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    doneX[0] = doneX[1] = doneB[0] = 0;
+    fence_mbarrier_init();
+  }
+  exp_table_load(exptab, tid);
+  // columns [ldq, Dk) of the B tile are never written by the bulk copies: zero them once
+  for (int e = tid; e < TC * (Dk - a.ldq); e += NT) {
+    const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
+    Bs[c * xs_ld + k] = 0.0;
+  }
+  fence_proxy_async();
+  __syncthreads();  // the only block-wide barrier of the kernel
+
+  const unsigned row_bytes = (unsigned)Dk * 8u, q_bytes = (unsigned)a.ldq * 8u;
+  // issued by one whole warp: X tile + y slice of iteration `it2` into its buffer
+  auto load_x = [&](long long it2) {
+    const int buf = (int)(it2 & 1);
+    const int rt2 = (int)(it2 % n_rt);
+    double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const long long row0 = row_begin + (long long)rt2 * TR;
+    const int valid = (int)((row_end - row0) < TR ? (row_end - row0) : TR);
+    // generic-proxy part of the tile first (y slice, zero rows past the end of the group): released by the arrive below
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      const int yv = r < valid ? a.y[row0 + r] : 0;
+      ys0[buf * TR + r] = LINK == 0 ? 2.0 * yv - 1.0 : (double)yv;
+      if (r >= valid)
+        for (int k = 0; k < Dk; k += 2) *reinterpret_cast<double2*>(Xs + r * xs_ld + k) = make_double2(0.0, 0.0);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&bars[buf], (unsigned)valid * row_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      if (r < valid) tma_load_1d(Xs + r * xs_ld, a.X + (size_t)(row0 + r) * a.ldx, row_bytes, &bars[buf]);
+    }
+  };
+  auto load_b = [&](int ct2) {  // one whole warp: q rows of chain tile ct2
+    const int nbq = n_list - ct2 * TC < TC ? n_list - ct2 * TC : TC;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(&bars[2], (unsigned)nbq * q_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TC / 32; h++) {
+      const int c = lane + 32 * h;
+      if (c < nbq) {
+        const int slot = ct2 * TC + c;
+        tma_load_1d(Bs + c * xs_ld, a.Q + (size_t)(a.list ? a.list[slot] : slot) * a.ldq, q_bytes, &bars[2]);
+      }
+    }
+  };
+  if (warp == 0) {
+    load_b(0);
+    load_x(0);
+    if (n_it > 1) load_x(1);
+  }
+
+  // phase-A tiling: warp -> 32 rows x 16 chains (4 x 2 mma tiles); phase-B tiling: warp -> MB m-blocks x 16 chains
+  const int a_rb = (gw & 1) * 32, a_cb = grp * 32 + (gw >> 1) * 16;
+  const int b_mh = (gw & 1) * MB, b_cb = a_cb;
+  const int bar_id = 1 + grp;   // named barrier of this group (barrier 0 is __syncthreads')
+
+  double gacc[MB][2][2];
+  double lpacc[2][2];       // poisson: running sums of the log-likelihood terms
+  LogitAcc lacc[2][2];      // logistic: the same in product form (fastmath.cuh)
+  int n_pad = 0;            // logistic: rows past the end of the row group (X == 0 => eta == 0) this lane evaluated
+  int ct = 0, rt = 0;
+  for (long long it = 0; it < n_it; it++) {
+    const int buf = (int)(it & 1);
+    if (rt == 0) {
+#pragma unroll
+      for (int m = 0; m < MB; m++)
+#pragma unroll
+        for (int n = 0; n < 2; n++) gacc[m][n][0] = gacc[m][n][1] = 0.0;
+      lpacc[0][0] = lpacc[0][1] = lpacc[1][0] = lpacc[1][1] = 0.0;
+      if (LINK == 0) {
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+          logit_acc_init(lacc[n][0]);
+          logit_acc_init(lacc[n][1]);
+        }
+        n_pad = 0;
+      }
+      mbar_wait(&bars[2], (unsigned)(ct & 1));
+    }
+    mbar_wait(&bars[buf], (unsigned)((it >> 1) & 1));
+    if (it == 0 && grp == 1) group_bar_sync(3, NT);   // group 1 starts when group 0 has finished its first phase A
+    const double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const double* ys = ys0 + buf * TR;
+    const long long row0 = row_begin + (long long)rt * TR;
+    // 8-chain column blocks of this warp's 16 chains that hold requesting chains (warp-uniform)
+    const int in_tile = n_list - ct * TC;
+    const int nb = in_tile - a_cb >= 16 ? 2 : (in_tile - a_cb > 8 ? 2 : (in_tile - a_cb > 0 ? 1 : 0));
+    // ---- phase A
+    double acc[4][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    {
+      const double* xa = Xs + (a_rb + gid) * xs_ld + tig;
+      const double* ba = Bs + (a_cb + gid) * xs_ld + tig;
+      if (nb == 2) phase_a<2>(acc, xa, ba, Dk, xs_ld);
+      else if (nb == 1) phase_a<1>(acc, xa, ba, Dk, xs_ld);
+    }
+    if (it == 0 && grp == 0) group_bar_arrive(3, NT);
+    if (rt == n_rt - 1 && ct + 1 < n_ct) {  // last row tile of this chain tile: this warp is done with the q tile
+      if (warp_arrive_is_last8(doneB, lane)) load_b(ct + 1);
+    }
+    group_bar_sync(bar_id, 128);  // every warp of the group has finished phase B of the previous tile: Ds (our columns) is free
+    // ---- link on the accumulator fragments: element (row = a_rb + mi*8 + gid, chain = a_cb + ni*8 + 2*tig + j)
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+      const int r = a_rb + mi * 8 + gid;
+      const bool valid = row0 + r < row_end;
+      const double yd = ys[r];
+      if (LINK == 0) n_pad += valid ? 0 : 1;
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        if (ni >= nb) continue;
+        double dv[2];
+        if (LINK == 0) {
+#pragma unroll
+          for (int j = 0; j < 2; j++) dv[j] = logit_term(lacc[ni][j], acc[mi][ni][j], yd, exptab);
+        } else {
+          double lv[2];
+#pragma unroll
+          for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
+#pragma unroll
+          for (int j = 0; j < 2; j++) lpacc[ni][j] += valid ? lv[j] : 0.0;
+        }
+        *reinterpret_cast<double2*>(&Ds[r * DS_LD + a_cb + ni * 8 + 2 * tig]) = make_double2(dv[0], dv[1]);
+      }
+    }
+    if (LINK == 0) {
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        logit_acc_fold(lacc[ni][0]);
+        logit_acc_fold(lacc[ni][1]);
+      }
+    }
+    group_bar_sync(bar_id, 128);  // the group's derivative tile is complete
+    // ---- phase B: G[m][chain] += sum_r Xs[r][m] * Ds[r][chain]
+    {
+      const double* xb = Xs + tig * xs_ld + b_mh * 8 + gid;
+      const double* db = Ds + tig * DS_LD + b_cb + gid;
+      if (nb == 2) phase_b<2, MB>(gacc, xb, db, b_mh, Dk, xs_ld);
+      else if (nb == 1) phase_b<1, MB>(gacc, xb, db, b_mh, Dk, xs_ld);
+    }
+    // this warp is done with Xs[buf] and ys[buf]: the last of the eight warps to get here refills them for iteration it + 2
+    if (it + 2 < n_it) {
+      if (warp_arrive_is_last8(&doneX[buf], lane)) load_x(it + 2);
+    } else {
+      __syncwarp();
+    }
+    if (rt == n_rt - 1) {
+      const int slot0 = ct * TC;
+      // ---- partial gradient of this (row group, chain tile)
+#pragma unroll
+      for (int m = 0; m < MB; m++) {
+        const int k = (b_mh + m) * 8 + gid;
+        if (k < Dk) {
+#pragma unroll
+          for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int slot = slot0 + b_cb + ni * 8 + 2 * tig + j;
+              if (slot < n_list) a.Gp[((size_t)p * a.cap + slot) * Dk + k] = gacc[m][ni][j];
+            }
+        }
+      }
+      // ---- partial log-likelihood: sum over the 8 row-lanes (gid) by shuffles, then the two row halves via shared memory
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          double v = LINK == 0 ? (ni < nb ? logit_acc_value(lacc[ni][j], n_pad) : 0.0) : lpacc[ni][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          lpacc[ni][j] = v;
+        }
+      if (gid == 0) {
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) lpred[(gw & 1) * TC + a_cb + ni * 8 + 2 * tig + j] = lpacc[ni][j];
+      }
+      group_bar_sync(bar_id, 128);
+      if (gtid < 32 && slot0 + grp * 32 + gtid < n_list)
+        a.LPp[(size_t)p * a.cap + slot0 + grp * 32 + gtid] = lpred[grp * 32 + gtid] + lpred[TC + grp * 32 + gtid];
+      group_bar_sync(bar_id, 128);  // lpred (our columns) is read before the next chain tile's partials are written
+      rt = 0;
+      ct++;
+    } else {
+      rt++;
+    }
+  }
+}
+
+size_t glm_tc5_smem_bytes(int Dk) {
+  return ((size_t)TC * xs_ld_for(Dk) + (size_t)2 * TR * xs_ld_for(Dk) + (size_t)TR * DS_LD + 2 * TR + 2 * TC + 32 + 3 + 2) * sizeof(double);
+}
+
+
+// =====================================================================================================================
 // v3: the same fused product, with NO block-wide barrier in steady state (profiles/README.md r01c: with three
 // __syncthreads per tile all eight warps run the same phase at the same time, the link phase cannot saturate the shared
 // FP64 pipe on its own, and 24 % of its cycles idle).
@@ -882,6 +1160,26 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
       if (logistic) LAUNCH3(0, 14) else LAUNCH3(1, 14)
     }
 #undef LAUNCH3
+    return 1;
+  }
+  if (ws.variant == 4) {  // v5: two out-of-phase groups of four warps
+    const size_t smem5 = glm_tc5_smem_bytes(a.Dk);
+#define LAUNCH5(LINK, MB)                                                                     \
+  {                                                                                           \
+    auto k = glm_dmma5_kernel<LINK, MB>;                                                      \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);         \
+    B200_LAUNCH(k, ws.P, NT, smem5, stream, a);                                               \
+  }
+    if (a.Dk <= 16) {
+      if (logistic) LAUNCH5(0, 1) else LAUNCH5(1, 1)
+    } else if (a.Dk <= 32) {
+      if (logistic) LAUNCH5(0, 2) else LAUNCH5(1, 2)
+    } else if (a.Dk <= 64) {
+      if (logistic) LAUNCH5(0, 4) else LAUNCH5(1, 4)
+    } else {
+      if (logistic) LAUNCH5(0, 7) else LAUNCH5(1, 7)
+    }
+#undef LAUNCH5
     return 1;
   }
   const size_t smem = glm_tc_smem_bytes(a.Dk);

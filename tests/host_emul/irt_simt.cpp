@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>  // tests/host_emul/simt/cuda_runtime.h
 
 #include "../../cmdstan_b200/csrc/irt.cu"
+#include "../../cmdstan_b200/csrc/advance_cta.cu"
 #include "../../cmdstan_b200/csrc/host_seed.h"
 
 using namespace b200;
@@ -26,6 +27,9 @@ extern "C" int irt_simt_grad(int form, int I, int J, int C, int ld, const signed
   setenv("B200NUTS_IRT_VARIANT", form == 2 ? "2" : "1", 1);
   return launch_irt_grad(m, b, nullptr);
 }
+
+static int g_advance_cta = 0;
+extern "C" void irt_simt_set_advance_cta(int on) { g_advance_cta = on; }
 
 // C chains of the IRT model through the lock-step engine (advance kernel + irt_grad_kernel per leapfrog); after
 // `tail_after` lock-steps (< 0: never) the chains still requesting a gradient are handed to irt_solo_kernel (one CTA per chain),
@@ -62,7 +66,8 @@ extern "C" long long irt_simt_run(int C, int I, int J, const signed char* y, uns
   long long launches = 0;
   for (long long step = 0;; step++) {
     int n_active = 0;
-    simt::launch((C + kChainsPerBlock - 1) / kChainsPerBlock, 32 * kChainsPerBlock, 0, [&] { advance_kernel<1>(cfg, d, C, active.data(), list.data(), &n_active); });
+    if (g_advance_cta) launch_advance_cta(cfg, d, C, active.data(), list.data(), &n_active, nullptr);   // one CTA per chain (advance_cta.cu)
+    else simt::launch((C + kChainsPerBlock - 1) / kChainsPerBlock, 32 * kChainsPerBlock, 0, [&] { advance_kernel<1>(cfg, d, C, active.data(), list.data(), &n_active); });
     launches++;
     if (n_active == 0) break;
     b.n_list = &n_active;

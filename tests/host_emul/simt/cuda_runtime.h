@@ -132,8 +132,36 @@ struct MBar {
   }
 };
 
+// bar.sync / bar.arrive with a barrier id and a thread count (named barriers): arrivals are counted; the arrival that completes
+// the count opens the barrier for the waiters of this generation
+struct NamedBar {
+  std::atomic<int> count{0};
+  std::atomic<unsigned> gen{0};
+  void arrive(int n) {
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      count.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+    }
+  }
+  bool sync(int n) {
+    const unsigned g = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      count.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+      return true;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0; gen.load(std::memory_order_acquire) == g; spins++) {
+      std::this_thread::yield();
+      if ((spins & 0xfff) == 0xfff && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(wait_seconds())) return false;
+    }
+    return true;
+  }
+};
+
 struct Block {
   Barrier bar;
+  NamedBar named[16];
   std::atomic<int> votes[3] = {};  // __syncthreads_or: three rotating accumulators
   std::vector<std::unique_ptr<Warp>> warps;
   std::vector<unsigned char> dyn;
@@ -287,6 +315,12 @@ inline const uint64_t (*exchange(uint64_t w0, uint64_t w1))[2] {
 }  // namespace simt
 
 inline void __syncthreads() { simt::tc.blk->bar.wait("__syncthreads: not all threads arrived"); }
+namespace simt {
+inline void named_bar_sync(int id, int nthreads) {
+  if (!tc.blk->named[id].sync(nthreads)) die("bar.sync (named): not all threads arrived");
+}
+inline void named_bar_arrive(int id, int nthreads) { tc.blk->named[id].arrive(nthreads); }
+}  // namespace simt
 inline int __syncthreads_or(int pred) {
   simt::Block* b = simt::tc.blk;
   const unsigned n = simt::tc.bop++;

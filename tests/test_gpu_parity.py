@@ -43,7 +43,7 @@ def test_log_prob_grad_matches_oracle(name, data):
     e.close()
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2"] + EXPERIMENTAL_GLM)
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
 def test_glm_kernel_variants_agree(variant, monkeypatch):
     """DFMA (0), block-synchronous DMMA (1) and warp-asynchronous DMMA (2) variants of the fused GLM gradient against the
     oracle: ragged sizes (N not a tile multiple, several row tiles per row group, chain counts that leave tiles underfilled)."""
@@ -60,7 +60,21 @@ def test_glm_kernel_variants_agree(variant, monkeypatch):
         e.close()
 
 
-@pytest.mark.parametrize("variant", ["1", "2"] + EXPERIMENTAL_GLM)
+def test_glm_v5_is_bit_identical_to_v2(monkeypatch):
+    """glm_dmma5_kernel (two out-of-phase groups of four warps, the default) keeps v2's summation order: same bits at c3's width
+    (D = 101, several chain tiles, ragged row count) and for the poisson link."""
+    for name, data, nq in (("logistic", cases.logistic_data(30011, 100), 200), ("poisson_glm", cases.poisson_data(20000, 50), 70)):
+        q = np.random.default_rng(9).uniform(-1, 1, size=(nq, data["X"].shape[1] + 1))
+        out = []
+        for v in ("1", "4"):
+            monkeypatch.setenv("B200NUTS_GLM_VARIANT", v)
+            e = _engine(name, data)
+            out.append(e.log_prob_grad(q))
+            e.close()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
 def test_glm_tensor_variants_batch_independent(variant, monkeypatch):
     """a chain's draws do not depend on which slot of which chain tile serves it (fixed summation order per chain)."""
     monkeypatch.setenv("B200NUTS_GLM_VARIANT", variant)
@@ -316,9 +330,12 @@ def test_irt_latency_kernel_bit_identical(C, shape, monkeypatch):
     data = cases.irt_data(*shape)
     nw, ns = (60, 25) if shape[0] < 500 else (12, 6)
     out = []
-    for solo, cl in (("0", "8"), ("48", "8"), ("48", "1")):
+    # baseline: one warp per chain in the advance step, no latency kernel; then the CTA-per-chain advance step (advance_cta.cu, used
+    # for D >= 512) and the two forms of the latency kernel
+    for solo, cl, cta in (("0", "8", "0"), ("0", "8", "1"), ("48", "8", "1"), ("48", "1", "1")):
         monkeypatch.setenv("B200NUTS_IRT_SOLO", solo)
         monkeypatch.setenv("B200NUTS_IRT_SOLO_CLUSTER", cl)
+        monkeypatch.setenv("B200NUTS_ADVANCE_CTA", cta)
         e = _engine("irt_2pl", data, num_chains=C, random_seed=77, num_warmup=nw, num_samples=ns, save_warmup=True)
         e.init_chains()
         for n in (nw * 2 // 3, nw + ns - nw * 2 // 3):   # two calls: the latency kernel must leave every chain resumable
@@ -327,7 +344,7 @@ def test_irt_latency_kernel_bit_identical(C, shape, monkeypatch):
         assert (err == 0).all() and (it == nw + ns).all()
         out.append((e.fetch_draws(constrained=False), e.adaptation(), ng))
         e.close()
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert np.array_equal(out[0][0], out[k][0]), k
         assert np.array_equal(out[0][1][0], out[k][1][0]) and np.array_equal(out[0][1][1], out[k][1][1]), k
         assert np.array_equal(out[0][2], out[k][2]), k

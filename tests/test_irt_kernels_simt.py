@@ -26,7 +26,7 @@ ROOT = os.path.dirname(HERE)
 EMUL = os.path.join(HERE, "host_emul")
 SRC = os.path.join(EMUL, "irt_simt.cpp")
 DEPS = [SRC, os.path.join(EMUL, "simt", "cuda_runtime.h")] + [os.path.join(ROOT, "cmdstan_b200", "csrc", f) for f in
-                                                               ("irt.cu", "solo_leaf.cuh", "irt_body.cuh", "chains.cuh", "nuts.cuh", "rng.cuh", "fastmath.cuh", "warp.cuh", "models.cuh")]
+                                                               ("irt.cu", "advance_cta.cu", "solo_leaf.cuh", "irt_body.cuh", "chains.cuh", "nuts.cuh", "rng.cuh", "fastmath.cuh", "warp.cuh", "models.cuh")]
 CXX = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-ffp-contract=off", "-Wno-tsan", "-Wno-unknown-pragmas", "-I", os.path.join(EMUL, "simt")]
 vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -108,6 +108,20 @@ def test_latency_kernel_finishes_chains_like_the_lock_step_engine(lib, shape):
         t = _run(lib, Cn, I, J, nw, ns, 4, tail_after)
         assert np.array_equal(t[0], base[0]) and np.array_equal(t[1], base[1]) and np.all(t[2] == 0)
         assert t[3] == 2 * tail_after + 3   # tail_after x (advance + gradient), advance, latency kernel, the advance that finds every chain idle
+
+
+def test_cta_per_chain_advance_equals_warp_per_chain_advance(lib):
+    """advance_cta.cu (long parameter vectors: the CTA's 256 threads share the element-wise work of the leaf path) against
+    advance_kernel (one warp per chain): identical draws and gradient counts."""
+    Cn, I, J, nw, ns = 2, 20, 6, 8, 4
+    lib.irt_simt_set_advance_cta(0)
+    base = _run(lib, Cn, I, J, nw, ns, 4, -1)
+    lib.irt_simt_set_advance_cta(1)
+    try:
+        t = _run(lib, Cn, I, J, nw, ns, 4, -1)
+    finally:
+        lib.irt_simt_set_advance_cta(0)
+    assert np.array_equal(t[0], base[0]) and np.array_equal(t[1], base[1]) and np.all(t[2] == 0) and t[3] == base[3]
 
 
 def test_straggler_kernel_has_no_race():
