@@ -212,6 +212,7 @@ struct b200nuts_engine {
   double *d_X = nullptr, *d_yr = nullptr, *d_sigma = nullptr;
   int* d_yi = nullptr;
   signed char* d_y8 = nullptr;
+  unsigned short* d_ypk = nullptr;
   DeviceChains dc{};
   double *d_user_q0 = nullptr, *d_user_im = nullptr;
   std::vector<double> h_user_q0, h_user_im;
@@ -324,7 +325,7 @@ void b200nuts_destroy(b200nuts_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   if (e->plug && e->plug_model && e->plug->destroy) e->plug->destroy(e->plug_model);
-  free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8);
+  free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8); free_dev(e->d_ypk);
   free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws); free_dev(e->dc.mat);
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
@@ -520,6 +521,12 @@ static int finalize_data(b200nuts_engine* e) {
       m.D = 4 + m.N + 2 * m.K;
       CUDA_TRY(e, upload((void**)&e->d_y8, e->h_y8.data(), e->h_y8.size()));
       m.y8 = e->d_y8;
+      {
+        std::vector<unsigned short> pk((size_t)m.N * 8);
+        irt_pack_responses(e->h_y8.data(), m.N, m.K, pk.data());
+        CUDA_TRY(e, upload((void**)&e->d_ypk, pk.data(), pk.size() * sizeof(unsigned short)));
+        m.ypk = e->d_ypk;
+      }
       break;
     }
   }

@@ -149,32 +149,38 @@ __device__ __forceinline__ double logit_acc_value(const LogitAcc& a, int pad_ter
 //   t = yd eta;  term = -log1p(exp(-t)), t < -20: t, t > 20: -exp(-t);  derivative = yd e / (1 + e) with e = exp(-t),
 //   t < -20: yd, t > 20: -e (the reference drops the sign there).
 // Written for the instruction mix of sm_100 (one FP64 instruction occupies the pipe for two issue slots, so integer / select
-// instructions cost as much as FP64 ones once they outnumber them): 21 FP64 + ~25 other instructions.
+// instructions cost as much as FP64 ones once they outnumber them): 19 FP64 + ~25 other instructions.
 //  * with em := 0 below the lower cut-off, 1 + em == 1 and 1 / (1 + em) == 1 give term and derivative of that branch exactly;
 //  * above the upper cut-off the product form differs from -e by e^2 / 2 < 3e-18; the derivative's sign quirk is a sign-bit edit;
 //  * the derivative is yd (1/2 - copysign(s - 1/2, t)), s = 1 / (1 + em): no select, absolute error < 2.5e-16;
 //  * a padding observation (eta == 0 exactly) needs no mask: see logit_acc_value;
 //  * non-finite eta: +-inf behaves like the cut-off branches; NaN arises only from non-finite parameters, which the prior terms
 //    of every model turn into a non-finite log density on their own (checked by the GPU edge-case tests).
-__device__ __forceinline__ double logit_term(LogitAcc& acc, double eta, double yd, const double* tab) {
-  const double t = yd * eta;
-  const int hi = __double2hiint(t);
+// `negmask` carries the observation: 0 for y = 1, 0x80000000 for y = 0 (the sign bit of 2y - 1): multiplications by +-1 are sign-bit
+// edits on the integer pipe.
+__device__ __forceinline__ double logit_term(LogitAcc& acc, double eta, int negmask, const double* tab) {
+  const int lo = __double2loint(eta);
+  const int hi = __double2hiint(eta) ^ negmask;                  // t = (2y - 1) eta
   const unsigned ahi = (unsigned)hi & 0x7fffffffu;
-  const bool big = ahi > 0x40340000u || (ahi == 0x40340000u && __double2loint(t) != 0);   // |t| > 20 (20.0 = 0x4034000000000000)
+  const bool big = ahi > 0x40340000u || (ahi == 0x40340000u && lo != 0);   // |t| > 20 (20.0 = 0x4034000000000000)
   const bool neg = hi < 0;
-  double em = fast_exp_t(-fabs(t), tab);                         // exp(-|t|) in (0, 1]; garbage beyond 700, replaced next
+  double em = fast_exp_t(__hiloint2double((int)(ahi | 0x80000000u), lo), tab);   // exp(-|t|) in (0, 1]; garbage beyond 700, replaced next
   em = ((big && neg) || ahi >= 0x4085e000u) ? 0.0 : em;          // |t| >= 700 (0x4085e00000000000): exp(-|t|) < 1e-304 -> 0
   const double f1 = 1.0 + em;
   const double s = fast_rcp3(f1);                                // 1 / (1 + em) in [1/2, 1]
   const double h = s - 0.5;
   const double hs = __hiloint2double(__double2hiint(h) | (hi & 0x80000000), __double2loint(h));   // copysign(h, t), h >= 0
-  const double w = 0.5 - hs;                                     // t < 0: s;  t >= 0: 1 - s = em s
-  const int ydhi = __double2hiint(yd) | ((big && !neg) ? 0x80000000 : 0);
-  const double d = __hiloint2double(ydhi, 0) * w;
+  const double w = 0.5 - hs;                                     // t < 0: s;  t >= 0: 1 - s = em s;  w >= 0
+  const int dsign = (big && !neg) ? (int)0x80000000 : negmask;   // (2y - 1) w, except above the upper cut-off: -w
+  const double d = __hiloint2double(__double2hiint(w) | dsign, __double2loint(w));
   acc.prod *= f1;
   const int m = hi >> 31;                                        // all ones when t < 0
-  acc.sum += __hiloint2double((int)ahi & m, __double2loint(t) & m);   // max(-t, 0)
+  acc.sum += __hiloint2double((int)ahi & m, lo & m);             // max(-t, 0)
   return d;
+}
+// the same with the observation given as the double 2y - 1
+__device__ __forceinline__ double logit_term(LogitAcc& acc, double eta, double yd, const double* tab) {
+  return logit_term(acc, eta, __double2hiint(yd) & (int)0x80000000, tab);
 }
 
 // per-observation log-likelihood term and d(term)/d(eta).  `yd` is 2y-1 (logistic) or y (poisson) as a double.

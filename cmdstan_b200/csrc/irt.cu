@@ -42,7 +42,7 @@ int irt_max_items() { return IRT_MAXJ; }
 // OCC = 1: item parameters in registers, one CTA per SM.  OCC = 2: exp(a), b in shared memory and a 128-register budget, two
 // CTAs (16 warps) per SM: the one-CTA form is latency-bound at two warps per sub-partition (r01c / r01d captures).
 template <int IPL, int OCC>
-__global__ void __launch_bounds__(IRT_NT, OCC) irt_grad_kernel(const signed char* __restrict__ y, int I, int J, int D,
+__global__ void __launch_bounds__(IRT_NT, OCC) irt_grad_kernel(const unsigned short* __restrict__ y, int I, int J, int D,
                                                              const double* __restrict__ Q, double* __restrict__ G,
                                                              double* __restrict__ zV, const int* __restrict__ active,
                                                              const int* __restrict__ list, const int* __restrict__ n_list, int ld) {
@@ -69,8 +69,8 @@ int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream)
   {                                                                                                                              \
     auto k1 = irt_grad_kernel<IPL, 1>;                                                                                           \
     auto k2 = irt_grad_kernel<IPL, 2>;                                                                                           \
-    if (occ == 2) IRT_KERNEL_LAUNCH(k2, b.C, stream, m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);     \
-    else IRT_KERNEL_LAUNCH(k1, b.C, stream, m.y8, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);              \
+    if (occ == 2) IRT_KERNEL_LAUNCH(k2, b.C, stream, m.ypk, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);     \
+    else IRT_KERNEL_LAUNCH(k1, b.C, stream, m.ypk, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);              \
   }
   if (ipl <= 2) IRT_LAUNCH(2)
   else if (ipl <= 4) IRT_LAUNCH(4)
@@ -102,7 +102,7 @@ struct SoloShared {
 // CL = 8: one cluster of eight CTAs per chain (hardware only).  CL = 1: one CTA per chain walks the eight person blocks itself
 // (same bits; the CPU test rig runs this one, and it is the fallback where a cluster launch is not available).
 template <int IPL, int CL>
-__global__ void __launch_bounds__(IRT_NT, 1) irt_solo_kernel(SamplerCfg cfg, DeviceChains d, const signed char* __restrict__ y, int I, int J,
+__global__ void __launch_bounds__(IRT_NT, 1) irt_solo_kernel(SamplerCfg cfg, DeviceChains d, const unsigned short* __restrict__ y, int I, int J,
                                                              const int* __restrict__ list, const int* __restrict__ n_list) {
   __shared__ __align__(16) SoloShared sh;
   B200_DYN_SMEM(red);   // CTA 0: 6 * ld doubles (solo_leaf_step)
@@ -264,7 +264,7 @@ cudaError_t launch_irt_solo(const SamplerCfg& cfg, const DeviceChains& d, const 
 #ifdef B200_SIMT_EMUL
 #define SOLO_LAUNCH(IPL)                                                                                              \
   {                                                                                                                   \
-    simt::launch(n_max, IRT_NT, smem, [&] { irt_solo_kernel<IPL, 1>(cfg, d, m.y8, m.N, m.K, list, n_list); });        \
+    simt::launch(n_max, IRT_NT, smem, [&] { irt_solo_kernel<IPL, 1>(cfg, d, m.ypk, m.N, m.K, list, n_list); });        \
     return 0;                                                                                                         \
   }
 #else
@@ -286,12 +286,12 @@ cudaError_t launch_irt_solo(const SamplerCfg& cfg, const DeviceChains& d, const 
       at[0].val.clusterDim.z = 1;                                                                                     \
       lc.attrs = at;                                                                                                  \
       lc.numAttrs = 1;                                                                                                \
-      return cudaLaunchKernelEx(&lc, k, cfg, d, (const signed char*)m.y8, m.N, m.K, list, n_list);                    \
+      return cudaLaunchKernelEx(&lc, k, cfg, d, (const unsigned short*)m.ypk, m.N, m.K, list, n_list);                    \
     }                                                                                                                 \
     auto k = irt_solo_kernel<IPL, 1>;                                                                                 \
     cudaError_t e1 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     if (e1 != cudaSuccess) return e1;                                                                                 \
-    k<<<n_max, IRT_NT, smem, stream>>>(cfg, d, m.y8, m.N, m.K, list, n_list);                                         \
+    k<<<n_max, IRT_NT, smem, stream>>>(cfg, d, m.ypk, m.N, m.K, list, n_list);                                         \
     return cudaGetLastError();                                                                                        \
   }
 #endif

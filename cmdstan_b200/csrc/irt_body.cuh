@@ -100,7 +100,7 @@ __device__ __forceinline__ void irt_prologue(IrtShared& sm, const IrtChainPtrs& 
 // partials: va[t], vb[t] for item j = sub + 8 t, and the log-likelihood in product form (w_prod in [1, 2), w_expo, w_sum) plus
 // the sum of squared standardised abilities w_s2.
 template <int IPL, int OCC, bool COHERENT>
-__device__ __forceinline__ void irt_block(const IrtShared& sm, const IrtChainPtrs& c, const signed char* __restrict__ y, int I, int J, int blk,
+__device__ __forceinline__ void irt_block(const IrtShared& sm, const IrtChainPtrs& c, const unsigned short* __restrict__ ypk, int I, int J, int blk,
                                           const double (&a)[OCC == 2 ? 1 : IPL], const double (&b)[OCC == 2 ? 1 : IPL], double* __restrict__ g,
                                           double (&va)[IPL], double (&vb)[IPL], double& w_prod, int& w_expo, double& w_sum, double& w_s2) {
   const int tid = threadIdx.x;
@@ -121,18 +121,17 @@ __device__ __forceinline__ void irt_block(const IrtShared& sm, const IrtChainPtr
     const int i = i0 + grp;
     const bool person = i < end;
     const double th = person ? IRT_LDQ(c.theta + i) : 0.0;
-    const signed char* yrow = y + (size_t)(person ? i : 0) * J;
+    const unsigned ybits = person ? (unsigned)ypk[(size_t)i * IRT_G + sub] : 0u;   // this lane's responses of the person, bit t = item sub + 8 t
     double gth = 0.0;
     if (person) {
       my_persons++;
 #pragma unroll
       for (int t = 0; t < IPL; t++) {
         const int j = sub + IRT_G * t;
-        const int yv = j < J ? yrow[j] : 0;
-        const double sgn = __hiloint2double((int)(0xbff00000u ^ ((unsigned)yv << 31)), 0);   // 2y - 1
+        const int negmask = (int)((~ybits << (31 - t)) & 0x80000000u);   // sign bit of 2y - 1
         const double at = OCC == 2 ? sm.a[j] : a[t], bt = OCC == 2 ? sm.b[j] : b[t];
         const double diff = th - bt;
-        const double d = logit_term(lacc, at * diff, sgn, sm.exptab);   // padding items: at == 0 => eta == 0 (see logit_acc_value)
+        const double d = logit_term(lacc, at * diff, negmask, sm.exptab);   // padding items: at == 0 => eta == 0 (see logit_acc_value)
         const double da = d * at;
         gth += da;
         vb[t] -= da;
@@ -289,7 +288,7 @@ __device__ __forceinline__ void irt_finish(IrtShared& sm, const IrtChainPtrs& c,
 // g: -grad lp out [D]; zVc: -lp out.  Every shared array is consumed before the function returns except sm.it / sm.lp / sm.s2,
 // read by thread 0 after the last barrier: a caller that loops must synchronise before the next call.
 template <int IPL, int OCC, bool COHERENT = false>
-__device__ __forceinline__ void irt_chain_body(IrtShared& sm, const signed char* __restrict__ y, int I, int J, int D, const double* __restrict__ q,
+__device__ __forceinline__ void irt_chain_body(IrtShared& sm, const unsigned short* __restrict__ y, int I, int J, int D, const double* __restrict__ q,
                                                double* __restrict__ g, double* __restrict__ zVc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = tid & (IRT_G - 1);
   const IrtChainPtrs c = irt_chain_ptrs<COHERENT>(q, I, J);

@@ -54,6 +54,16 @@ int launch_glm_grad(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
 
 // ---- IRT 2PL: irt.cu -------------------------------------------------------------------------------------------
 int irt_max_items();
+// host: responses y [I][J] (0 / 1) -> ModelData::ypk layout [I][8] (item j = s + 8 t is bit t of word s: the 16 bits a lane of the
+// gradient kernels needs for one person, so that a response costs no load and no branch in the inner loop)
+inline void irt_pack_responses(const signed char* y, int I, int J, unsigned short* out) {
+  for (int i = 0; i < I; i++)
+    for (int s = 0; s < 8; s++) {
+      unsigned v = 0;
+      for (int t = 0; s + 8 * t < J; t++) v |= (unsigned)(y[(size_t)i * J + s + 8 * t] != 0) << t;
+      out[(size_t)i * 8 + s] = (unsigned short)v;
+    }
+}
 int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream);
 
 }  // namespace b200

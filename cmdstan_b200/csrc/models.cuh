@@ -32,6 +32,7 @@ struct ModelData {
   const double* yr;   // eight schools y
   const double* sigma;// eight schools sigma
   const signed char* y8;  // IRT responses, persons x items row-major
+  const unsigned short* ypk;  // IRT responses packed for the gradient kernels: [persons][8], bit t of word s = y[person][s + 8 t]
 };
 
 B200_DEV double dev_log1p_exp(double a) { return a > 0.0 ? a + dev_log1p(dev_exp(-a)) : dev_log1p(dev_exp(a)); }

@@ -20,6 +20,9 @@ extern "C" int irt_simt_grad(int form, int I, int J, int C, int ld, const signed
   ModelData m{};
   m.kind = MODEL_IRT2PL;
   m.N = I; m.K = J; m.D = 4 + I + 2 * J; m.y8 = y;
+  std::vector<unsigned short> ypk_((size_t)I * 8);
+  irt_pack_responses(y, I, J, ypk_.data());
+  m.ypk = ypk_.data();
   GradBatch b{};
   b.Q = Q; b.G = G; b.zV = zV; b.active = active; b.C = C; b.ld = ld;
   int nl = n_list;
@@ -39,6 +42,9 @@ extern "C" long long irt_simt_run(int C, int I, int J, const signed char* y, uns
   ModelData m{};
   m.kind = MODEL_IRT2PL;
   m.N = I; m.K = J; m.D = 4 + I + 2 * J; m.y8 = y;
+  std::vector<unsigned short> ypk_((size_t)I * 8);
+  irt_pack_responses(y, I, J, ypk_.data());
+  m.ypk = ypk_.data();
   const int D = m.D, ld = (D + 3) & ~3;
   SamplerCfg cfg{};
   cfg.D = D; cfg.ld = ld; cfg.max_depth = max_depth;
