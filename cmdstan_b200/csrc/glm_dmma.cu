@@ -640,6 +640,289 @@ size_t glm_tc5_smem_bytes(int Dk) {
 
 
 // =====================================================================================================================
+// v6 (round 2): SIXTEEN warps in two out-of-phase groups of eight.  What r02d / r02e established: a warp's DMMA stream carries
+// a fixed issue gap after every DMMA.8x8x4 (the NOP ptxas pairs with it; sm_100a has no larger FP64 shape -- ptxas lowers
+// m16n8k16 to 8x8x4 too), so the pipe is only saturated while at least TWO warps of an SM sub-partition issue DMMAs.  v2 (eight
+// warps) satisfies that inside its tensor phases but idles the pipe whenever its warps do anything else together (38 % of the
+// time); v5 (two groups of four) de-phased the groups but left each group with ONE warp per sub-partition, which cannot fill the
+// pipe alone.  Here each group has two warps per sub-partition: while one group evaluates the link, waits at its barrier or
+// writes partials, the other one keeps the pipe full.  512 threads at <= 128 registers: per-warp tiles shrink to 16 rows x 16
+// chains (phase A, 4 fragment loads per 4 DMMAs) and 7 design-column blocks x 8 chains (phase B, 8 loads per 7 DMMAs).
+// Row partials are summed over four row quarters (not v2's two halves): same accuracy, not the same bits as v2.
+// =====================================================================================================================
+constexpr int NT6 = 512, NW6 = NT6 / 32;
+
+__device__ __forceinline__ bool warp_arrive_is_last16(int* cnt, int lane) {
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(cnt, 1) == NW6 - 1;
+    if (last) {
+      *cnt = 0;
+      __threadfence_block();
+    }
+  }
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+template <int LINK, int MB>   // MB: 8-row blocks of G per warp in phase B (Dk <= 16 MB)
+__global__ void __launch_bounds__(NT6, 1) glm_dmma6_kernel(const GlmTcArgs a) {
+  B200_DYN_SMEM(smem);
+  const int Dk = a.Dk;
+  const int xs_ld = xs_ld_for(Dk);
+  double* Bs = smem;                               // [TC][xs_ld]     chain-major copy of the q rows of the chain tile
+  double* Xs0 = Bs + (size_t)TC * xs_ld;           // [2][TR][xs_ld]  double-buffered X tile
+  double* Ds = Xs0 + (size_t)2 * TR * xs_ld;       // [TR][DS_LD]     columns [32 g, 32 g + 32): group g's derivative tile
+  double* ys0 = Ds + (size_t)TR * DS_LD;           // [2][TR]  2y-1 / y as double
+  double* lpred = ys0 + 2 * TR;                    // [4][TC]  log-likelihood partials of the four row quarters
+  double* exptab = lpred + 4 * TC;                 // [32]     2^(j/32) (fastmath.cuh)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(exptab + 32);  // fullX[0], fullX[1], fullB
+  int* doneX = reinterpret_cast<int*>(bars + 3);   // [2] warps done with X buffer b
+  int* doneB = doneX + 2;                          // warps done with the q tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int grp = warp >> 3, gw = warp & 7;        // group, warp inside the group (two warps of each group per sub-partition)
+  const int gtid = tid & 255;                      // thread inside the group
+  const int p = blockIdx.x;
+  const int n_list = a.n_list ? *a.n_list : a.n_fixed;
+  const int n_ct = (n_list + TC - 1) / TC;
+
+  const long long t_begin = (long long)p * a.n_row_tiles / a.P, t_end = (long long)(p + 1) * a.n_row_tiles / a.P;
+  const long long row_begin = t_begin * TR;
+  long long row_end = t_end * TR;
+  if (row_end > a.N) row_end = a.N;
+  const int n_rt = (int)(t_end - t_begin);
+  const long long n_it = (long long)n_ct * n_rt;
+  if (n_it == 0) return;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    doneX[0] = doneX[1] = doneB[0] = 0;
+    fence_mbarrier_init();
+  }
+  exp_table_load(exptab, tid);
+  for (int e = tid; e < TC * (Dk - a.ldq); e += NT6) {  // columns [ldq, Dk) of the q tile are never written by the bulk copies
+    const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
+    Bs[c * xs_ld + k] = 0.0;
+  }
+  fence_proxy_async();
+  __syncthreads();  // the only block-wide barrier of the kernel
+
+  const unsigned row_bytes = (unsigned)Dk * 8u, q_bytes = (unsigned)a.ldq * 8u;
+  auto load_x = [&](long long it2) {  // one whole warp: X tile + y slice of iteration it2 into its buffer
+    const int buf = (int)(it2 & 1);
+    const int rt2 = (int)(it2 % n_rt);
+    double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const long long row0 = row_begin + (long long)rt2 * TR;
+    const int valid = (int)((row_end - row0) < TR ? (row_end - row0) : TR);
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      const int yv = r < valid ? a.y[row0 + r] : 0;
+      ys0[buf * TR + r] = LINK == 0 ? 2.0 * yv - 1.0 : (double)yv;
+      if (r >= valid)
+        for (int k = 0; k < Dk; k += 2) *reinterpret_cast<double2*>(Xs + r * xs_ld + k) = make_double2(0.0, 0.0);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&bars[buf], (unsigned)valid * row_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TR / 32; h++) {
+      const int r = lane + 32 * h;
+      if (r < valid) tma_load_1d(Xs + r * xs_ld, a.X + (size_t)(row0 + r) * a.ldx, row_bytes, &bars[buf]);
+    }
+  };
+  auto load_b = [&](int ct2) {  // one whole warp: q rows of chain tile ct2
+    const int nbq = n_list - ct2 * TC < TC ? n_list - ct2 * TC : TC;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(&bars[2], (unsigned)nbq * q_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TC / 32; h++) {
+      const int c = lane + 32 * h;
+      if (c < nbq) {
+        const int slot = ct2 * TC + c;
+        tma_load_1d(Bs + c * xs_ld, a.Q + (size_t)(a.list ? a.list[slot] : slot) * a.ldq, q_bytes, &bars[2]);
+      }
+    }
+  };
+  if (warp == 0) {
+    load_b(0);
+    load_x(0);
+    if (n_it > 1) load_x(1);
+  }
+
+  // phase A: warp -> 16 rows x 16 chains (2 x 2 mma tiles); phase B: warp -> MB design-column blocks x 8 chains
+  const int a_rq = gw & 3;                               // row quarter
+  const int a_rb = a_rq * 16, a_cb = grp * 32 + (gw >> 2) * 16;
+  const int b_mh = (gw >> 2) * MB, b_cb = grp * 32 + (gw & 3) * 8;
+  const int bar_id = 1 + grp;
+
+  double gacc[MB][2];
+  double lpacc[2][2];
+  LogitAcc lacc[2][2];
+  int n_pad = 0;
+  int ct = 0, rt = 0;
+  for (long long it = 0; it < n_it; it++) {
+    const int buf = (int)(it & 1);
+    if (rt == 0) {
+#pragma unroll
+      for (int m = 0; m < MB; m++) gacc[m][0] = gacc[m][1] = 0.0;
+      lpacc[0][0] = lpacc[0][1] = lpacc[1][0] = lpacc[1][1] = 0.0;
+      if (LINK == 0) {
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+          logit_acc_init(lacc[n][0]);
+          logit_acc_init(lacc[n][1]);
+        }
+        n_pad = 0;
+      }
+      mbar_wait(&bars[2], (unsigned)(ct & 1));
+    }
+    mbar_wait(&bars[buf], (unsigned)((it >> 1) & 1));
+    if (it == 0 && grp == 1) group_bar_sync(3, NT6);   // group 1 starts when group 0 has finished its first phase A
+    const double* Xs = Xs0 + (size_t)buf * TR * xs_ld;
+    const double* ys = ys0 + buf * TR;
+    const long long row0 = row_begin + (long long)rt * TR;
+    const int in_tile = n_list - ct * TC;
+    // 8-chain blocks of this warp's 16 phase-A chains that hold requesting chains; does its phase-B block hold any? (warp-uniform)
+    const int nb = in_tile - a_cb > 8 ? 2 : (in_tile - a_cb > 0 ? 1 : 0);
+    const bool haveB = in_tile - b_cb > 0;
+    // ---- phase A: Eta[16 rows][16 chains]
+    double acc[2][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    if (nb > 0) {
+      const double* xa = Xs + (a_rb + gid) * xs_ld + tig;
+      const double* ba = Bs + (a_cb + gid) * xs_ld + tig;
+#pragma unroll 2
+      for (int k0 = 0; k0 < Dk; k0 += 4) {
+        const double av0 = xa[k0], av1 = xa[8 * xs_ld + k0];
+        const double bv0 = ba[k0], bv1 = nb == 2 ? ba[8 * xs_ld + k0] : 0.0;
+        dmma(acc[0][0][0], acc[0][0][1], av0, bv0);
+        dmma(acc[1][0][0], acc[1][0][1], av1, bv0);
+        if (nb == 2) {
+          dmma(acc[0][1][0], acc[0][1][1], av0, bv1);
+          dmma(acc[1][1][0], acc[1][1][1], av1, bv1);
+        }
+      }
+    }
+    if (it == 0 && grp == 0) group_bar_arrive(3, NT6);
+    if (rt == n_rt - 1 && ct + 1 < n_ct) {  // last row tile of this chain tile: this warp is done with the q tile
+      if (warp_arrive_is_last16(doneB, lane)) load_b(ct + 1);
+    }
+    group_bar_sync(bar_id, 256);  // every warp of the group has finished phase B of the previous tile: Ds (our columns) is free
+    // ---- link: element (row = a_rb + mi*8 + gid, chain = a_cb + ni*8 + 2*tig + j)
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+      const int r = a_rb + mi * 8 + gid;
+      const bool valid = row0 + r < row_end;
+      const double yd = ys[r];
+      if (LINK == 0) n_pad += valid ? 0 : 1;
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        if (ni >= nb) continue;
+        double dv[2];
+        if (LINK == 0) {
+#pragma unroll
+          for (int j = 0; j < 2; j++) dv[j] = logit_term(lacc[ni][j], acc[mi][ni][j], yd, exptab);
+        } else {
+          double lv[2];
+#pragma unroll
+          for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
+#pragma unroll
+          for (int j = 0; j < 2; j++) lpacc[ni][j] += valid ? lv[j] : 0.0;
+        }
+        *reinterpret_cast<double2*>(&Ds[r * DS_LD + a_cb + ni * 8 + 2 * tig]) = make_double2(dv[0], dv[1]);
+      }
+    }
+    if (LINK == 0) {
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        logit_acc_fold(lacc[ni][0]);
+        logit_acc_fold(lacc[ni][1]);
+      }
+    }
+    group_bar_sync(bar_id, 256);  // the group's derivative tile is complete
+    // ---- phase B: G[m][8 chains] += sum_r Xs[r][m] * Ds[r][chain]
+    if (haveB) {
+      const double* xb = Xs + tig * xs_ld + b_mh * 8 + gid;
+      const double* db = Ds + tig * DS_LD + b_cb + gid;
+#pragma unroll 2
+      for (int r0 = 0; r0 < TR; r0 += 4) {
+        const double bv = db[r0 * DS_LD];
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          if ((b_mh + m) * 8 < Dk) {  // warp-uniform
+            const double av = xb[r0 * xs_ld + m * 8];
+            dmma(gacc[m][0], gacc[m][1], av, bv);
+          }
+        }
+      }
+    }
+    if (it + 2 < n_it) {
+      if (warp_arrive_is_last16(&doneX[buf], lane)) load_x(it + 2);
+    } else {
+      __syncwarp();
+    }
+    if (rt == n_rt - 1) {
+      const int slot0 = ct * TC;
+      if (haveB) {
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          const int k = (b_mh + m) * 8 + gid;
+          if (k < Dk) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int slot = slot0 + b_cb + 2 * tig + j;
+              if (slot < n_list) a.Gp[((size_t)p * a.cap + slot) * Dk + k] = gacc[m][j];
+            }
+          }
+        }
+      }
+      // ---- partial log-likelihood: sum over the 8 row-lanes (gid) by shuffles, then the four row quarters via shared memory
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          double v = LINK == 0 ? (ni < nb ? logit_acc_value(lacc[ni][j], n_pad) : 0.0) : lpacc[ni][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          lpacc[ni][j] = v;
+        }
+      if (gid == 0) {
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) lpred[a_rq * TC + a_cb + ni * 8 + 2 * tig + j] = lpacc[ni][j];
+      }
+      group_bar_sync(bar_id, 256);
+      if (gtid < 32 && slot0 + grp * 32 + gtid < n_list) {
+        const int c = grp * 32 + gtid;
+        a.LPp[(size_t)p * a.cap + slot0 + c] = ((lpred[c] + lpred[TC + c]) + lpred[2 * TC + c]) + lpred[3 * TC + c];
+      }
+      group_bar_sync(bar_id, 256);  // lpred (our columns) is read before the next chain tile's partials are written
+      rt = 0;
+      ct++;
+    } else {
+      rt++;
+    }
+  }
+}
+
+size_t glm_tc6_smem_bytes(int Dk) {
+  return ((size_t)TC * xs_ld_for(Dk) + (size_t)2 * TR * xs_ld_for(Dk) + (size_t)TR * DS_LD + 2 * TR + 4 * TC + 32 + 3 + 2) * sizeof(double);
+}
+
+
+// =====================================================================================================================
 // v3: the same fused product, with NO block-wide barrier in steady state (profiles/README.md r01c: with three
 // __syncthreads per tile all eight warps run the same phase at the same time, the link phase cannot saturate the shared
 // FP64 pipe on its own, and 24 % of its cycles idle).
@@ -1160,6 +1443,26 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
       if (logistic) LAUNCH3(0, 14) else LAUNCH3(1, 14)
     }
 #undef LAUNCH3
+    return 1;
+  }
+  if (ws.variant == 5) {  // v6: sixteen warps, two out-of-phase groups of eight
+    const size_t smem6 = glm_tc6_smem_bytes(a.Dk);
+#define LAUNCH6(LINK, MB)                                                                     \
+  {                                                                                           \
+    auto k = glm_dmma6_kernel<LINK, MB>;                                                      \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);         \
+    B200_LAUNCH(k, ws.P, NT6, smem6, stream, a);                                              \
+  }
+    if (a.Dk <= 16) {
+      if (logistic) LAUNCH6(0, 1) else LAUNCH6(1, 1)
+    } else if (a.Dk <= 32) {
+      if (logistic) LAUNCH6(0, 2) else LAUNCH6(1, 2)
+    } else if (a.Dk <= 64) {
+      if (logistic) LAUNCH6(0, 4) else LAUNCH6(1, 4)
+    } else {
+      if (logistic) LAUNCH6(0, 7) else LAUNCH6(1, 7)
+    }
+#undef LAUNCH6
     return 1;
   }
   if (ws.variant == 4) {  // v5: two out-of-phase groups of four warps
