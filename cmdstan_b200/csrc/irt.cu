@@ -39,8 +39,8 @@ namespace b200 {
 
 int irt_max_items() { return IRT_MAXJ; }
 
-// OCC = 1: item parameters in registers, one CTA per SM.  OCC = 2: exp(a), b in shared memory and a 128-register budget, two
-// CTAs (16 warps) per SM: the one-CTA form is latency-bound at two warps per sub-partition (r01c / r01d captures).
+// OCC = 1: item parameters in registers, one CTA per SM.  OCC = 2 / 3: exp(a), b in shared memory and a 128- / 80-register budget,
+// two / three CTAs (16 / 24 warps) per SM: the one-CTA form is latency-bound at two warps per sub-partition (r01c / r01d captures).
 template <int IPL, int OCC>
 __global__ void __launch_bounds__(IRT_NT, OCC) irt_grad_kernel(const unsigned short* __restrict__ y, int I, int J, int D,
                                                              const double* __restrict__ Q, double* __restrict__ G,
@@ -69,7 +69,9 @@ int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream)
   {                                                                                                                              \
     auto k1 = irt_grad_kernel<IPL, 1>;                                                                                           \
     auto k2 = irt_grad_kernel<IPL, 2>;                                                                                           \
-    if (occ == 2) IRT_KERNEL_LAUNCH(k2, b.C, stream, m.ypk, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);     \
+    auto k3 = irt_grad_kernel<IPL, 3>;                                                                                           \
+    if (occ == 3) IRT_KERNEL_LAUNCH(k3, b.C, stream, m.ypk, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);     \
+    else if (occ == 2) IRT_KERNEL_LAUNCH(k2, b.C, stream, m.ypk, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld); \
     else IRT_KERNEL_LAUNCH(k1, b.C, stream, m.ypk, m.N, m.K, m.D, b.Q, b.G, b.zV, b.active, b.list, b.n_list, b.ld);              \
   }
   if (ipl <= 2) IRT_LAUNCH(2)

@@ -68,14 +68,14 @@ __device__ __forceinline__ IrtChainPtrs irt_chain_ptrs(const double* __restrict_
   return c;
 }
 
-// item parameters of the chain: registers a[], b[] (OCC == 1) or sm.a / sm.b (OCC == 2); the exp table; zeroes the running
+// item parameters of the chain: registers a[], b[] (OCC == 1) or sm.a / sm.b (OCC >= 2); the exp table; zeroes the running
 // per-warp item partials.  Ends with a block-wide barrier.
 template <int IPL, int OCC, bool COHERENT>
-__device__ __forceinline__ void irt_prologue(IrtShared& sm, const IrtChainPtrs& c, int J, double (&a)[OCC == 2 ? 1 : IPL], double (&b)[OCC == 2 ? 1 : IPL]) {
+__device__ __forceinline__ void irt_prologue(IrtShared& sm, const IrtChainPtrs& c, int J, double (&a)[OCC >= 2 ? 1 : IPL], double (&b)[OCC >= 2 ? 1 : IPL]) {
   const int tid = threadIdx.x, sub = tid & (IRT_G - 1);
   exp_table_load(sm.exptab, tid);
   if (tid < IRT_MAXJ) {
-    if (OCC == 2) {
+    if (OCC >= 2) {
       sm.a[tid] = tid < J ? exp(IRT_LDQ(c.u_a + tid)) : 0.0;   // a = 0 for padding items: eta = 0 exactly (logit_acc_value)
       sm.b[tid] = tid < J ? IRT_LDQ(c.bq + tid) : 0.0;
     }
@@ -85,7 +85,7 @@ __device__ __forceinline__ void irt_prologue(IrtShared& sm, const IrtChainPtrs& 
       sm.gb[w][tid] = 0.0;
     }
   }
-  if (OCC != 2) {
+  if (OCC < 2) {
 #pragma unroll
     for (int t = 0; t < IPL; t++) {
       const int j = sub + IRT_G * t;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void irt_prologue(IrtShared& sm, const IrtChainPtrs& 
 // the sum of squared standardised abilities w_s2.
 template <int IPL, int OCC, bool COHERENT>
 __device__ __forceinline__ void irt_block(const IrtShared& sm, const IrtChainPtrs& c, const unsigned short* __restrict__ ypk, int I, int J, int blk,
-                                          const double (&a)[OCC == 2 ? 1 : IPL], const double (&b)[OCC == 2 ? 1 : IPL], double* __restrict__ g,
+                                          const double (&a)[OCC >= 2 ? 1 : IPL], const double (&b)[OCC >= 2 ? 1 : IPL], double* __restrict__ g,
                                           double (&va)[IPL], double (&vb)[IPL], double& w_prod, int& w_expo, double& w_sum, double& w_s2) {
   const int tid = threadIdx.x;
   const int sub = tid & (IRT_G - 1);             // item lane inside the group
@@ -129,7 +129,7 @@ __device__ __forceinline__ void irt_block(const IrtShared& sm, const IrtChainPtr
       for (int t = 0; t < IPL; t++) {
         const int j = sub + IRT_G * t;
         const int negmask = (int)((~ybits << (31 - t)) & 0x80000000u);   // sign bit of 2y - 1
-        const double at = OCC == 2 ? sm.a[j] : a[t], bt = OCC == 2 ? sm.b[j] : b[t];
+        const double at = OCC >= 2 ? sm.a[j] : a[t], bt = OCC >= 2 ? sm.b[j] : b[t];
         const double diff = th - bt;
         const double d = logit_term(lacc, at * diff, negmask, sm.exptab);   // padding items: at == 0 => eta == 0 (see logit_acc_value)
         const double da = d * at;
@@ -292,7 +292,7 @@ __device__ __forceinline__ void irt_chain_body(IrtShared& sm, const unsigned sho
                                                double* __restrict__ g, double* __restrict__ zVc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = tid & (IRT_G - 1);
   const IrtChainPtrs c = irt_chain_ptrs<COHERENT>(q, I, J);
-  double a[OCC == 2 ? 1 : IPL], b[OCC == 2 ? 1 : IPL];
+  double a[OCC >= 2 ? 1 : IPL], b[OCC >= 2 ? 1 : IPL];
   irt_prologue<IPL, OCC, COHERENT>(sm, c, J, a, b);
   IrtWarpTotals tot;
   for (int blk = 0; blk < IRT_NB; blk++) {

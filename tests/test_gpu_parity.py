@@ -86,9 +86,9 @@ def test_glm_tensor_variants_batch_independent(variant, monkeypatch):
         assert np.array_equal(dA[c], d1[0]) and epsA[c] == eps1[0]
 
 
-@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
 def test_irt_kernel_variants_agree(variant, monkeypatch):
-    """one-CTA-per-SM (1) and two-CTAs-per-SM (2) forms of the IRT gradient kernel against the oracle."""
+    """one- (1), two- (2) and three-CTAs-per-SM (3) forms of the IRT gradient kernel against the oracle."""
     monkeypatch.setenv("B200NUTS_IRT_VARIANT", variant)
     for data in (cases.irt_data(100, 20), cases.irt_data(37, 100), cases.irt_data(300, 128)):
         m = O.Model("irt_2pl", data)
@@ -311,12 +311,13 @@ def test_irt_kernel_forms_bit_identical(monkeypatch):
     data = cases.irt_data(211, 100)
     q = np.random.default_rng(8).uniform(-1.5, 1.5, size=(40, 4 + 211 + 200))
     out = []
-    for v in ("1", "2"):
+    for v in ("1", "2", "3"):
         monkeypatch.setenv("B200NUTS_IRT_VARIANT", v)
         e = _engine("irt_2pl", data)
         out.append(e.log_prob_grad(q))
         e.close()
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    for k in (1, 2):
+        assert np.array_equal(out[0][0], out[k][0]) and np.array_equal(out[0][1], out[k][1])
 
 
 @pytest.mark.parametrize("C,shape", [(5, (60, 12)), (400, (60, 12)), (20, (1000, 100))], ids=["5chains", "400chains", "c4size"])
