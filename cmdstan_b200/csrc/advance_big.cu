@@ -7,9 +7,10 @@
 
 namespace b200 {
 
-void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream) {
+void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream,
+                        int only_pending) {
   const int blocks = (C + kChainsPerBlock - 1) / kChainsPerBlock;
-  advance_kernel<1><<<blocks, 32 * kChainsPerBlock, 0, stream>>>(cfg, d, C, active, list, n_active);
+  advance_kernel<1><<<blocks, 32 * kChainsPerBlock, 0, stream>>>(cfg, d, C, active, list, n_active, only_pending);
 }
 
 }  // namespace b200

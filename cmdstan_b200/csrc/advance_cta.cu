@@ -1,9 +1,14 @@
-// The lock-step engine's advance step for LONG parameter vectors (D >= kAdvanceCtaD): one CTA of 256 threads per chain instead of
-// one warp.  With a warp per chain a vector pass over D = 1204 elements (c4) is five rounds of eight dependent global loads per
-// lane and a leaf needs ~29 passes, so the step is bound by memory latency at a quarter of the HBM rate (r02c: 1.3 ms per
-// lock-step of 8192 chains beside a 2.9 ms gradient stage).  Here the 256 threads share the element-wise work of the leaf path
-// (solo_leaf.cuh: every pass is one round trip) and warp 0 runs the rest of the state machine (advance(), a few times per
-// transition).  Same bits as advance_kernel by construction (solo_leaf.cuh explains why), so the engine may pick either.
+// The lock-step engine's advance step for LONG parameter vectors (D >= kAdvanceCtaD), in two kernels.
+//
+// With a warp per chain a vector pass over D = 1204 elements (c4) is five rounds of eight dependent global loads per lane and a
+// tree leaf needs ~29 passes, so the step is bound by memory latency (r02f: 1.57 ms per lock-step of 8192 chains beside a 2.6 ms
+// gradient stage).  Four out of five requests come from the leaf path of the tree (ST_LEAF), so:
+//   1. advance_cta_kernel: one CTA of 256 threads per chain that is in ST_LEAF; its threads share the element-wise work of the
+//      leaf (solo_leaf.cuh: every pass is one round trip).  A chain in any other state, or whose subtree just ended, is only
+//      MARKED (active[c] = -1): running the rest of the state machine on warp 0 of a 256-thread CTA would idle seven warps out of
+//      eight for the longest requests of the step (r02h capture: 68 % of the samples at the final barrier);
+//   2. advance_kernel<1> (advance_big.cu) with only_pending = 1: one warp per marked chain, sixteen of them per SM.
+// Same bits as the one-kernel step by construction (solo_leaf.cuh explains why), so the engine may pick either.
 #define B200_VEC_UNROLL 8
 #define B200_WITH_DENSE 0
 #include "chains.cuh"
@@ -17,7 +22,6 @@ namespace {
 struct AdvanceCtaShared {
   ChainS chain;
   SoloFlags fl;
-  int need;
 };
 
 __global__ void __launch_bounds__(SOLO_NT, 3) advance_cta_kernel(SamplerCfg cfg, DeviceChains d, int C, int* active, int* list, int* n_active) {
@@ -28,32 +32,23 @@ __global__ void __launch_bounds__(SOLO_NT, 3) advance_cta_kernel(SamplerCfg cfg,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ChainView v = make_view(d, cfg, c);
   ChainS* gs = v.s;
+  if (gs->state != ST_LEAF) {  // CTA-uniform: left to the warp-per-chain kernel that follows
+    if (tid == 0) active[c] = -1;
+    return;
+  }
   if (warp == 0) warp_copy_words(&sh.chain, gs, kChainWords, lane);
   __syncthreads();
   v.s = &sh.chain;
-  const int st = sh.chain.state;
-  __syncthreads();  // every warp has read the state before anyone changes it
-  int r = SOLO_GENERIC;
-  if (st == ST_LEAF) r = solo_leaf_step(v, cfg, red, &sh.fl);
-  if (r == SOLO_GENERIC) {
-    if (warp == 0) {
-      ChainView vw = v;
-      B200_SCALARS_BEGIN(vw);   // CPU test rig only: its free-running lanes work on replicas of the scalar block (chains.cuh)
-      const int a = advance(vw, cfg, lane);
-      B200_SCALARS_END(vw, lane);
-      __syncwarp();
-      if (lane == 0) sh.need = a == ADV_NEED_GRAD ? 1 : 0;
-    }
-  } else if (tid == 0) {
-    sh.need = 1;
-  }
-  __syncthreads();
+  const int r = solo_leaf_step(v, cfg, red, &sh.fl);
   if (warp == 0) {
     warp_copy_words(gs, &sh.chain, kChainWords, lane);
     if (lane == 0) {
-      const int a = sh.need;
-      active[c] = a;
-      if (a) list[atomicAdd(n_active, 1)] = c;
+      if (r == SOLO_NEED_GRAD) {
+        active[c] = 1;
+        list[atomicAdd(n_active, 1)] = c;
+      } else {
+        active[c] = -1;  // the subtree ended: advance() continues from ST_SUBTREE_END in the next kernel
+      }
     }
   }
 }
@@ -70,8 +65,10 @@ cudaError_t launch_advance_cta(const SamplerCfg& cfg, const DeviceChains& d, int
   }
   B200_LAUNCH(advance_cta_kernel, C, SOLO_NT, smem, stream, cfg, d, C, active, list, n_active);
 #ifdef B200_SIMT_EMUL
+  simt::launch((C + kChainsPerBlock - 1) / kChainsPerBlock, 32 * kChainsPerBlock, 0, [&] { advance_kernel<1>(cfg, d, C, active, list, n_active, 1); });
   return 0;
 #else
+  launch_advance_big(cfg, d, C, active, list, n_active, stream, 1);
   return cudaGetLastError();
 #endif
 }

@@ -68,13 +68,16 @@ constexpr int kChainWords = (int)(sizeof(ChainS) / 8);
 // and collect the requesting chains: active[c] flag + compacted index list (order irrelevant: a chain's gradient
 // depends on its own q only).  The chain's scalar block is staged in shared memory for the launch (one coalesced
 // load + store instead of dozens of dependent global accesses).
+// only_pending != 0: second half of a two-kernel advance step (advance_cta.cu): only the chains the first kernel marked with
+// active[c] == -1 are advanced, the others have already been served.
 template <int TAG>
 __global__ void __launch_bounds__(32 * kChainsPerBlock) advance_kernel(SamplerCfg cfg, DeviceChains d, int C, int* active,
-                                                                          int* list, int* n_active) {
+                                                                          int* list, int* n_active, int only_pending = 0) {
   __shared__ __align__(16) ChainS sh[kChainsPerBlock];
   const int w = threadIdx.x >> 5;
   const int c = blockIdx.x * kChainsPerBlock + w;
   if (c >= C) return;
+  if (only_pending && active[c] != -1) return;
   const int lane = threadIdx.x & 31;
   ChainView v = make_view(d, cfg, c);
   ChainS* gs = v.s;
@@ -148,7 +151,8 @@ constexpr int kAdvanceCtaD = 512;
 constexpr int kAdvanceCtaMaxLd = 4608;  // 6 * ld doubles of shared memory must fit (216 KB)
 cudaError_t launch_advance_cta(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
 // advance_big.cu: the same kernel built with B200_VEC_UNROLL = 8 (bit-identical results)
-void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream);
+void launch_advance_big(const SamplerCfg& cfg, const DeviceChains& d, int C, int* active, int* list, int* n_active, cudaStream_t stream,
+                        int only_pending = 0);
 // irt.cu: latency form for the stragglers of an IRT run (one cluster of 8 CTAs, or one CTA, per remaining chain)
 bool irt_solo_supported(const ModelData& m);
 cudaError_t launch_irt_solo(const SamplerCfg& cfg, const DeviceChains& d, const ModelData& m, const int* list, const int* n_list, int n_max,

@@ -895,7 +895,10 @@ int b200nuts_run(b200nuts_engine* e, int n_iter) {
       int* counter = e->d_nactive + (step % kCounterRing);  // one counter per step of the ring, zeroed together
       if (check) CUDA_TRY(e, cudaMemsetAsync(e->d_nactive, 0, sizeof(int) * kCounterRing, e->stream));
       if (e->scfg.dense || e->scfg.diag || e->scfg.static_hmc) launch_advance_dense(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
-      else if (e->advance_cta && e->D >= kAdvanceCtaD && e->ld <= kAdvanceCtaMaxLd) CUDA_TRY(e, launch_advance_cta(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream));
+      else if (e->advance_cta && e->D >= kAdvanceCtaD && e->ld <= kAdvanceCtaMaxLd) {  // two kernels: leaf path per CTA, the rest per warp
+        CUDA_TRY(e, launch_advance_cta(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream));
+        launches++;
+      }
       else if (e->D >= kAdvanceBigD) launch_advance_big(e->scfg, e->dc, C, e->d_active, e->d_list, counter, e->stream);
       else advance_kernel<0><<<blocks, 32 * kChainsPerBlock, 0, e->stream>>>(e->scfg, e->dc, C, e->d_active, e->d_list, counter);
       launches++;
