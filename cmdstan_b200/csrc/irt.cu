@@ -59,12 +59,13 @@ __global__ void __launch_bounds__(IRT_NT, OCC) irt_grad_kernel(const unsigned sh
 
 int launch_irt_grad(const ModelData& m, const GradBatch& b, cudaStream_t stream) {
   const int ipl = (m.K + IRT_G - 1) / IRT_G;
-  // B200NUTS_IRT_VARIANT: 1 one CTA per SM; 2 two CTAs per SM; default "auto": two per SM when the launch is known to be dense
-  // (16 resident warps hide the link's dependency chains), one per SM when only a few chains are left (lower latency of a
-  // single CTA).  The two forms are the same arithmetic in the same order (irt_body.cuh; GPU test), so the choice never shows in
-  // a chain's draws.  Read per launch (a handful of ns next to a > 100 us kernel): tests switch it.
+  // B200NUTS_IRT_VARIANT: 1 / 2 / 3 CTAs per SM; default "auto": three per SM when the launch is known to be dense (24 resident
+  // warps hide the link's dependency chains: r02i, 8192 chains: gradient stage 2.51 s with three, 2.74 s with two, 3.68 s with one),
+  // one per SM when only a few chains are left (lower latency of a single CTA).  The forms are the same arithmetic in the same
+  // order (irt_body.cuh; GPU test), so the choice never shows in a chain's draws.  Read per launch (a handful of ns next to a
+  // > 100 us kernel): tests switch it.
   const char* var = getenv("B200NUTS_IRT_VARIANT");
-  int occ = (var && var[0] != 'a') ? atoi(var) : ((b.hint_active < 0 ? b.C : b.hint_active) >= 296 ? 2 : 1);
+  int occ = (var && var[0] != 'a') ? atoi(var) : ((b.hint_active < 0 ? b.C : b.hint_active) >= 296 ? 3 : 1);
 #define IRT_LAUNCH(IPL)                                                                                                          \
   {                                                                                                                              \
     auto k1 = irt_grad_kernel<IPL, 1>;                                                                                           \
