@@ -923,6 +923,350 @@ size_t glm_tc6_smem_bytes(int Dk) {
 
 
 // =====================================================================================================================
+// v7 (round 2): ONE warp per SM sub-partition, the link evaluated in the shadow of the tensor work.
+// What the r02d / r02h measurements say: (i) a single warp per sub-partition issuing DMMAs back to back reaches 93 % of the FP64
+// tensor pipe (tools/microbench/dmma_shapes.cu: 34.1 of 37.1 TFLOP/s) -- the pipe does not need several warps, it needs a warp
+// that always has a DMMA to issue; (ii) v2's tensor phases are pipe-bound but are only 62 % of its time: the rest is link,
+// block-wide barriers and tile set-up, during which all eight warps leave the pipe idle together; (iii) splitting the CTA into
+// groups (v5, v6) does not help because the groups still meet at the shared tile buffers.
+// So: four warps per CTA, each owning 16 chains of the chain tile for ALL rows of a (32-row) tile -- phase B's operand is then
+// produced by the warp itself (a private derivative tile in shared memory, __syncwarp instead of barriers), nothing is shared
+// between warps but the read-only X / q tiles -- and inside one warp the tensor work never pauses: iteration k issues phase A
+// of tile k + 1 (208 DMMAs), then phase B of tile k (208 DMMAs) with the link of tile k + 1 woven into its eight r-steps, two
+// elements per step, so the link's scalar instructions issue in the 15 free slots behind every DMMA.  X tiles are three TMA
+// stages deep (tile k is released after phase B of tile k, and tile k + 3 has a whole iteration to arrive).
+// 16 chains per warp keep v2's operand reuse (0.75 / 0.58 fragment loads per DMMA; v3 / v4 had 8 chains per warp and 1.1).
+// Summation order per chain: a lane adds its rows tile by tile, the eight row-lanes are combined by shuffles -- not v2's bits,
+// fixed all the same.
+// =====================================================================================================================
+constexpr int NT7 = 128, TR7 = 32, NST7 = 3, DW7_LD = 20;   // 4 warps; 32-row tiles; 3 X stages; leading dimension of a warp's D tile (== 4 mod 8)
+
+__device__ __forceinline__ bool warp_arrive_is_last4(int* cnt, int lane) {
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(cnt, 1) == NT7 / 32 - 1;
+    if (last) {
+      *cnt = 0;
+      __threadfence_block();
+    }
+  }
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+template <int LINK, int NMB>   // NMB: 8-row blocks of G (Dk <= 8 NMB)
+__global__ void __launch_bounds__(NT7, 1) glm_dmma7_kernel(const GlmTcArgs a) {
+  B200_DYN_SMEM(smem);
+  const int Dk = a.Dk;
+  const int xs_ld = xs_ld_for(Dk);
+  double* Bs = smem;                                   // [TC][xs_ld]          q rows of the chain tile
+  double* Xs0 = Bs + (size_t)TC * xs_ld;               // [NST7][TR7][xs_ld]   X tiles
+  double* Dw0 = Xs0 + (size_t)NST7 * TR7 * xs_ld;      // [4 warps][2][TR7][DW7_LD]  each warp's derivative tiles (double-buffered)
+  double* ys0 = Dw0 + (size_t)4 * 2 * TR7 * DW7_LD;    // [NST7][TR7]
+  double* exptab = ys0 + NST7 * TR7;                   // [32]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(exptab + 32);  // fullX[NST7], fullB
+  unsigned long long* fullX = bars;
+  unsigned long long* fullB = bars + NST7;
+  int* doneX = reinterpret_cast<int*>(bars + NST7 + 1);   // [NST7]
+  int* doneB = doneX + NST7;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int p = blockIdx.x;
+  const int n_list = a.n_list ? *a.n_list : a.n_fixed;
+  const int n_ct = (n_list + TC - 1) / TC;
+
+  // fixed row group of this CTA, in tiles of TR7 rows (a function of N only)
+  const long long n_row_tiles = ((long long)a.N + TR7 - 1) / TR7;
+  const long long t_begin = (long long)p * n_row_tiles / a.P, t_end = (long long)(p + 1) * n_row_tiles / a.P;
+  const long long row_begin = t_begin * TR7;
+  long long row_end = t_end * TR7;
+  if (row_end > a.N) row_end = a.N;
+  const int n_rt = (int)(t_end - t_begin);
+  const long long n_it = (long long)n_ct * n_rt;
+  if (n_it == 0) return;
+
+  if (tid == 0) {
+    for (int b = 0; b < NST7; b++) {
+      mbar_init(&fullX[b], 1);
+      doneX[b] = 0;
+    }
+    mbar_init(fullB, 1);
+    doneB[0] = 0;
+    fence_mbarrier_init();
+  }
+  exp_table_load(exptab, tid);
+  for (int e = tid; e < TC * (Dk - a.ldq); e += NT7) {  // columns [ldq, Dk) of the q tile are never written by the bulk copies
+    const int c = e / (Dk - a.ldq), k = a.ldq + e - c * (Dk - a.ldq);
+    Bs[c * xs_ld + k] = 0.0;
+  }
+  fence_proxy_async();
+  __syncthreads();  // the only block-wide barrier of the kernel
+
+  const unsigned row_bytes = (unsigned)Dk * 8u, q_bytes = (unsigned)a.ldq * 8u;
+  auto load_x = [&](long long it2) {  // one whole warp: X tile + y slice of iteration it2 into stage it2 % NST7
+    const int buf = (int)(it2 % NST7);
+    const int rt2 = (int)(it2 % n_rt);
+    double* Xs = Xs0 + (size_t)buf * TR7 * xs_ld;
+    const long long row0 = row_begin + (long long)rt2 * TR7;
+    const int valid = (int)((row_end - row0) < TR7 ? (row_end - row0) : TR7);
+    {
+      const int r = lane;
+      const int yv = r < valid ? a.y[row0 + r] : 0;
+      ys0[buf * TR7 + r] = LINK == 0 ? 2.0 * yv - 1.0 : (double)yv;
+      if (r >= valid)
+        for (int k = 0; k < Dk; k += 2) *reinterpret_cast<double2*>(Xs + r * xs_ld + k) = make_double2(0.0, 0.0);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&fullX[buf], (unsigned)valid * row_bytes);
+    __syncwarp();
+    if (lane < valid) tma_load_1d(Xs + lane * xs_ld, a.X + (size_t)(row0 + lane) * a.ldx, row_bytes, &fullX[buf]);
+  };
+  auto load_b = [&](int ct2) {  // one whole warp: q rows of chain tile ct2
+    const int nbq = n_list - ct2 * TC < TC ? n_list - ct2 * TC : TC;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(fullB, (unsigned)nbq * q_bytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < TC / 32; h++) {
+      const int c = lane + 32 * h;
+      if (c < nbq) {
+        const int slot = ct2 * TC + c;
+        tma_load_1d(Bs + c * xs_ld, a.Q + (size_t)(a.list ? a.list[slot] : slot) * a.ldq, q_bytes, fullB);
+      }
+    }
+  };
+  if (warp == 0) {
+    load_b(0);
+    for (int b = 0; b < NST7; b++)
+      if (b < n_it) load_x(b);
+  }
+
+  const int cb = warp * 16;                                  // this warp's chains inside the chain tile
+  double* Dw = Dw0 + (size_t)warp * 2 * TR7 * DW7_LD;
+  double gacc[NMB][2][2];
+  double acc[TR7 / 8][2][2];                                 // Eta of the tile whose link is pending
+  double lpacc[2][2];
+  LogitAcc lacc[2][2];
+  int n_pad = 0;
+  unsigned xphase = 0;                                       // bit b: parity of the next phase of fullX[b] this warp waits for
+#pragma unroll
+  for (int m = 0; m < NMB; m++)
+#pragma unroll
+    for (int n = 0; n < 2; n++) gacc[m][n][0] = gacc[m][n][1] = 0.0;
+  lpacc[0][0] = lpacc[0][1] = lpacc[1][0] = lpacc[1][1] = 0.0;
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    logit_acc_init(lacc[n][0]);
+    logit_acc_init(lacc[n][1]);
+  }
+
+  // phase A of iteration `it` (chain tile ctA, row tile rtA): acc <- X tile . q columns of this warp
+  auto phase_a7 = [&](long long it, int ctA, int rtA, int nbA) {
+    const int buf = (int)(it % NST7);
+    if (rtA == 0) mbar_wait(fullB, (unsigned)(ctA & 1));
+    mbar_wait(&fullX[buf], (xphase >> buf) & 1u);
+    xphase ^= 1u << buf;
+#pragma unroll
+    for (int mi = 0; mi < TR7 / 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    if (nbA > 0) {
+      const double* xa = Xs0 + (size_t)buf * TR7 * xs_ld + gid * xs_ld + tig;
+      const double* ba = Bs + (cb + gid) * xs_ld + tig;
+#pragma unroll 2
+      for (int k0 = 0; k0 < Dk; k0 += 4) {
+        double av[TR7 / 8];
+#pragma unroll
+        for (int mi = 0; mi < TR7 / 8; mi++) av[mi] = xa[mi * 8 * xs_ld + k0];
+        const double bv0 = ba[k0], bv1 = nbA == 2 ? ba[8 * xs_ld + k0] : 0.0;
+#pragma unroll
+        for (int mi = 0; mi < TR7 / 8; mi++) {
+          dmma(acc[mi][0][0], acc[mi][0][1], av[mi], bv0);
+          if (nbA == 2) dmma(acc[mi][1][0], acc[mi][1][1], av[mi], bv1);
+        }
+      }
+    }
+    if (rtA == n_rt - 1 && ctA + 1 < n_ct) {  // last row tile of the chain tile: this warp is done with the q tile
+      if (warp_arrive_is_last4(doneB, lane)) load_b(ctA + 1);
+    }
+  };
+  // link of the pending tile, elements (mi, ni): acc -> derivative, stored to the warp's D tile `dbuf`
+  auto link7 = [&](int mi, int ni, int nbL, const double* ysL, long long row0L, double* DwL) {
+    if (ni >= nbL) return;
+    const int r = mi * 8 + gid;
+    const double yd = ysL[r];
+    double dv[2];
+    if (LINK == 0) {
+#pragma unroll
+      for (int j = 0; j < 2; j++) dv[j] = logit_term(lacc[ni][j], acc[mi][ni][j], yd, exptab);
+    } else {
+      const bool valid = row0L + r < row_end;
+      double lv[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
+#pragma unroll
+      for (int j = 0; j < 2; j++) lpacc[ni][j] += valid ? lv[j] : 0.0;
+    }
+    *reinterpret_cast<double2*>(&DwL[r * DW7_LD + ni * 8 + 2 * tig]) = make_double2(dv[0], dv[1]);
+  };
+  auto pad_rows = [&](long long row0L) {   // rows of the tile past the end of the row group this lane evaluates (LINK 0 bookkeeping)
+    int n = 0;
+#pragma unroll
+    for (int mi = 0; mi < TR7 / 8; mi++) n += (row0L + mi * 8 + gid < row_end) ? 0 : 1;
+    return n;
+  };
+  // partial log-likelihood of the chain tile `ctL` whose link just finished: rows are all in this warp
+  auto flush_lp = [&](int ctL, int nbL) {
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        double v = LINK == 0 ? (ni < nbL ? logit_acc_value(lacc[ni][j], n_pad) : 0.0) : lpacc[ni][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        const int slot = ctL * TC + cb + ni * 8 + 2 * tig + j;
+        if (gid == 0 && slot < n_list) a.LPp[(size_t)p * a.cap + slot] = v;
+        lpacc[ni][j] = 0.0;
+        logit_acc_init(lacc[ni][j]);
+      }
+    n_pad = 0;
+  };
+
+  // ---- prologue: phase A and link of iteration 0
+  int ctA = 0, rtA = 0;   // (chain tile, row tile) of the tile phase A / the link work on; phase B runs one tile behind
+  {
+    const int in_tile = n_list - ctA * TC;
+    const int nbA = in_tile - cb > 8 ? 2 : (in_tile - cb > 0 ? 1 : 0);
+    phase_a7(0, ctA, rtA, nbA);
+    const long long row0L = row_begin + (long long)rtA * TR7;
+    if (LINK == 0) n_pad += pad_rows(row0L);
+#pragma unroll
+    for (int s = 0; s < TR7 / 4; s++) link7(s >> 1, s & 1, nbA, ys0 + 0 * TR7, row0L, Dw);
+    if (LINK == 0) {
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        logit_acc_fold(lacc[ni][0]);
+        logit_acc_fold(lacc[ni][1]);
+      }
+    }
+    __syncwarp();
+  }
+  for (long long it = 0; it < n_it; it++) {
+    // tile `it` = (ctB, rtB): its derivative tile is in Dw[it & 1]; tile it + 1 = (ctA', rtA') is next for phase A + link
+    const int ctB = ctA, rtB = rtA;
+    const int in_tileB = n_list - ctB * TC;
+    const int nbB = in_tileB - cb > 8 ? 2 : (in_tileB - cb > 0 ? 1 : 0);
+    const bool more = it + 1 < n_it;
+    int nbA = 0;
+    long long row0L = 0;
+    if (more) {
+      rtA = rtB + 1 < n_rt ? rtB + 1 : 0;
+      ctA = rtA == 0 ? ctB + 1 : ctB;
+      if (rtA == 0) flush_lp(ctB, nbB);   // the link of chain tile ctB is complete (it ran ahead of phase B)
+      const int in_tileA = n_list - ctA * TC;
+      nbA = in_tileA - cb > 8 ? 2 : (in_tileA - cb > 0 ? 1 : 0);
+      phase_a7(it + 1, ctA, rtA, nbA);
+      row0L = row_begin + (long long)rtA * TR7;
+      if (LINK == 0) n_pad += pad_rows(row0L);
+    }
+    // ---- phase B of tile `it` with the link of tile it + 1 woven in: r-step s is followed by elements (s >> 1, s & 1)
+    {
+      const int bufB = (int)(it % NST7);
+      const double* xb = Xs0 + (size_t)bufB * TR7 * xs_ld + tig * xs_ld + gid;
+      const double* db = Dw + (size_t)(it & 1) * TR7 * DW7_LD + tig * DW7_LD + gid;
+      double* DwL = Dw + (size_t)((it + 1) & 1) * TR7 * DW7_LD;
+      const double* ysL = ys0 + (int)((it + 1) % NST7) * TR7;
+      if (Dk == 8 * NMB && nbB == 2 && more && nbA == 2) {
+        // steady state (full chain blocks, every design-column block in use): ONE basic block, so that the scheduler can place the
+        // link's scalar instructions between the DMMAs
+#pragma unroll
+        for (int s = 0; s < TR7 / 4; s++) {
+          const double bv0 = db[4 * s * DW7_LD], bv1 = db[4 * s * DW7_LD + 8];
+#pragma unroll
+          for (int m = 0; m < NMB; m++) {
+            const double av = xb[4 * s * xs_ld + m * 8];
+            dmma(gacc[m][0][0], gacc[m][0][1], av, bv0);
+            dmma(gacc[m][1][0], gacc[m][1][1], av, bv1);
+          }
+          {
+            const int mi = s >> 1, ni = s & 1;
+            const int r = mi * 8 + gid;
+            const double yd = ysL[r];
+            double dv[2];
+            if (LINK == 0) {
+#pragma unroll
+              for (int j = 0; j < 2; j++) dv[j] = logit_term(lacc[ni][j], acc[mi][ni][j], yd, exptab);
+            } else {
+              const bool valid = row0L + r < row_end;
+              double lv[2];
+#pragma unroll
+              for (int j = 0; j < 2; j++) link_eval<LINK>(acc[mi][ni][j], yd, lv[j], dv[j]);
+#pragma unroll
+              for (int j = 0; j < 2; j++) lpacc[ni][j] += valid ? lv[j] : 0.0;
+            }
+            *reinterpret_cast<double2*>(&DwL[r * DW7_LD + ni * 8 + 2 * tig]) = make_double2(dv[0], dv[1]);
+          }
+        }
+      } else
+#pragma unroll
+      for (int s = 0; s < TR7 / 4; s++) {
+        if (nbB > 0) {
+          const double bv0 = db[4 * s * DW7_LD], bv1 = nbB == 2 ? db[4 * s * DW7_LD + 8] : 0.0;
+#pragma unroll
+          for (int m = 0; m < NMB; m++) {
+            if (m * 8 < Dk) {  // warp-uniform
+              const double av = xb[4 * s * xs_ld + m * 8];
+              dmma(gacc[m][0][0], gacc[m][0][1], av, bv0);
+              if (nbB == 2) dmma(gacc[m][1][0], gacc[m][1][1], av, bv1);
+            }
+          }
+        }
+        if (more) link7(s >> 1, s & 1, nbA, ysL, row0L, DwL);
+      }
+      if (more && LINK == 0) {
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) {
+          logit_acc_fold(lacc[ni][0]);
+          logit_acc_fold(lacc[ni][1]);
+        }
+      }
+    }
+    // this warp is done with X stage `it % NST7`: the last of the four warps to get here refills it for iteration it + NST7
+    if (it + NST7 < n_it) {
+      if (warp_arrive_is_last4(&doneX[it % NST7], lane)) load_x(it + NST7);
+    } else {
+      __syncwarp();
+    }
+    if (rtB == n_rt - 1) {  // partial gradient of this (row group, chain tile)
+      const int slot0 = ctB * TC + cb;
+#pragma unroll
+      for (int m = 0; m < NMB; m++) {
+        const int k = m * 8 + gid;
+        if (k < Dk) {
+#pragma unroll
+          for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int slot = slot0 + ni * 8 + 2 * tig + j;
+              if (slot < n_list) a.Gp[((size_t)p * a.cap + slot) * Dk + k] = gacc[m][ni][j];
+              gacc[m][ni][j] = 0.0;
+            }
+        }
+      }
+      if (!more) flush_lp(ctB, nbB);
+    }
+  }
+}
+
+size_t glm_tc7_smem_bytes(int Dk) {
+  return ((size_t)TC * xs_ld_for(Dk) + (size_t)NST7 * TR7 * xs_ld_for(Dk) + (size_t)4 * 2 * TR7 * DW7_LD + NST7 * TR7 + 32 + NST7 + 1 + NST7) * sizeof(double);
+}
+
+
+// =====================================================================================================================
 // v3: the same fused product, with NO block-wide barrier in steady state (profiles/README.md r01c: with three
 // __syncthreads per tile all eight warps run the same phase at the same time, the link phase cannot saturate the shared
 // FP64 pipe on its own, and 24 % of its cycles idle).
@@ -1443,6 +1787,28 @@ int launch_glm_dmma(const ModelData& m, const GradBatch& b, const GlmWorkspace& 
       if (logistic) LAUNCH3(0, 14) else LAUNCH3(1, 14)
     }
 #undef LAUNCH3
+    return 1;
+  }
+  if (ws.variant == 6) {  // v7: one warp per sub-partition, link in the shadow of the tensor work
+    const size_t smem7 = glm_tc7_smem_bytes(a.Dk);
+#define LAUNCH7(LINK, NMB)                                                                    \
+  {                                                                                           \
+    auto k = glm_dmma7_kernel<LINK, NMB>;                                                     \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7);         \
+    B200_LAUNCH(k, ws.P, NT7, smem7, stream, a);                                              \
+  }
+    if (a.Dk <= 16) {
+      if (logistic) LAUNCH7(0, 2) else LAUNCH7(1, 2)
+    } else if (a.Dk <= 32) {
+      if (logistic) LAUNCH7(0, 4) else LAUNCH7(1, 4)
+    } else if (a.Dk <= 56) {
+      if (logistic) LAUNCH7(0, 7) else LAUNCH7(1, 7)
+    } else if (a.Dk <= 104) {
+      if (logistic) LAUNCH7(0, 13) else LAUNCH7(1, 13)
+    } else {
+      if (logistic) LAUNCH7(0, 14) else LAUNCH7(1, 14)
+    }
+#undef LAUNCH7
     return 1;
   }
   if (ws.variant == 5) {  // v6: sixteen warps, two out-of-phase groups of eight

@@ -43,6 +43,7 @@ extern "C" size_t glm_simt_smem_bytes(int variant, int Dk) {
   if (variant == 2) return b200::glm_tc3_smem_bytes(Dk);
   if (variant == 4) return b200::glm_tc5_smem_bytes(Dk);
   if (variant == 5) return b200::glm_tc6_smem_bytes(Dk);
+  if (variant == 6) return b200::glm_tc7_smem_bytes(Dk);
   return b200::glm_tc_smem_bytes(Dk);
 }
 

@@ -96,7 +96,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "-".join(str(v) for v in s))
 def test_partials_against_numpy(lib, variant, shape):
     logistic, N, D, Cn, n_list, P, use_list = shape
@@ -136,7 +136,7 @@ def test_v4_has_the_summation_order_of_v3(lib, shape):
     assert np.array_equal(a[0][:, :n_list], b[0][:, :n_list]) and np.array_equal(a[1][:, :n_list], b[1][:, :n_list])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_a_chain_does_not_depend_on_its_batch(lib, variant):
     """kernels.h: results for a chain depend only on that chain's q -- whichever other chains request a gradient in the same
     launch and whichever slot of the chain tile it lands in (hmc_nuts_diag_e_adapt_parallel_match_test.cpp:73-153)"""
@@ -150,7 +150,7 @@ def test_a_chain_does_not_depend_on_its_batch(lib, variant):
 
 
 # ---- the whole gradient stage (partial kernel of each variant, reduction over row groups, priors and signs) vs the oracle -------
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("name,N,K", [("logistic", 300, 12), ("poisson_glm", 257, 30), ("logistic", 200, 100)])
 def test_gradient_stage_against_the_oracle(lib, variant, name, N, K):
     """launch_glm_grad (kernels.h): zV = -lp, G = -grad lp with lp = log_prob_propto_jacobian of the oracle's GLM
@@ -181,7 +181,7 @@ def test_gradient_stage_against_the_oracle(lib, variant, name, N, K):
     assert np.all(np.isnan(zV[idle])) and np.all(np.isnan(G[idle]))   # chains that did not ask are not touched
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5, 6])
 def test_gradient_stage_edge_values(lib, variant):
     """the +-20 cut-offs of bernoulli_logit_glm (linear predictors of +-60), and poisson_log_glm with exp(eta) overflowing:
     the reference throws a domain error there (non-finite sum of the derivative) => rejected proposal, V = +inf"""
@@ -236,7 +236,8 @@ def _tsan_run(exe, args):
 # variant logistic N D chains requesting P
 TSAN_CASES = [(0, 1, 300, 51, 70, 70, 3), (1, 1, 700, 51, 200, 77, 3), (2, 1, 640, 101, 140, 130, 2), (3, 1, 640, 101, 140, 130, 2), (3, 0, 900, 110, 70, 70, 3), (3, 1, 200, 13, 70, 70, 3),
               (4, 1, 640, 101, 140, 130, 2), (4, 0, 900, 110, 70, 40, 3), (4, 1, 200, 13, 70, 70, 3),
-              (5, 1, 640, 101, 140, 130, 2), (5, 0, 900, 110, 70, 40, 3), (5, 1, 200, 13, 70, 70, 3)]
+              (5, 1, 640, 101, 140, 130, 2), (5, 0, 900, 110, 70, 40, 3), (5, 1, 200, 13, 70, 70, 3),
+              (6, 1, 640, 101, 140, 130, 2), (6, 0, 900, 110, 70, 40, 3), (6, 1, 200, 13, 70, 70, 3)]
 
 
 @pytest.mark.parametrize("case", TSAN_CASES, ids=lambda c: "-".join(str(v) for v in c))

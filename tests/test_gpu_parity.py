@@ -43,7 +43,7 @@ def test_log_prob_grad_matches_oracle(name, data):
     e.close()
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "6"])
 def test_glm_kernel_variants_agree(variant, monkeypatch):
     """DFMA (0), block-synchronous DMMA (1) and warp-asynchronous DMMA (2) variants of the fused GLM gradient against the
     oracle: ragged sizes (N not a tile multiple, several row tiles per row group, chain counts that leave tiles underfilled)."""
@@ -74,7 +74,7 @@ def test_glm_v5_is_bit_identical_to_v2(monkeypatch):
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5", "6"])
 def test_glm_tensor_variants_batch_independent(variant, monkeypatch):
     """a chain's draws do not depend on which slot of which chain tile serves it (fixed summation order per chain)."""
     monkeypatch.setenv("B200NUTS_GLM_VARIANT", variant)
