@@ -95,6 +95,15 @@ __global__ void __launch_bounds__(128) grad_small_kernel(ModelData md, const dou
   if (lane == 0) zV[c] = -lp;
 }
 
+// padded design matrix [1 | X | 0 ...]: the covariates were copied into columns 1 .. K (cudaMemcpy2D); column 0 and the padding here
+__global__ void glm_pad_design_kernel(double* X, long long N, int K, int ldx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double* row = X + (size_t)i * ldx;
+  row[0] = 1.0;
+  for (int k = K + 1; k < ldx; k++) row[k] = 0.0;
+}
+
 __global__ void set_iter_end_kernel(ChainS* cs, int C, int add, int cap) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -199,7 +208,7 @@ struct b200nuts_engine {
   int C = 0, D = 0, ld = 0, K_out = 0;
   int sm_count = 148;
   // host staging of model data
-  std::vector<double> h_X, h_yr, h_sigma;
+  std::vector<double> h_yr, h_sigma;
   std::vector<int> h_yi;
   std::vector<int8_t> h_y8;
   int64_t x_rows = 0, x_cols = 0, y8_rows = 0, y8_cols = 0;
@@ -373,7 +382,21 @@ int b200nuts_set_data_f64(b200nuts_engine* e, const char* name, const double* ho
   const std::string n(name);
   const int64_t cnt = prod(dims, nd);
   if (n == "X" && nd == 2) {
-    e->h_X.assign(host, host + cnt);
+    // straight to the device in the kernels' layout (row-major [N][ldx], column 0 = 1, zero padded): no host staging copy, no
+    // padded host copy -- this upload is the host->device leg of the end-to-end time (80 MB at c3, 4 GB at c5).  The call returns
+    // after the copy (synchronous), so the caller's buffer is consumed as the C ABI promises.
+    if (dims[0] < 1 || dims[1] < 1 || dims[0] > 2147483647ll || ((dims[1] + 1 + 7) & ~7ll) > glm_max_dim()) {
+      e->err = "glm: X must be [N >= 1][1 <= K], with K + 1 <= 176 in this build";
+      return dims[1] < 1 || dims[0] < 1 ? B200NUTS_DATAERR : B200NUTS_CONFIG;
+    }
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const int K = (int)dims[1], ldx = (K + 1 + 7) & ~7;
+    free_dev(e->d_X);
+    e->d_X = nullptr;
+    CUDA_TRY(e, cudaMalloc(&e->d_X, sizeof(double) * (size_t)dims[0] * ldx));
+    CUDA_TRY(e, cudaMemcpy2DAsync(e->d_X + 1, sizeof(double) * ldx, host, sizeof(double) * K, sizeof(double) * K, (size_t)dims[0], cudaMemcpyHostToDevice, e->stream));
+    glm_pad_design_kernel<<<(unsigned)((dims[0] + 255) / 256), 256, 0, e->stream>>>(e->d_X, dims[0], K, ldx);
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     e->x_rows = dims[0];
     e->x_cols = dims[1];
   } else if (n == "y" && e->cfg.model == B200NUTS_EIGHT_SCHOOLS_NC) {
@@ -494,20 +517,12 @@ static int finalize_data(b200nuts_engine* e) {
     }
     case B200NUTS_LOGISTIC_GLM:
     case B200NUTS_POISSON_GLM: {
-      if (e->h_X.empty() || (int64_t)e->h_yi.size() != e->x_rows) { e->err = "glm: X[N][K] and y[N] must be given"; return B200NUTS_NOINPUT; }
+      if (!e->d_X || (int64_t)e->h_yi.size() != e->x_rows) { e->err = "glm: X[N][K] and y[N] must be given"; return B200NUTS_NOINPUT; }
       m.N = (int)e->x_rows;
       m.K = (int)e->x_cols;
       m.D = m.K + 1;
       if (((m.D + 7) & ~7) > glm_max_dim()) { e->err = "glm: too many covariates for this build (D <= 176)"; return B200NUTS_CONFIG; }
-      m.ldx = (m.D + 7) & ~7;
-      // padded design matrix [1 | X | 0]
-      std::vector<double> xp((size_t)m.N * m.ldx, 0.0);
-      for (int i = 0; i < m.N; i++) {
-        double* row = xp.data() + (size_t)i * m.ldx;
-        row[0] = 1.0;
-        std::memcpy(row + 1, e->h_X.data() + (size_t)i * m.K, (size_t)m.K * 8);
-      }
-      CUDA_TRY(e, upload((void**)&e->d_X, xp.data(), xp.size() * 8));
+      m.ldx = (m.D + 7) & ~7;  // the padded design matrix [1 | X | 0] is already on the device (b200nuts_set_data_f64)
       CUDA_TRY(e, upload((void**)&e->d_yi, e->h_yi.data(), e->h_yi.size() * 4));
       m.X = e->d_X;
       m.yi = e->d_yi;

@@ -244,11 +244,27 @@ def test_cli_plugin_model(tmp_path):
     # unknown model name, with and without a library
     r = _cli("no_such_model", ["sample", "data", f"file={dj}"], tmp_path, env=env)
     assert r.returncode != 0 and "unknown model" in (r.stdout + r.stderr)
-    # user inits are refused for plug-ins (no unconstraining transform in the interface)
+    # init=<file> for a plug-in model goes through the model's transform_inits (include/b200nuts_model.h, model_base.hpp:348): the run
+    # with every parameter given starts where the Python host starts with the hand-computed unconstrained vector (identical files'
+    # draws); a partial file works too; a negative scale is refused with lb_free's message
+    import cmdstan_b200 as B
+    B.load_model_library(_build.build_example_plugins())
     ini = tmp_path / "init.json"
-    ini.write_text(json.dumps({"alpha": 0.0}))
+    ini.write_text(json.dumps({"alpha": 0.9, "beta": [0.4, -0.8, 1.5], "sigma": 0.5}))
+    args = ["sample", "num_samples=30", "num_warmup=40", "data", f"file={dj}", f"init={ini}", "random", "seed=5", "output", "file=ini.csv", "sig_figs=18"]
+    r = _cli("linreg", args, tmp_path, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    body = [x for x in (tmp_path / "ini.csv").read_text().splitlines() if x and not x.startswith("#")]
+    cli_draws = np.array([x.split(",") for x in body[1:]], dtype=float)
+    rc, res = B.hmc_nuts_diag_e_adapt("linreg", {"X": X, "y": y}, num_chains=1, random_seed=5, num_warmup=40, num_samples=30,
+                                      init=np.array([[0.9, 0.4, -0.8, 1.5, np.log(0.5)]]))
+    assert rc == 0 and np.allclose(res["draws"][0], cli_draws, rtol=1e-15, atol=0)
+    ini.write_text(json.dumps({"sigma": 0.5}))
+    r = _cli("linreg", ["sample", "num_samples=5", "num_warmup=20", "data", f"file={dj}", f"init={ini}", "output", "file=p.csv"], tmp_path, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ini.write_text(json.dumps({"alpha": 0.0, "beta": [0, 0, 0], "sigma": -1.0}))
     r = _cli("linreg", ["sample", "data", f"file={dj}", f"init={ini}"], tmp_path, env=env)
-    assert r.returncode != 0 and "plug-in" in (r.stdout + r.stderr)
+    assert r.returncode != 0 and "lb_free" in (r.stdout + r.stderr)
 
 
 @pytest.mark.skipif(not O.have_ref("bernoulli"), reason="oracle/_ref not built")

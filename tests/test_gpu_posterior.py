@@ -103,7 +103,9 @@ def test_posterior_irt_vs_reference():
     data = cases.irt_data(100, 30)
     # reference seed 778: with seed 777 one of the reference's own 16 chains lingers at small sigma_a (split R-hat 1.044) and two
     # reference runs differ from EACH OTHER by 4 MCSE (measured on the CPU, r02f) -- the yardstick has to have converged itself
-    _check_against_reference("irt_2pl", data, _gpu_draws("irt_2pl", data, 256, 1000, 3000), 16, 5000, ref_seed=778)
+    # 8000 draws per chain: the slope scale sigma_a has an autocorrelation time of ~50 transitions, and split R-hat compares half
+    # chains (r02j: 1.0109 with 3000 draws)
+    _check_against_reference("irt_2pl", data, _gpu_draws("irt_2pl", data, 256, 1000, 8000), 16, 5000, ref_seed=778)
 
 
 # ---- full sizes -----------------------------------------------------------------------------------------------------
