@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 EXAMPLES = os.path.join(HERE, "..", "examples", "plugin_models")
 EXAMPLE_PLUGIN = os.path.join(EXAMPLES, "libb200models_example.so")
-UNITS = [("engine.cu", ["--fmad=false"]), ("advance_big.cu", ["--fmad=false"]), ("advance_cta.cu", ["--fmad=false"]), ("dense.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("irt.cu", ["--fmad=false"]), ("summary.cu", ["--fmad=false"])]
+UNITS = [("engine.cu", ["--fmad=false"]), ("advance_big.cu", ["--fmad=false"]), ("advance_cta.cu", ["--fmad=false"]), ("dense.cu", ["--fmad=false"]), ("glm.cu", []), ("glm_dmma.cu", []), ("glm_i8.cu", []), ("irt.cu", ["--fmad=false"]), ("summary.cu", ["--fmad=false"])]
 
 
 def _nvcc():

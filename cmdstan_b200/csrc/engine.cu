@@ -337,6 +337,7 @@ void b200nuts_destroy(b200nuts_engine* e) {
   free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8); free_dev(e->d_ypk);
   free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws); free_dev(e->dc.mat);
   free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
+  glm_i8_destroy(e->glm_ws.i8);
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
   for (auto ev : e->grad_events) cudaEventDestroy(ev);
@@ -714,6 +715,8 @@ static int ensure_glm_ws(b200nuts_engine* e, int C) {
   if (e->d_glm_ws && e->glm_ws.C >= C && e->glm_ws_N == e->md.N && e->glm_ws_D == e->md.D) return B200NUTS_OK;
   free_dev(e->d_glm_ws);
   e->d_glm_ws = nullptr;
+  glm_i8_destroy(e->glm_ws.i8);
+  e->glm_ws.i8 = nullptr;
   size_t bytes = glm_workspace_bytes(e->md.N, e->md.D, C, e->sm_count, &e->glm_ws);
   CUDA_TRY(e, cudaMalloc(&e->d_glm_ws, bytes));
   glm_workspace_bind(&e->glm_ws, e->d_glm_ws);
@@ -723,6 +726,10 @@ static int ensure_glm_ws(b200nuts_engine* e, int C) {
   CUDA_TRY(e, cudaMemsetAsync(e->glm_ws.R, 0, sizeof(double) * (size_t)e->glm_ws.C * (1 + e->glm_ws.Dp), e->stream));
   const char* v = getenv("B200NUTS_GLM_VARIANT");
   e->glm_ws.variant = v ? atoi(v) : 1;
+  if (e->glm_ws.variant == 7) {  // INT8 digit planes on tcgen05; where it does not apply (nullptr) the FP64 tensor kernel v2 serves
+    e->glm_ws.i8 = glm_i8_create(e->md, e->glm_ws.Dp, e->glm_ws.C, e->sm_count, e->glm_ws.P, e->stream);
+    if (!e->glm_ws.i8) e->glm_ws.variant = 1;
+  }
   return B200NUTS_OK;
 }
 

@@ -263,10 +263,15 @@ int glm_tc_max_dk();
 template <int LINK>
 static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, allreduce_fn ar, void* ar_user,
                         cudaStream_t stream) {
-  const int Dp = ws.Dp, C = b.C, P = ws.P;
+  const int Dp = ws.Dp, C = b.C;
+  int P = ws.P;
   int launches = 0;
-  const bool tc = ws.variant >= 1 && Dp <= glm_tc_max_dk();
-  if (tc) {
+  const bool i8 = LINK == 0 && ws.variant == 7 && ws.i8 != nullptr;
+  const bool tc = i8 || (ws.variant >= 1 && Dp <= glm_tc_max_dk());
+  if (i8) {  // INT8 digit planes on tcgen05 (glm_i8.cu): its own, coarser row groups
+    launches += launch_glm_i8(m, b, ws, stream);
+    P = glm_i8_row_groups(ws.i8);
+  } else if (tc) {
     launches += launch_glm_dmma(m, b, ws, stream);
   } else {
     const long long T = ((long long)m.N + TR - 1) / TR;

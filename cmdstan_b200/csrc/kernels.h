@@ -43,8 +43,14 @@ struct GlmWorkspace {
   double* LPp = nullptr;  // [P][C]       per row-group partial log-likelihood
   double* R = nullptr;    // [C][1 + Dp]  reduced (lp, gradient): the all-reduce payload for row sharding
   int P = 0, C = 0, Dp = 0;
-  int variant = 0;        // 0: register-tiled DFMA kernel, 1: DMMA kernel v2 (block-synchronous), 2: DMMA kernel v3 (warp-asynchronous)
+  int variant = 0;        // 0: register-tiled DFMA kernel, 1: DMMA kernel v2 (block-synchronous), 2..6: other DMMA formulations, 7: INT8 (glm_i8.cu)
+  void* i8 = nullptr;     // variant 7: state of the Ozaki-split INT8 kernel (digit-plane image of X, column scales), or nullptr
 };
+// glm_i8.cu: logistic regression on tcgen05 kind::i8.  glm_i8_create returns nullptr when the formulation does not apply.
+void* glm_i8_create(const ModelData& m, int Dk, int cap, int sm_count, int max_row_groups, cudaStream_t stream);
+void glm_i8_destroy(void* state);
+int glm_i8_row_groups(const void* state);
+int launch_glm_i8(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws, cudaStream_t stream);
 size_t glm_workspace_bytes(int N, int D, int C, int sm_count, GlmWorkspace* ws);  // fills P, C, Dp (= D padded to 8); returns total bytes
 void glm_workspace_bind(GlmWorkspace* ws, void* base);
 int glm_max_dim();

@@ -113,6 +113,74 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(const Args a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
 }
 
+
+// issue-rate kernel: the MMA stream of one row tile with every descriptor a compile-time offset from two bases (what the real kernel
+// issues): NSL slice products, concatenated along N, 4 K steps each; MODE 0 = first product (K-major), 1 = second (MN-major)
+__host__ __device__ constexpr uint32_t idesc_c(int M, int N, int a_mn, int b_mn) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <int MODE, int NSL, int CNT>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int repeat, long long* cycles, int* err) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid * 16; i < 200 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x01010101u, 0x02020202u, 0x03030303u, 0x04040404u);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t abase = smem_u32(smem), bbase = abase + 96 * 1024;
+    const uint64_t ad0 = MODE == 0 ? make_desc(abase, 128, 1024) : make_desc(abase, 1024, 128);
+    const uint64_t bd0 = MODE == 0 ? make_desc(bbase, 128, 1024) : make_desc(bbase, 128, 2048);
+    const long long t0 = clock64();
+    for (int rep = 0; rep < repeat; rep++) {
+#pragma unroll
+      for (int i = 0; i < NSL; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t aoff = i * 16384 + k * (MODE == 0 ? 256 : 4096), boff = k * (MODE == 0 ? 256 : 512);
+          mma_i8(tbase + i * CNT, ad0 + (aoff >> 4), bd0 + (boff >> 4), idesc_c(128, (NSL - i) * CNT, MODE, MODE), 1u);
+        }
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t done = 0;
+    for (long long spin = 0; spin < (1ll << 26) && !done; spin++)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    if (!done) *err = 1;
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+}
+template <int MODE, int NSL, int CNT>
+static void run_rate(const char* name) {
+  int* d_err; CK(cudaMalloc(&d_err, 4)); CK(cudaMemset(d_err, 0, 4));
+  long long* dC; CK(cudaMalloc(&dC, 148 * 8));
+  auto k = rate_kernel<MODE, NSL, CNT>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int repeat = 400;
+  for (int it = 0; it < 2; it++) { k<<<148, 128, 200 * 1024>>>(repeat, dC, d_err); CK(cudaDeviceSynchronize()); }
+  std::vector<long long> cyc(148); int err = 0;
+  CK(cudaMemcpy(cyc.data(), dC, 148 * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto c : cyc) mx = c > mx ? c : mx;
+  const double macs = 0.5 * NSL * (NSL + 1) * 128.0 * CNT * 128;
+  printf("unrolled %s, %d slices, %d chains: %.0f cycles per row tile, %.0f MAC/clk/SM, timeout=%d\n", name, NSL, CNT, (double)mx / repeat, macs * repeat / (double)mx, err);
+  CK(cudaFree(dC)); CK(cudaFree(d_err));
+}
+
 static uint32_t idesc_i8(int M, int N, int a_mn, int b_mn) {
   uint32_t d = 0;
   d |= 2u << 4;                 // accumulator format S32
@@ -293,5 +361,13 @@ int main() {
     printf("%s: %.0f cycles per row tile (max over CTAs), %.1f MAC/clk/SM, kernel %.3f ms, timeout=%d\n", name, (double)mx / a.repeat,
            macs * a.repeat / (double)mx, ms, err);
   }
+  run_rate<0, 5, 32>("first product ");
+  run_rate<1, 5, 32>("second product");
+  run_rate<0, 5, 48>("first product ");
+  run_rate<1, 5, 48>("second product");
+  run_rate<0, 6, 32>("first product ");
+  run_rate<1, 6, 32>("second product");
+  run_rate<0, 4, 64>("first product ");
+  run_rate<1, 4, 64>("second product");
   return 0;
 }
