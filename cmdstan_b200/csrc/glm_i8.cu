@@ -39,10 +39,13 @@ namespace {
 
 constexpr int TRW = 128;      // rows per tile = M of the first product = K of the second
 constexpr int CN = 32;        // chains per tile
-constexpr int NTH = 320;      // warp 0: loads, warp 1: MMA issue + TMEM allocation, warps 2..9: epilogue
+constexpr int NTH = 576;      // warp 0: loads, warp 1: MMA issue + TMEM allocation, warps 2..17: epilogue (four per SM sub-partition)
+constexpr int ECH = 8;        // chains per epilogue thread: warp group wg = (warp - 2) / 4 owns chains [8 wg, 8 wg + 8) of the tile
+constexpr int NEW = 16;       // epilogue warps
 constexpr int KQ = 4;         // chain-tile classes: CTA (p, kq) serves row group p and the chain tiles ct == kq (mod KQ)
 constexpr uint32_t ACOL = 0, GCOL = 256;   // TMEM columns of the Eta / G diagonals (NS * 32 <= 192 each)
-constexpr long long kTimeoutCycles = 4000000000ll;   // ~2 s: a protocol error must end the kernel (trap), never hang the device
+constexpr unsigned kMaxPolls = 1u << 24;   // a protocol error must end the kernel (trap), never hang the device: each try_wait suspends
+                                            // the thread for a bounded time of its own, so this is seconds, not microseconds
 
 struct GlmI8Args {
   const uint8_t* Ximg;      // [T][NS][16][DC][8][16]
@@ -72,10 +75,9 @@ __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  unsigned polls = 0;
   while (!mbar_try(bar, parity))
-    if (clock64() - t0 > kTimeoutCycles) mbar_timeout(bar, parity);
+    if (++polls > kMaxPolls) mbar_timeout(bar, parity);
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc, unsigned bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
@@ -131,6 +133,19 @@ __device__ __forceinline__ void i8_digits(double v, uint32_t& lo, uint32_t& hi) 
   lo ^= 0x80808080u;
 }
 
+// S = sum_k d[k] 256^(NS-1-k) from the INT32 diagonals: three (NS = 6) wide multiply-adds and two 64-bit additions instead of a
+// Horner chain of 64-bit shifts
+template <int NS>
+__device__ __forceinline__ long long i8_combine(const int (&d)[NS]) {
+  if (NS == 6) {
+    const long long w3 = (long long)d[0] * 256 + d[1], w2 = (long long)d[2] * 256 + d[3], w1 = (long long)d[4] * 256 + d[5];
+    return (w3 << 32) + (w2 << 16) + w1;
+  } else {
+    const long long w2 = (long long)d[1] * 256 + d[2], w1 = (long long)d[3] * 256 + d[4];
+    return ((long long)d[0] << 32) + (w2 << 16) + w1;
+  }
+}
+
 // ---- the main kernel ------------------------------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
@@ -167,11 +182,11 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(a_full, 1);
-    mbar_init(a_empty, 8);
-    mbar_init(dm_full, 8);
+    mbar_init(a_empty, NEW);
+    mbar_init(dm_full, NEW);
     mbar_init(dm_empty, 1);
     mbar_init(g_full, 1);
-    mbar_init(g_empty, 8);
+    mbar_init(g_empty, NEW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -186,88 +201,111 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
 
   if (warp == 0) {
     // ===== producer: q planes of each chain tile, X planes of each row tile through the ring =====
+    // (one thread; every index is carried incrementally: a division or a modulo costs this lone thread more than an MMA takes)
     if (lane == 0) {
       const size_t q_tile = i8_q_tile_bytes(NS, KA);
-      uint32_t cnt = 0;
-      for (int j = 0; j < n_my; j++) {
-        const int ct = kq + KQ * j;
+      const uint32_t ring_u = smem_u32(ring);
+      uint32_t slot = 0, pass = 0;   // pass over the ring: use number of `slot`
+      const uint8_t* qsrc = a.Qimg + (size_t)kq * q_tile;
+      for (int j = 0; j < n_my; j++, qsrc += (size_t)KQ * q_tile) {
         if (j > 0) mbar_wait(q_empty, (uint32_t)(j - 1) & 1u);
         mbar_expect_tx(q_full, q_digit_bytes + CN * (unsigned)sizeof(double));
-        tma_load_1d(smem_u32(qs), a.Qimg + (size_t)ct * q_tile, q_digit_bytes, q_full);
-        tma_load_1d(smem_u32(scs + (j & 1) * CN), a.Qimg + (size_t)ct * q_tile + q_digit_bytes, CN * (unsigned)sizeof(double), q_full);
-        for (int rt = 0; rt < n_rt; rt++)
-          for (int i = 0; i < NS; i++, cnt++) {
-            const uint32_t slot = cnt % NB, use = cnt / NB;
-            if (use > 0) mbar_wait(x_empty(slot), (use - 1) & 1u);
+        tma_load_1d(smem_u32(qs), qsrc, q_digit_bytes, q_full);
+        tma_load_1d(smem_u32(scs + (j & 1) * CN), qsrc + q_digit_bytes, CN * (unsigned)sizeof(double), q_full);
+        const uint8_t* xsrc = a.Ximg + (size_t)t_begin * NS * slice_bytes;
+        for (int rt = 0; rt < n_rt; rt++) {
+#pragma unroll
+          for (int i = 0; i < NS; i++, xsrc += slice_bytes) {
+            if (pass > 0) mbar_wait(x_empty(slot), (pass - 1) & 1u);
             mbar_expect_tx(x_full(slot), slice_bytes);
-            tma_load_1d(smem_u32(ring) + slot * slice_bytes, a.Ximg + ((size_t)(t_begin + rt) * NS + i) * slice_bytes, slice_bytes, x_full(slot));
+            tma_load_1d(ring_u + slot * slice_bytes, xsrc, slice_bytes, x_full(slot));
+            if (++slot == (uint32_t)NB) {
+              slot = 0;
+              pass++;
+            }
           }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread): first product of tile it + 1 before the second product of tile it =====
     if (lane == 0) {
       const uint32_t ring_u = smem_u32(ring), qs_u = smem_u32(qs), dm_u = smem_u32(dms);
-      auto issue_a = [&](uint32_t it) {
-        const int rt = (int)(it % (uint32_t)n_rt), j = (int)(it / (uint32_t)n_rt);
-        if (it > 0) mbar_wait(a_empty, (it - 1) & 1u);
-        if (rt == 0) mbar_wait(q_full, (uint32_t)j & 1u);
+      const uint64_t bdesc_a = make_desc(qs_u, 128, DCQ * 128), bdesc_b = make_desc(dm_u, 128, 2048);
+      const uint64_t adesc_a0 = make_desc(ring_u, 128, DC * 128), adesc_b0 = make_desc(ring_u, DC * 128, 128);
+      const uint32_t slice16 = slice_bytes >> 4, kstep_b = (uint32_t)(4 * DC * 8);
+      // cursors of the two issue streams (both walk the ring in the same order)
+      uint32_t a_slot = 0, a_par = 0, a_it = 0, b_slot = 0, b_it = 0;
+      int a_rt = 0, a_j = 0, b_rt = 0, b_j = 0;
+      auto issue_a = [&]() {
+        if (a_it > 0) mbar_wait(a_empty, (a_it - 1) & 1u);
+        if (a_rt == 0) mbar_wait(q_full, (uint32_t)a_j & 1u);
         tc_fence_after();
-        const uint64_t bdesc = make_desc(qs_u, 128, DCQ * 128);
 #pragma unroll
         for (int i = 0; i < NS; i++) {
-          const uint32_t cnt = it * NS + i, slot = cnt % NB, use = cnt / NB;
-          mbar_wait(x_full(slot), use & 1u);
+          mbar_wait(x_full(a_slot), a_par);
           tc_fence_after();
-          const uint64_t adesc = make_desc(ring_u + slot * slice_bytes, 128, DC * 128);
+          const uint64_t adesc = adesc_a0 + (uint64_t)(a_slot * slice16);
           for (int k = 0; k < KA; k++)
-            mma_i8(tbase + ACOL + 32 * i, adesc + (uint64_t)(k * 16), bdesc + (uint64_t)(k * 16), idesc_i8(128, 32 * (NS - i), 0), (i > 0 || k > 0) ? 1u : 0u);
+            mma_i8(tbase + ACOL + 32 * i, adesc + (uint64_t)(k * 16), bdesc_a + (uint64_t)(k * 16), idesc_i8(128, 32 * (NS - i), 0), (i > 0 || k > 0) ? 1u : 0u);
+          if (++a_slot == (uint32_t)NB) {
+            a_slot = 0;
+            a_par ^= 1u;
+          }
         }
         tc_commit(a_full);
-        if (rt == n_rt - 1) tc_commit(q_empty);
+        a_it++;
+        if (++a_rt == n_rt) {
+          tc_commit(q_empty);
+          a_rt = 0;
+          a_j++;
+        }
       };
-      auto issue_b = [&](uint32_t it) {
-        const int rt = (int)(it % (uint32_t)n_rt), j = (int)(it / (uint32_t)n_rt);
-        mbar_wait(dm_full, it & 1u);
-        if (rt == 0 && j > 0) mbar_wait(g_empty, (uint32_t)(j - 1) & 1u);
+      auto issue_b = [&]() {
+        mbar_wait(dm_full, b_it & 1u);
+        if (b_rt == 0 && b_j > 0) mbar_wait(g_empty, (uint32_t)(b_j - 1) & 1u);
         tc_fence_after();
-        const uint64_t bdesc = make_desc(dm_u, 128, 2048);
 #pragma unroll
         for (int i = 0; i < NS; i++) {
-          const uint32_t cnt = it * NS + i, slot = cnt % NB;
-          const uint64_t adesc = make_desc(ring_u + slot * slice_bytes, DC * 128, 128);
+          const uint64_t adesc = adesc_b0 + (uint64_t)(b_slot * slice16);
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            mma_i8(tbase + GCOL + 32 * i, adesc + (uint64_t)(k * 4 * DC * 8), bdesc + (uint64_t)(k * 32), idesc_i8(128, 32 * (NS - i), 1),
-                   (rt > 0 || i > 0 || k > 0) ? 1u : 0u);
-          tc_commit(x_empty(slot));
+            mma_i8(tbase + GCOL + 32 * i, adesc + (uint64_t)(k * kstep_b), bdesc_b + (uint64_t)(k * 32), idesc_i8(128, 32 * (NS - i), 1),
+                   (b_rt > 0 || i > 0 || k > 0) ? 1u : 0u);
+          tc_commit(x_empty(b_slot));
+          if (++b_slot == (uint32_t)NB) b_slot = 0;
         }
         tc_commit(dm_empty);
-        if (rt == n_rt - 1) tc_commit(g_full);
+        b_it++;
+        if (++b_rt == n_rt) {
+          tc_commit(g_full);
+          b_rt = 0;
+          b_j++;
+        }
       };
-      issue_a(0);
+      issue_a();
       for (uint32_t it = 0; it < n_it; it++) {
-        if (it + 1 < n_it) issue_a(it + 1);
-        issue_b(it);
+        if (it + 1 < n_it) issue_a();
+        issue_b();
       }
     }
   } else {
-    // ===== epilogue: thread = row r of the tile (TMEM lane), chains [16 wg, 16 wg + 16) of the chain tile =====
+    // ===== epilogue: thread = row r of the tile (TMEM lane), chains [8 wg, 8 wg + 8) of the chain tile =====
     const int ew = warp - 2, wg = ew >> 2, quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int et = ew * 32 + lane;
     const uint32_t lane_base = tbase + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t dm_row = smem_u32(dms) + (uint32_t)wg * 2048u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    const uint32_t dm_row = smem_u32(dms) + (uint32_t)(wg >> 1) * 2048u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(wg & 1) * 8u;
     const double gscale = ldexp(1.0, I8Fmt<NS>::SEXP) * (r < a.Dk ? a.colscale[r] : 0.0);
-    LogitAcc lacc[16];
+    LogitAcc lacc[ECH];
     uint32_t it = 0;
     for (int j = 0; j < n_my; j++) {
       const int slot0 = (kq + KQ * j) * CN;
 #pragma unroll
-      for (int c = 0; c < 16; c++) logit_acc_init(lacc[c]);
+      for (int c = 0; c < ECH; c++) logit_acc_init(lacc[c]);
       int n_pad = 0;
       mbar_wait(q_full, (uint32_t)j & 1u);
-      const double* sc = scs + (j & 1) * CN + wg * 16;
+      const double* sc = scs + (j & 1) * CN + wg * ECH;
       for (int rt = 0; rt < n_rt; rt++, it++) {
         const long long row = (long long)(t_begin + rt) * TRW + r;
         const bool valid = row < a.N;
@@ -275,28 +313,27 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         n_pad += valid ? 0 : 1;
         mbar_wait(a_full, it & 1u);
         tc_fence_after();
-        double eta[16];
+        double eta[ECH];
+        {
+          int v[NS][ECH];
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
-          int v[NS][8];
-#pragma unroll
-          for (int k = 0; k < NS; k++) tmem_ld8(lane_base + ACOL + 32 * k + 16 * wg + 8 * b, v[k]);
+          for (int k = 0; k < NS; k++) tmem_ld8(lane_base + ACOL + 32 * k + ECH * wg, v[k]);
           tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_empty);   // the next tile's first product may overwrite the Eta diagonals now
 #pragma unroll
-          for (int c = 0; c < 8; c++) {
-            long long S = v[0][c];
+          for (int c = 0; c < ECH; c++) {
+            int d[NS];
 #pragma unroll
-            for (int k = 1; k < NS; k++) S = S * 256 + v[k][c];
-            eta[8 * b + c] = (double)S * sc[8 * b + c];
+            for (int k = 0; k < NS; k++) d[k] = v[k][c];
+            eta[c] = (double)i8_combine<NS>(d) * sc[c];
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty);   // the next tile's first product may overwrite the Eta diagonals now
         // ---- link + digits of dm: pk[s][g] = digit plane s of chains 4 g .. 4 g + 3
-        uint32_t pk[NS][4];
+        uint32_t pk[NS][ECH / 4];
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
+        for (int g = 0; g < ECH / 4; g++) {
           uint32_t lo[4], hi[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
@@ -320,12 +357,12 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         }
         if ((rt & 255) == 255) {
 #pragma unroll
-          for (int c = 0; c < 16; c++) logit_acc_fold(lacc[c]);
+          for (int c = 0; c < ECH; c++) logit_acc_fold(lacc[c]);
         }
         if (it > 0) mbar_wait(dm_empty, (it - 1) & 1u);   // the second product of the previous tile has read the dm planes
 #pragma unroll
         for (int s = 0; s < NS; s++)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dm_row + (uint32_t)s * 4096u), "r"(pk[s][0]), "r"(pk[s][1]), "r"(pk[s][2]), "r"(pk[s][3]) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dm_row + (uint32_t)s * 4096u), "r"(pk[s][0]), "r"(pk[s][1]) : "memory");
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(dm_full);
@@ -333,26 +370,25 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       // ---- end of the chain tile: partial gradient and log-likelihood of (row group p, chain tile)
       mbar_wait(g_full, (uint32_t)j & 1u);
       tc_fence_after();
+      {
+        int v[NS][ECH];
 #pragma unroll
-      for (int b = 0; b < 2; b++) {
-        int v[NS][8];
-#pragma unroll
-        for (int k = 0; k < NS; k++) tmem_ld8(lane_base + GCOL + 32 * k + 16 * wg + 8 * b, v[k]);
+        for (int k = 0; k < NS; k++) tmem_ld8(lane_base + GCOL + 32 * k + ECH * wg, v[k]);
         tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_empty);
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
+        for (int c = 0; c < ECH; c++) {
           long long S = v[0][c];
 #pragma unroll
           for (int k = 1; k < NS; k++) S = S * 256 + v[k][c];
-          const int slot = slot0 + 16 * wg + 8 * b + c;
+          const int slot = slot0 + ECH * wg + c;
           if (r < a.Dk && slot < n_list) a.Gp[((size_t)p * a.cap + slot) * a.Dk + r] = (double)S * gscale;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(g_empty);
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
+      for (int c = 0; c < ECH; c++) {
         logit_acc_fold(lacc[c]);
         double v = logit_acc_value(lacc[c], n_pad);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -360,11 +396,11 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (lane == 0) red[quarter * CN + 16 * wg + c] = v;
+        if (lane == 0) red[quarter * CN + ECH * wg + c] = v;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       if (et < CN && slot0 + et < n_list) a.LPp[(size_t)p * a.cap + slot0 + et] = ((red[et] + red[CN + et]) + red[2 * CN + et]) + red[3 * CN + et];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
     }
   }
   tc_fence_before();
