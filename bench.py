@@ -19,6 +19,7 @@ Launch: python bench.py --gpus N --steps K --warmup W     (N > 1: torchrun, one 
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -369,14 +370,29 @@ def run_gpu_workload(wname, K, W, num_warmup, chains_per_gpu, scale, rank, world
             fl = work["flops"] * n_chain_grads / world   # per rank: chains/world (chain mode) or rows/world (row mode)
             ach = fl / grad_s / 1e12 if grad_s > 0 else None
             peak = measure_fp64_peak(dev)
-            tr = ncu_traffic(model) if scale == 1.0 and world == 1 else None
+            # which formulation served: the INT8 digit-plane kernel on tcgen05 (variant 7) is the default for the logistic link
+            glm_variant = int(os.environ.get("B200NUTS_GLM_VARIANT", "7" if model == "logistic" else "1"))
+            i8 = glm_variant == 7 and model == "logistic"
+            tr = ncu_traffic("logistic_i8" if i8 else model) if scale == 1.0 and world == 1 else None
             bytes_rank = work["bytes_per_batch"] / (world if row_mode else 1)
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp64)", "frac": (ach / peak) if ach and peak else None,
                     "traffic": tr["bytes"] if tr else None, "traffic_detail": tr, "algorithmic_bytes_per_launch": bytes_rank,
-                    "kernel": "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
+                    "kernel": "glm_i8_kernel (+q planes, reduce, finish)" if i8 else "glm_dmma_kernel (+reduce, finish)", "launches": n_grad_launch,
                     "avg_launch_ms": 1e3 * grad_s / n_grad_launch, "avg_chains_per_launch": n_chain_grads / (1 if row_mode else world) / n_grad_launch,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
                     "hbm_gbs_achieved": bytes_rank / (grad_s / n_grad_launch) / 1e9 if grad_s > 0 else None, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src}
+            if i8:
+                # the same algorithmic fp64 flops, executed as 21 + 21 exact INT8 digit-plane products per (128 rows x 32 chains) tile
+                # padded to K = 128 design columns / M = 128 gradient rows: the tensor work actually issued, against the INT8 peak
+                N_rows = data["X"].shape[0]
+                macs = (n_chain_grads / world / 32.0) * math.ceil(N_rows / 128.0) * 2 * 21 * 128 * 32 * 128
+                roof["formulation"] = ("fp64 contractions as exact INT8 digit-plane products (6 planes x 8 bit, 46-bit operands, diagonals below 2^-48 dropped) on "
+                                       "tcgen05.mma kind::i8 with INT32 accumulators in tensor memory; `achieved` counts the ALGORITHMIC fp64 flops (4 N Dp per "
+                                       "chain-gradient), so frac > 1 of the DGEMM rate is possible: the work left the FP64 pipe")
+                roof["int8_top_s_issued"] = 2.0 * macs / grad_s / 1e12 if grad_s > 0 else None
+                roof["int8_peak_top_s"] = 4550.0
+                roof["int8_peak_source"] = "tools/microbench/umma_i8.cu on this pool (profiles/r02m_umma_i8.txt: 7 825 MAC/clk/SM x 148 SMs x 1.965 GHz); nominal 4 500"
+                roof["int8_frac"] = roof["int8_top_s_issued"] / roof["int8_peak_top_s"] if roof["int8_top_s_issued"] else None
             if row_mode:
                 roof["allreduce_us_per_leapfrog"] = ar_us
                 roof["allreduce_payload_bytes"] = ar_bytes

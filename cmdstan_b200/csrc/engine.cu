@@ -725,7 +725,8 @@ static int ensure_glm_ws(b200nuts_engine* e, int C) {
   // the all-reduce payload of a row-sharded run covers the rows of every chain, requesting or not: never uninitialised memory
   CUDA_TRY(e, cudaMemsetAsync(e->glm_ws.R, 0, sizeof(double) * (size_t)e->glm_ws.C * (1 + e->glm_ws.Dp), e->stream));
   const char* v = getenv("B200NUTS_GLM_VARIANT");
-  e->glm_ws.variant = v ? atoi(v) : 1;
+  // default: the INT8 digit-plane kernel on tcgen05 for the logistic link (r02: 2x the FP64 tensor kernel), the FP64 tensor kernel v2 else
+  e->glm_ws.variant = v ? atoi(v) : (e->md.kind == MODEL_LOGISTIC ? 7 : 1);
   if (e->glm_ws.variant == 7) {  // INT8 digit planes on tcgen05; where it does not apply (nullptr) the FP64 tensor kernel v2 serves
     e->glm_ws.i8 = glm_i8_create(e->md, e->glm_ws.Dp, e->glm_ws.C, e->sm_count, e->glm_ws.P, e->stream);
     if (!e->glm_ws.i8) e->glm_ws.variant = 1;

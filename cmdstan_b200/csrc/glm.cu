@@ -266,11 +266,17 @@ static int launch_glm_t(const ModelData& m, const GradBatch& b, const GlmWorkspa
   const int Dp = ws.Dp, C = b.C;
   int P = ws.P;
   int launches = 0;
+#ifdef B200_SIMT_EMUL   // the CPU rig has no stand-in for tcgen05 / tensor memory: the INT8 kernel is validated on hardware only
+  const bool i8 = false;
+#else
   const bool i8 = LINK == 0 && ws.variant == 7 && ws.i8 != nullptr;
+#endif
   const bool tc = i8 || (ws.variant >= 1 && Dp <= glm_tc_max_dk());
   if (i8) {  // INT8 digit planes on tcgen05 (glm_i8.cu): its own, coarser row groups
+#ifndef B200_SIMT_EMUL
     launches += launch_glm_i8(m, b, ws, stream);
     P = glm_i8_row_groups(ws.i8);
+#endif
   } else if (tc) {
     launches += launch_glm_dmma(m, b, ws, stream);
   } else {

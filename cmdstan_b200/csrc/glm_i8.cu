@@ -56,7 +56,9 @@ struct GlmI8Args {
   double* Gp;               // [P][cap][Dk]
   double* LPp;              // [P][cap]
   int n_fixed, N, Dk, DC, KA, cap, P, T, NB;
+  long long* trace;         // TRACE builds only: [3 roles][kTraceIt][8] clock64 stamps of CTA 0 (tools/i8_trace.py)
 };
+constexpr int kTraceIt = 96;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -81,6 +83,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc, unsigned bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+// the same with an L2 eviction-priority hint: the digit planes of X are re-read by every chain tile of every launch while the
+// advance kernel streams the chains' state through L2 in between (r02q: 25 % of the plane reads missed L2)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t smem_dst, const void* gsrc, unsigned bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -147,8 +159,11 @@ __device__ __forceinline__ long long i8_combine(const int (&d)[NS]) {
 }
 
 // ---- the main kernel ------------------------------------------------------------------------------------------------
-template <int NS>
+template <int NS, bool TRACE>
 __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
+  auto stamp = [&](int role, uint32_t it, int k) {
+    if (TRACE && blockIdx.x == 0 && it < (uint32_t)kTraceIt) a.trace[((size_t)role * kTraceIt + it) * 8 + k] = clock64();
+  };
   extern __shared__ __align__(128) uint8_t smem_i8[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int DC = a.DC, KA = a.KA, DCQ = 2 * KA, NB = a.NB;
@@ -206,6 +221,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       const size_t q_tile = i8_q_tile_bytes(NS, KA);
       const uint32_t ring_u = smem_u32(ring);
       uint32_t slot = 0, pass = 0;   // pass over the ring: use number of `slot`
+      const uint64_t pol = l2_policy_evict_last();
       const uint8_t* qsrc = a.Qimg + (size_t)kq * q_tile;
       for (int j = 0; j < n_my; j++, qsrc += (size_t)KQ * q_tile) {
         if (j > 0) mbar_wait(q_empty, (uint32_t)(j - 1) & 1u);
@@ -217,8 +233,9 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
 #pragma unroll
           for (int i = 0; i < NS; i++, xsrc += slice_bytes) {
             if (pass > 0) mbar_wait(x_empty(slot), (pass - 1) & 1u);
+            stamp(2, (uint32_t)(j * n_rt + rt), i);
             mbar_expect_tx(x_full(slot), slice_bytes);
-            tma_load_1d(ring_u + slot * slice_bytes, xsrc, slice_bytes, x_full(slot));
+            tma_load_1d_hint(ring_u + slot * slice_bytes, xsrc, slice_bytes, x_full(slot), pol);
             if (++slot == (uint32_t)NB) {
               slot = 0;
               pass++;
@@ -238,12 +255,15 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       uint32_t a_slot = 0, a_par = 0, a_it = 0, b_slot = 0, b_it = 0;
       int a_rt = 0, a_j = 0, b_rt = 0, b_j = 0;
       auto issue_a = [&]() {
+        stamp(0, a_it, 0);
         if (a_it > 0) mbar_wait(a_empty, (a_it - 1) & 1u);
         if (a_rt == 0) mbar_wait(q_full, (uint32_t)a_j & 1u);
         tc_fence_after();
+        stamp(0, a_it, 1);
 #pragma unroll
         for (int i = 0; i < NS; i++) {
           mbar_wait(x_full(a_slot), a_par);
+          if (i == 0) stamp(0, a_it, 2);
           tc_fence_after();
           const uint64_t adesc = adesc_a0 + (uint64_t)(a_slot * slice16);
           for (int k = 0; k < KA; k++)
@@ -254,6 +274,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           }
         }
         tc_commit(a_full);
+        stamp(0, a_it, 3);
         a_it++;
         if (++a_rt == n_rt) {
           tc_commit(q_empty);
@@ -262,7 +283,9 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         }
       };
       auto issue_b = [&]() {
+        stamp(0, b_it, 4);
         mbar_wait(dm_full, b_it & 1u);
+        stamp(0, b_it, 5);
         if (b_rt == 0 && b_j > 0) mbar_wait(g_empty, (uint32_t)(b_j - 1) & 1u);
         tc_fence_after();
 #pragma unroll
@@ -276,6 +299,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           if (++b_slot == (uint32_t)NB) b_slot = 0;
         }
         tc_commit(dm_empty);
+        stamp(0, b_it, 6);
         b_it++;
         if (++b_rt == n_rt) {
           tc_commit(g_full);
@@ -304,15 +328,19 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
 #pragma unroll
       for (int c = 0; c < ECH; c++) logit_acc_init(lacc[c]);
       int n_pad = 0;
-      mbar_wait(q_full, (uint32_t)j & 1u);
+      // (no wait on q_full here: with one row tile per chain tile the MMA thread may run two chain tiles ahead of a warp that is
+      // still in its flush, and a parity wait cannot tell phase j from phase j + 2 -- r02u deadlock.  The scales of chain tile j
+      // are in place before the first product of the tile is issued, and a_full is waited for before they are read)
       const double* sc = scs + (j & 1) * CN + wg * ECH;
       for (int rt = 0; rt < n_rt; rt++, it++) {
         const long long row = (long long)(t_begin + rt) * TRW + r;
         const bool valid = row < a.N;
         const int negmask = (valid && a.y[row] == 0) ? (int)0x80000000 : 0;
         n_pad += valid ? 0 : 1;
+        if (et == 0) stamp(1, it, 0);
         mbar_wait(a_full, it & 1u);
         tc_fence_after();
+        if (et == 0) stamp(1, it, 1);
         double eta[ECH];
         {
           int v[NS][ECH];
@@ -322,6 +350,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_empty);   // the next tile's first product may overwrite the Eta diagonals now
+          if (et == 0) stamp(1, it, 2);
 #pragma unroll
           for (int c = 0; c < ECH; c++) {
             int d[NS];
@@ -359,13 +388,16 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
 #pragma unroll
           for (int c = 0; c < ECH; c++) logit_acc_fold(lacc[c]);
         }
+        if (et == 0) stamp(1, it, 3);
         if (it > 0) mbar_wait(dm_empty, (it - 1) & 1u);   // the second product of the previous tile has read the dm planes
+        if (et == 0) stamp(1, it, 4);
 #pragma unroll
         for (int s = 0; s < NS; s++)
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dm_row + (uint32_t)s * 4096u), "r"(pk[s][0]), "r"(pk[s][1]) : "memory");
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(dm_full);
+        if (et == 0) stamp(1, it, 5);
       }
       // ---- end of the chain tile: partial gradient and log-likelihood of (row group p, chain tile)
       mbar_wait(g_full, (uint32_t)j & 1u);
@@ -617,16 +649,35 @@ int launch_glm_i8(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws
   a.T = s->T;
   a.NB = s->NB;
   const int n_tiles = (b.C + CN - 1) / CN;
+  a.trace = nullptr;
+  // developer aid: B200NUTS_I8_TRACE=<file> writes the clock stamps of CTA 0 of the B200NUTS_I8_TRACE_LAUNCH-th launch (default 3)
+  static const char* trace_path = getenv("B200NUTS_I8_TRACE");
+  static int trace_countdown = getenv("B200NUTS_I8_TRACE_LAUNCH") ? atoi(getenv("B200NUTS_I8_TRACE_LAUNCH")) : 3;
+  const bool trace = trace_path && s->NS == 6 && trace_countdown-- == 0;
+  if (trace) {
+    cudaMalloc(&a.trace, sizeof(long long) * 3 * kTraceIt * 8);
+    cudaMemsetAsync(a.trace, 0, sizeof(long long) * 3 * kTraceIt * 8, stream);
+  }
   if (s->NS == 6) {
     glm_i8_qprep_kernel<6><<<n_tiles, 128, 0, stream>>>(b.Q, b.ld, m.D, b.list, b.n_list, b.C, s->colscale, s->KA, s->Qimg);
-    auto k = glm_i8_kernel<6>;
+    auto k = trace ? glm_i8_kernel<6, true> : glm_i8_kernel<6, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
     k<<<s->P * KQ, NTH, s->smem, stream>>>(a);
   } else {
     glm_i8_qprep_kernel<5><<<n_tiles, 128, 0, stream>>>(b.Q, b.ld, m.D, b.list, b.n_list, b.C, s->colscale, s->KA, s->Qimg);
-    auto k = glm_i8_kernel<5>;
+    auto k = glm_i8_kernel<5, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
     k<<<s->P * KQ, NTH, s->smem, stream>>>(a);
+  }
+  if (trace) {
+    static long long host[3 * kTraceIt * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, a.trace, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(a.trace);
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(host, 1, sizeof(host), f);
+      fclose(f);
+    }
   }
   return 2;
 }
