@@ -56,7 +56,7 @@ struct GlmI8Args {
   double* Gp;               // [P][cap][Dk]
   double* LPp;              // [P][cap]
   int n_fixed, N, Dk, DC, KA, cap, P, T, NB;
-  long long* trace;         // TRACE builds only: [3 roles][kTraceIt][8] clock64 stamps of CTA 0 (tools/i8_trace.py)
+  long long* trace;         // TRACE builds only: [4 roles][kTraceIt][8] clock64 stamps of CTA 0 (tools/i8_trace.py)
 };
 constexpr int kTraceIt = 96;
 
@@ -80,6 +80,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   unsigned polls = 0;
   while (!mbar_try(bar, parity))
     if (++polls > kMaxPolls) mbar_timeout(bar, parity);
+}
+// the same for the producer and the MMA thread: they wait for most of a tile's time next to four working epilogue warps of their SM
+// sub-partition; a tight polling loop takes issue slots from those (and every tile waits for the slowest of the sixteen)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  unsigned polls = 0;
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(40);
+    if (++polls > kMaxPolls) mbar_timeout(bar, parity);
+  }
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc, unsigned bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
@@ -129,32 +138,130 @@ __host__ __device__ inline size_t i8_smem_bytes(int NS, int DC, int KA, int NB) 
          32 * sizeof(double) /* exp table */ + 4 * CN * sizeof(double) /* lp partials */ + (size_t)(2 * NB + 8) * 8 + 16;
 }
 
-// V + bias in balanced digits: the NS - 1 lower bytes of (V + 0x80..80) ^ 0x80..80 are the digits in [-128, 127], the rest is the top digit
+// Balanced base-256 digits of V = rint(v 2^F) for four values at once.  Adding 0x80 at each of the NS - 1 lower byte positions
+// turns the digits into the bytes of V + BIAS (each byte = digit + 128, carries propagate as they must), and BIAS is folded into
+// the magic constant of the double -> integer conversion: the mantissa of fma(v, 2^F, 1.5 2^52 + BIAS) holds 2^51 + V + BIAS.  One
+// FP64 instruction per value; the "+ 128" is undone after the byte transposes, once per packed word of four chains.
 template <int NS>
-__device__ __forceinline__ void i8_digits(double v, uint32_t& lo, uint32_t& hi) {
-  const double t = fma(v, (double)(1ll << I8Fmt<NS>::F), 6755399441055744.0);   // 1.5 2^52 + V: the mantissa holds 2^51 + V
-  const uint32_t vlo = (uint32_t)__double2loint(t);
-  const uint32_t vhi = ((uint32_t)__double2hiint(t) & 0xfffffu) - 0x80000u;        // V >> 32 (two's complement)
-  lo = vlo + 0x80808080u;
-  const uint32_t carry = lo < vlo ? 1u : 0u;
-  if (NS == 6) {
-    hi = (vhi + 0x80u + carry) ^ 0x80u;
-  } else {
-    hi = vhi + carry;
+__device__ __forceinline__ void i8_digit_planes4(const double (&v)[4], uint32_t (&pk)[NS]) {
+  constexpr double kMagic = 6755399441055744.0 + (NS == 6 ? 551911719040.0 /* 0x8080808080 */ : 2155905152.0 /* 0x80808080 */);
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double t = fma(v[c], (double)(1ll << I8Fmt<NS>::F), kMagic);
+    lo[c] = (uint32_t)__double2loint(t);
+    hi[c] = (uint32_t)__double2hiint(t);
   }
-  lo ^= 0x80808080u;
+  // byte b of lo is digit plane NS - 1 - b; hi: plane 0 in byte 0 (NS = 5); plane 1 in byte 0 and plane 0 in byte 1 (NS = 6)
+  const uint32_t l01a = __byte_perm(lo[0], lo[1], 0x5140), l01b = __byte_perm(lo[0], lo[1], 0x7362);   // (b0 b0' b1 b1'), (b2 b2' b3 b3')
+  const uint32_t l23a = __byte_perm(lo[2], lo[3], 0x5140), l23b = __byte_perm(lo[2], lo[3], 0x7362);
+  pk[NS - 1] = __byte_perm(l01a, l23a, 0x5410) ^ 0x80808080u;
+  pk[NS - 2] = __byte_perm(l01a, l23a, 0x7632) ^ 0x80808080u;
+  pk[NS - 3] = __byte_perm(l01b, l23b, 0x5410) ^ 0x80808080u;
+  pk[NS - 4] = __byte_perm(l01b, l23b, 0x7632) ^ 0x80808080u;
+  const uint32_t h01 = __byte_perm(hi[0], hi[1], 0x5140), h23 = __byte_perm(hi[2], hi[3], 0x5140);
+  if (NS == 6) {
+    pk[1] = __byte_perm(h01, h23, 0x5410) ^ 0x80808080u;
+    pk[0] = __byte_perm(h01, h23, 0x7632);
+  } else {
+    pk[0] = __byte_perm(h01, h23, 0x5410);
+  }
+}
+
+// fastmath.cuh's logit_term for four chains at once, written stage by stage: the FP64 instructions of one chain form a dependent
+// chain of ~20 (magic-number rounding, argument reduction, degree-6 polynomial, table factor, reciprocal with one cubic step), each
+// waiting for its predecessor; stated per chain, the compiler (96 registers) issues them chain after chain and a warp spends ~23
+// cycles per FP64 instruction (r02q / r02t: 6 900 cycles of link per tile).  Four independent chains per stage fill those gaps.
+// Same operations in the same order per chain as logit_term: same bits.  prod / sum: the running product of the factors 1 + e and
+// the running sum of max(-t, 0) (LogitAcc without its exponent: at most ~900 factors in (1, 2] are multiplied between two folds).
+__device__ __forceinline__ void logit_terms4(double (&prod)[4], double (&sum)[4], const double (&eta)[4], int negmask, const double* tab, double (&d)[4]) {
+  const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+  int lo[4], hi[4], n[4];
+  unsigned ahi[4];
+  double x[4], t[4], nf[4], r[4], p[4], tv[4], em[4], f1[4], s[4], e[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    lo[c] = __double2loint(eta[c]);
+    hi[c] = __double2hiint(eta[c]) ^ negmask;                       // t = (2y - 1) eta
+    ahi[c] = (unsigned)hi[c] & 0x7fffffffu;
+    x[c] = __hiloint2double((int)(ahi[c] | 0x80000000u), lo[c]);    // -|t|
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) t[c] = fma(x[c], 46.166241308446828384, kMagic);   // 32 / ln2
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    nf[c] = t[c] - kMagic;
+    n[c] = __double2loint(t[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) r[c] = fma(nf[c], -0x1.62e42fee00000p-6, x[c]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) r[c] = fma(nf[c], -5.9631716539705866e-12, r[c]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    tv[c] = tab[n[c] & 31];
+    p[c] = fma(1.0 / 720.0, r[c], 1.0 / 120.0);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = fma(p[c], r[c], 1.0 / 24.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = fma(p[c], r[c], 1.0 / 6.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = fma(p[c], r[c], 0.5);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = fma(p[c], r[c], 1.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = fma(p[c], r[c], 1.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double v = tv[c] * p[c];
+    em[c] = __hiloint2double(__double2hiint(v) + ((n[c] >> 5) << 20), __double2loint(v));   // exp(-|t|)
+    const bool big = ahi[c] > 0x40340000u || (ahi[c] == 0x40340000u && lo[c] != 0);          // |t| > 20
+    em[c] = ((big && hi[c] < 0) || ahi[c] >= 0x4085e000u) ? 0.0 : em[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) f1[c] = 1.0 + em[c];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+#ifdef B200_FASTMATH_HOST
+    s[c] = 1.0 / f1[c];
+#else
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s[c]) : "d"(f1[c]));
+#endif
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) e[c] = fma(-f1[c], s[c], 1.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) e[c] = fma(e[c], e[c], e[c]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) s[c] = fma(s[c], e[c], s[c]);                                    // 1 / (1 + em)
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double h = s[c] - 0.5;
+    const double hs = __hiloint2double(__double2hiint(h) | (hi[c] & (int)0x80000000), __double2loint(h));   // copysign(h, t)
+    const double w = 0.5 - hs;
+    const bool big = ahi[c] > 0x40340000u || (ahi[c] == 0x40340000u && lo[c] != 0);
+    const int dsign = (big && hi[c] >= 0) ? (int)0x80000000 : negmask;
+    d[c] = __hiloint2double(__double2hiint(w) | dsign, __double2loint(w));
+    prod[c] *= f1[c];
+    const int m = hi[c] >> 31;
+    sum[c] += __hiloint2double((int)ahi[c] & m, lo[c] & m);                                     // max(-t, 0)
+  }
 }
 
 // S = sum_k d[k] 256^(NS-1-k) from the INT32 diagonals: three (NS = 6) wide multiply-adds and two 64-bit additions instead of a
 // Horner chain of 64-bit shifts
 template <int NS>
 __device__ __forceinline__ long long i8_combine(const int (&d)[NS]) {
+  // the upper diagonals are small (the top digits are at most 64): d0 256 + d1 and d2 256 + d3 fit 32 bits for K <= 128
   if (NS == 6) {
-    const long long w3 = (long long)d[0] * 256 + d[1], w2 = (long long)d[2] * 256 + d[3], w1 = (long long)d[4] * 256 + d[5];
-    return (w3 << 32) + (w2 << 16) + w1;
+    const int u3 = d[0] * 256 + d[1], u2 = d[2] * 256 + d[3];
+    const long long w1 = (long long)d[4] * 256 + d[5];
+    return ((long long)u3 << 32) + ((long long)u2 << 16) + w1;
   } else {
-    const long long w2 = (long long)d[1] * 256 + d[2], w1 = (long long)d[3] * 256 + d[4];
-    return ((long long)d[0] << 32) + (w2 << 16) + w1;
+    const int u2 = d[1] * 256 + d[2];
+    const long long w1 = (long long)d[3] * 256 + d[4];
+    return ((long long)d[0] << 32) + ((long long)u2 << 16) + w1;
   }
 }
 
@@ -224,7 +331,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       const uint64_t pol = l2_policy_evict_last();
       const uint8_t* qsrc = a.Qimg + (size_t)kq * q_tile;
       for (int j = 0; j < n_my; j++, qsrc += (size_t)KQ * q_tile) {
-        if (j > 0) mbar_wait(q_empty, (uint32_t)(j - 1) & 1u);
+        if (j > 0) mbar_wait_relaxed(q_empty, (uint32_t)(j - 1) & 1u);
         mbar_expect_tx(q_full, q_digit_bytes + CN * (unsigned)sizeof(double));
         tma_load_1d(smem_u32(qs), qsrc, q_digit_bytes, q_full);
         tma_load_1d(smem_u32(scs + (j & 1) * CN), qsrc + q_digit_bytes, CN * (unsigned)sizeof(double), q_full);
@@ -232,7 +339,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         for (int rt = 0; rt < n_rt; rt++) {
 #pragma unroll
           for (int i = 0; i < NS; i++, xsrc += slice_bytes) {
-            if (pass > 0) mbar_wait(x_empty(slot), (pass - 1) & 1u);
+            if (pass > 0) mbar_wait_relaxed(x_empty(slot), (pass - 1) & 1u);
             stamp(2, (uint32_t)(j * n_rt + rt), i);
             mbar_expect_tx(x_full(slot), slice_bytes);
             tma_load_1d_hint(ring_u + slot * slice_bytes, xsrc, slice_bytes, x_full(slot), pol);
@@ -256,13 +363,13 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       int a_rt = 0, a_j = 0, b_rt = 0, b_j = 0;
       auto issue_a = [&]() {
         stamp(0, a_it, 0);
-        if (a_it > 0) mbar_wait(a_empty, (a_it - 1) & 1u);
-        if (a_rt == 0) mbar_wait(q_full, (uint32_t)a_j & 1u);
+        if (a_it > 0) mbar_wait_relaxed(a_empty, (a_it - 1) & 1u);
+        if (a_rt == 0) mbar_wait_relaxed(q_full, (uint32_t)a_j & 1u);
         tc_fence_after();
         stamp(0, a_it, 1);
 #pragma unroll
         for (int i = 0; i < NS; i++) {
-          mbar_wait(x_full(a_slot), a_par);
+          mbar_wait_relaxed(x_full(a_slot), a_par);
           if (i == 0) stamp(0, a_it, 2);
           tc_fence_after();
           const uint64_t adesc = adesc_a0 + (uint64_t)(a_slot * slice16);
@@ -284,9 +391,9 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       };
       auto issue_b = [&]() {
         stamp(0, b_it, 4);
-        mbar_wait(dm_full, b_it & 1u);
+        mbar_wait_relaxed(dm_full, b_it & 1u);
         stamp(0, b_it, 5);
-        if (b_rt == 0 && b_j > 0) mbar_wait(g_empty, (uint32_t)(b_j - 1) & 1u);
+        if (b_rt == 0 && b_j > 0) mbar_wait_relaxed(g_empty, (uint32_t)(b_j - 1) & 1u);
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < NS; i++) {
@@ -321,12 +428,16 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
     const uint32_t lane_base = tbase + ((uint32_t)(quarter * 32) << 16);
     const uint32_t dm_row = smem_u32(dms) + (uint32_t)(wg >> 1) * 2048u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(wg & 1) * 8u;
     const double gscale = ldexp(1.0, I8Fmt<NS>::SEXP) * (r < a.Dk ? a.colscale[r] : 0.0);
-    LogitAcc lacc[ECH];
+    double lprod[ECH], lsum[ECH];
     uint32_t it = 0;
+    int y_next = (long long)t_begin * TRW + r < a.N ? a.y[(long long)t_begin * TRW + r] : 1;
     for (int j = 0; j < n_my; j++) {
       const int slot0 = (kq + KQ * j) * CN;
 #pragma unroll
-      for (int c = 0; c < ECH; c++) logit_acc_init(lacc[c]);
+      for (int c = 0; c < ECH; c++) {
+        lprod[c] = 1.0;
+        lsum[c] = 0.0;
+      }
       int n_pad = 0;
       // (no wait on q_full here: with one row tile per chain tile the MMA thread may run two chain tiles ahead of a warp that is
       // still in its flush, and a parity wait cannot tell phase j from phase j + 2 -- r02u deadlock.  The scales of chain tile j
@@ -335,12 +446,16 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       for (int rt = 0; rt < n_rt; rt++, it++) {
         const long long row = (long long)(t_begin + rt) * TRW + r;
         const bool valid = row < a.N;
-        const int negmask = (valid && a.y[row] == 0) ? (int)0x80000000 : 0;
+        const int negmask = (valid && y_next == 0) ? (int)0x80000000 : 0;
         n_pad += valid ? 0 : 1;
-        if (et == 0) stamp(1, it, 0);
+        {   // the observation of the next tile's row: its latency hides behind this tile's work
+          const long long rown = rt + 1 < n_rt ? row + TRW : (long long)t_begin * TRW + r;
+          y_next = rown < a.N ? a.y[rown] : 1;
+        }
+        if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 0);
         mbar_wait(a_full, it & 1u);
         tc_fence_after();
-        if (et == 0) stamp(1, it, 1);
+        if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 1);
         double eta[ECH];
         {
           int v[NS][ECH];
@@ -350,54 +465,50 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_empty);   // the next tile's first product may overwrite the Eta diagonals now
-          if (et == 0) stamp(1, it, 2);
+          if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 2);
 #pragma unroll
           for (int c = 0; c < ECH; c++) {
             int d[NS];
 #pragma unroll
             for (int k = 0; k < NS; k++) d[k] = v[k][c];
-            eta[c] = (double)i8_combine<NS>(d) * sc[c];
+            eta[c] = (double)i8_combine<NS>(d) * sc[c];   // (I2F.F64.S64 + DMUL: the magic-number conversion costs two more FP64
+                                                          // instructions and measured slower, r02z)
           }
         }
-        // ---- link + digits of dm: pk[s][g] = digit plane s of chains 4 g .. 4 g + 3
-        uint32_t pk[NS][ECH / 4];
+        if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 6);
+        // ---- link + digits of dm, four chains at a time; the digit planes of a group go to shared memory at once (the second
+        // product of the previous tile has long read the buffer by then: dm_empty)
 #pragma unroll
         for (int g = 0; g < ECH / 4; g++) {
-          uint32_t lo[4], hi[4];
+          double e4[4], d4[4], pr[4], sm[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            const double d = logit_term(lacc[4 * g + c], eta[4 * g + c], negmask, exptab);
-            i8_digits<NS>(d, lo[c], hi[c]);
+            e4[c] = eta[4 * g + c];
+            pr[c] = lprod[4 * g + c];
+            sm[c] = lsum[4 * g + c];
           }
-          // byte b of lo is digit plane NS - 1 - b; hi holds plane 0 (NS = 5) or planes 1 (byte 0) and 0 (byte 1) (NS = 6)
-          const uint32_t l01a = __byte_perm(lo[0], lo[1], 0x5140), l01b = __byte_perm(lo[0], lo[1], 0x7362);   // (b0 b0' b1 b1'), (b2 b2' b3 b3')
-          const uint32_t l23a = __byte_perm(lo[2], lo[3], 0x5140), l23b = __byte_perm(lo[2], lo[3], 0x7362);
-          pk[NS - 1][g] = __byte_perm(l01a, l23a, 0x5410);
-          pk[NS - 2][g] = __byte_perm(l01a, l23a, 0x7632);
-          pk[NS - 3][g] = __byte_perm(l01b, l23b, 0x5410);
-          pk[NS - 4][g] = __byte_perm(l01b, l23b, 0x7632);
-          const uint32_t h01 = __byte_perm(hi[0], hi[1], 0x5140), h23 = __byte_perm(hi[2], hi[3], 0x5140);
-          if (NS == 6) {
-            pk[1][g] = __byte_perm(h01, h23, 0x5410);
-            pk[0][g] = __byte_perm(h01, h23, 0x7632);
-          } else {
-            pk[0][g] = __byte_perm(h01, h23, 0x5410);
+          logit_terms4(pr, sm, e4, negmask, exptab, d4);
+          if (g == 0 && (et == 0 || et == 96)) stamp(et ? 3 : 1, it, 7);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            lprod[4 * g + c] = pr[c];
+            lsum[4 * g + c] = sm[c];
           }
-        }
-        if ((rt & 255) == 255) {
+          uint32_t pk[NS];
+          i8_digit_planes4<NS>(d4, pk);
+          if (g == 0) {
+            if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 3);
+            if (it > 0) mbar_wait(dm_empty, (it - 1) & 1u);   // the second product of the previous tile has read the dm planes
+            if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 4);
+          }
 #pragma unroll
-          for (int c = 0; c < ECH; c++) logit_acc_fold(lacc[c]);
+          for (int s = 0; s < NS; s++)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dm_row + (uint32_t)s * 4096u + (uint32_t)g * 4u), "r"(pk[s]) : "memory");
         }
-        if (et == 0) stamp(1, it, 3);
-        if (it > 0) mbar_wait(dm_empty, (it - 1) & 1u);   // the second product of the previous tile has read the dm planes
-        if (et == 0) stamp(1, it, 4);
-#pragma unroll
-        for (int s = 0; s < NS; s++)
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dm_row + (uint32_t)s * 4096u), "r"(pk[s][0]), "r"(pk[s][1]) : "memory");
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(dm_full);
-        if (et == 0) stamp(1, it, 5);
+        if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 5);
       }
       // ---- end of the chain tile: partial gradient and log-likelihood of (row group p, chain tile)
       mbar_wait(g_full, (uint32_t)j & 1u);
@@ -421,8 +532,12 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       }
 #pragma unroll
       for (int c = 0; c < ECH; c++) {
-        logit_acc_fold(lacc[c]);
-        double v = logit_acc_value(lacc[c], n_pad);
+        LogitAcc la;
+        la.prod = lprod[c];
+        la.sum = lsum[c];
+        la.expo = 0;
+        logit_acc_fold(la);
+        double v = logit_acc_value(la, n_pad);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -588,7 +703,8 @@ void* glm_i8_create(const ModelData& m, int Dk, int cap, int sm_count, int max_r
   s->P = P;
   s->cap = (cap + CN - 1) / CN * CN;
   const long long rows_per_group = ((long long)(s->T + P - 1) / P) * TRW;
-  if (rows_per_group * 16384ll * NS >= (1ll << 31)) {   // |digit product| <= 2^14, NS pairs on the last diagonal
+  // INT32 sums: |digit product| <= 2^14, NS pairs on the last diagonal; log-likelihood: at most ~900 factors in (1, 2] per running product
+  if (rows_per_group * 16384ll * NS >= (1ll << 31) || rows_per_group / TRW > 900) {
     delete s;
     return nullptr;
   }
@@ -655,8 +771,8 @@ int launch_glm_i8(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws
   static int trace_countdown = getenv("B200NUTS_I8_TRACE_LAUNCH") ? atoi(getenv("B200NUTS_I8_TRACE_LAUNCH")) : 3;
   const bool trace = trace_path && s->NS == 6 && trace_countdown-- == 0;
   if (trace) {
-    cudaMalloc(&a.trace, sizeof(long long) * 3 * kTraceIt * 8);
-    cudaMemsetAsync(a.trace, 0, sizeof(long long) * 3 * kTraceIt * 8, stream);
+    cudaMalloc(&a.trace, sizeof(long long) * 4 * kTraceIt * 8);
+    cudaMemsetAsync(a.trace, 0, sizeof(long long) * 4 * kTraceIt * 8, stream);
   }
   if (s->NS == 6) {
     glm_i8_qprep_kernel<6><<<n_tiles, 128, 0, stream>>>(b.Q, b.ld, m.D, b.list, b.n_list, b.C, s->colscale, s->KA, s->Qimg);
@@ -670,7 +786,7 @@ int launch_glm_i8(const ModelData& m, const GradBatch& b, const GlmWorkspace& ws
     k<<<s->P * KQ, NTH, s->smem, stream>>>(a);
   }
   if (trace) {
-    static long long host[3 * kTraceIt * 8];
+    static long long host[4 * kTraceIt * 8];
     cudaStreamSynchronize(stream);
     cudaMemcpy(host, a.trace, sizeof(host), cudaMemcpyDeviceToHost);
     cudaFree(a.trace);

@@ -10,7 +10,7 @@ import sys
 import numpy as np
 
 K = 96
-t = np.fromfile(sys.argv[1], dtype=np.int64).reshape(3, K, 8)
+t = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, K, 8)
 t0 = t[t > 0].min()
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 rel = lambda v: (v - t0) if v > 0 else -1
@@ -31,3 +31,9 @@ if valid:
     print("MMA thread: A waits a_empty/q", int(np.median([m[i, 1] - m[i, 0] for i in valid])), " first X plane", int(np.median([m[i, 2] - m[i, 1] for i in valid])),
           " issue A", int(np.median([m[i, 3] - m[i, 2] for i in valid])), " B wait dm_full", int(np.median([m[i, 5] - m[i, 4] for i in valid])),
           " issue B", int(np.median([m[i, 6] - m[i, 5] for i in valid])))
+
+for role, name in ((1, "warp 2 (sub-partition 2)"), (3, "warp 5 (sub-partition 1, beside the MMA thread)")):
+    if t.shape[0] > role and valid:
+        e = t[role]
+        f = lambda a, b: int(np.median([e[i, a] - e[i, b] for i in valid if e[i, a] > 0 and e[i, b] > 0] or [0]))
+        print(f"{name}: wait a_full {f(1, 0)}  read Eta {f(2, 1)}  recombine {f(6, 2)}  link g0 {f(7, 6)}  digits+wait g0 {f(4, 7)}  group 1 + stores {f(5, 4)}  next tile {int(np.median([e[i + 1, 0] - e[i, 5] for i in valid[:-1]]))}")
