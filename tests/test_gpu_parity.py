@@ -73,6 +73,21 @@ def test_glm_kernel_variants_agree(variant, monkeypatch):
         e.close()
 
 
+def test_glm_i8_five_planes(monkeypatch):
+    """B200NUTS_I8_SLICES=5: 38-bit operands, 15 digit-plane products per contraction -- inside north_star's 1e-10 (lp and the
+    gradient relative to its largest component), as tools/ozaki_i8_model.py predicts (tests/test_i8_numerics_model.py)."""
+    monkeypatch.setenv("B200NUTS_GLM_VARIANT", "7")
+    monkeypatch.setenv("B200NUTS_I8_SLICES", "5")
+    for data, nq in ((cases.logistic_data(1234, 100), 70), (cases.logistic_data(30011, 37), 131)):
+        m = O.Model("logistic", data)
+        q = np.random.default_rng(6).uniform(-1, 1, size=(nq, m.D))
+        lp0, g0 = m.lp_grad(q)
+        e = _engine("logistic", data)
+        lp, g = e.log_prob_grad(q)
+        e.close()
+        assert _rel(lp, lp0) < 1e-10 and np.max(np.abs(g - g0)) / np.max(np.abs(g0)) < 1e-10
+
+
 def test_glm_v5_is_bit_identical_to_v2(monkeypatch):
     """glm_dmma5_kernel (two out-of-phase groups of four warps, the default) keeps v2's summation order: same bits at c3's width
     (D = 101, several chain tiles, ragged row count) and for the poisson link."""
