@@ -43,6 +43,14 @@ constexpr int NTH = 576;      // warp 0: loads, warp 1: MMA issue + TMEM allocat
 constexpr int ECH = 8;        // chains per epilogue thread: warp group wg = (warp - 2) / 4 owns chains [8 wg, 8 wg + 8) of the tile
 constexpr int NEW = 16;       // epilogue warps
 constexpr int KQ = 4;         // chain-tile classes: CTA (p, kq) serves row group p and the chain tiles ct == kq (mod KQ)
+// When may the next tile's first product start?  1 (shipped): as soon as the Eta accumulator has been read -- the product then
+// runs under this tile's link and stretches it (scalar FP64 is starved while the tensor core runs), but its slow single-thread
+// issue is off the critical path.  0: only after the link -- the FP64 phase runs undisturbed (2 x 1.45 k cycles instead of
+// 3.6 k + 1.8 k) but the tile then waits for the 24 MMAs to be issued (2.7 k cycles).  Measured r03e / r03f: 0.618 vs 0.582 ms per
+// c3 launch.  Both keep the integer-only recombination in front of the FP64 phase, under the previous tile's second product.
+#ifndef I8_EARLY_RELEASE
+#define I8_EARLY_RELEASE 1
+#endif
 constexpr uint32_t ACOL = 0, GCOL = 256;   // TMEM columns of the Eta / G diagonals (NS * 32 <= 192 each)
 constexpr unsigned kMaxPolls = 1u << 24;   // a protocol error must end the kernel (trap), never hang the device: each try_wait suspends
                                             // the thread for a bounded time of its own, so this is seconds, not microseconds
@@ -90,6 +98,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     if (++polls > kMaxPolls) mbar_timeout(bar, parity);
   }
 }
+// the MMA warp waits as ONE: the vote makes the loop's exit warp-uniform, so that everything computed after it (ring cursors,
+// descriptors) can live in uniform registers and an MMA costs a handful of instructions instead of an R2UR per operand word
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  unsigned polls = 0;
+  while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {
+    __nanosleep(40);
+    if (++polls > kMaxPolls) mbar_timeout(bar, parity);
+  }
+}
 __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc, unsigned bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
@@ -117,9 +134,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 __host__ __device__ constexpr uint32_t idesc_i8(int M, int N, int mn_major) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Issued by the whole (converged) warp 1 with one elected lane executing it: with a single active thread the compiler cannot keep
+// the descriptors in uniform registers and wraps every MMA in an ELECT / R2UR.BROADCAST loop of ~25 instructions (150 cycles per
+// MMA on a sub-partition shared with four working warps: r03d, 3.6 k cycles to issue the 24 MMAs of one product)
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
                ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -328,6 +351,9 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       const size_t q_tile = i8_q_tile_bytes(NS, KA);
       const uint32_t ring_u = smem_u32(ring);
       uint32_t slot = 0, pass = 0;   // pass over the ring: use number of `slot`
+      // every CTA runs the same schedule, so all 148 would ask L2 for their six planes (86 KB each) at the same moment of every tile
+      // and a plane would take ~4 500 cycles to arrive (r02t / r03c); offsets spread over one tile period keep the bursts apart
+      __nanosleep((blockIdx.x % 16u) * 200u);
       const uint64_t pol = l2_policy_evict_last();
       const uint8_t* qsrc = a.Qimg + (size_t)kq * q_tile;
       for (int j = 0; j < n_my; j++, qsrc += (size_t)KQ * q_tile) {
@@ -352,8 +378,8 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread): first product of tile it + 1 before the second product of tile it =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp 1, converged; one elected lane issues): first product of tile it + 1 before the second product of tile it =====
+    {
       const uint32_t ring_u = smem_u32(ring), qs_u = smem_u32(qs), dm_u = smem_u32(dms);
       const uint64_t bdesc_a = make_desc(qs_u, 128, DCQ * 128), bdesc_b = make_desc(dm_u, 128, 2048);
       const uint64_t adesc_a0 = make_desc(ring_u, 128, DC * 128), adesc_b0 = make_desc(ring_u, DC * 128, 128);
@@ -363,13 +389,13 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
       int a_rt = 0, a_j = 0, b_rt = 0, b_j = 0;
       auto issue_a = [&]() {
         stamp(0, a_it, 0);
-        if (a_it > 0) mbar_wait_relaxed(a_empty, (a_it - 1) & 1u);
-        if (a_rt == 0) mbar_wait_relaxed(q_full, (uint32_t)a_j & 1u);
+        if (a_it > 0) mbar_wait_warp(a_empty, (a_it - 1) & 1u);
+        if (a_rt == 0) mbar_wait_warp(q_full, (uint32_t)a_j & 1u);
         tc_fence_after();
         stamp(0, a_it, 1);
 #pragma unroll
         for (int i = 0; i < NS; i++) {
-          mbar_wait_relaxed(x_full(a_slot), a_par);
+          mbar_wait_warp(x_full(a_slot), a_par);
           if (i == 0) stamp(0, a_it, 2);
           tc_fence_after();
           const uint64_t adesc = adesc_a0 + (uint64_t)(a_slot * slice16);
@@ -380,20 +406,20 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
             a_par ^= 1u;
           }
         }
-        tc_commit(a_full);
+        tc_commit_elect(a_full);
         stamp(0, a_it, 3);
         a_it++;
         if (++a_rt == n_rt) {
-          tc_commit(q_empty);
+          tc_commit_elect(q_empty);
           a_rt = 0;
           a_j++;
         }
       };
       auto issue_b = [&]() {
         stamp(0, b_it, 4);
-        mbar_wait_relaxed(dm_full, b_it & 1u);
+        mbar_wait_warp(dm_full, b_it & 1u);
         stamp(0, b_it, 5);
-        if (b_rt == 0 && b_j > 0) mbar_wait_relaxed(g_empty, (uint32_t)(b_j - 1) & 1u);
+        if (b_rt == 0 && b_j > 0) mbar_wait_warp(g_empty, (uint32_t)(b_j - 1) & 1u);
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < NS; i++) {
@@ -402,14 +428,14 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           for (int k = 0; k < 4; k++)
             mma_i8(tbase + GCOL + 32 * i, adesc + (uint64_t)(k * kstep_b), bdesc_b + (uint64_t)(k * 32), idesc_i8(128, 32 * (NS - i), 1),
                    (b_rt > 0 || i > 0 || k > 0) ? 1u : 0u);
-          tc_commit(x_empty(b_slot));
+          tc_commit_elect(x_empty(b_slot));
           if (++b_slot == (uint32_t)NB) b_slot = 0;
         }
-        tc_commit(dm_empty);
+        tc_commit_elect(dm_empty);
         stamp(0, b_it, 6);
         b_it++;
         if (++b_rt == n_rt) {
-          tc_commit(g_full);
+          tc_commit_elect(g_full);
           b_rt = 0;
           b_j++;
         }
@@ -456,34 +482,38 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         mbar_wait(a_full, it & 1u);
         tc_fence_after();
         if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 1);
-        double eta[ECH];
+        long long Sv[ECH];   // the recombination is integer-only, so that it can run under the previous tile's second product
         {
           int v[NS][ECH];
 #pragma unroll
           for (int k = 0; k < NS; k++) tmem_ld8(lane_base + ACOL + 32 * k + ECH * wg, v[k]);
           tmem_wait_ld();
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(a_empty);   // the next tile's first product may overwrite the Eta diagonals now
+          if (I8_EARLY_RELEASE) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_empty);
+          }
           if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 2);
 #pragma unroll
           for (int c = 0; c < ECH; c++) {
             int d[NS];
 #pragma unroll
             for (int k = 0; k < NS; k++) d[k] = v[k][c];
-            eta[c] = (double)i8_combine<NS>(d) * sc[c];   // (I2F.F64.S64 + DMUL: the magic-number conversion costs two more FP64
-                                                          // instructions and measured slower, r02z)
+            Sv[c] = i8_combine<NS>(d);
           }
         }
         if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 6);
-        // ---- link + digits of dm, four chains at a time; the digit planes of a group go to shared memory at once (the second
-        // product of the previous tile has long read the buffer by then: dm_empty)
+        // ---- the FP64 phase: conversion + link of all eight chains, four at a time.  Scalar FP64 is starved while the tensor core
+        // runs (tools/microbench/fp64_link.cu: 72x): what precedes (read, integer recombination) and what follows (digit planes,
+        // transposes, stores, hand-over) is integer-only and costs nothing extra under an MMA stream; see I8_EARLY_RELEASE.
+        double dv[ECH];
 #pragma unroll
         for (int g = 0; g < ECH / 4; g++) {
           double e4[4], d4[4], pr[4], sm[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            e4[c] = eta[4 * g + c];
+            e4[c] = (double)Sv[4 * g + c] * sc[4 * g + c];   // (I2F.F64.S64 + DMUL: the magic-number conversion costs two more FP64
+                                                             // instructions and measured slower, r02z)
             pr[c] = lprod[4 * g + c];
             sm[c] = lsum[4 * g + c];
           }
@@ -493,14 +523,23 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           for (int c = 0; c < 4; c++) {
             lprod[4 * g + c] = pr[c];
             lsum[4 * g + c] = sm[c];
+            dv[4 * g + c] = d4[c];
           }
+        }
+        if (!I8_EARLY_RELEASE) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_empty);   // the next tile's first product may start (and overwrite the Eta diagonals)
+        }
+        if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 3);
+        if (it > 0) mbar_wait(dm_empty, (it - 1) & 1u);   // the second product of the previous tile has read the dm planes
+        if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 4);
+#pragma unroll
+        for (int g = 0; g < ECH / 4; g++) {
+          double d4[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) d4[c] = dv[4 * g + c];
           uint32_t pk[NS];
           i8_digit_planes4<NS>(d4, pk);
-          if (g == 0) {
-            if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 3);
-            if (it > 0) mbar_wait(dm_empty, (it - 1) & 1u);   // the second product of the previous tile has read the dm planes
-            if (et == 0 || et == 96) stamp(et ? 3 : 1, it, 4);
-          }
 #pragma unroll
           for (int s = 0; s < NS; s++)
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(dm_row + (uint32_t)s * 4096u + (uint32_t)g * 4u), "r"(pk[s]) : "memory");
