@@ -46,7 +46,7 @@ constexpr int KQ = 4;         // chain-tile classes: CTA (p, kq) serves row grou
 // When may the next tile's first product start?  1 (shipped): as soon as the Eta accumulator has been read -- the product then
 // runs under this tile's link and stretches it (scalar FP64 is starved while the tensor core runs), but its slow single-thread
 // issue is off the critical path.  0: only after the link -- the FP64 phase runs undisturbed (2 x 1.45 k cycles instead of
-// 3.6 k + 1.8 k) but the tile then waits for the 24 MMAs to be issued (2.7 k cycles).  Measured r03e / r03f: 0.618 vs 0.582 ms per
+// 3.6 k + 1.8 k) but the tile then waits for the 24 MMAs to be issued (2.2 k cycles).  Measured r03h / r03g: 0.597 vs 0.576 ms per
 // c3 launch.  Both keep the integer-only recombination in front of the FP64 phase, under the previous tile's second product.
 #ifndef I8_EARLY_RELEASE
 #define I8_EARLY_RELEASE 1
@@ -140,6 +140,23 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N, int mn_major) {
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
                ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// four K steps of one plane product in one block: one election, the descriptor increments next to the MMAs
+__device__ __forceinline__ void mma_i8_x4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t astep, uint32_t bstep, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a1, b1, a2, b2, a3, b3, sa, sb;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "cvt.u64.u32 sa, %3;\n\tcvt.u64.u32 sb, %4;\n\t"
+      "add.s64 a1, %1, sa;\n\tadd.s64 b1, %2, sb;\n\t"
+      "add.s64 a2, a1, sa;\n\tadd.s64 b2, b1, sb;\n\t"
+      "add.s64 a3, a2, sa;\n\tadd.s64 b3, b2, sb;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %5, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], a1, b1, %5, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], a2, b2, %5, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], a3, b3, %5, t;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(astep), "r"(bstep), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar) : "memory");
@@ -399,8 +416,12 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
           if (i == 0) stamp(0, a_it, 2);
           tc_fence_after();
           const uint64_t adesc = adesc_a0 + (uint64_t)(a_slot * slice16);
-          for (int k = 0; k < KA; k++)
-            mma_i8(tbase + ACOL + 32 * i, adesc + (uint64_t)(k * 16), bdesc_a + (uint64_t)(k * 16), idesc_i8(128, 32 * (NS - i), 0), (i > 0 || k > 0) ? 1u : 0u);
+          if (KA == 4) {
+            mma_i8_x4(tbase + ACOL + 32 * i, adesc, bdesc_a, 16u, 16u, idesc_i8(128, 32 * (NS - i), 0), i > 0 ? 1u : 0u);
+          } else {
+            for (int k = 0; k < KA; k++)
+              mma_i8(tbase + ACOL + 32 * i, adesc + (uint64_t)(k * 16), bdesc_a + (uint64_t)(k * 16), idesc_i8(128, 32 * (NS - i), 0), (i > 0 || k > 0) ? 1u : 0u);
+          }
           if (++a_slot == (uint32_t)NB) {
             a_slot = 0;
             a_par ^= 1u;
@@ -424,10 +445,7 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
 #pragma unroll
         for (int i = 0; i < NS; i++) {
           const uint64_t adesc = adesc_b0 + (uint64_t)(b_slot * slice16);
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            mma_i8(tbase + GCOL + 32 * i, adesc + (uint64_t)(k * kstep_b), bdesc_b + (uint64_t)(k * 32), idesc_i8(128, 32 * (NS - i), 1),
-                   (b_rt > 0 || i > 0 || k > 0) ? 1u : 0u);
+          mma_i8_x4(tbase + GCOL + 32 * i, adesc, bdesc_b, kstep_b, 32u, idesc_i8(128, 32 * (NS - i), 1), (b_rt > 0 || i > 0) ? 1u : 0u);
           tc_commit_elect(x_empty(b_slot));
           if (++b_slot == (uint32_t)NB) b_slot = 0;
         }
