@@ -580,11 +580,14 @@ __global__ void __launch_bounds__(NTH, 1) glm_i8_kernel(const GlmI8Args a) {
         if (lane == 0) mbar_arrive(g_empty);
 #pragma unroll
         for (int c = 0; c < ECH; c++) {
-          long long S = v[0][c];
+          // sum_k diag_k 256^(NS-1-k): the top diagonal separately in FP64 -- with up to 21 k rows per group it reaches 2^30, and
+          // 2^30 2^40 does not fit 64 bits; the rest stays below 2^61
+          long long S = v[1][c];
 #pragma unroll
-          for (int k = 1; k < NS; k++) S = S * 256 + v[k][c];
+          for (int k = 2; k < NS; k++) S = S * 256 + v[k][c];
           const int slot = slot0 + ECH * wg + c;
-          if (r < a.Dk && slot < n_list) a.Gp[((size_t)p * a.cap + slot) * a.Dk + r] = (double)S * gscale;
+          if (r < a.Dk && slot < n_list)
+            a.Gp[((size_t)p * a.cap + slot) * a.Dk + r] = fma((double)v[0][c], (double)(1ll << (8 * (NS - 1))), (double)S) * gscale;
         }
       }
 #pragma unroll
