@@ -135,8 +135,13 @@ def ncu_traffic(model):
     None when this workload has no capture."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(model)
-        return None if not t else {"bytes": t["read_bytes"] + t["write_bytes"], "kernel": t["kernel"], "chains_in_launch": t["chains_in_launch"],
-                                   "source": t["capture"]}
+        if not t:
+            return None
+        out = {"bytes": t["read_bytes"] + t["write_bytes"], "kernel": t["kernel"], "chains_in_launch": t["chains_in_launch"], "source": t["capture"]}
+        for k in ("note", "cold_cache_bytes", "cold_cache_capture"):
+            if k in t:
+                out[k] = t[k]
+        return out
     except Exception:
         return None
 
@@ -319,6 +324,7 @@ def run_gpu_workload(wname, K, W, num_warmup, chains_per_gpu, scale, rank, world
     assert (err == 0).all(), f"chains stopped with errors: {np.unique(err)}"
     # ---- D2H of the timed draws through the C ABI (part of e2e), into pinned host memory allocated outside the timed leg
     draws = _pinned((C, K, 7 + e.K))
+    e.fetch_draws(chain0=0, nchains=1, row0=Wx, nrows=1, constrained=True, out=draws[:1, :1])   # untimed: one-off costs of the path
     t0 = time.time()
     e.fetch_draws(row0=Wx, nrows=K, constrained=True, out=draws)
     fetch_s = time.time() - t0
@@ -411,6 +417,10 @@ def run_gpu_workload(wname, K, W, num_warmup, chains_per_gpu, scale, rank, world
                 roof["int8_peak_top_s"] = 4550.0
                 roof["int8_peak_source"] = "tools/microbench/umma_i8.cu on this pool (profiles/r02m_umma_i8.txt: 7 825 MAC/clk/SM x 148 SMs x 1.965 GHz); nominal 4 500"
                 roof["int8_frac"] = roof["int8_top_s_issued"] / roof["int8_peak_top_s"] if roof["int8_top_s_issued"] else None
+                # what this formulation has to move per launch: the six digit planes of X once (they are re-read per chain tile from L2),
+                # the partial gradients of 37 row groups written once and read once by the reduction
+                n_req = n_chain_grads / world / n_grad_launch
+                roof["i8_algorithmic_bytes_per_launch"] = 6.0 * math.ceil(N_rows / 128.0) * 128 * 112 + 2.0 * 37 * n_req * 104 * 8
             if row_mode:
                 roof["allreduce_us_per_leapfrog"] = ar_us
                 roof["allreduce_payload_bytes"] = ar_bytes

@@ -777,6 +777,8 @@ void* glm_i8_create(const ModelData& m, int Dk, int cap, int sm_count, int max_r
   }
   s->NB = NB;
   s->smem = i8_smem_bytes(NS, s->DC, s->KA, NB);
+  // (a persisting-L2 set-aside for the digit planes, cudaLimitPersistingL2CacheSize, measured within noise -- r03l -- and would take
+  // L2 capacity from every other kernel of the process: not used)
   const size_t slice_bytes = (size_t)2048 * s->DC;
   unsigned long long* colmax = nullptr;
   int* bad = nullptr;
