@@ -219,6 +219,8 @@ struct b200nuts_engine {
   std::vector<PluginVar> plug_data;
   // device
   double *d_X = nullptr, *d_yr = nullptr, *d_sigma = nullptr;
+  double* d_fetch = nullptr;   // staging buffer of b200nuts_fetch_draws
+  size_t fetch_bytes = 0;
   int* d_yi = nullptr;
   signed char* d_y8 = nullptr;
   unsigned short* d_ypk = nullptr;
@@ -336,7 +338,7 @@ void b200nuts_destroy(b200nuts_engine* e) {
   if (e->plug && e->plug_model && e->plug->destroy) e->plug->destroy(e->plug_model);
   free_dev(e->d_X); free_dev(e->d_yr); free_dev(e->d_sigma); free_dev(e->d_yi); free_dev(e->d_y8); free_dev(e->d_ypk);
   free_dev(e->dc.cs); free_dev(e->dc.q); free_dev(e->dc.g); free_dev(e->dc.zV); free_dev(e->dc.slab); free_dev(e->dc.draws); free_dev(e->dc.mat);
-  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws);
+  free_dev(e->d_user_q0); free_dev(e->d_user_im); free_dev(e->d_active); free_dev(e->d_list); free_dev(e->d_nactive); free_dev(e->d_glm_ws); free_dev(e->d_fetch);
   glm_i8_destroy(e->glm_ws.i8);
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
@@ -392,9 +394,11 @@ int b200nuts_set_data_f64(b200nuts_engine* e, const char* name, const double* ho
     }
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     const int K = (int)dims[1], ldx = (K + 1 + 7) & ~7;
-    free_dev(e->d_X);
-    e->d_X = nullptr;
-    CUDA_TRY(e, cudaMalloc(&e->d_X, sizeof(double) * (size_t)dims[0] * ldx));
+    if (!e->d_X || e->x_rows != dims[0] || e->x_cols != dims[1]) {  // a data set of the same shape is uploaded into the buffer in place
+      free_dev(e->d_X);
+      e->d_X = nullptr;
+      CUDA_TRY(e, cudaMalloc(&e->d_X, sizeof(double) * (size_t)dims[0] * ldx));
+    }
     CUDA_TRY(e, cudaMemcpy2DAsync(e->d_X + 1, sizeof(double) * ldx, host, sizeof(double) * K, sizeof(double) * K, (size_t)dims[0], cudaMemcpyHostToDevice, e->stream));
     glm_pad_design_kernel<<<(unsigned)((dims[0] + 255) / 256), 256, 0, e->stream>>>(e->d_X, dims[0], K, ldx);
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1129,8 +1133,16 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
   // chunk over chains so that the staging buffer stays <= ~1 GiB
   int64_t chunk = std::max<int64_t>(1, (int64_t)((1ull << 30) / (row_bytes * (size_t)nrows)));
   chunk = std::min(chunk, nchains);
-  double* d_out;
-  CUDA_TRY(e, cudaMalloc(&d_out, row_bytes * nrows * chunk));
+  // device staging buffer of the (write_array'd) rows: kept in the engine and only ever grown -- a cudaMalloc / cudaFree pair per
+  // call was measured at 1 .. 700 ms on the bench boxes (r03j / r03m), more than the copy itself
+  if (e->fetch_bytes < row_bytes * nrows * chunk) {
+    free_dev(e->d_fetch);
+    e->d_fetch = nullptr;
+    e->fetch_bytes = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_fetch, row_bytes * nrows * chunk));
+    e->fetch_bytes = row_bytes * nrows * chunk;
+  }
+  double* d_out = e->d_fetch;
   for (int64_t off = 0; off < nchains; off += chunk) {
     const int64_t m = std::min(chunk, nchains - off);
     const long long tot = m * nrows;
@@ -1149,12 +1161,10 @@ int b200nuts_fetch_draws(b200nuts_engine* e, int64_t chain0, int64_t nchains, in
     cudaError_t r = cudaStreamSynchronize(e->stream);
     if (r == cudaSuccess) r = cudaGetLastError();
     if (r != cudaSuccess) {
-      cudaFree(d_out);
       e->err = std::string("fetch_draws: ") + cudaGetErrorString(r);
       return B200NUTS_SOFTWARE;
     }
   }
-  cudaFree(d_out);
   return B200NUTS_OK;
 }
 
