@@ -8,9 +8,12 @@ Metric (BASELINE.json): min bulk-ESS / s (and gradient evaluations / s) of the S
                 N=100k, D=100, 1024 chains | c2 eight schools 4096 chains | c1 bernoulli 4 chains | c4 IRT | c5 poisson
   value       = min over (lp__, every model column) of the split rank-normalised bulk ESS of the K timed transitions,
                 summed over ranks, / device time of those K transitions (max over ranks), inputs resident in HBM
-  e2e         = same ESS / (host->device upload of the data set + the K transitions + device->host fetch of their draws),
-                all through the C ABI with host buffers
-  roofline    = dominant kernel family (gradient stage) timed live with CUDA events on the engine's stream
+  e2e         = same ESS / (host->device upload of the data set + wall time of the K transitions + device->host fetch of their
+                draws), all through the C ABI with pinned host buffers; the two copy legs are timed on an engine whose device
+                buffers exist (the copies, not cudaMalloc / stream creation) and after one untimed fetch of the same shape
+  roofline    = dominant kernel family (gradient stage) timed live with CUDA events on the engine's stream; for the logistic
+                link the INT8 digit-plane kernel on tcgen05 serves: `achieved` counts the algorithmic fp64 flops against the
+                DGEMM rate measured in the run (a fraction above one is possible), `int8_*` what was issued to the tensor cores
   cpu_baseline= the UNMODIFIED reference (oracle/_ref/<model>, CmdStan 2.36 compiled from /root/reference) on the host
                 cores, chains in parallel, on a bounded sample of the same workload
   --impl reference  times only that CPU arm and prints the same JSON line shape.
